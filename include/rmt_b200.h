@@ -1,0 +1,196 @@
+/*
+ * rmt_b200.h -- C ABI of librmt_b200.so: the B200 (sm_100a) kernels behind the
+ * collocated Reference-Map-Technique timestep of pyRMT.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own (it is
+ * pure Python + Numba); its operator API is the set of Python functions in
+ * pyRMT/functions.py, pyRMT/interpolators.py and pyRMT/utils.py.  Each entry
+ * point below names the reference function (file:line, relative to the
+ * upstream repo root) it replaces; pyrmt_b200/functions.py binds them with
+ * ctypes under the reference's own names and signatures.
+ *
+ * Conventions
+ *   - Every array argument is a DEVICE pointer to C-contiguous fp64 data of
+ *     shape (Ny, Nx), element [j*Nx + i] (x fastest) -- the layout of the
+ *     reference's NumPy arrays -- unless stated otherwise.  Buffers are owned
+ *     by the caller (PyTorch allocates them); no entry point allocates on the
+ *     hot path (plans/workspaces are created once per grid).
+ *   - `stream` is a cudaStream_t passed as void*.  All calls are asynchronous.
+ *   - Return value: 0 = ok, -1 = invalid argument, -2 = unsupported size,
+ *     >0 = cudaError_t of a failed launch.  Nothing throws across the ABI.
+ *   - Input arrays are never modified unless the parameter says "in place".
+ */
+#ifndef RMT_B200_H
+#define RMT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int rmt_abi_version(void);
+
+/* ------------------------------------------------------------------ utils */
+/* pyRMT/utils.py:4-59,116-131.  op: 0 grad_central_x_2nd, 1 grad_central_y_2nd,
+ * 2 grad_central_x_4th, 3 grad_central_y_4th, 4 lap_2nd. */
+int rmt_stencil_op(const double *f, double *out, int Ny, int Nx, double hx, double hy, int op,
+                   void *stream);
+/* pyRMT/utils.py:61-114 diff_upwind_3rd(f, u, h, axis); axis 1 = x, 0 = y. */
+int rmt_diff_upwind_3rd(const double *f, const double *u, double *out, int Ny, int Nx, double h,
+                        int axis, void *stream);
+/* pyRMT/functions.py:660-671 smoothed_heaviside (the sin form). */
+int rmt_heaviside(const double *x, double *H, long n, double w_t, void *stream);
+/* H and rho_local=(1-H)*rho_s+H*rho_f in one pass (functions.py:695-698 and the
+ * driver glue benchmarks/soft_disc_in_lid_driven.py:102-103).  H may be NULL. */
+int rmt_heaviside_rho(const double *phi, double *H, double *rho, long n, double w_t, double rho_s,
+                      double rho_f, void *stream);
+/* out = q * (phi <= 0): the "* solid_mask" glue, soft_disc_in_lid_driven.py:88-91. */
+int rmt_mask_mul(const double *q, const double *phi, double *out, long n, void *stream);
+
+/* ------------------------------------------------------------- reductions */
+int rmt_reduce_workspace_doubles(void);
+/* compute_timestep's reduction (functions.py:176) + the isfinite guard of
+ * advect_reference_map (:524).  out2 = {max sqrt(a^2+b^2), #non-finite}. */
+int rmt_max_speed(const double *a, const double *b, long n, double *work, double *out2, void *stream);
+/* out4 = {sum, min, max, #non-finite} (np.mean / np.ptp call sites :1118,:1298,:1362). */
+int rmt_field_stats(const double *x, long n, double *work, double *out4, void *stream);
+
+/* ------------------------------------------------ boundary-condition table */
+/* A BC callable (benchmarks/common.py:27-50, tests/test_poisson.py:39-64) is
+ * classified once on the host into a gather table and applied in place:
+ *   field(dst[e])[cell] = ca[e] * field(src[e])[cell] + cb[e]   (src<0: constant)
+ * indices pack (field<<62 | cell), field 0 = u, 1 = v. */
+int rmt_apply_bc(double *u, double *v, const long long *dst, const long long *src, const double *ca,
+                 const double *cb, int n, void *stream);
+
+/* ---------------------------------------------------------- level set (a2) */
+/* rebuild_phi_from_reference_map (functions.py:1366) for the disc family of
+ * benchmarks/common.py:55-57:  phi = min_k(|xi - c_k| - R_k).  bin_start/cand
+ * describe a (gb x gb) candidate grid over [0,Lx]x[0,Ly]; gb = 0 -> exhaustive. */
+int rmt_disc_sdf(const double *X1, const double *X2, double *phi, long n, const double *cx,
+                 const double *cy, const double *R, int ndisc, const int *bin_start, const int *cand,
+                 int gb, double Lx, double Ly, void *stream);
+
+/* ------------------------------------------------------------ interpolators */
+/* pyRMT/interpolators.py:4-62 (cubic=0) and :64-141 (cubic=1); nq query points. */
+int rmt_sample(const double *u, const double *xq, const double *yq, double *out, long nq, double dx,
+               double dy, int Nx, int Ny, int cubic, void *stream);
+
+/* ---------------------------------------------------------------- advection */
+/* pyRMT/functions.py:194-227 (cubic=0) / :230-251 (cubic=1).  q1/out1 may be
+ * NULL; when given, a second component shares the backtrace. */
+int rmt_advect_sl_rk4(const double *q0, const double *q1, const double *a, const double *b,
+                      const double *X, const double *Y, double *out0, double *out1, int Ny, int Nx,
+                      double dt, double dx, double dy, int cubic, void *stream);
+/* pyRMT/functions.py:396-415 (scheme 1 weno5), :443-459 (0 central2), :489-496
+ * (2 conservative): SSP-RK3, RHS fused into each stage.  work1/work2: (Ny,Nx). */
+int rmt_advect_euler_rk3(const double *q, const double *a, const double *b, const double *phi,
+                         double *out, double *work1, double *work2, int Ny, int Nx, double dx,
+                         double dy, double dt, double w_cut, int scheme, void *stream);
+/* _central2_rhs :420-440 / _weno5_rhs :321-393 / _conservative_rhs :462-486. */
+int rmt_euler_rhs(const double *q, const double *a, const double *b, const double *phi, double *out,
+                  int Ny, int Nx, double dx, double dy, double w_cut, int scheme, void *stream);
+
+/* ------------------------------------------------------------ extrapolation */
+/* pyRMT/functions.py:48-163 extrapolate_reference_map + utils.py:134-167. */
+long rmt_extrapolate_workspace_bytes(int Ny, int Nx);
+int rmt_extrapolate(const double *X1, const double *X2, const double *phi, double *X1e, double *X2e,
+                    int Ny, int Nx, double dx, double dy, int max_layers, void *workspace,
+                    void *stream);
+/* device exp() used for the weights, exposed so tests can prove bit-equality
+ * with the host libm (functions.py:120). */
+int rmt_exp_probe(const double *x, double *y, long n, void *stream);
+
+/* ------------------------------------------------- stress + momentum (a10-a13) */
+/* pyRMT/functions.py:545-658 solid_cauchy_stress. */
+int rmt_solid_stress(const double *X1, const double *X2, const double *phi, double *sxx, double *sxy,
+                     double *syy, double *J, int Ny, int Nx, double dx, double dy, double mu_s,
+                     double kappa, double w_cut, double detg_clamp, int isochoric, void *stream);
+/* pyRMT/functions.py:837-861 compute_curvature. */
+int rmt_curvature(const double *phi, double *curv, int Ny, int Nx, double dx, double dy, void *stream);
+/* functions.py:700-704: st_force = -gamma * curvature(phi) * grad(H(phi)). */
+int rmt_surface_tension(const double *phi, double *fsx, double *fsy, int Ny, int Nx, double dx,
+                        double dy, double w_t, double gamma, void *stream);
+/* pyRMT/functions.py:897-944 velocity_rhs_blended_optimized (H and rho_local
+ * are arrays as in the reference; fsx/fsy may be NULL = 0.0). */
+int rmt_velocity_rhs(const double *u, const double *v, const double *p, const double *sxx,
+                     const double *sxy, const double *syy, const double *H, const double *rho,
+                     const double *fsx, const double *fsy, double *ru, double *rv, int Ny, int Nx,
+                     double dx, double dy, double mu_f, void *stream);
+/* One classical-RK4 stage of momentum_step_rk4 (functions.py:711-758): the RHS
+ * of the BC-applied stage state (us, vs) with the Kelvin-Voigt term (:717-730),
+ * fused with the stage update.  H and rho_local are evaluated from phi in-kernel.
+ *   stage 1: acc = k            out = u0 + (dt/2) k
+ *   stage 2: acc += 2k          out = u0 + (dt/2) k
+ *   stage 3: acc += 2k          out = u0 + dt k
+ *   stage 4:                    out = u0 + (dt/6)(acc + k)
+ * The caller applies the BC table to `out` between stages (rmt_apply_bc). */
+int rmt_momentum_stage(const double *us, const double *vs, const double *p, const double *sxx,
+                       const double *sxy, const double *syy, const double *phi, const double *fsx,
+                       const double *fsy, const double *u0, const double *v0, double *acc_u,
+                       double *acc_v, double *out_u, double *out_v, int Ny, int Nx, double dx,
+                       double dy, double dt, double mu_f, double eta_s, double w_t, double rho_s,
+                       double rho_f, int stage, void *stream);
+
+/* ------------------------------------------------------ projection (a14-a17) */
+/* _compute_divergence (functions.py:1005-1014). */
+int rmt_divergence(const double *a, const double *b, double *div, int Ny, int Nx, double dx,
+                   double dy, void *stream);
+/* _compute_divergence_rc (:1016-1071), constant-density branch; d_f = dt/mean(rho)
+ * is read from the device scalar rho_sum[0] / (Ny*Nx) (no host sync). */
+int rmt_divergence_rc(const double *a, const double *b, const double *p_prev, const double *rho_sum,
+                      double *div, int Ny, int Nx, double dx, double dy, double dt, void *stream);
+/* _compute_pressure_gradient (:1073-1089). */
+int rmt_pressure_gradient(const double *p, double *gx, double *gy, int Ny, int Nx, double dx,
+                          double dy, void *stream);
+/* periodic: _compute_divergence_periodic :1236-1243, _compute_pressure_gradient_periodic :1246-1252 */
+int rmt_divergence_periodic(const double *a, const double *b, double *div, int Ny, int Nx, double dx,
+                            double dy, void *stream);
+int rmt_pressure_gradient_periodic(const double *p, double *gx, double *gy, int Ny, int Nx, double dx,
+                                   double dy, void *stream);
+/* Fused projection front end (:1292-1295,:1331 / :1286-1290):
+ *   rhs = rho * div / dt      (Neumann: rho elementwise; rho==NULL -> rho_scalar)
+ *   rhs = rho_bar * div / dt  (periodic: rho_bar = rho_sum[0]/(Ny*Nx))
+ * div is Rhie-Chow when p_prev != NULL (Neumann only), else plain / periodic. */
+int rmt_projection_rhs(const double *a, const double *b, const double *p_prev, const double *rho,
+                       double rho_scalar, const double *rho_sum, double *rhs, int Ny, int Nx,
+                       double dx, double dy, double dt, int periodic, void *stream);
+/* Fused projection back end (:1350-1362 / :1284-1290):
+ *   pc = sol - sol_sum[0]/(Ny*Nx)   (sol_sum: device scalar from the solver; NULL = already centred)
+ *   a = a* - (dt/rho) dpc/dx ; b likewise ; p = (p_prev or 0) + pc
+ * rho == NULL -> rho_scalar.  The caller removes mean(p) afterwards
+ * (rmt_field_stats + rmt_subtract_mean) and applies the BC table to (a, b). */
+int rmt_projection_correct(const double *sol, const double *sol_sum, const double *a_star,
+                           const double *b_star, const double *rho, double rho_scalar,
+                           const double *p_prev, double *a, double *b, double *p, int Ny, int Nx,
+                           double dx, double dy, double dt, int periodic, void *stream);
+/* x[k] = x[k] - s[0]/n  in place (the np.mean removals :1118,:1232,:1362). */
+int rmt_subtract_mean(double *x, const double *sum, long n, void *stream);
+
+/* -------------------------------------------------- spectral Poisson solves */
+/* Plan for one grid.  kind 0: DCT-I / Neumann (_solve_poisson_dct :1107-1119,
+ * scipy.fft.dctn/idctn type 1); kind 1: periodic FFT on the reduced
+ * (Ny-1, Nx-1) grid (_solve_poisson_fft :1216-1233, numpy.fft.fft2/ifft2).
+ * Power-of-two transform lengths run hand-written shared-memory FFTs; other
+ * lengths (N <= RMT_DENSE_MAX) run dense O(N^2) transforms per line. */
+#define RMT_DENSE_MAX 1536
+typedef struct rmt_poisson_plan rmt_poisson_plan;
+int rmt_poisson_plan_create(int Ny, int Nx, int kind, rmt_poisson_plan **plan);
+void rmt_poisson_plan_destroy(rmt_poisson_plan *plan);
+/* 1 if the plan uses the shared-memory FFT path in both directions, else 0. */
+int rmt_poisson_plan_is_fast(const rmt_poisson_plan *plan);
+/* sol = idctn(dctn(rhs)/eig), then sol -= mean(sol).  eig: (Ny, Nx).
+ * sum_out (device, 1 double): if non-NULL the mean is NOT removed; sum(sol) is
+ * written there instead so the consumer (rmt_projection_correct) can fold the
+ * shift into its own pass. */
+int rmt_poisson_solve_dct(rmt_poisson_plan *plan, const double *rhs, const double *eig, double *sol,
+                          double *sum_out, void *stream);
+/* r = rhs[:-1,:-1]; r -= mean(r); spec = fft2(r)/eig; spec[null] = 0;
+ * sol = tile_overlap(real(ifft2(spec))); sol -= mean(sol).
+ * eig: (Ny-1, Nx-1) doubles; null: (Ny-1, Nx-1) bytes. */
+int rmt_poisson_solve_fft(rmt_poisson_plan *plan, const double *rhs, const double *eig,
+                          const unsigned char *null_mask, double *sol, double *sum_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMT_B200_H */

@@ -1,0 +1,385 @@
+// advect.cu -- reference-map advection kernels.
+//
+// Replaces (reference file:line):
+//   pyRMT/interpolators.py:4-62,64-141,143-154   bilinear / monotone bicubic sampling
+//   pyRMT/functions.py:194-251                   semi-Lagrangian RK4 backtrace (bilinear, cubic)
+//   pyRMT/functions.py:256-415                   WENO5 faces + RHS + SSP-RK3
+//   pyRMT/functions.py:420-459                   central2 RHS + SSP-RK3
+//   pyRMT/functions.py:462-496                   conservative RHS + SSP-RK3
+//
+// Semi-Lagrangian: one thread per node does the whole RK4 backtrace (8 velocity
+// samples) and the final sample of q -- nine 4-tap gathers served by L1/L2
+// (displacements are <= 1 cell at CFL 0.2), one coalesced store.
+// Eulerian schemes: one launch per SSP-RK3 stage; the stage kernel fuses the
+// RHS with the Shu-Osher combination so no RHS array ever reaches HBM.
+#include "common.cuh"
+#include "../../include/rmt_b200.h"
+
+using namespace rmt;
+
+namespace {
+
+// ---------------------------------------------------------------- sampling
+__device__ __forceinline__ bool clamp_coords(double xq, double yq, double inv_dx_unused, double dx,
+                                             double dy, int Nx, int Ny, double &x, double &y)
+{
+    x = xq / dx;
+    y = yq / dy;
+    if (!(isfinite(x) && isfinite(y))) return false;
+    if (x < 0.0) x = 0.0;
+    else if (x > Nx - 1.0) x = Nx - 1.0;
+    if (y < 0.0) y = 0.0;
+    else if (y > Ny - 1.0) y = Ny - 1.0;
+    return true;
+}
+
+__device__ __forceinline__ double bilinear(const double *__restrict__ u, double xq, double yq,
+                                           double dx, double dy, int Nx, int Ny)
+{
+    double x, y;
+    if (!clamp_coords(xq, yq, 0.0, dx, dy, Nx, Ny, x, y)) return nan("");
+    int ix = (int)floor(x), iy = (int)floor(y);
+    if (ix >= Nx - 1) ix = Nx - 2;
+    if (iy >= Ny - 1) iy = Ny - 2;
+    double fx = x - ix, fy = y - iy;
+    const double *r0 = u + (size_t)iy * Nx + ix;
+    const double *r1 = r0 + Nx;
+    double v00 = __ldg(r0), v10 = __ldg(r0 + 1), v01 = __ldg(r1), v11 = __ldg(r1 + 1);
+    return (1 - fx) * (1 - fy) * v00 + fx * (1 - fy) * v10 + (1 - fx) * fy * v01 + fx * fy * v11;
+}
+
+// Two fields sampled at the same point share the index/weight computation.
+__device__ __forceinline__ void bilinear2(const double *__restrict__ a, const double *__restrict__ b,
+                                          double xq, double yq, double dx, double dy, int Nx, int Ny,
+                                          double &va, double &vb)
+{
+    double x, y;
+    if (!clamp_coords(xq, yq, 0.0, dx, dy, Nx, Ny, x, y)) { va = vb = nan(""); return; }
+    int ix = (int)floor(x), iy = (int)floor(y);
+    if (ix >= Nx - 1) ix = Nx - 2;
+    if (iy >= Ny - 1) iy = Ny - 2;
+    double fx = x - ix, fy = y - iy;
+    double w00 = (1 - fx) * (1 - fy), w10 = fx * (1 - fy), w01 = (1 - fx) * fy, w11 = fx * fy;
+    size_t o = (size_t)iy * Nx + ix;
+    va = w00 * __ldg(a + o) + w10 * __ldg(a + o + 1) + w01 * __ldg(a + o + Nx) + w11 * __ldg(a + o + Nx + 1);
+    vb = w00 * __ldg(b + o) + w10 * __ldg(b + o + 1) + w01 * __ldg(b + o + Nx) + w11 * __ldg(b + o + Nx + 1);
+}
+
+__device__ __forceinline__ double catmull_rom(double v0, double v1, double v2, double v3, double x)
+{
+    double a0 = -0.5 * v0 + 1.5 * v1 - 1.5 * v2 + 0.5 * v3;
+    double a1 = v0 - 2.5 * v1 + 2.0 * v2 - 0.5 * v3;
+    double a2 = -0.5 * v0 + 0.5 * v2;
+    return a0 * (x * x * x) + a1 * (x * x) + a2 * x + v1;
+}
+
+__device__ __forceinline__ double bicubic(const double *__restrict__ u, double xq, double yq,
+                                          double dx, double dy, int Nx, int Ny)
+{
+    double x, y;
+    if (!clamp_coords(xq, yq, 0.0, dx, dy, Nx, Ny, x, y)) return nan("");
+    int ix = (int)floor(x), iy = (int)floor(y);
+    double fx = x - ix, fy = y - iy;
+    double rows[4], lo = 1e18, hi = -1e18;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        int yg = min(max(iy - 1 + m, 0), Ny - 1);
+        double c[4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            int xg = min(max(ix - 1 + n, 0), Nx - 1);
+            double v = __ldg(u + (size_t)yg * Nx + xg);
+            c[n] = v;
+            if (v < lo) lo = v;
+            if (v > hi) hi = v;
+        }
+        rows[m] = catmull_rom(c[0], c[1], c[2], c[3], fx);
+    }
+    double r = catmull_rom(rows[0], rows[1], rows[2], rows[3], fy);
+    if (r < lo) r = lo;
+    if (r > hi) r = hi;
+    return r;
+}
+
+template <bool CUBIC>
+__global__ void k_sample(const double *__restrict__ u, const double *__restrict__ xq,
+                         const double *__restrict__ yq, double *__restrict__ out, long nq, double dx,
+                         double dy, int Nx, int Ny)
+{
+    for (long k = blockIdx.x * (long)blockDim.x + threadIdx.x; k < nq; k += (long)gridDim.x * blockDim.x)
+        out[k] = CUBIC ? bicubic(u, xq[k], yq[k], dx, dy, Nx, Ny)
+                       : bilinear(u, xq[k], yq[k], dx, dy, Nx, Ny);
+}
+
+// ------------------------------------------------- semi-Lagrangian RK4 backtrace
+// NQ reference-map components share one backtrace (NQ=1 is the reference's
+// per-component call; NQ=2 is the fused form the driver can use because X1 and
+// X2 are advected with the same (a, b, dt)).
+template <bool CUBIC, int NQ>
+__global__ void k_advect_sl(const double *__restrict__ q0, const double *__restrict__ q1,
+                            const double *__restrict__ a, const double *__restrict__ b,
+                            const double *__restrict__ X, const double *__restrict__ Y,
+                            double *__restrict__ o0, double *__restrict__ o1, int Ny, int Nx,
+                            double dt, double dx, double dy)
+{
+    int i = blockIdx.x * TX + threadIdx.x;
+    int j = blockIdx.y * TY + threadIdx.y;
+    if (i >= Nx || j >= Ny) return;
+    size_t c = (size_t)j * Nx + i;
+    double x = X[c], y = Y[c];
+    const double half_dt = 0.5 * dt, sixth_dt = dt / 6.0;
+    double k1x, k1y, k2x, k2y, k3x, k3y, k4x, k4y;
+    auto vel = [&](double xx, double yy, double &vx, double &vy) {
+        if (CUBIC) {
+            vx = bicubic(a, xx, yy, dx, dy, Nx, Ny);
+            vy = bicubic(b, xx, yy, dx, dy, Nx, Ny);
+        } else {
+            bilinear2(a, b, xx, yy, dx, dy, Nx, Ny, vx, vy);
+        }
+    };
+    vel(x, y, k1x, k1y);
+    vel(x - half_dt * k1x, y - half_dt * k1y, k2x, k2y);
+    vel(x - half_dt * k2x, y - half_dt * k2y, k3x, k3y);
+    vel(x - dt * k3x, y - dt * k3y, k4x, k4y);
+    double xb = x - sixth_dt * (k1x + 2 * k2x + 2 * k3x + k4x);
+    double yb = y - sixth_dt * (k1y + 2 * k2y + 2 * k3y + k4y);
+    if (CUBIC) {
+        o0[c] = bicubic(q0, xb, yb, dx, dy, Nx, Ny);
+        if (NQ == 2) o1[c] = bicubic(q1, xb, yb, dx, dy, Nx, Ny);
+    } else if (NQ == 2) {
+        double r0, r1;
+        bilinear2(q0, q1, xb, yb, dx, dy, Nx, Ny, r0, r1);
+        o0[c] = r0;
+        o1[c] = r1;
+    } else {
+        o0[c] = bilinear(q0, xb, yb, dx, dy, Nx, Ny);
+    }
+}
+
+// ------------------------------------------------------------------- WENO5
+__device__ __forceinline__ double sq(double v) { return v * v; }
+
+__device__ __forceinline__ double weno_mix(double r0, double r1, double r2, double b0, double b1,
+                                           double b2)
+{
+    const double eps = 1.0e-6;
+    double a0 = 0.1 / sq(eps + b0), a1 = 0.6 / sq(eps + b1), a2 = 0.3 / sq(eps + b2);
+    double s = a0 + a1 + a2;
+    return (a0 / s) * r0 + (a1 / s) * r1 + (a2 / s) * r2;
+}
+
+// left-biased value at k+1/2 from (k-2..k+2), functions.py:256-286
+__device__ __forceinline__ double weno_minus(double vm2, double vm1, double v0, double vp1, double vp2)
+{
+    double r0 = (2.0 * vm2 - 7.0 * vm1 + 11.0 * v0) / 6.0;
+    double r1 = (-vm1 + 5.0 * v0 + 2.0 * vp1) / 6.0;
+    double r2 = (2.0 * v0 + 5.0 * vp1 - vp2) / 6.0;
+    double b0 = (13.0 / 12.0) * sq(vm2 - 2.0 * vm1 + v0) + 0.25 * sq(vm2 - 4.0 * vm1 + 3.0 * v0);
+    double b1 = (13.0 / 12.0) * sq(vm1 - 2.0 * v0 + vp1) + 0.25 * sq(vm1 - vp1);
+    double b2 = (13.0 / 12.0) * sq(v0 - 2.0 * vp1 + vp2) + 0.25 * sq(3.0 * v0 - 4.0 * vp1 + vp2);
+    return weno_mix(r0, r1, r2, b0, b1, b2);
+}
+
+// right-biased value at k+1/2 from (k-1..k+3), functions.py:289-318
+__device__ __forceinline__ double weno_plus(double vm1, double v0, double vp1, double vp2, double vp3)
+{
+    double r0 = (2.0 * vp3 - 7.0 * vp2 + 11.0 * vp1) / 6.0;
+    double r1 = (-vp2 + 5.0 * vp1 + 2.0 * v0) / 6.0;
+    double r2 = (2.0 * vp1 + 5.0 * v0 - vm1) / 6.0;
+    double b0 = (13.0 / 12.0) * sq(vp3 - 2.0 * vp2 + vp1) + 0.25 * sq(3.0 * vp1 - 4.0 * vp2 + vp3);
+    double b1 = (13.0 / 12.0) * sq(vp2 - 2.0 * vp1 + v0) + 0.25 * sq(vp2 - v0);
+    double b2 = (13.0 / 12.0) * sq(vp1 - 2.0 * v0 + vm1) + 0.25 * sq(vp1 - 4.0 * v0 + 3.0 * vm1);
+    return weno_mix(r0, r1, r2, b0, b1, b2);
+}
+
+// d q / d(line) at index k of n with the reference's face selection and rim
+// fallbacks (functions.py:347-389).  `g(o)` returns q at line index k+o.
+// For vel < 0 the reference feeds BOTH faces the same five points, so the
+// difference is exactly zero unless the upper-rim fallback kicks in; that
+// behaviour is reproduced, not repaired.
+template <class G>
+__device__ __forceinline__ double weno5_dq(G g, int k, int n, double vel, double invh,
+                                           double q_last /* q at line index n-1 */)
+{
+    double qp, qm;
+    if (vel >= 0.0) {
+        double m2 = g(-2), m1 = g(-1), c0 = g(0), p1 = g(1), p2 = g(2);
+        qp = weno_minus(m2, m1, c0, p1, p2);
+        qm = (k >= 3) ? weno_minus(g(-3), m2, m1, c0, p1) : qp;
+    } else {
+        double m1 = g(-1), c0 = g(0), p1 = g(1), p2 = g(2);
+        if (k + 3 < n) {
+            qp = weno_plus(m1, c0, p1, p2, g(3));
+            qm = qp;
+        } else {
+            qp = weno_minus(g(-2), m1, c0, p1, p2);
+            qm = weno_plus(m1, c0, p1, p2, q_last);
+        }
+    }
+    return (qp - qm) * invh;
+}
+
+// SSP-RK3 stage:  out = c0*q0 + c1*(qs + dt*RHS(qs))   (functions.py:406-415)
+//   stage 1: c0=0,   c1=1   (q0 unused)      q1 = q + dt R(q)
+//   stage 2: c0=3/4, c1=1/4                  q2 = 3/4 q + 1/4 (q1 + dt R(q1))
+//   stage 3: c0=1/3, c1=2/3                  q' = 1/3 q + 2/3 (q2 + dt R(q2))
+// SCHEME: 0 central2, 1 weno5, 2 conservative.  RHS is zero where phi > w_cut
+// or outside the scheme's interior range.
+template <int SCHEME>
+__global__ void k_euler_stage(const double *__restrict__ q0, const double *__restrict__ qs,
+                              const double *__restrict__ a, const double *__restrict__ b,
+                              const double *__restrict__ phi, double *__restrict__ out, int Ny,
+                              int Nx, double dx, double dy, double dt, double w_cut, double c0,
+                              double c1, int first)
+{
+    int i = blockIdx.x * TX + threadIdx.x;
+    int j = blockIdx.y * TY + threadIdx.y;
+    if (i >= Nx || j >= Ny) return;
+    size_t c = (size_t)j * Nx + i;
+    const int halo = (SCHEME == 1) ? 2 : 1;
+    double qc = qs[c];
+    double rhs = 0.0;
+    bool interior = (i >= halo && i < Nx - halo && j >= halo && j < Ny - halo);
+    if (interior && !(phi[c] > w_cut)) {
+        if (SCHEME == 0) {
+            double dqdx = (__ldg(qs + c + 1) - __ldg(qs + c - 1)) * (0.5 / dx);
+            double dqdy = (__ldg(qs + c + Nx) - __ldg(qs + c - Nx)) * (0.5 / dy);
+            rhs = -(a[c] * dqdx + b[c] * dqdy);
+        } else if (SCHEME == 2) {
+            double fx = (__ldg(a + c + 1) * __ldg(qs + c + 1) - __ldg(a + c - 1) * __ldg(qs + c - 1)) * (0.5 / dx);
+            double fy = (__ldg(b + c + Nx) * __ldg(qs + c + Nx) - __ldg(b + c - Nx) * __ldg(qs + c - Nx)) * (0.5 / dy);
+            rhs = -(fx + fy);
+        } else {
+            double u = a[c], v = b[c];
+            const double *row = qs + (size_t)j * Nx;
+            const double *col = qs + i;
+            double dqdx = weno5_dq([&](int o) { return __ldg(row + i + o); }, i, Nx, u, 1.0 / dx,
+                                   __ldg(row + Nx - 1));
+            double dqdy = weno5_dq([&](int o) { return __ldg(col + (size_t)(j + o) * Nx); }, j, Ny, v,
+                                   1.0 / dy, __ldg(col + (size_t)(Ny - 1) * Nx));
+            rhs = -(u * dqdx + v * dqdy);
+        }
+    }
+    double upd = qc + dt * rhs;
+    out[c] = first ? upd : (c0 * q0[c] + c1 * upd);
+}
+
+// standalone RHS (API parity for _weno5_rhs/_central2_rhs/_conservative_rhs)
+template <int SCHEME>
+__global__ void k_euler_rhs(const double *__restrict__ qs, const double *__restrict__ a,
+                            const double *__restrict__ b, const double *__restrict__ phi,
+                            double *__restrict__ out, int Ny, int Nx, double dx, double dy, double w_cut)
+{
+    int i = blockIdx.x * TX + threadIdx.x;
+    int j = blockIdx.y * TY + threadIdx.y;
+    if (i >= Nx || j >= Ny) return;
+    size_t c = (size_t)j * Nx + i;
+    const int halo = (SCHEME == 1) ? 2 : 1;
+    double rhs = 0.0;
+    bool interior = (i >= halo && i < Nx - halo && j >= halo && j < Ny - halo);
+    if (interior && !(phi[c] > w_cut)) {
+        if (SCHEME == 0) {
+            double dqdx = (__ldg(qs + c + 1) - __ldg(qs + c - 1)) * (0.5 / dx);
+            double dqdy = (__ldg(qs + c + Nx) - __ldg(qs + c - Nx)) * (0.5 / dy);
+            rhs = -(a[c] * dqdx + b[c] * dqdy);
+        } else if (SCHEME == 2) {
+            double fx = (__ldg(a + c + 1) * __ldg(qs + c + 1) - __ldg(a + c - 1) * __ldg(qs + c - 1)) * (0.5 / dx);
+            double fy = (__ldg(b + c + Nx) * __ldg(qs + c + Nx) - __ldg(b + c - Nx) * __ldg(qs + c - Nx)) * (0.5 / dy);
+            rhs = -(fx + fy);
+        } else {
+            double u = a[c], v = b[c];
+            const double *row = qs + (size_t)j * Nx;
+            const double *col = qs + i;
+            double dqdx = weno5_dq([&](int o) { return __ldg(row + i + o); }, i, Nx, u, 1.0 / dx,
+                                   __ldg(row + Nx - 1));
+            double dqdy = weno5_dq([&](int o) { return __ldg(col + (size_t)(j + o) * Nx); }, j, Ny, v,
+                                   1.0 / dy, __ldg(col + (size_t)(Ny - 1) * Nx));
+            rhs = -(u * dqdx + v * dqdy);
+        }
+    }
+    out[c] = rhs;
+}
+
+inline int flat_blocks(long n) { long b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
+
+template <int SCHEME>
+static int euler_rk3(const double *q, const double *a, const double *b, const double *phi, double *out,
+                     double *w1, double *w2, int Ny, int Nx, double dx, double dy, double dt,
+                     double w_cut, cudaStream_t s)
+{
+    dim3 blk(TX, TY), grd(rmt_cdiv(Nx, TX), rmt_cdiv(Ny, TY));
+    k_euler_stage<SCHEME><<<grd, blk, 0, s>>>(q, q, a, b, phi, w1, Ny, Nx, dx, dy, dt, w_cut, 0.0, 1.0, 1);
+    RMT_LAUNCH_CHECK();
+    k_euler_stage<SCHEME><<<grd, blk, 0, s>>>(q, w1, a, b, phi, w2, Ny, Nx, dx, dy, dt, w_cut, 0.75, 0.25, 0);
+    RMT_LAUNCH_CHECK();
+    k_euler_stage<SCHEME><<<grd, blk, 0, s>>>(q, w2, a, b, phi, out, Ny, Nx, dx, dy, dt, w_cut,
+                                            1.0 / 3.0, 2.0 / 3.0, 0);
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rmt_sample(const double *u, const double *xq, const double *yq, double *out, long nq, double dx,
+               double dy, int Nx, int Ny, int cubic, void *stream)
+{
+    if (!u || !xq || !yq || !out || nq <= 0 || Nx < 2 || Ny < 2) return RMT_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cubic) k_sample<true><<<flat_blocks(nq), 256, 0, s>>>(u, xq, yq, out, nq, dx, dy, Nx, Ny);
+    else k_sample<false><<<flat_blocks(nq), 256, 0, s>>>(u, xq, yq, out, nq, dx, dy, Nx, Ny);
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
+
+int rmt_advect_sl_rk4(const double *q0, const double *q1, const double *a, const double *b,
+                      const double *X, const double *Y, double *out0, double *out1, int Ny, int Nx,
+                      double dt, double dx, double dy, int cubic, void *stream)
+{
+    if (!q0 || !a || !b || !X || !Y || !out0 || Nx < 2 || Ny < 2) return RMT_EINVAL;
+    if ((q1 == nullptr) != (out1 == nullptr)) return RMT_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 blk(TX, TY), grd(rmt_cdiv(Nx, TX), rmt_cdiv(Ny, TY));
+    if (q1) {
+        if (cubic) k_advect_sl<true, 2><<<grd, blk, 0, s>>>(q0, q1, a, b, X, Y, out0, out1, Ny, Nx, dt, dx, dy);
+        else k_advect_sl<false, 2><<<grd, blk, 0, s>>>(q0, q1, a, b, X, Y, out0, out1, Ny, Nx, dt, dx, dy);
+    } else {
+        if (cubic) k_advect_sl<true, 1><<<grd, blk, 0, s>>>(q0, q1, a, b, X, Y, out0, out1, Ny, Nx, dt, dx, dy);
+        else k_advect_sl<false, 1><<<grd, blk, 0, s>>>(q0, q1, a, b, X, Y, out0, out1, Ny, Nx, dt, dx, dy);
+    }
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
+
+int rmt_advect_euler_rk3(const double *q, const double *a, const double *b, const double *phi,
+                         double *out, double *work1, double *work2, int Ny, int Nx, double dx,
+                         double dy, double dt, double w_cut, int scheme, void *stream)
+{
+    if (!q || !a || !b || !phi || !out || !work1 || !work2 || Nx < 5 || Ny < 5) return RMT_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (scheme) {
+    case 0: return euler_rk3<0>(q, a, b, phi, out, work1, work2, Ny, Nx, dx, dy, dt, w_cut, s);
+    case 1: return euler_rk3<1>(q, a, b, phi, out, work1, work2, Ny, Nx, dx, dy, dt, w_cut, s);
+    case 2: return euler_rk3<2>(q, a, b, phi, out, work1, work2, Ny, Nx, dx, dy, dt, w_cut, s);
+    }
+    return RMT_EINVAL;
+}
+
+int rmt_euler_rhs(const double *q, const double *a, const double *b, const double *phi, double *out,
+                  int Ny, int Nx, double dx, double dy, double w_cut, int scheme, void *stream)
+{
+    if (!q || !a || !b || !phi || !out || Nx < 5 || Ny < 5) return RMT_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 blk(TX, TY), grd(rmt_cdiv(Nx, TX), rmt_cdiv(Ny, TY));
+    switch (scheme) {
+    case 0: k_euler_rhs<0><<<grd, blk, 0, s>>>(q, a, b, phi, out, Ny, Nx, dx, dy, w_cut); break;
+    case 1: k_euler_rhs<1><<<grd, blk, 0, s>>>(q, a, b, phi, out, Ny, Nx, dx, dy, w_cut); break;
+    case 2: k_euler_rhs<2><<<grd, blk, 0, s>>>(q, a, b, phi, out, Ny, Nx, dx, dy, w_cut); break;
+    default: return RMT_EINVAL;
+    }
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
+
+}  // extern "C"

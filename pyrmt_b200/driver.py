@@ -1,0 +1,105 @@
+"""The FSI time loop of the reference's drivers, written against the drop-in
+operator API, plus the synthetic multi-disc cases of SURVEY 8(d).
+
+``fsi_step`` is benchmarks/soft_disc_in_lid_driven.py:78-106 (identical in
+disc_in_taylor_green.py:78-106) line for line; it works on ndarrays (host
+round trips inside every operator) or on CUDA tensors (device resident).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import functions as F
+from .bc import free_slip_box_bc, no_slip_lid_bc, periodic_bc
+from .levelset import DiscSDF
+
+
+def fsi_step(state, prm, dt=None):
+    """Advance (a, b, p, X1, X2) by one step.  Returns (state, dt, extras)."""
+    a, b, p, X1, X2 = state
+    dx, dy = prm["dx"], prm["dy"]
+    if dt is None:
+        dt = F.compute_timestep(a, b, dx, dy, prm["CFL"], prm["dt_cap"], prm["mu_s"], prm["rho_s"],
+                                prm.get("gamma", 0.0), prm["rho_f"], mu_f=prm["mu_f"], eta_s=prm["eta_s"],
+                                kappa=prm["kappa"])
+    phi = F.rebuild_phi_from_reference_map(X1, X2, prm["phi_init"])
+    phi = F.reinitialize_level_set(phi, dx, dy, "none")
+    sch, wc = prm["scheme"], prm.get("w_cut", 0.0)
+    X1 = F.mask_solid(F.advect_reference_map(X1, a, b, prm["X"], prm["Y"], dt, dx, dy, phi, sch, wc), phi)
+    X2 = F.mask_solid(F.advect_reference_map(X2, a, b, prm["X"], prm["Y"], dt, dx, dy, phi, sch, wc), phi)
+    X1, X2 = F.extrapolate_reference_map(X1, X2, phi, dx, dy, prm["layers"])
+    phi = F.rebuild_phi_from_reference_map(X1, X2, prm["phi_init"])
+    a_s, b_s, sxx, sxy, syy, J = F.momentum_step_rk4(
+        a, b, p, X1, X2, prm["bc"], prm["mu_s"], prm["kappa"], prm["eta_s"], dx, dy, dt, prm["rho_s"],
+        prm["rho_f"], phi, prm["mu_f"], prm["w_t"], prm.get("gamma", 0.0))
+    _, rho_local = F.heaviside_and_density(phi, prm["w_t"], prm["rho_s"], prm["rho_f"])
+    a, b, p, _, _ = F.pressure_projection_amg(a_s, b_s, dx, dy, dt, rho_local, prm["bc"], p_prev=p,
+                                              eigenvalues=prm["eig"], bc_type=prm.get("bc_type", "neumann"))
+    return (a, b, p, X1, X2), dt, dict(phi=phi, sxx=sxx, sxy=sxy, syy=syy, J=J)
+
+
+class LidBC:
+    """no_slip_lid_bc with a fixed lid speed (a picklable callable)."""
+
+    def __init__(self, lid_speed=1.0):
+        self.lid_speed = float(lid_speed)
+
+    def __call__(self, u, v):
+        return no_slip_lid_bc(u, v, self.lid_speed)
+
+
+def disc_lattice(k_side, L, R_frac, seed=20240607):
+    """K = k_side^2 discs on a jittered lattice."""
+    rng = np.random.default_rng(seed)
+    m, n = np.meshgrid(np.arange(k_side), np.arange(k_side))
+    jx = rng.uniform(-0.01, 0.01, size=m.shape)
+    jy = rng.uniform(-0.01, 0.01, size=m.shape)
+    cx = ((m + 0.5) / k_side + jx) * L
+    cy = ((n + 0.5) / k_side + jy) * L
+    return cx.ravel(), cy.ravel(), np.full(cx.size, R_frac * L)
+
+
+def make_case(N, L=1.0, k_side=8, R_frac=0.04, scheme="weno5", bc_kind="lid", device=None,
+              mu_s=0.1, kappa=0.0, rho=1.0, eta_s=0.01, mu_f=0.01, CFL=0.2, dt_cap=1e-3, layers=3,
+              taylor_green_U0=None, as_numpy=False):
+    """Synthetic multi-disc FSI case on an N x N node grid.
+
+    Returns (state, prm) with device-resident fp64 tensors (or ndarrays)."""
+    X, Y, dx, dy = F.create_grid(N, N, L, L)
+    cx, cy, R = disc_lattice(k_side, L, R_frac)
+    sdf = DiscSDF(cx, cy, R, domain=(L, L))
+    if bc_kind == "lid":
+        bc, bc_type = LidBC(1.0), "neumann"
+        eig = F._precompute_poisson_eigenvalues(N, N, dx, dy)
+    elif bc_kind == "free_slip":
+        bc, bc_type = free_slip_box_bc, "neumann"
+        eig = F._precompute_poisson_eigenvalues(N, N, dx, dy)
+    elif bc_kind == "periodic":
+        bc, bc_type = periodic_bc, "periodic"
+        eig = F._precompute_poisson_eigenvalues_periodic(N, N, dx, dy)
+    else:
+        raise ValueError("bc_kind must be 'lid', 'free_slip' or 'periodic'")
+    if as_numpy:
+        up = lambda arr: np.ascontiguousarray(arr, dtype=np.float64)
+    else:
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        up = lambda arr: torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(dev)
+    Xd, Yd = up(X), up(Y)
+    phi0 = sdf(Xd, Yd)
+    X1 = F.mask_solid(Xd, phi0)
+    X2 = F.mask_solid(Yd, phi0)
+    X1, X2 = F.extrapolate_reference_map(X1, X2, phi0, dx, dy, layers)
+    if taylor_green_U0 is not None:
+        k = 2.0 * np.pi / L
+        a0 = taylor_green_U0 * k * np.sin(k * X) * np.cos(k * Y)
+        b0 = -taylor_green_U0 * k * np.cos(k * X) * np.sin(k * Y)
+    else:
+        a0, b0 = np.zeros_like(X), np.zeros_like(X)
+    a, b = bc(a0, b0)
+    state = (up(a), up(b), up(np.zeros_like(X)), X1, X2)
+    prm = dict(dx=dx, dy=dy, CFL=CFL, dt_cap=dt_cap, mu_s=mu_s, kappa=kappa, rho_s=rho, rho_f=rho,
+               eta_s=eta_s, mu_f=mu_f, w_t=2.0 * dx, layers=layers, scheme=scheme, w_cut=0.0,
+               phi_init=sdf, bc=bc, bc_type=bc_type, eig=eig, X=Xd, Y=Yd, N=N, L=L,
+               discs=(cx, cy, R))
+    return state, prm

@@ -1,0 +1,439 @@
+"""GPU parity tests: the CUDA path (through the drop-in API, hence through the
+C ABI of librmt_b200.so) against
+
+  * the golden vectors recorded from the real reference (tests/golden/*.npz), and
+  * the CPU oracle (oracle/rmt_oracle.py) on seeded inputs at larger sizes.
+
+Tolerances: BIT-EXACT for the narrow-band extrapolation and everything that only
+copies/gathers; relative L-inf <= 1e-10 (BASELINE.json north_star) for the
+floating-point operators -- in practice they sit at 1e-14..1e-12.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_linf
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10          # north_star: per-step relative L-inf on u, v, p, xi
+TIGHT = 5e-13        # what well-conditioned stencil operators actually achieve
+
+
+@pytest.fixture(scope="module")
+def P():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import pyrmt_b200
+    from pyrmt_b200 import functions
+    return functions
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import rmt_oracle
+    return rmt_oracle
+
+
+def same(x, ref):
+    return np.array_equal(np.asarray(x), np.asarray(ref), equal_nan=True)
+
+
+def joint_rel(xs, refs):
+    """max|x-ref| over several fields / max|ref| over the same fields (H10: compare
+    stress components against max|sigma| jointly)."""
+    scale = max(float(np.max(np.abs(r))) for r in refs)
+    err = max(float(np.max(np.abs(np.asarray(x) - r))) for x, r in zip(xs, refs))
+    return err / scale if scale > 0 else err
+
+
+# ----------------------------------------------------------------- utils
+def test_utils(P, golden):
+    g = golden("utils")
+    f, w, dx, dy = g["f"], g["w"], float(g["dx"]), float(g["dy"])
+    assert rel_linf(P.grad_central_x_2nd(f, dx), g["gx2"]) < TIGHT
+    assert rel_linf(P.grad_central_y_2nd(f, dy), g["gy2"]) < TIGHT
+    assert rel_linf(P.grad_central_x_4th(f, dx), g["gx4"]) < TIGHT
+    assert rel_linf(P.grad_central_y_4th(f, dy), g["gy4"]) < TIGHT
+    assert rel_linf(P.diff_upwind_3rd(f, w, dx, 1), g["up_x"]) < TIGHT
+    assert rel_linf(P.diff_upwind_3rd(f, w, dy, 0), g["up_y"]) < TIGHT
+    assert rel_linf(P.lap_2nd(f, dx, dy), g["lap"]) < 1e-11
+    assert same(P.fast_solve_3x3(g["A"], g["b"]), g["x"])
+    assert same(P.fast_solve_3x3(g["As"], g["bs"]), g["xs"])
+
+
+def test_interpolators(P, golden):
+    g = golden("interp")
+    args = (g["u"], g["xq"], g["yq"], float(g["dx"]), float(g["dy"]), int(g["Nx"]), int(g["Ny"]))
+    assert rel_linf(P.bilinear_interpolate(*args), g["bil"]) < TIGHT      # NaN pattern must coincide
+    assert rel_linf(P.bicubic_interpolate(*args), g["bic"]) < TIGHT
+
+
+def test_interpolators_linear_exact(P):
+    # tests/test_interp_extrap_energy.py:10-36 of the reference
+    N = 41
+    X, Y, dx, dy = P.create_grid(N, N, 1.0, 1.0)
+    f = 1.0 + 2.0 * X - 3.0 * Y
+    rng = np.random.default_rng(0)
+    xq, yq = rng.uniform(0.05, 0.95, 200), rng.uniform(0.05, 0.95, 200)
+    exact = 1.0 + 2.0 * xq - 3.0 * yq
+    assert np.max(np.abs(P.bilinear_interpolate(f, xq, yq, dx, dy, N, N) - exact)) < 1e-10
+    assert np.max(np.abs(P.bicubic_interpolate(f, xq, yq, dx, dy, N, N) - exact)) < 1e-9
+
+
+# ----------------------------------------------------------------- exp / extrapolation
+def test_device_exp_is_libm_exp(O):
+    import torch
+    from pyrmt_b200 import _lib
+    from pyrmt_b200._runtime import ctx, ptr, stream
+    rng = np.random.default_rng(7)
+    x = np.concatenate([-rng.random(2_000_000), -np.arange(0, 82) ** 2 / 32.0 / 81 * 1.0,
+                        [-1.0, -0.5, -1e-300, -2.0 ** -60]])
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty_like(xd)
+    _lib.check(ctx().lib.rmt_exp_probe(ptr(xd), ptr(yd), xd.numel(), stream()), "exp")
+    assert same(yd.cpu().numpy(), O.libm_exp(x)), "device exp differs from host libm exp"
+
+
+def test_extrapolation_bit_exact_golden(P, golden):
+    g = golden("extrap")
+    dx, dy = float(g["dx"]), float(g["dy"])
+    for a, b, ph, ea, eb, L in (("X1", "X2", "phi", "X1e", "X2e", "layers"),
+                               ("Z1", "Z2", "phi2", "Z1e", "Z2e", "layers2"),
+                               ("X1", "X2", "phi3", "W1e", "W2e", "layers3")):
+        r1, r2 = P.extrapolate_reference_map(g[a], g[b], g[ph], dx, dy, int(g[L]))
+        assert same(r1, g[ea]) and same(r2, g[eb]), (a, ph)
+
+
+@pytest.mark.parametrize("N,L,layers", [(128, 1.0, 3), (257, 1.0, 3), (513, 4.0, 5)])
+def test_extrapolation_bit_exact_oracle(P, O, N, L, layers):
+    X, Y, dx, dy = O.create_grid(N, N, L, L)
+    cx = np.array([0.3, 0.68, 0.5]) * L
+    cy = np.array([0.3, 0.35, 0.75]) * L
+    R = np.array([0.17, 0.12, 0.2]) * L
+    phi = O.disc_sdf(X, Y, cx, cy, R)
+    m = (phi <= 0).astype(float)
+    X1 = (X + 0.03 * L * np.sin(2.2 * X / L) * np.cos(1.7 * Y / L)) * m
+    X2 = (Y + 0.02 * L * np.cos(1.3 * X / L) * np.sin(2.9 * Y / L)) * m
+    r1, r2 = P.extrapolate_reference_map(X1, X2, phi, dx, dy, layers)
+    o1, o2 = O.extrapolate_reference_map(X1, X2, phi, dx, dy, layers)
+    assert same(r1, o1) and same(r2, o2)
+
+
+def test_extrapolation_linear_exact(P):
+    # tests/test_interp_extrap_energy.py:39-56 of the reference
+    N = 65
+    X, Y, dx, dy = P.create_grid(N, N, 1.0, 1.0)
+    phi = np.sqrt((X - 0.5) ** 2 + (Y - 0.5) ** 2) - 0.25
+    m = (phi <= 0).astype(float)
+    X1e, X2e = P.extrapolate_reference_map(X * m, Y * m, phi, dx, dy, 3)
+    band = (phi > 0) & (phi < 2.5 * dx)
+    assert np.max(np.abs(X1e[band] - X[band])) < 1e-8
+    assert np.max(np.abs(X2e[band] - Y[band])) < 1e-8
+
+
+# ----------------------------------------------------------------- advection
+@pytest.mark.parametrize("scheme", ["semilagrangian", "semilagrangian_cubic", "central2", "weno5",
+                                    "conservative"])
+def test_advection_golden(P, golden, scheme):
+    g = golden("advect")
+    dx, dy, dt = float(g["dx"]), float(g["dy"]), float(g["dt"])
+    r = P.advect_reference_map(g["q"], g["a"], g["b"], g["X"], g["Y"], dt, dx, dy, g["phi"], scheme, 0.0)
+    assert rel_linf(r, g["out_" + scheme]) < TIGHT
+    r = P.advect_reference_map(g["q2"], g["a"], g["b"], g["X"], g["Y"], dt, dx, dy, g["phi"], scheme,
+                               1.5 * dx)
+    assert rel_linf(r, g["out2_" + scheme]) < TIGHT
+
+
+def test_advection_rim_and_clamp(P, golden):
+    g = golden("advect")
+    dx, dy, dt = float(g["dx"]), float(g["dy"]), float(g["dt"])
+    phin = -np.ones_like(g["phi"])
+    for sch in ("weno5", "central2", "conservative"):
+        r = P.advect_reference_map(g["full_q"], g["a"], g["b"], g["X"], g["Y"], dt, dx, dy, phin, sch, 0.0)
+        assert rel_linf(r, g["full_" + sch]) < TIGHT, sch
+    assert rel_linf(P._weno5_rhs(g["full_q"], g["a"], g["b"], dx, dy, phin, 0.0), g["rhs_weno5"]) < 1e-11
+    r = P.advect_reference_map(g["full_q"], g["a"], g["b"], g["X"], g["Y"], float(g["far_dt"]), dx, dy,
+                               g["phi"], "semilagrangian", 0.0)
+    assert rel_linf(r, g["far_sl"]) < TIGHT
+
+
+def test_advection_errors(P):
+    z = np.zeros((8, 8))
+    bad = z.copy()
+    bad[3, 3] = np.nan
+    with pytest.raises(FloatingPointError):
+        P.advect_reference_map(z, bad, z, z, z, 0.1, 0.1, 0.1, z)
+    with pytest.raises(ValueError):
+        P.advect_reference_map(z, z, z, z, z, 0.1, 0.1, 0.1, z, scheme="upwind1")
+
+
+def test_sl_identity_on_index_grid(P):
+    # tests/test_mac.py:134-147 of the reference: X, Y are caller supplied
+    N, dx = 33, 0.03
+    Xg, Yg = np.meshgrid(np.arange(N) * dx, np.arange(N) * dx)
+    q = np.sin(Xg) + Yg ** 2
+    z = np.zeros_like(q)
+    r = P.advect_reference_map(q, z, z, Xg, Yg, 0.01, dx, dx, z, "semilagrangian")
+    assert np.max(np.abs(r - q)) < 1e-12
+
+
+def test_sl_pair_equals_two_calls(P, golden):
+    g = golden("advect")
+    dx, dy, dt = float(g["dx"]), float(g["dy"]), float(g["dt"])
+    r0, r1 = P.advect_semilagrangian_pair(g["q"], g["q2"], g["a"], g["b"], g["X"], g["Y"], dt, dx, dy)
+    assert same(r0, P.advect_semilagrangian_rk4(g["q"], g["a"], g["b"], g["X"], g["Y"], dt, dx, dy))
+    assert same(r1, P.advect_semilagrangian_rk4(g["q2"], g["a"], g["b"], g["X"], g["Y"], dt, dx, dy))
+
+
+# ----------------------------------------------------------------- stress / heaviside
+def test_stress_golden(P, golden):
+    g = golden("stress")
+    dx, dy = float(g["dx"]), float(g["dy"])
+    cases = (("legacy", dict(mu_s=0.7, kappa=0.0)), ("kappa", dict(mu_s=0.7, kappa=2.0)),
+             ("band", dict(mu_s=1.3, kappa=0.5, w_cut=2 * dx, detg_clamp=3.0)),
+             ("iso", dict(mu_s=1.1, kappa=0.4, isochoric=True)))
+    for tag, kw in cases:
+        r = P.solid_cauchy_stress(g["X1"], g["X2"], dx, dy, phi=g["phi"], **kw)
+        assert joint_rel(r[:3], [g[f"{tag}_{n}"] for n in ("sxx", "sxy", "syy")]) < 1e-11, tag
+        assert rel_linf(r[3], g[f"{tag}_J"]) < 1e-11, tag
+    X, Y = np.meshgrid(np.linspace(0, 1.2, 36), np.linspace(0, 0.9, 28))
+    r = P.solid_cauchy_stress(10.0 * X, Y.copy(), dx, dy, 1.0, 0.0, g["phi"], w_cut=2 * dx, detg_clamp=3.0)
+    assert rel_linf(r[3], g["clamp_J"]) < 1e-11
+
+
+def test_heaviside_golden(P, golden):
+    g = golden("stress")
+    w = float(g["hv_w"])
+    assert np.max(np.abs(P.smoothed_heaviside(g["hv_x"], w) - g["hv"])) < 1e-15
+    assert np.max(np.abs(P.smoothed_heaviside(g["phi"], w) - g["hv_phi"])) < 1e-15
+
+
+def test_timestep_golden(P, golden):
+    g = golden("timestep")
+    dx, dy = float(g["dx"]), float(g["dy"])
+    for row in g["table"]:
+        CFL, cap, mu_s, rho_s, gam, rho_f, mu_f, eta, kap, ref = row
+        dt = P.compute_timestep(g["u"], g["v"], dx, dy, CFL, cap, mu_s, rho_s, gam, rho_f, mu_f=mu_f,
+                                eta_s=eta, kappa=kap)
+        assert abs(dt - ref) <= 1e-15 * abs(ref)
+    ph = g["phibc_in"].copy()
+    assert same(P.apply_phi_BCs(ph), g["phibc_out"])
+
+
+# ----------------------------------------------------------------- momentum
+def _bcs():
+    from pyrmt_b200.bc import free_slip_box_bc, no_slip_lid_bc
+
+    def rim(f):
+        m = np.zeros(f.shape, dtype=bool)
+        m[0, :] = m[-1, :] = m[:, 0] = m[:, -1] = True
+        return m
+    return {"lid": lambda u, v: no_slip_lid_bc(u, v, 1.0), "slip": free_slip_box_bc,
+            "wall": lambda u, v: (np.where(rim(u), 0.0, u), np.where(rim(v), 0.0, v))}
+
+
+def test_velocity_rhs_golden(P, golden):
+    g = golden("momentum")
+    dx, dy, w_t = float(g["dx"]), float(g["dy"]), float(g["w_t"])
+    phi = g["phi"]
+    H = P.smoothed_heaviside(phi, w_t)
+    rho_local = (1 - H) * float(g["rhs_rho_s"]) + H * float(g["rhs_rho_f"])
+    exx, exy, eyy, _ = P.solid_cauchy_stress(g["X1"], g["X2"], dx, dy, float(g["rhs_mu_s"]), 0.0, phi)
+    ru, rv = P.velocity_rhs_blended_optimized(
+        g["u"], g["v"], g["p"], exx, exy, eyy, dx, dy, phi, float(g["rhs_mu_f"]), H,
+        P.grad_central_x_2nd(H, dx), P.grad_central_y_2nd(H, dy), rho_local, 0.0, 0.0)
+    assert rel_linf(ru, g["rhs_u"]) < 1e-11
+    assert rel_linf(rv, g["rhs_v"]) < 1e-11
+
+
+@pytest.mark.parametrize("case,bcn", [("lid_eta", "lid"), ("lid_noeta", "lid"), ("slip_eta", "slip"),
+                                      ("lid_band", "lid"), ("lid_gamma", "lid"), ("wall_fluid", "wall")])
+def test_momentum_step_golden(P, golden, case, bcn):
+    g = golden("momentum")
+    dx, dy, dt, w_t = float(g["dx"]), float(g["dy"]), float(g["dt"]), float(g["w_t"])
+    mu_s, kap, eta, rs, rf, muf, gam, band, clamp = g[case + "_prm"]
+    phi = np.ones_like(g["phi"]) if case == "wall_fluid" else g["phi"]
+    r = P.momentum_step_rk4(g["u"], g["v"], g["p"], g["X1"], g["X2"], _bcs()[bcn], mu_s, kap, eta, dx, dy, dt,
+                            rs, rf, phi, muf, w_t, gam, stress_band=bool(band), detg_clamp=clamp)
+    assert rel_linf(r[0], g[case + "_un"]) < TOL * 1e-2
+    assert rel_linf(r[1], g[case + "_vn"]) < TOL * 1e-2
+    refs = [g[f"{case}_{n}"] for n in ("sxx", "sxy", "syy")]
+    assert joint_rel(r[2:5], refs) < 1e-11
+    assert rel_linf(r[5], g[case + "_J"]) < 1e-11
+
+
+def test_curvature_golden(P, golden):
+    g = golden("momentum")
+    assert rel_linf(P.compute_curvature(g["phi"], float(g["dx"]), float(g["dy"])), g["curv"]) < 1e-10
+
+
+# ----------------------------------------------------------------- projection
+def test_projection_neumann_golden(P, golden):
+    g = golden("projection")
+    dx, dy, dt = float(g["dx"]), float(g["dy"]), float(g["dt"])
+    bcs = _bcs()
+    assert rel_linf(P._solve_poisson_dct(g["rhs"], g["eig"]), g["sol"]) < 1e-11
+    assert rel_linf(P._compute_divergence(g["a"], g["b"], dx, dy), g["div"]) < TIGHT
+    assert rel_linf(P._compute_divergence_rc(g["a"], g["b"], g["p"], dt, 1.0, dx, dy), g["div_rc"]) < 1e-11
+    gx, gy = P._compute_pressure_gradient(g["p"], dx, dy)
+    assert rel_linf(gx, g["gx"]) < TIGHT and rel_linf(gy, g["gy"]) < TIGHT
+    eig = P._precompute_poisson_eigenvalues(36, 28, dx, dy)
+    assert same(eig, g["eig"])
+    for tag, rho, bc, pp in (("A", g["rho_arr"], bcs["lid"], g["p"]), ("B", 1.0, bcs["slip"], None),
+                             ("C", 0.8, bcs["lid"], g["p"])):
+        a, b, p, A_, ml_ = P.pressure_projection_amg(g["a"], g["b"], dx, dy, dt, rho, bc, p_prev=pp,
+                                                     eigenvalues=eig)
+        assert A_ is None and ml_ is None
+        assert rel_linf(a, g[tag + "_a"]) < TOL * 1e-1, tag
+        assert rel_linf(b, g[tag + "_b"]) < TOL * 1e-1, tag
+        assert rel_linf(p, g[tag + "_p"]) < TOL * 1e-1, tag
+
+
+def test_projection_pow2_golden(P, golden):
+    """33 x 17 nodes: the shared-memory FFT path (lengths 64 and 32)."""
+    g = golden("projection_pow2")
+    dx, dy, dt = float(g["dx"]), float(g["dy"]), float(g["dt"])
+    from pyrmt_b200._runtime import ctx
+    assert ctx().lib.rmt_poisson_plan_is_fast(ctx().plan(17, 33, 0)) == 1
+    assert rel_linf(P._solve_poisson_dct(g["rhs"], g["eig"]), g["sol"]) < 1e-12
+    a, b, p, _, _ = P.pressure_projection_amg(g["a"], g["b"], dx, dy, dt, 1.0, _bcs()["lid"], p_prev=g["p"],
+                                              eigenvalues=g["eig"])
+    assert rel_linf(a, g["A_a"]) < TOL * 1e-1
+    assert rel_linf(b, g["A_b"]) < TOL * 1e-1
+    assert rel_linf(p, g["A_p"]) < TOL * 1e-1
+
+
+@pytest.mark.parametrize("tag,nx,ny", [("odd", 36, 28), ("pow2", 33, 17)])
+def test_projection_periodic_golden(P, golden, tag, nx, ny):
+    from pyrmt_b200.bc import periodic_bc
+    g = golden("periodic")
+    dx, dy, dt = float(g[tag + "_dx"]), float(g[tag + "_dy"]), float(g["dt"])
+    eg, nl = P._precompute_poisson_eigenvalues_periodic(nx, ny, dx, dy)
+    assert same(eg, g[tag + "_eig"]) and same(nl, g[tag + "_null"])
+    a, b, p = g[tag + "_a"], g[tag + "_b"], g[tag + "_p"]
+    assert rel_linf(P._solve_poisson_fft(g[tag + "_rhs"], (eg, nl)), g[tag + "_sol"]) < 1e-11
+    assert rel_linf(P._compute_divergence_periodic(a, b, dx, dy), g[tag + "_div"]) < TIGHT
+    gx, gy = P._compute_pressure_gradient_periodic(p, dx, dy)
+    assert rel_linf(gx, g[tag + "_gx"]) < TIGHT and rel_linf(gy, g[tag + "_gy"]) < TIGHT
+    r1 = P.pressure_projection_amg(a, b, dx, dy, dt, np.ones_like(a), periodic_bc, p_prev=p,
+                                   eigenvalues=(eg, nl), bc_type='periodic')
+    r2 = P.pressure_projection_amg(a, b, dx, dy, dt, 1.0, periodic_bc, p_prev=None, eigenvalues=None,
+                                   bc_type='periodic')
+    for r, t in ((r1, "A"), (r2, "B")):
+        for k, nm in enumerate("abp"):
+            assert rel_linf(r[k], g[f"{tag}_{t}_{nm}"]) < TOL * 1e-1, (t, nm)
+
+
+def test_projection_properties(P):
+    # tests/test_poisson.py:11-57 of the reference: DCT solve recovers cos*cos; projection cuts div
+    from pyrmt_b200.bc import wall_bc
+    N = 65
+    X, Y, dx, dy = P.create_grid(N, N, 1.0, 1.0)
+    eig = P._precompute_poisson_eigenvalues(N, N, dx, dy)
+    pe = np.cos(np.pi * X) * np.cos(2 * np.pi * Y)
+    sol = P._solve_poisson_dct(-(np.pi ** 2 + 4 * np.pi ** 2) * pe, eig)
+    assert np.max(np.abs(sol - (pe - pe.mean()))) < 5e-3
+    u = np.sin(np.pi * X) * np.cos(np.pi * Y) + 0.3 * np.sin(2 * np.pi * X) * np.sin(np.pi * Y)
+    v = -np.cos(np.pi * X) * np.sin(np.pi * Y) + 0.2 * np.sin(np.pi * X) * np.sin(2 * np.pi * Y)
+    u, v = wall_bc(u, v)
+    d0 = np.max(np.abs(P._compute_divergence(u, v, dx, dy)))
+    a, b, p, _, _ = P.pressure_projection_amg(u, v, dx, dy, 1e-2, 1.0, wall_bc, eigenvalues=eig)
+    d1 = np.max(np.abs(P._compute_divergence(a, b, dx, dy)[2:-2, 2:-2]))
+    assert d1 < d0 / 50.0
+
+
+def test_variable_density_raises(P):
+    from pyrmt_b200.bc import wall_bc
+    N = 17
+    X, Y, dx, dy = P.create_grid(N, N, 1.0, 1.0)
+    eig = P._precompute_poisson_eigenvalues(N, N, dx, dy)
+    rho = 1.0 + 0.5 * X
+    with pytest.raises(NotImplementedError):
+        P.pressure_projection_amg(X, Y, dx, dy, 1e-2, rho, wall_bc, eigenvalues=eig)
+    with pytest.raises(NotImplementedError):
+        P.pressure_projection_amg(X, Y, dx, dy, 1e-2, 1.0, wall_bc, eigenvalues=None)
+
+
+@pytest.mark.parametrize("N", [129, 257, 1025])
+def test_dct_solve_vs_oracle(P, O, N):
+    """Fast (shared-memory FFT) DCT-I solve against scipy's pocketfft through the oracle."""
+    rng = np.random.default_rng(N)
+    X, Y, dx, dy = O.create_grid(N, N, 1.0, 1.0)
+    eig = O._precompute_poisson_eigenvalues(N, N, dx, dy)
+    rhs = np.sin(3 * np.pi * X) * np.cos(2 * np.pi * Y) * 40 + rng.standard_normal((N, N))
+    from pyrmt_b200._runtime import ctx
+    assert ctx().lib.rmt_poisson_plan_is_fast(ctx().plan(N, N, 0)) == 1
+    assert rel_linf(P._solve_poisson_dct(rhs, eig), O._solve_poisson_dct(rhs, eig)) < 1e-11
+
+
+def test_dct_nonsquare_vs_oracle(P, O):
+    Ny, Nx = 65, 257
+    rng = np.random.default_rng(5)
+    X, Y, dx, dy = O.create_grid(Nx, Ny, 2.0, 0.5)
+    eig = O._precompute_poisson_eigenvalues(Nx, Ny, dx, dy)
+    rhs = rng.standard_normal((Ny, Nx))
+    assert rel_linf(P._solve_poisson_dct(rhs, eig), O._solve_poisson_dct(rhs, eig)) < 1e-11
+
+
+# ----------------------------------------------------------------- full steps
+def _fsi_prm(P, g, scheme, tensors):
+    import torch
+    from pyrmt_b200.bc import no_slip_lid_bc
+    from pyrmt_b200.levelset import DiscSDF
+    x0, y0, R = g["disc"]
+    mu_s, kappa, rho_s, eta_s, mu_f, rho_f, w_t, layers, CFL, cap = g["prm"]
+    up = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()) if tensors else (lambda a: a)
+    return dict(dx=float(g["dx"]), dy=float(g["dy"]), CFL=CFL, dt_cap=cap, mu_s=mu_s, kappa=kappa,
+                rho_s=rho_s, rho_f=rho_f, eta_s=eta_s, mu_f=mu_f, w_t=w_t, layers=int(layers),
+                scheme=scheme, w_cut=0.0, phi_init=DiscSDF([x0], [y0], [R]),
+                bc=lambda u, v: no_slip_lid_bc(u, v, 1.0), eig=g["eig"], X=up(g["X"]), Y=up(g["Y"])), up
+
+
+@pytest.mark.parametrize("tensors", [False, True])
+@pytest.mark.parametrize("scheme", ["semilagrangian", "weno5", "central2"])
+def test_full_fsi_step_golden(P, golden, scheme, tensors):
+    """One complete FSI step from recorded reference states (steps 0, 30, 59)."""
+    from pyrmt_b200.driver import fsi_step
+    g = golden("fsi_steps")
+    prm, up = _fsi_prm(P, g, scheme, tensors)
+    for n in (0, 30, 59):
+        st = tuple(up(g[f"{scheme}_{n}_in_{k}"]) for k in ("a", "b", "p", "X1", "X2"))
+        (a, b, p, X1, X2), dt, ex = fsi_step(st, prm)
+        assert abs(dt - float(g[f"{scheme}_{n}_dt"])) <= 1e-15
+        back = (lambda t: t.cpu().numpy()) if tensors else (lambda t: t)
+        for nm, val in (("a", a), ("b", b), ("p", p), ("X1", X1), ("X2", X2), ("phi", ex["phi"]),
+                        ("J", ex["J"]), ("sxx", ex["sxx"])):
+            ref = g[f"{scheme}_{n}_out_{nm}"]
+            err = rel_linf(back(val), ref)
+            assert err < TOL, (scheme, n, nm, err)
+
+
+@pytest.mark.parametrize("N,scheme", [(129, "semilagrangian"), (257, "weno5")])
+def test_fsi_steps_vs_oracle(P, O, N, scheme):
+    """A few steps of a 3-disc lid-driven case at pow2+1 sizes (fast DCT path),
+    each step fed the oracle's state (the parity protocol of SURVEY 8d)."""
+    from pyrmt_b200.bc import no_slip_lid_bc
+    from pyrmt_b200.driver import fsi_step
+    from pyrmt_b200.levelset import DiscSDF
+    X, Y, dx, dy = O.create_grid(N, N, 1.0, 1.0)
+    cx, cy, R = np.array([0.3, 0.7, 0.5]), np.array([0.3, 0.4, 0.72]), np.array([0.15, 0.12, 0.14])
+    phi0 = lambda A, B: O.disc_sdf(A, B, cx, cy, R)
+    lid = lambda u, v: no_slip_lid_bc(u, v, 1.0)
+    eig = O._precompute_poisson_eigenvalues(N, N, dx, dy)
+    base = dict(dx=dx, dy=dy, CFL=0.2, dt_cap=1e-3, mu_s=0.1, kappa=0.0, rho_s=1.0, rho_f=1.0, eta_s=0.01,
+                mu_f=0.01, w_t=2 * dx, layers=3, scheme=scheme, w_cut=0.0, bc=lid, eig=eig, X=X, Y=Y)
+    po = dict(base, phi_init=phi0)
+    pg = dict(base, phi_init=DiscSDF(cx, cy, R))
+    ph = phi0(X, Y)
+    m = (ph <= 0).astype(float)
+    X1, X2 = O.extrapolate_reference_map(X * m, Y * m, ph, dx, dy, 3)
+    z = np.zeros_like(X)
+    a, b = lid(z, z)
+    state = (a, b, z.copy(), X1, X2)
+    for n in range(4):
+        so, dto, _ = O.fsi_step(state, po)
+        sg, dtg, _ = fsi_step(state, pg, dt=dto)
+        for nm, x, r in zip(("a", "b", "p", "X1", "X2"), sg, so):
+            err = rel_linf(x, r)
+            assert err < TOL, (N, scheme, n, nm, err)
+        state = so

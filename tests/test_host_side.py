@@ -1,0 +1,185 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol the header
+declares (no compute calls without a GPU), and the host-side logic of the
+drop-in layer (BC classification, disc binning, signatures, error behaviour).
+"""
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from pyrmt_b200 import build, _lib
+    build.build()                      # nvcc cross-compiles without a GPU
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "rmt_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rmt_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    from pyrmt_b200 import _lib
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(built_lib, name), name
+    assert built_lib.rmt_abi_version() == 1            # pure host call
+    assert built_lib.rmt_reduce_workspace_doubles() > 0
+
+
+def test_library_is_sm100a_only(built_lib):
+    import subprocess
+    from pyrmt_b200 import _lib
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "pyrmt_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("SURVEY", ""), f
+
+
+def test_signatures_match_reference_names():
+    """Names / positional order / defaults of the drop-in API.  The
+    expected strings were transcribed from the reference's def lines."""
+    import pyrmt_b200.functions as F
+    import pyrmt_b200.interpolators as I
+    import pyrmt_b200.utils as U
+    expect = {
+        F.create_grid: "(Nx, Ny, Lx, Ly)",
+        F.apply_phi_BCs: "(phi)",
+        F.extrapolate_reference_map: "(X1, X2, phi, dx, dy, max_layers)",
+        F.compute_timestep: "(a, b, dx, dy, CFL, dt_min_cap, mu_s, rho_s, gamma, rho_f, mu_f=0.0, eta_s=0.0, kappa=0.0)",
+        F.advect_semilagrangian_rk4: "(q, a, b, X, Y, dt, dx, dy)",
+        F.advect_semilagrangian_cubic_rk4: "(q, a, b, X, Y, dt, dx, dy)",
+        F.advect_weno5_rk3: "(q, a, b, dx, dy, dt, phi, w_cut=0.0)",
+        F.advect_central2_rk3: "(q, a, b, dx, dy, dt, phi, w_cut=0.0)",
+        F.advect_conservative_rk3: "(q, a, b, dx, dy, dt, phi, w_cut=0.0)",
+        F.advect_reference_map: "(q, a, b, X, Y, dt, dx, dy, phi, scheme='semilagrangian', w_cut=0.0)",
+        F.solid_cauchy_stress: "(X1, X2, dx, dy, mu_s, kappa, phi, w_cut=0.0, detg_clamp=0.0, isochoric=False)",
+        F.smoothed_heaviside: "(x, w_t)",
+        F.momentum_step_rk4: "(u, v, p, X1, X2, velocity_bc, mu_s, kappa, eta_s, dx, dy, dt, rho_s, rho_f, phi, mu_f, w_t, gamma=0.0, stress_band=False, detg_clamp=3.0)",
+        F.compute_curvature: "(phi, dx, dy)",
+        F.velocity_rhs_blended_optimized: "(u, v, p, sigma_sxx, sigma_sxy, sigma_syy, dx, dy, phi, mu_f, H, dH_dx, dH_dy, rho_local, st_force_x, st_force_y)",
+        F.apply_velocity_BCs: "(bc, u, v)",
+        F.build_poisson_matrix: "(Nx, Ny, dx, dy)",
+        F._compute_divergence: "(a_star, b_star, dx, dy)",
+        F._compute_divergence_rc: "(a_star, b_star, p_prev, dt, rho, dx, dy)",
+        F._compute_pressure_gradient: "(p, dx, dy)",
+        F._precompute_poisson_eigenvalues: "(Nx, Ny, dx, dy)",
+        F._solve_poisson_dct: "(rhs_2d, eigenvalues)",
+        F._precompute_poisson_eigenvalues_periodic: "(Nx, Ny, dx, dy)",
+        F._solve_poisson_fft: "(rhs_full, eigenvalues_periodic)",
+        F.pressure_projection_amg: "(a_star, b_star, dx, dy, dt, rho, velocity_bc, A=None, ml=None, p_prev=None, eigenvalues=None, bc_type='neumann')",
+        F.rebuild_phi_from_reference_map: "(X1, X2, phi_init_func)",
+        F.reinitialize_level_set: "(phi, dx, dy, method='none', num_iters=20, dt_reinit_factor=0.2, apply_phi_BCs_func=None)",
+        I.bilinear_interpolate: "(u, xq, yq, dx, dy, Nx, Ny)",
+        I.bicubic_interpolate: "(u, xq, yq, dx, dy, Nx, Ny)",
+        I.cubic_convolution: "(v0, v1, v2, v3, x)",
+        U.grad_central_x_2nd: "(f, dx)",
+        U.grad_central_y_2nd: "(f, dy)",
+        U.diff_upwind_3rd: "(f, u, h, axis)",
+        U.lap_2nd: "(f, dx, dy)",
+        U.fast_solve_3x3: "(A, b)",
+    }
+    for fn, sig in expect.items():
+        assert str(inspect.signature(fn)) == sig, fn.__name__
+
+
+def test_host_tables_match_oracle(golden):
+    import pyrmt_b200.functions as F
+    from oracle import rmt_oracle as O
+    for nx, ny, dx, dy in ((36, 28, 1.2 / 35, 0.9 / 27), (129, 129, 1 / 128, 1 / 128)):
+        assert np.array_equal(F._precompute_poisson_eigenvalues(nx, ny, dx, dy),
+                              O._precompute_poisson_eigenvalues(nx, ny, dx, dy))
+        e1, n1 = F._precompute_poisson_eigenvalues_periodic(nx, ny, dx, dy)
+        e2, n2 = O._precompute_poisson_eigenvalues_periodic(nx, ny, dx, dy)
+        assert np.array_equal(e1, e2) and np.array_equal(n1, n2)
+    assert np.array_equal(F.fast_solve_3x3(golden("utils")["A"], golden("utils")["b"]), golden("utils")["x"])
+    X, Y, dx, dy = F.create_grid(36, 28, 1.2, 0.9)
+    X2, Y2, dx2, dy2 = O.create_grid(36, 28, 1.2, 0.9)
+    assert np.array_equal(X, X2) and np.array_equal(Y, Y2) and dx == dx2 and dy == dy2
+
+
+def test_reinit_and_unbuilt_rows():
+    import pyrmt_b200.functions as F
+    phi = np.ones((8, 8))
+    assert F.reinitialize_level_set(phi, 0.1, 0.1, "none") is phi
+    with pytest.raises(ValueError):
+        F.reinitialize_level_set(phi, 0.1, 0.1, "bogus")
+    with pytest.raises(ImportError):
+        F.reinitialize_level_set(phi, 0.1, 0.1, "fmm")
+    with pytest.raises(NotImplementedError):
+        F.momentum_step_rk4_2solids()
+    A = F.build_poisson_matrix(129, 129, 0.1, 0.1)         # lazy placeholder
+    assert A.shape == (129 * 129, 129 * 129)
+
+
+# ----------------------------------------------------------------- BC classifier
+def _bcs():
+    from pyrmt_b200.bc import free_slip_box_bc, no_slip_lid_bc, periodic_bc, wall_bc
+    return {"lid": lambda u, v: no_slip_lid_bc(u, v, 1.0), "lid2": lambda u, v: no_slip_lid_bc(u, v, 2.5),
+            "slip": free_slip_box_bc, "periodic": periodic_bc, "wall": wall_bc,
+            "identity": lambda u, v: (u.copy(), v.copy()),
+            "odd": lambda u, v: (np.concatenate([-u[:, 1:2], u[:, 1:]], axis=1), v.copy())}
+
+
+@pytest.mark.parametrize("name", ["lid", "lid2", "slip", "periodic", "wall", "identity", "odd"])
+def test_bc_classifier_reproduces_callable(name):
+    from pyrmt_b200.bc import classify
+    bc = _bcs()[name]
+    for Ny, Nx in ((9, 13), (28, 36)):
+        t = classify(bc, Ny, Nx)
+        assert t is not None, name
+        rng = np.random.default_rng(Ny)
+        u, v = rng.standard_normal((Ny, Nx)), rng.standard_normal((Ny, Nx))
+        ru, rv = bc(u.copy(), v.copy())
+        tu, tv = t.apply_host(u, v)
+        assert np.array_equal(tu, ru) and np.array_equal(tv, rv)
+        if name == "identity":
+            assert t.n == 0
+        else:
+            assert 0 < t.n <= 4 * (Ny + Nx)
+
+
+def test_bc_classifier_rejects_non_gather():
+    from pyrmt_b200.bc import classify
+    assert classify(lambda u, v: (u * 2.0, v), 8, 8) is None               # scaling, not a gather
+    assert classify(lambda u, v: (u + v, v), 8, 8) is None                  # mixes two cells
+
+    def shifted(u, v):                                                      # sources are rewritten too
+        u = u.copy()
+        u[:, 0], u[:, 1] = u[:, 1].copy(), u[:, 0].copy()
+        return u, v.copy()
+    assert classify(shifted, 8, 8) is None
+
+
+def test_disc_bins_are_a_superset():
+    """The per-bin candidate lists must contain the exact minimiser for any point."""
+    from pyrmt_b200.driver import disc_lattice
+    from pyrmt_b200.levelset import DiscSDF
+    L = 1.0
+    cx, cy, R = disc_lattice(8, L, 0.04)
+    sdf = DiscSDF(cx, cy, R, domain=(L, L))
+    gb, start, cand, Lx, Ly = sdf._bins
+    rng = np.random.default_rng(1)
+    pts = rng.uniform(0, L, size=(20000, 2))
+    pts[:50] = 0.0
+    d = np.hypot(pts[:, :1] - cx[None, :], pts[:, 1:] - cy[None, :]) - R[None, :]
+    best = d.argmin(axis=1)
+    bx = np.minimum((pts[:, 0] * gb / Lx).astype(int), gb - 1)
+    by = np.minimum((pts[:, 1] * gb / Ly).astype(int), gb - 1)
+    for k in range(pts.shape[0]):
+        b = by[k] * gb + bx[k]
+        assert best[k] in cand[start[b]:start[b + 1]]
+    assert start[-1] < 12 * gb * gb          # the lists stay short
