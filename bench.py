@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- Mcell-steps/s of the full collocated FSI step on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[3]): synthetic multi-disc
+lid-driven FSI on a 4097 x 4097 node grid (4096^2 cells), 64 neo-Hookean discs,
+WENO5 + SSP-RK3 reference-map advection, 3 extrapolation layers, RK4 momentum
+predictor, Rhie-Chow + DCT-I projection; fp64 throughout.  One "step" is one pass
+of the loop of benchmarks/soft_disc_in_lid_driven.py:78-106 through the drop-in
+operator API (pyrmt_b200.driver.fsi_step).
+
+  value         device-resident loop, state already in HBM, CUDA-event timed
+  e2e           the same step called with HOST state: the five state fields are
+                copied from pinned host memory to the device and the five results
+                back, every step, inside the timed region
+  roofline      the dominant kernel (by summed CUDA-event time in the timed
+                region): algorithmic bytes per launch / mean launch duration
+  cpu_baseline  the CPU oracle (oracle/, a port of the reference's Numba/NumPy
+                path) on a bounded sample of the same workload, on this box's cores
+
+--impl reference times that CPU oracle alone (the reference itself is pure
+Python + Numba and cannot travel to the GPU box).
+N > 1: the slab-decomposed step is not built yet -- every rank runs an
+independent replica of the workload ("replicas only", weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_CELL_STEP = {"semilagrangian": 496.0, "weno5": 512.0, "central2": 512.0}
+
+# Algorithmic (compulsory) bytes per cell and launch of each entry point: every input
+# field read once + every output written once, 8 B each ("Kernels").
+ALG_BYTES_PER_CELL_LAUNCH = {
+    "rmt_momentum_stage": 8.0 * 13.5,     # stages 1..4: 11, 15, 15, 13 fields
+    "rmt_advect_euler_rk3": 8.0 * 17.0,   # 3 stage kernels per call: 5 + 6 + 6 fields
+    "rmt_poisson_solve_dct": 8.0 * 7.0,   # rows 2, columns (+eig) 3, rows 2
+    "rmt_solid_stress": 8.0 * 7.0,
+    "rmt_projection_rhs": 8.0 * 5.0,
+    "rmt_projection_correct": 8.0 * 8.0,
+    "rmt_extrapolate": 8.0 * 5.0,
+    "rmt_disc_sdf": 8.0 * 3.0,
+    "rmt_mask_mul": 8.0 * 3.0,
+    "rmt_heaviside_rho": 8.0 * 3.0,
+    "rmt_advect_sl_rk4": 8.0 * 6.0,
+    "rmt_max_speed": 8.0 * 2.0,
+    "rmt_field_stats": 8.0 * 1.0,
+    "rmt_subtract_mean": 8.0 * 2.0,
+    "rmt_apply_bc": 0.0,
+}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def oracle_rate(n_nodes, steps, warmup, scheme):
+    """Mcell-steps/s of the CPU oracle on a bounded sample (same physics, fewer cells)."""
+    import numpy as np
+    from oracle import rmt_oracle as O
+    from pyrmt_b200.bc import no_slip_lid_bc
+    from pyrmt_b200.driver import disc_lattice
+    N = n_nodes
+    X, Y, dx, dy = O.create_grid(N, N, 1.0, 1.0)
+    cx, cy, R = disc_lattice(8, 1.0, 0.04)
+    phi0 = lambda A, B: O.disc_sdf(A, B, cx, cy, R)
+    lid = lambda u, v: no_slip_lid_bc(u, v, 1.0)
+    prm = dict(dx=dx, dy=dy, CFL=0.2, dt_cap=1e-3, mu_s=0.1, kappa=0.0, rho_s=1.0, rho_f=1.0, eta_s=0.01,
+               mu_f=0.01, w_t=2 * dx, layers=3, scheme=scheme, w_cut=0.0, bc=lid, X=X, Y=Y, phi_init=phi0,
+               eig=O._precompute_poisson_eigenvalues(N, N, dx, dy))
+    ph = phi0(X, Y)
+    m = (ph <= 0).astype(float)
+    X1, X2 = O.extrapolate_reference_map(X * m, Y * m, ph, dx, dy, 3)
+    z = np.zeros_like(X)
+    a, b = lid(z, z)
+    state = (a, b, z.copy(), X1, X2)
+    for _ in range(warmup):
+        state, _, _ = O.fsi_step(state, prm)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        state, _, _ = O.fsi_step(state, prm)
+    el = time.perf_counter() - t0
+    return N * N * steps / el / 1e6, el / steps * 1e3
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n = args.ref_size
+    rate, ms = oracle_rate(n, args.steps, min(args.warmup, 2), args.scheme)
+    cores = os.cpu_count() or 1
+    sample = ("%d steps of the same 64-disc lid-driven %s step on a %dx%d node grid (1/%d of the cells); "
+              "CPU oracle = C/OpenMP port of the reference's Numba kernels + NumPy/pocketfft, "
+              "OpenMP kernels on %d threads, NumPy parts single-threaded as upstream"
+              % (args.steps, args.scheme, n, n, round((args.size / n) ** 2), cores))
+    line = {"impl": "reference", "metric": "Mcell-steps/s full FSI step", "value": rate,
+            "unit": "Mcell-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 2),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic 64-disc lid-driven FSI, %s + SSP-RK3, DCT Poisson" % args.scheme,
+                       "grid": "%dx%d nodes (bounded sample of the 4097x4097 workload)" % (n, n)},
+            "cpu_baseline": {"value": rate, "unit": "Mcell-steps/s", "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": rate, "unit": "Mcell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=4097, help="nodes per side (4097 = 4096^2 cells)")
+    ap.add_argument("--scheme", default="weno5")
+    ap.add_argument("--ref-size", type=int, default=1025)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pyrmt_b200._runtime import profiler
+    from pyrmt_b200.driver import fsi_step, fsi_step_host, make_case
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    N = args.size
+    state, prm = make_case(N, L=1.0, k_side=8, R_frac=0.04, scheme=args.scheme, bc_kind="lid")
+    for _ in range(args.warmup):
+        state, dt, _ = fsi_step(state, prm)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    profiler.reset(timing=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        state, dt, _ = fsi_step(state, prm)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = profiler.launches
+    per_kernel = profiler.summary()
+    profiler.reset(timing=False)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    finite = bool(torch.isfinite(state[0]).all().item())
+
+    cells = N * N
+    value = cells * args.steps * world / (ms * 1e-3) / 1e6
+    peak, peak_kind = peaks()
+
+    # ---- dominant kernel -> roofline --------------------------------------
+    top = max(per_kernel.items(), key=lambda kv: kv[1][1])
+    kname, (kcalls, ktotal) = top
+    alg_launch = ALG_BYTES_PER_CELL_LAUNCH.get(kname, 0.0) * cells
+    kavg_ms = ktotal / kcalls
+    achieved = alg_launch / (kavg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                "launches_timed": kcalls, "avg_launch_ms": kavg_ms,
+                "share_of_step": ktotal / ms,
+                "alg_bytes_per_launch": alg_launch}
+    step_gbs = cells * ALG_BYTES_PER_CELL_STEP.get(args.scheme, 512.0) * args.steps / (ms * 1e-3) / 1e9
+    breakdown = {k: {"calls": c, "ms_per_step": t / args.steps} for k, (c, t) in
+                 sorted(per_kernel.items(), key=lambda kv: -kv[1][1])}
+
+    # ---- end to end: host state in, host state out, every step --------------
+    e2e = None
+    if not args.no_e2e:
+        hstate = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in state)
+        hstate = fsi_step_host(hstate, prm)            # warm-up
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.e2e_steps):
+            hstate = fsi_step_host(hstate, prm)
+        f1.record()
+        barrier()
+        ems = f0.elapsed_time(f1)
+        if world > 1:
+            t = torch.tensor([ems], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        nbytes = 5 * cells * 8
+        e2e = {"value": cells * args.e2e_steps * world / (ems * 1e-3) / 1e6, "unit": "Mcell-steps/s",
+               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": args.e2e_steps,
+               "ms_per_step": ems / args.e2e_steps,
+               "call": "pyrmt_b200.driver.fsi_step_host (pinned host state -> device -> step -> host)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n = args.ref_size
+        rate, cms = oracle_rate(n, args.cpu_steps, 1, args.scheme)
+        cpu = {"value": rate, "unit": "Mcell-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "%d steps of the same workload on a %dx%d node grid (1/%d of the cells), %.0f ms/step; "
+                         "C/OpenMP + NumPy/pocketfft port of the reference's Numba path"
+                         % (args.cpu_steps, n, n, round((N / n) ** 2), cms)}
+
+    if rank == 0:
+        line = {"metric": "Mcell-steps/s full FSI step", "value": value, "unit": "Mcell-steps/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "synthetic 64-disc lid-driven FSI at %dx%d nodes (%d^2 cells), %s + SSP-RK3 "
+                                       "ref-map advection, 3-layer extrapolation, RK4 momentum, Rhie-Chow + "
+                                       "DCT-I projection" % (N, N, N - 1, args.scheme),
+                           "grid": [N, N], "discs": 64, "scheme": args.scheme,
+                           "cache": "working set ~%.1f GB per step >> 126 MB L2 (no flush needed)"
+                                    % (25 * cells * 8 / 1e9),
+                           "parallelism": "replicas x%d (slab decomposition not built yet)" % world
+                           if world > 1 else "single GPU"},
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+                "step_roofline": {"alg_bytes_per_cell_step": ALG_BYTES_PER_CELL_STEP.get(args.scheme, 512.0),
+                                  "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak},
+                "cpu_baseline": cpu, "kernels": breakdown, "finite": finite}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

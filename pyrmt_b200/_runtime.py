@@ -59,13 +59,70 @@ def shape2(t):
     return int(t.shape[0]), int(t.shape[1])
 
 
+# Kernels launched by one call of each entry point (for bench.py's gpu_launches;
+# rmt_extrapolate launches 1 + 4 per layer and is counted by its caller).
+_LAUNCHES = {"rmt_max_speed": 2, "rmt_field_stats": 2, "rmt_advect_euler_rk3": 3, "rmt_extrapolate": 0,
+             "rmt_poisson_solve_dct": 4, "rmt_poisson_solve_fft": 16, "rmt_abi_version": 0,
+             "rmt_reduce_workspace_doubles": 0, "rmt_extrapolate_workspace_bytes": 0,
+             "rmt_poisson_plan_create": 0, "rmt_poisson_plan_destroy": 0, "rmt_poisson_plan_is_fast": 0}
+
+
+class Profiler:
+    """Optional per-entry-point CUDA-event timing and launch counting (bench.py)."""
+
+    def __init__(self):
+        self.timing = False
+        self.launches = 0
+        self.events = {}
+
+    def reset(self, timing=False):
+        self.timing = timing
+        self.launches = 0
+        self.events = {}
+
+    def summary(self):
+        """name -> (calls, total ms); call after torch.cuda.synchronize()."""
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.events.items()}
+
+
+profiler = Profiler()
+
+
+class _LibProxy:
+    """Forwards to the ctypes library, counting launches and (optionally) timing
+    each entry point with CUDA events on the launching stream."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        n_launch = _LAUNCHES.get(name, 1)
+        prof = profiler
+
+        def call(*args):
+            prof.launches += n_launch
+            if prof.timing and n_launch:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = fn(*args)
+                e1.record()
+                prof.events.setdefault(name, []).append((e0, e1))
+                return r
+            return fn(*args)
+
+        self.__dict__[name] = call
+        return call
+
+
 class _Ctx:
     """Per-device scratch: reduction workspace, Poisson plans, extrapolation
     workspace, device copies of eigenvalue tables."""
 
     def __init__(self, dev):
         self.dev = dev
-        self.lib = _lib.load()
+        self.lib = _LibProxy(_lib.load())
         n = self.lib.rmt_reduce_workspace_doubles()
         self.red = torch.empty(n, dtype=F64, device=dev)
         self.plans = {}

@@ -3,10 +3,12 @@
     python -m pyrmt_b200.build [--force]
 
 Every translation unit is compiled with
-``-gencode arch=compute_100a,code=sm_100a -lineinfo``.  ``extrap.cu`` is built
-with ``-fmad=false``: the narrow-band extrapolation has to reproduce the
-reference's IEEE operation order bit for bit; its
-explicit ``fma()`` calls are unaffected by that flag.
+``-gencode arch=compute_100a,code=sm_100a -lineinfo``.  The units on the
+reference-map path (``extrap.cu``, ``advect.cu``, ``stencil_ops.cu``) are built
+with ``-fmad=false``: the narrow-band extrapolation amplifies 1-ulp differences
+by up to 1e6, so it and everything feeding it (advected xi, the level set, the
+solid mask) reproduce the reference's IEEE operation order bit for bit (SURVEY
+Appendix A, H2); explicit ``fma()`` calls are unaffected by that flag.
 """
 from __future__ import annotations
 
@@ -24,8 +26,8 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE]
 UNITS = {
-    "stencil_ops.cu": [],
-    "advect.cu": [],
+    "stencil_ops.cu": ["-fmad=false"],   # disc SDF / mask feed the bit-exact xi path
+    "advect.cu": ["-fmad=false"],        # advected xi must equal the reference bit for bit
     "momentum.cu": [],
     "projection.cu": [],
     "fft.cu": [],

@@ -39,6 +39,20 @@ def fsi_step(state, prm, dt=None):
     return (a, b, p, X1, X2), dt, dict(phi=phi, sxx=sxx, sxy=sxy, syy=syy, J=J)
 
 
+def fsi_step_host(host_state, prm, dt=None):
+    """One step with the state living in (pinned) HOST tensors: the five fields are
+    copied to the device, stepped, and the five results copied back into fresh
+    pinned tensors -- the end-to-end path bench.py times."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    st = tuple(t.to(dev, non_blocking=True) for t in host_state)
+    new, _, _ = fsi_step(st, prm, dt=dt)
+    out = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in new)
+    for h, d in zip(out, new):
+        h.copy_(d, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return out
+
+
 class LidBC:
     """no_slip_lid_bc with a fixed lid speed (a picklable callable)."""
 
