@@ -64,10 +64,17 @@ __global__ void k_exp_probe(const double *__restrict__ x, double *__restrict__ y
         y[k] = exp_glibc(x[k]);
 }
 
-__device__ __forceinline__ int ld_acquire(const int *p)
+// block-scope (L1-coherent within the SM) relaxed loads for rows this CTA owns
+__device__ __forceinline__ unsigned char ld_cta_u8(const unsigned char *p)
 {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    unsigned v;
+    asm volatile("ld.relaxed.cta.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return (unsigned char)v;
+}
+__device__ __forceinline__ double ld_cta_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.relaxed.cta.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release(int *p, int v)
@@ -75,8 +82,10 @@ __device__ __forceinline__ void st_release(int *p, int v)
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// state byte per cell: 0 unknown, 1 known, 2 target of the current layer
-constexpr unsigned char ST_UNKNOWN = 0, ST_KNOWN = 1, ST_TARGET = 2;
+// state byte per cell.  Odd = known: 1 = known before this layer's sweep, 3 = fitted by
+// this layer's sweep (turned into 1 by the next layer's flag pass).  Even = unknown:
+// 0 = not a target, 2 = target of the current layer (stays 2 if its fit is rejected).
+constexpr unsigned char ST_UNKNOWN = 0, ST_KNOWN = 1, ST_TARGET = 2, ST_FRESH = 3;
 
 // seed: copies of X1/X2, known = (phi < 0)          functions.py:69-74
 __global__ void k_ext_seed(const double *__restrict__ X1, const double *__restrict__ X2,
@@ -90,44 +99,53 @@ __global__ void k_ext_seed(const double *__restrict__ X1, const double *__restri
     }
 }
 
+constexpr int XT = 256;                // columns per x-tile of the sweep (multiple of 32)
+constexpr int MRB = 32;                // row blocks a CTA sweeps in sequence (macro-tile = MRB*RB rows x XT columns)
+
 // frontier of the current layer: unknown interior cells with a known 3x3
-// neighbour (functions.py:79-90); one warp per row, also counts them.
-__global__ void k_ext_flag(unsigned char *__restrict__ st, int *__restrict__ row_cnt, int Ny, int Nx)
+// neighbour (functions.py:79-90); one warp per row, counts them per x-tile.
+__global__ void k_ext_flag(unsigned char *__restrict__ st, int *__restrict__ seg_cnt, int Ny, int Nx,
+                           int nxt)
 {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int nwarp = (gridDim.x * blockDim.x) >> 5;
     for (int j = warp; j < Ny; j += nwarp) {
-        int cnt = 0;
-        if (j >= 1 && j < Ny - 1) {
-            const unsigned char *r0 = st + (size_t)(j - 1) * Nx, *r1 = r0 + Nx, *r2 = r1 + Nx;
-            for (int base = 0; base < Nx; base += 32) {
+        const unsigned char *r1 = st + (size_t)j * Nx;
+        const bool inner = (j >= 1 && j < Ny - 1);
+        const unsigned char *r0 = inner ? r1 - Nx : r1, *r2 = inner ? r1 + Nx : r1;
+        for (int xt = 0; xt < nxt; ++xt) {
+            int cnt = 0;
+            const int cend = min((xt + 1) * XT, Nx);
+            for (int base = xt * XT; base < cend; base += 32) {
                 int i = base + lane;
                 bool tgt = false;
-                if (i >= 1 && i < Nx - 1 && r1[i] != ST_KNOWN) {
-                    // neighbours in rows j-1 / j+1 can only be KNOWN or not; a
-                    // concurrent UNKNOWN<->TARGET rewrite there is harmless.
-                    tgt = (r0[i - 1] == ST_KNOWN) | (r0[i] == ST_KNOWN) | (r0[i + 1] == ST_KNOWN) |
-                          (r1[i - 1] == ST_KNOWN) | (r1[i + 1] == ST_KNOWN) |
-                          (r2[i - 1] == ST_KNOWN) | (r2[i] == ST_KNOWN) | (r2[i + 1] == ST_KNOWN);
+                unsigned char me = (i < Nx) ? r1[i] : ST_KNOWN;
+                if (inner && i >= 1 && i < Nx - 1 && !(me & 1)) {
+                    // neighbour rows are rewritten concurrently only between values of the
+                    // same parity (0<->2, 3->1), so the "known" bit read here is stable.
+                    tgt = ((r0[i - 1] | r0[i] | r0[i + 1] | r1[i - 1] | r1[i + 1] | r2[i - 1] | r2[i] |
+                            r2[i + 1]) & 1) != 0;
                 }
-                if (i < Nx && r1[i] != ST_KNOWN) st[(size_t)j * Nx + i] = tgt ? ST_TARGET : ST_UNKNOWN;
+                if (i < Nx) {
+                    unsigned char nv = (me & 1) ? ST_KNOWN : (tgt ? ST_TARGET : ST_UNKNOWN);
+                    if (nv != me) st[(size_t)j * Nx + i] = nv;
+                }
                 cnt += __popc(__ballot_sync(0xffffffffu, tgt));
             }
+            if (lane == 0) seg_cnt[j * nxt + xt] = cnt;
         }
-        if (lane == 0) row_cnt[j] = cnt;
     }
 }
 
-// exclusive scan of the per-row counts -> row_off[0..Ny]; resets the per-row
-// progress counters (rows without targets are "finished").
-__global__ void k_ext_scan(const int *__restrict__ row_cnt, int *__restrict__ row_off,
-                           int *__restrict__ prog, int Ny)
+// exclusive scan of the per-(row, x-tile) counts -> seg_off[0..n]; resets the tile counter
+__global__ void k_ext_scan(const int *__restrict__ seg_cnt, int *__restrict__ seg_off, int n,
+                           int *__restrict__ tile_counter)
 {
     __shared__ int sh[1024];
-    int per = (Ny + blockDim.x - 1) / blockDim.x;
-    int lo = threadIdx.x * per, hi = min(lo + per, Ny);
+    int per = (n + blockDim.x - 1) / blockDim.x;
+    int lo = min((int)threadIdx.x * per, n), hi = min(lo + per, n);
     int s = 0;
-    for (int j = lo; j < hi; ++j) s += row_cnt[j];
+    for (int k = lo; k < hi; ++k) s += seg_cnt[k];
     sh[threadIdx.x] = s;
     __syncthreads();
     for (int o = 1; o < blockDim.x; o <<= 1) {
@@ -137,146 +155,348 @@ __global__ void k_ext_scan(const int *__restrict__ row_cnt, int *__restrict__ ro
         __syncthreads();
     }
     int run = sh[threadIdx.x] - s;
-    for (int j = lo; j < hi; ++j) {
-        row_off[j] = run;
-        int c = row_cnt[j];
-        prog[j] = c ? 0 : INT_MAX;
-        run += c;
+    for (int k = lo; k < hi; ++k) {
+        seg_off[k] = run;
+        run += seg_cnt[k];
     }
-    if (threadIdx.x == blockDim.x - 1) row_off[Ny] = sh[threadIdx.x];
+    if (threadIdx.x == blockDim.x - 1) seg_off[n] = sh[threadIdx.x];
+    if (threadIdx.x == 0) *tile_counter = 0;
 }
 
-// column indices of each row's targets, in increasing column order
-__global__ void k_ext_fill(const unsigned char *__restrict__ st, const int *__restrict__ row_off,
-                           int *__restrict__ tcol, int Ny, int Nx)
+// column indices of each row's targets in increasing column order (so the list of
+// segment (j, xt) is tcol[seg_off[j*nxt+xt] .. seg_off[j*nxt+xt+1])), and each
+// segment's initial progress marker = column of its first target (INT_MAX if
+// none): "segment (j, xt) has dealt with every column < prog[j*nxt+xt]".
+__global__ void k_ext_fill(const unsigned char *__restrict__ st, const int *__restrict__ seg_off,
+                           int *__restrict__ tcol, int *__restrict__ prog, int Ny, int Nx, int nxt)
 {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int nwarp = (gridDim.x * blockDim.x) >> 5;
-    for (int j = warp + 1; j < Ny - 1; j += nwarp) {
-        int off = row_off[j];
-        if (row_off[j + 1] == off) continue;
+    for (int j = warp; j < Ny; j += nwarp) {
         const unsigned char *r1 = st + (size_t)j * Nx;
-        for (int base = 0; base < Nx; base += 32) {
-            int i = base + lane;
-            bool tgt = (i < Nx) && (r1[i] == ST_TARGET);
-            unsigned m = __ballot_sync(0xffffffffu, tgt);
-            if (tgt) tcol[off + __popc(m & ((1u << lane) - 1u))] = i;
-            off += __popc(m);
+        for (int xt = 0; xt < nxt; ++xt) {
+            int off = seg_off[j * nxt + xt];
+            if (seg_off[j * nxt + xt + 1] == off) {
+                if (lane == 0) prog[j * nxt + xt] = INT_MAX;
+                continue;
+            }
+            bool first = true;
+            const int cend = min((xt + 1) * XT, Nx);
+            for (int base = xt * XT; base < cend; base += 32) {
+                int i = base + lane;
+                bool tgt = (i < Nx) && (r1[i] == ST_TARGET);
+                unsigned m = __ballot_sync(0xffffffffu, tgt);
+                if (tgt) tcol[off + __popc(m & ((1u << lane) - 1u))] = i;
+                if (first && m) {
+                    if (lane == 0) prog[j * nxt + xt] = base + __ffs(m) - 1;
+                    first = false;
+                }
+                off += __popc(m);
+            }
         }
     }
 }
 
-constexpr int FIT_WARPS = 4;           // warps per CTA in the sweep kernel (31 KB of products)
+#ifdef RMT_EXT_TIMING
+__device__ unsigned long long g_ext_dbg[8];
+#define EXT_T(k) do { if (lane == 0) { long long now__ = clock64(); atomicAdd(&g_ext_dbg[k], (unsigned long long)(now__ - tmark)); tmark = now__; } } while (0)
+#else
+#define EXT_T(k) do { } while (0)
+#endif
+
+constexpr int RB = 16;                 // rows per CTA block = warps per CTA in the sweep
 constexpr int WIN = 81;                // 9x9 window
 constexpr int NACC = 12;               // running sums: B1[3], B2[3], A00 A01 A02 A11 A12 A22
+constexpr int RING = 16;               // direct-mapped cache of a row's freshly fitted cells
+constexpr int MAXPEND = 40;            // window cells that precede the target in raster order
+
+struct SweepWarp {
+    double prod[WIN][NACC];            // per contributing cell (in gather order): the 12 products
+    double pw[MAXPEND], px[MAXPEND], py[MAXPEND];   // weight / coordinates of the undecided cells
+    double sums[NACC];                 // the twelve running sums, handed from 12 lanes to all
+    double ring_v[RING][2];            // freshly fitted (xi1, xi2) of this row, slot = column & (RING-1)
+    int ring_tag[RING];                // column held by the slot (-1: none / being rewritten)
+    unsigned char pn[MAXPEND], pslot[MAXPEND];      // window index and prod[] slot of the undecided cells
+};
+struct SweepSmem {
+    SweepWarp w[RB];
+    int prog[RB];                      // per-row progress marker of the tile being swept
+    int tile;                          // tile index handed out by the global counter
+};
+
+__device__ __forceinline__ int ld_relaxed_gpu(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+#define SMEM_ORDER() asm volatile("" ::: "memory")   // compiler barrier; shared memory itself is in-order per warp
+
+// the 12 products of one contributing cell, in the order of the running sums:
+//   B1[k] += (w*a_k)*v1, B2[k] += (w*a_k)*v2, A[r][c] += (w*a_r)*a_c   with a = (1, x, y)
+// (w*1.0 == w exactly, so the reference's wg*a0 factors drop out bit for bit)
+__device__ __forceinline__ void store_products(double *q, double w, double x, double y, double v1, double v2)
+{
+    const double wx = w * x, wy = w * y;
+    q[0] = w * v1;  q[1] = wx * v1; q[2] = wy * v1;
+    q[3] = w * v2;  q[4] = wx * v2; q[5] = wy * v2;
+    q[6] = w;       q[7] = wx;      q[8] = wy;
+    q[9] = wx * x;  q[10] = wx * y; q[11] = wy * y;
+}
 
 // The row-pipelined sweep (functions.py:95-161).
-__global__ void __launch_bounds__(FIT_WARPS * 32)
+//
+// The grid is cut into tiles of RB rows x XT columns, handed out to the
+// (co-resident) CTAs in raster order by a global counter; one warp sweeps one row
+// of the tile, left to right.  Before fitting (j, i) a warp waits until rows
+// j-4..j-1 have dealt with every column <= i+4 and its own row with every column
+// < i -- that is exactly the dependency set of the serial raster sweep, so every
+// fit sees the inputs the reference's fit saw.  The serial dependency chain that
+// runs along the flank of a body is hundreds of targets long and a lone warp
+// retires only one instruction every few cycles, so the work that sits between
+// "my predecessor published" and "I publish" is cut to the bone and kept inside
+// one SM:
+//   * rows of the same tile publish progress AND their freshly fitted values
+//     through shared memory (a small direct-mapped ring per row, seqlock-style);
+//     a row publishes through global memory only where another tile can depend
+//     on it (last four rows, columns next to the tile's x-edges, end of its list),
+//     and other tiles poll those markers with relaxed L2 loads;
+//   * BEFORE the wait: cells known before the sweep (state 1, final) are gathered,
+//     weighted and turned into their 12 products, compacted in gather order; the
+//     cells that are this layer's earlier targets get a slot, their weight and a
+//     place in a to-do list;
+//   * AFTER the wait: one lane per to-do cell looks the value up (ring, else L2)
+//     and fills its slot -- with zeros if that target was rejected: adding +-0.0
+//     never changes a running sum that started at +0.0, so the sums still equal
+//     the reference's sums over the known cells bit for bit;
+//   * twelve lanes then run the twelve dependent-add chains over the compacted
+//     slots (1 shared-memory load + 1 DADD per term), the sums are exchanged
+//     through shared memory (no shuffles), lanes 0/1 solve for xi1/xi2.
+// Different bodies fall into different tiles and are swept concurrently.
+__global__ void __launch_bounds__(RB * 32, 1)
 k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__restrict__ st,
-            const int *__restrict__ row_off, const int *__restrict__ tcol, int *__restrict__ prog,
-            int Ny, int Nx, double dx, double dy, double r2)
+            const int *__restrict__ seg_off, const int *__restrict__ tcol, int *__restrict__ prog,
+            int *__restrict__ tile_counter, int Ny, int Nx, int nxt, double dx, double dy, double r2)
 {
-    __shared__ double prod_s[FIT_WARPS][WIN * NACC];
+    extern __shared__ unsigned char s_raw[];
+    SweepSmem &S = *reinterpret_cast<SweepSmem *>(s_raw);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int gw = blockIdx.x * FIT_WARPS + wib, nw = gridDim.x * FIT_WARPS;
-    double *P = prod_s[wib];
+    SweepWarp &W = S.w[wib];
+    volatile int *sp = S.prog;
+    const int nrb = (Ny - 2 + RB - 1) / RB;            // row blocks over rows 1 .. Ny-2
+    const int nmrb = (nrb + MRB - 1) / MRB;            // macro row blocks
+    const int ntiles = nmrb * nxt;
+    const int la = (lane < NACC) ? lane : 0;
+    const unsigned lt = (1u << lane) - 1u;
 
-    for (int j = 1 + gw; j < Ny - 1; j += nw) {
-        const int t0 = row_off[j], t1 = row_off[j + 1];
+    // A CTA takes a macro-tile (MRB row blocks x one x-tile) and sweeps its row blocks
+    // top to bottom itself, so the chain that runs along a flank stays on this SM for
+    // MRB*RB rows; macro-tiles are handed out in raster order (their dependencies point
+    // to raster-earlier macro-tiles, which are resident or finished: no deadlock).
+    for (;;) {
+        if (threadIdx.x == 0) S.tile = atomicAdd(tile_counter, 1);
+        __syncthreads();
+        const int tile = S.tile;
+        if (tile >= ntiles) break;
+        const int mrb = tile / nxt, xt = tile - mrb * nxt;
+        const int xc0 = xt * XT, xc1 = min(xc0 + XT, Nx); // its column range
+      for (int rb = mrb * MRB; rb < min((mrb + 1) * MRB, nrb); ++rb) {
+        const int row0 = 1 + rb * RB;                  // first row of this row block
+        const int j = row0 + wib;
+        const bool live = j < Ny - 1;
+        const int t0 = live ? seg_off[j * nxt + xt] : 0, t1 = live ? seg_off[j * nxt + xt + 1] : 0;
+        if (__syncthreads_or(t1 > t0) == 0) continue;  // nothing to fit in this row block
+        if (lane == 0) sp[wib] = (t1 > t0) ? tcol[t0] : INT_MAX;
+        if (lane < RING) W.ring_tag[lane] = -1;
+        __syncthreads();
+
         for (int t = t0; t < t1; ++t) {
             const int i = tcol[t];
-            // ---- wait for the rows above to pass column i+4 ---------------
-            if (lane < 4) {
-                int jr = j - 1 - lane;
-                if (jr >= 1)
-                    while (ld_acquire(prog + jr) <= i + 4) { /* spin */ }
-            }
-            __syncwarp();
-            __threadfence();
-
             const double x0 = dx * i, y0 = dy * j;
-            unsigned vmask[3];
+#ifdef RMT_EXT_TIMING
+            long long tmark = clock64();
+#endif
+            // ---- phase A (before the wait) ----------------------------------------
+            int cls[3];                                 // 0 no contribution, 1 known, 2 undecided
+            double cw[3], cx_[3], cy_[3], c1[3], c2[3];
+            unsigned mk[3], mp[3];
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-                int n = lane + 32 * s;
-                bool valid = false;
+                const int n = lane + 32 * s;
+                cls[s] = 0;
+                cw[s] = cx_[s] = cy_[s] = c1[s] = c2[s] = 0.0;
                 if (n < WIN) {
-                    int dj = n / 9 - 4, di = n % 9 - 4;
-                    int jj = j + dj, ii = i + di;
+                    const int dj = n / 9 - 4, di = n % 9 - 4;
+                    const int jj = j + dj, ii = i + di;
                     if (jj >= 0 && jj < Ny && ii >= 0 && ii < Nx) {
-                        size_t cc = (size_t)jj * Nx + ii;
-                        if (__ldcg(st + cc) == ST_KNOWN) {
-                            double xi = dx * ii, yi = dy * jj;
-                            double ex = xi - x0, ey = yi - y0;
-                            double dist_sq = ex * ex + ey * ey;
-                            if (dist_sq <= r2) {
-                                valid = true;
-                                double w = exp_glibc(-dist_sq / r2);
-                                double v1 = __ldcg(X1e + cc), v2 = __ldcg(X2e + cc);
-                                double wx = w * xi, wy = w * yi;
-                                double *p = P + n * NACC;
-                                p[0] = w * v1;  p[1] = wx * v1;  p[2] = wy * v1;
-                                p[3] = w * v2;  p[4] = wx * v2;  p[5] = wy * v2;
-                                p[6] = w;       p[7] = wx;       p[8] = wy;
-                                p[9] = wx * xi; p[10] = wx * yi; p[11] = wy * yi;
+                        const size_t cc = (size_t)jj * Nx + ii;
+                        const unsigned char sv = st[cc];     // 1 is final; 2/3 decided after the wait
+                        const double v1 = X1e[cc], v2 = X2e[cc];   // only meaningful if sv == 1
+                        const double xi = dx * ii, yi = dy * jj;
+                        const double ex = xi - x0, ey = yi - y0;
+                        const double dist_sq = ex * ex + ey * ey;
+                        const bool earlier = (dj < 0) || (dj == 0 && di < 0);
+                        if (dist_sq <= r2 && (sv == ST_KNOWN || (sv != ST_UNKNOWN && earlier))) {
+                            cls[s] = (sv == ST_KNOWN) ? 1 : 2;
+                            cw[s] = exp_glibc(-dist_sq / r2);
+                            cx_[s] = xi; cy_[s] = yi; c1[s] = v1; c2[s] = v2;
+                        }
+                    }
+                }
+                mk[s] = __ballot_sync(0xffffffffu, cls[s] == 1);
+                mp[s] = __ballot_sync(0xffffffffu, cls[s] == 2);
+            }
+            int slot_base = 0, pend_base = 0;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const unsigned mv = mk[s] | mp[s];
+                const int slot = slot_base + __popc(mv & lt);
+                if (cls[s] == 1) {
+                    store_products(W.prod[slot], cw[s], cx_[s], cy_[s], c1[s], c2[s]);
+                } else if (cls[s] == 2) {
+                    const int r = pend_base + __popc(mp[s] & lt);
+                    W.pw[r] = cw[s]; W.px[r] = cx_[s]; W.py[r] = cy_[s];
+                    W.pn[r] = (unsigned char)(lane + 32 * s);
+                    W.pslot[r] = (unsigned char)slot;
+                }
+                slot_base += __popc(mv);
+                pend_base += __popc(mp[s]);
+            }
+            const int nslots = slot_base, npend = pend_base;
+            const int nknown = nslots - npend;
+            __syncwarp();
+            EXT_T(0);
+            // ---- wait: rows j-4..j-1 past column i+4, own row past column i-1 ---------
+            //   lanes 0-3: the tile holding column i+4 (normally this one), rows j-1-lane
+            //   lanes 4-7: the tile holding column i-4 when that is the left neighbour
+            //   lane 8   : the left neighbour's part of the own row
+            if (lane < 9) {
+                const int xr = min(i + 4, Nx - 1) / XT, xl = max(i - 4, 0) / XT;
+                int jr = j, xq = -1, need = i + 4;
+                if (lane < 4) { jr = j - 1 - lane; xq = xr; }
+                else if (lane < 8) { jr = j - 1 - (lane - 4); xq = (xl != xr) ? xl : -1; }
+                else { xq = (xl != xt) ? xl : -1; need = i - 1; }
+                if (jr >= 1 && xq >= 0) {
+                    if (xq == xt && jr >= row0) {
+                        if (jr != j) while (sp[jr - row0] <= need) __nanosleep(20);
+                    } else {
+                        const int *g = prog + jr * nxt + xq;
+                        while (ld_relaxed_gpu(g) <= need) __nanosleep(100);
+                    }
+                }
+            }
+            __syncwarp();
+            SMEM_ORDER();
+            EXT_T(1);
+            // ---- phase C: one lane per undecided cell ----------------------------------
+            int nfail = 0;
+            for (int r0 = 0; r0 < npend; r0 += 32) {
+                const int r = r0 + lane;
+                bool fail = false;
+                if (r < npend) {
+                    const int n = W.pn[r];
+                    const int dj = n / 9 - 4, di = n % 9 - 4;
+                    const int jj = j + dj, ii = i + di;
+                    double v1 = 0.0, v2 = 0.0;
+                    bool got = false;
+                    if (jj >= row0 && ii >= xc0 && ii < xc1) {  // a row of this tile: its shared-memory ring
+                        SweepWarp &R = S.w[jj - row0];
+                        const int slot = ii & (RING - 1);
+                        volatile int *tag = &R.ring_tag[slot];
+                        volatile double *rv = R.ring_v[slot];
+                        if (*tag == ii) {
+                            v1 = rv[0]; v2 = rv[1];
+                            SMEM_ORDER();
+                            got = (*tag == ii);
+                        }
+                        if (!got) {                           // slot recycled long ago / target rejected
+                            const size_t cc = (size_t)jj * Nx + ii;
+                            if (ld_cta_u8(st + cc) == ST_FRESH) {
+                                v1 = ld_cta_f64(X1e + cc); v2 = ld_cta_f64(X2e + cc);
+                                got = true;
                             }
                         }
-                    }
-                }
-                vmask[s] = __ballot_sync(0xffffffffu, valid);
-            }
-            __syncwarp();
-            const int count = __popc(vmask[0]) + __popc(vmask[1]) + __popc(vmask[2]);
-            bool fitted = false;
-            if (count >= 3) {
-                // ---- ordered accumulation: lane a owns running sum a -------
-                double acc = 0.0;
-                if (lane < NACC) {
-#pragma unroll
-                    for (int s = 0; s < 3; ++s) {
-                        unsigned m = vmask[s];
-                        while (m) {
-                            int bit = __ffs(m) - 1;
-                            m &= m - 1;
-                            acc += P[(32 * s + bit) * NACC + lane];
+                    } else {                                  // fitted by another tile (L2)
+                        const size_t cc = (size_t)jj * Nx + ii;
+                        if (__ldcg(st + cc) == ST_FRESH) {
+                            v1 = __ldcg(X1e + cc); v2 = __ldcg(X2e + cc);
+                            got = true;
                         }
                     }
+                    // a rejected target contributes exact zeros (weight 0)
+                    store_products(W.prod[W.pslot[r]], got ? W.pw[r] : 0.0, got ? W.px[r] : 0.0,
+                                   got ? W.py[r] : 0.0, v1, v2);
+                    fail = !got;
                 }
-                double B10 = __shfl_sync(0xffffffffu, acc, 0), B11 = __shfl_sync(0xffffffffu, acc, 1);
-                double B12 = __shfl_sync(0xffffffffu, acc, 2), B20 = __shfl_sync(0xffffffffu, acc, 3);
-                double B21 = __shfl_sync(0xffffffffu, acc, 4), B22 = __shfl_sync(0xffffffffu, acc, 5);
-                double A00 = __shfl_sync(0xffffffffu, acc, 6), A01 = __shfl_sync(0xffffffffu, acc, 7);
-                double A02 = __shfl_sync(0xffffffffu, acc, 8), A11 = __shfl_sync(0xffffffffu, acc, 9);
-                double A12 = __shfl_sync(0xffffffffu, acc, 10), A22 = __shfl_sync(0xffffffffu, acc, 11);
-                const double A10 = A01, A20 = A02, A21 = A12;
-                double det = (A00 * (A11 * A22 - A12 * A21) - A01 * (A10 * A22 - A12 * A20) +
-                              A02 * (A10 * A21 - A11 * A20));
-                if (fabs(det) > 1e-10) {
-                    fitted = true;
-                    if (lane < 2) {
-                        double b0 = lane ? B20 : B10, b1 = lane ? B21 : B11, b2 = lane ? B22 : B12;
-                        double inv_det = 1.0 / det;
-                        double cx = (b0 * (A11 * A22 - A12 * A21) - A01 * (b1 * A22 - A12 * b2) +
-                                     A02 * (b1 * A21 - A11 * b2)) * inv_det;
-                        double cy = (A00 * (b1 * A22 - A12 * b2) - b0 * (A10 * A22 - A12 * A20) +
-                                     A02 * (A10 * b2 - b1 * A20)) * inv_det;
-                        double cz = (A00 * (A11 * b2 - b1 * A21) - A01 * (A10 * b2 - b1 * A20) +
-                                     b0 * (A10 * A21 - A11 * A20)) * inv_det;
-                        double val = cx + cy * x0 + cz * y0;
-                        size_t c = (size_t)j * Nx + i;
-                        if (lane) __stcg(X2e + c, val);
-                        else __stcg(X1e + c, val);
+                nfail += __popc(__ballot_sync(0xffffffffu, fail));
+            }
+            const int count = nknown + npend - nfail;    // known cells in the window (functions.py:147)
+            __syncwarp();
+            EXT_T(2);
+            // ---- ordered accumulation: lane a owns running sum a ----------------------
+            double acc = 0.0;
+            {
+                const double *q = &W.prod[0][la];
+#pragma unroll 8
+                for (int k = 0; k < nslots; ++k) acc += q[k * NACC];
+            }
+            if (lane < NACC) W.sums[lane] = acc;
+            __syncwarp();
+            EXT_T(3);
+            const volatile double *sm = W.sums;
+            const int h = (lane & 1) * 3;                 // lane 0 solves for xi1, lane 1 for xi2
+            const double b0 = sm[h], b1 = sm[h + 1], b2 = sm[h + 2];
+            const double A00 = sm[6], A01 = sm[7], A02 = sm[8], A11 = sm[9], A12 = sm[10], A22 = sm[11];
+            const double A10 = A01, A20 = A02, A21 = A12;
+            const double m00 = A11 * A22 - A12 * A21, m01 = A10 * A22 - A12 * A20, m02 = A10 * A21 - A11 * A20;
+            const double det = (A00 * m00 - A01 * m01 + A02 * m02);
+            const bool fitted = (count >= 3) && (fabs(det) > 1e-10);
+            // Cramer's rule (fast_solve_3x3; its own |det| >= 1e-15 gate holds whenever fitted)
+            const double inv_det = 1.0 / det;
+            const double cx = (b0 * m00 - A01 * (b1 * A22 - A12 * b2) + A02 * (b1 * A21 - A11 * b2)) * inv_det;
+            const double cy = (A00 * (b1 * A22 - A12 * b2) - b0 * m01 + A02 * (A10 * b2 - b1 * A20)) * inv_det;
+            const double cz = (A00 * (A11 * b2 - b1 * A21) - A01 * (A10 * b2 - b1 * A20) + b0 * m02) * inv_det;
+            const double val = cx + cy * x0 + cz * y0;
+            EXT_T(4);
+            // ---- publish: shared memory first (that is what the next row waits for) ----
+            {
+                const int next = (t + 1 < t1) ? tcol[t + 1] : INT_MAX;
+                const size_t c = (size_t)j * Nx + i;
+                const int slot = i & (RING - 1);
+                if (fitted) {
+                    if (lane == 0) {
+                        // the entry being recycled must be readable from global memory first
+                        if (W.ring_tag[slot] >= 0) __threadfence_block();
+                        *((volatile int *)&W.ring_tag[slot]) = -1;        // seqlock: invalidate, write, validate
                     }
+                    SMEM_ORDER();
+                    if (lane < 2) *((volatile double *)&W.ring_v[slot][lane]) = val;
+                    SMEM_ORDER();
+                    if (lane == 0) *((volatile int *)&W.ring_tag[slot]) = i;
+                    SMEM_ORDER();
+                }
+                if (lane == 0) sp[wib] = next;                // shared-memory stores retire in order
+                SMEM_ORDER();
+                if (fitted) {
+                    if (lane == 0) X1e[c] = val;
+                    if (lane == 1) X2e[c] = val;
+                    __syncwarp();
+                    if (lane == 0) st[c] = ST_FRESH;
+                }
+                // global marker: only where another tile can be waiting on this row
+                if (lane == 0 && (wib >= RB - 4 || i < xc0 + 8 || i >= xc1 - 8 || next == INT_MAX)) {
+                    __threadfence();
+                    st_release(prog + j * nxt + xt, next);
                 }
             }
             __syncwarp();
-            if (lane == 0) {
-                if (fitted) __stcg(st + (size_t)j * Nx + i, ST_KNOWN);
-                __threadfence();
-                st_release(prog + j, (t + 1 < t1) ? tcol[t + 1] : INT_MAX);
-            }
-            __syncwarp();
+            EXT_T(5);
+#ifdef RMT_EXT_TIMING
+            if (lane == 0) atomicAdd(&g_ext_dbg[7], 1ull);
+#endif
         }
+        __syncthreads();                                       // shared state is reused by the next row block
+      }
     }
 }
 
@@ -286,13 +506,16 @@ inline int flat_blocks(long n) { long b = (n + 255) / 256; return (int)(b > 148 
 
 extern "C" {
 
+static inline int ext_nxt(int Nx) { return (Nx + XT - 1) / XT; }
+
 long rmt_extrapolate_workspace_bytes(int Ny, int Nx)
 {
     size_t ncell = (size_t)Ny * (size_t)Nx;
     size_t st = (ncell + 255) & ~(size_t)255;
-    size_t rows = ((size_t)(3 * (Ny + 1)) * sizeof(int) + 255) & ~(size_t)255;
+    size_t nseg = (size_t)Ny * ext_nxt(Nx) + 2;
+    size_t segs = ((size_t)(3 * nseg + 16) * sizeof(int) + 255) & ~(size_t)255;
     size_t cols = ncell * sizeof(int);
-    return (long)(st + rows + cols);
+    return (long)(st + segs + cols);
 }
 
 int rmt_extrapolate(const double *X1, const double *X2, const double *phi, double *X1e, double *X2e,
@@ -302,13 +525,16 @@ int rmt_extrapolate(const double *X1, const double *X2, const double *phi, doubl
     if (!X1 || !X2 || !phi || !X1e || !X2e || !workspace || Ny < 3 || Nx < 3) return RMT_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     size_t ncell = (size_t)Ny * (size_t)Nx;
+    int nxt = ext_nxt(Nx);
+    int nseg = Ny * nxt;
     unsigned char *st = (unsigned char *)workspace;
     size_t st_bytes = (ncell + 255) & ~(size_t)255;
-    int *row_cnt = (int *)((char *)workspace + st_bytes);
-    int *row_off = row_cnt + (Ny + 1);
-    int *prog = row_off + (Ny + 1);
-    size_t rows_bytes = ((size_t)(3 * (Ny + 1)) * sizeof(int) + 255) & ~(size_t)255;
-    int *tcol = (int *)((char *)workspace + st_bytes + rows_bytes);
+    int *seg_cnt = (int *)((char *)workspace + st_bytes);
+    int *seg_off = seg_cnt + (nseg + 2);
+    int *prog = seg_off + (nseg + 2);
+    int *tile_counter = prog + (nseg + 2);
+    size_t segs_bytes = ((size_t)(3 * ((size_t)nseg + 2) + 16) * sizeof(int) + 255) & ~(size_t)255;
+    int *tcol = (int *)((char *)workspace + st_bytes + segs_bytes);
 
     // stencil_radius_sq = (4*sqrt(dx**2+dy**2))**2, functions.py:76 (no contraction)
     volatile double dx2 = dx * dx, dy2 = dy * dy;
@@ -319,12 +545,15 @@ int rmt_extrapolate(const double *X1, const double *X2, const double *phi, doubl
     k_ext_seed<<<flat_blocks((long)ncell), 256, 0, s>>>(X1, X2, phi, X1e, X2e, st, (long)ncell);
     RMT_LAUNCH_CHECK();
 
+    const size_t sweep_smem = sizeof(SweepSmem);
     static int sweep_blocks = 0;
     if (!sweep_blocks) {
         int dev = 0, sms = 0, per_sm = 0;
         RMT_CUDA(cudaGetDevice(&dev));
         RMT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        RMT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_sweep, FIT_WARPS * 32, 0));
+        RMT_CUDA(cudaFuncSetAttribute(k_ext_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sweep_smem));
+        RMT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_sweep, RB * 32, sweep_smem));
         if (per_sm < 1) return RMT_EINVAL;
         sweep_blocks = sms * per_sm;
     }
@@ -332,22 +561,34 @@ int rmt_extrapolate(const double *X1, const double *X2, const double *phi, doubl
     if (row_warps_blocks > 148 * 8) row_warps_blocks = 148 * 8;
 
     for (int layer = 0; layer < max_layers; ++layer) {
-        k_ext_flag<<<row_warps_blocks, 256, 0, s>>>(st, row_cnt, Ny, Nx);
+        k_ext_flag<<<row_warps_blocks, 256, 0, s>>>(st, seg_cnt, Ny, Nx, nxt);
         RMT_LAUNCH_CHECK();
-        k_ext_scan<<<1, 1024, 0, s>>>(row_cnt, row_off, prog, Ny);
+        k_ext_scan<<<1, 1024, 0, s>>>(seg_cnt, seg_off, nseg, tile_counter);
         RMT_LAUNCH_CHECK();
-        k_ext_fill<<<row_warps_blocks, 256, 0, s>>>(st, row_off, tcol, Ny, Nx);
+        k_ext_fill<<<row_warps_blocks, 256, 0, s>>>(st, seg_off, tcol, prog, Ny, Nx, nxt);
         RMT_LAUNCH_CHECK();
         // all CTAs must be co-resident (warps wait on each other): cooperative launch
         int blocks = sweep_blocks;
-        int need = rmt_cdiv(Ny, FIT_WARPS);
+        int need = rmt_cdiv(rmt_cdiv(Ny - 2, RB), MRB) * nxt;
         if (blocks > need) blocks = need;
-        void *args[] = {&X1e, &X2e, &st, &row_off, &tcol, &prog, &Ny, &Nx, &dx, &dy, &r2};
-        RMT_CUDA(cudaLaunchCooperativeKernel((void *)k_ext_sweep, dim3(blocks), dim3(FIT_WARPS * 32),
-                                             args, 0, s));
+        void *args[] = {&X1e, &X2e, &st, &seg_off, &tcol, &prog, &tile_counter, &Ny, &Nx, &nxt, &dx, &dy, &r2};
+        RMT_CUDA(cudaLaunchCooperativeKernel((void *)k_ext_sweep, dim3(blocks), dim3(RB * 32), args,
+                                             sweep_smem, s));
     }
     return RMT_OK;
 }
+
+#ifdef RMT_EXT_TIMING
+int rmt_ext_debug_read(unsigned long long *out8, int reset)
+{
+    RMT_CUDA(cudaMemcpyFromSymbol(out8, g_ext_dbg, sizeof(unsigned long long) * 8));
+    if (reset) {
+        unsigned long long z[8] = {0};
+        RMT_CUDA(cudaMemcpyToSymbol(g_ext_dbg, z, sizeof(z)));
+    }
+    return RMT_OK;
+}
+#endif
 
 // device exp() on an array -- lets the tests prove bit-equality with host libm
 int rmt_exp_probe(const double *x, double *y, long n, void *stream)
