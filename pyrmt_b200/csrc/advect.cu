@@ -238,7 +238,7 @@ __device__ __forceinline__ double weno5_dq(G g, int k, int n, double vel, double
 // SCHEME: 0 central2, 1 weno5, 2 conservative.  RHS is zero where phi > w_cut
 // or outside the scheme's interior range.
 template <int SCHEME>
-__global__ void k_euler_stage(const double *__restrict__ q0, const double *__restrict__ qs,
+__global__ void __launch_bounds__(256, 4) k_euler_stage(const double *__restrict__ q0, const double *__restrict__ qs,
                               const double *__restrict__ a, const double *__restrict__ b,
                               const double *__restrict__ phi, double *__restrict__ out, int Ny,
                               int Nx, double dx, double dy, double dt, double w_cut, double c0,

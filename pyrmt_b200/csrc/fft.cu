@@ -6,20 +6,25 @@
 //   pyRMT/functions.py:1216-1233  _solve_poisson_fft   (numpy.fft.fft2/ifft2       -> pocketfft)
 //   pyRMT/functions.py:1205-1213  _tile_overlap
 //
-// DCT-I of a line x[0..M] equals the DFT of its even extension of length 2M
-// (that is also how pocketfft evaluates it).  The DFT of a real even sequence is
-// real, so TWO real lines a, b are transformed at once as the complex even
-// sequence a + i b: Re = DCT-I(a), Im = DCT-I(b), no split post-processing.
-//
-// Fast path (M a power of two): the 2M-point complex FFT of a line pair lives in
-// shared memory (split re/im planes, padded against bank conflicts) and runs as
-// in-place radix-4 (+ one radix-2) butterflies:
-//   rows:    load 2 rows -> DIF FFT -> gather out of digit-reversed order -> store
-//   columns: load 2 columns -> DIF FFT -> scale by 1/(4 Mx My eig) in scrambled
-//            order -> DIT FFT (consumes the scrambled order) -> store in place
-// so the 2-D solve is three passes over HBM (rows, columns fwd+inv, rows) and
-// the digit reversal is never materialised.  The inverse DCT-I is the forward
-// one scaled by 1/(2M) (functions.py:1117 idctn).
+// DCT-I of a line x[0..M] equals the DFT of its even extension e of length 2M
+// (that is also how pocketfft evaluates it).  Fast path (M a power of two): the
+// real sequence e is packed into M complex points z[n] = e[2n] + i e[2n+1], one
+// M-point complex FFT is run in shared memory, and the DCT coefficients are
+// unpacked as  X_k = (Re Z_k + Re Z_{M-k} + c_k (Im Z_k + Im Z_{M-k}) - s_k (Re Z_k - Re Z_{M-k})) / 2
+// with (c_k, s_k) = (cos, sin)(pi k / M)  -- half the flops and half the shared
+// memory of transforming the extension directly.  The FFT is decimation in
+// frequency, in place on split re/im planes (padded: every pass is bank-conflict
+// free), and runs as fused radix-16 passes: a thread pulls 16 points into
+// registers, does two radix-4 levels, and writes them back -- three passes and
+// three barriers for M = 4096 instead of twelve radix-2 levels.  The output is
+// left in digit-reversed order and the unpack step reads it through rev_pos(),
+// so the permutation is never materialised.
+//   rows:    one CTA per row:    load+pack -> FFT -> unpack -> store (x scale)
+//   columns: one CTA per column: load+pack -> FFT -> unpack x 1/(4 Mx My eig) ->
+//            pack -> FFT -> unpack -> store in place   (forward and inverse DCT-I
+//            are the same transform; functions.py:1117 idctn = dctn / (2M))
+// so the 2-D solve is three passes over HBM.  4096^2 is fp64-pipe and
+// shared-memory bound at about the same level as HBM.
 // Other sizes (N <= RMT_DENSE_MAX) use dense cosine/sine matrices and a small
 // fp64 GEMM kernel -- O(N^3) but exact to rounding and only used on the small
 // awkward grids of the reference's benchmarks (N = 128 -> 2*127 and 127).
@@ -33,9 +38,14 @@ using namespace rmt;
 
 namespace {
 
-constexpr int kMaxSmemL = 8192;   // longest complex FFT held in one CTA's shared memory
+constexpr int kMaxSmemL = 8192;   // longest complex FFT held in one CTA's shared memory (N <= 8193)
 
-__host__ __device__ __forceinline__ int padi(int i) { return i + (i >> 4); }
+// Shared-memory index padding.  With 8-byte words a half-warp is conflict-free iff its
+// 16 indices differ mod 16.  i + (i>>4) does that for every FFT pass (strides 1, 16, 256,
+// ...); the extra (i>>8) term also spreads the digit-reversed addresses the unpack step
+// reads (16 consecutive frequencies sit 256 and 1024 words apart) and is constant within a
+// half-warp for all the passes.
+__host__ __device__ __forceinline__ int padi(int i) { return i + (i >> 4) + (i >> 8); }
 
 // Storage position of frequency k after the in-place DIF (radices 4,...,4[,2]).
 __device__ __forceinline__ int rev_pos(int k, int L)
@@ -57,8 +67,21 @@ __device__ __forceinline__ cplx cmul(cplx a, double2 w)
 {
     return {a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x};
 }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return {a.x - b.x, a.y - b.y}; }
 
-// radix-2 stage on adjacent pairs (the n = 2 level; no twiddles)
+// radix-4 forward DFT kernel:  y_q = sum_m a_m (-i)^(q m)
+__device__ __forceinline__ void bfly4(cplx &a0, cplx &a1, cplx &a2, cplx &a3)
+{
+    cplx t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3);
+    cplx d = csub(a1, a3), t3{d.y, -d.x};                 // -i (a1 - a3)
+    a0 = cadd(t0, t2);
+    a2 = csub(t0, t2);
+    a1 = cadd(t1, t3);
+    a3 = csub(t1, t3);
+}
+
+// radix-2 level on adjacent pairs (the n = 2 level; no twiddles)
 __device__ __forceinline__ void stage_radix2(double *re, double *im, int L)
 {
     for (int b = threadIdx.x; b < (L >> 1); b += blockDim.x) {
@@ -70,102 +93,128 @@ __device__ __forceinline__ void stage_radix2(double *re, double *im, int L)
     __syncthreads();
 }
 
-// Forward DFT, natural order in -> digit-reversed order out.  tw[m] = exp(-2 pi i m / L).
-__device__ void fft_dif(double *re, double *im, int L, const double2 *__restrict__ tw)
+// one radix-4 DIF level of sub-length n
+__device__ __forceinline__ void stage_radix4(double *re, double *im, int L, int n,
+                                             const double2 *__restrict__ tw)
 {
-    int n = L;
-    for (; n >= 4; n >>= 2) {
-        const int q = n >> 2, tstep = L / n;
-        for (int b = threadIdx.x; b < (L >> 2); b += blockDim.x) {
-            const int k = b & (q - 1), g = (b - k) << 2;
-            const int p0 = padi(g + k), p1 = padi(g + k + q), p2 = padi(g + k + 2 * q), p3 = padi(g + k + 3 * q);
-            cplx a0{re[p0], im[p0]}, a1{re[p1], im[p1]}, a2{re[p2], im[p2]}, a3{re[p3], im[p3]};
-            cplx t0{a0.x + a2.x, a0.y + a2.y}, t1{a0.x - a2.x, a0.y - a2.y};
-            cplx t2{a1.x + a3.x, a1.y + a3.y}, t3{a1.y - a3.y, -(a1.x - a3.x)};   // -i (a1 - a3)
-            cplx y0{t0.x + t2.x, t0.y + t2.y}, y2{t0.x - t2.x, t0.y - t2.y};
-            cplx y1{t1.x + t3.x, t1.y + t3.y}, y3{t1.x - t3.x, t1.y - t3.y};
-            if (k) {
-                y1 = cmul(y1, __ldg(tw + k * tstep));
-                y2 = cmul(y2, __ldg(tw + 2 * k * tstep));
-                y3 = cmul(y3, __ldg(tw + 3 * k * tstep));
-            }
-            re[p0] = y0.x; im[p0] = y0.y;
-            re[p1] = y1.x; im[p1] = y1.y;
-            re[p2] = y2.x; im[p2] = y2.y;
-            re[p3] = y3.x; im[p3] = y3.y;
+    const int q = n >> 2, tstep = L / n;
+    for (int b = threadIdx.x; b < (L >> 2); b += blockDim.x) {
+        const int k = b & (q - 1), g = (b - k) << 2;
+        const int p0 = padi(g + k), p1 = padi(g + k + q), p2 = padi(g + k + 2 * q), p3 = padi(g + k + 3 * q);
+        cplx a0{re[p0], im[p0]}, a1{re[p1], im[p1]}, a2{re[p2], im[p2]}, a3{re[p3], im[p3]};
+        bfly4(a0, a1, a2, a3);
+        if (k) {
+            a1 = cmul(a1, __ldg(tw + k * tstep));
+            a2 = cmul(a2, __ldg(tw + 2 * k * tstep));
+            a3 = cmul(a3, __ldg(tw + 3 * k * tstep));
         }
-        __syncthreads();
+        re[p0] = a0.x; im[p0] = a0.y;
+        re[p1] = a1.x; im[p1] = a1.y;
+        re[p2] = a2.x; im[p2] = a2.y;
+        re[p3] = a3.x; im[p3] = a3.y;
     }
-    if (n == 2) stage_radix2(re, im, L);
+    __syncthreads();
 }
 
-// Forward DFT, digit-reversed order in (as left by fft_dif) -> natural order out.
-__device__ void fft_dit(double *re, double *im, int L, const double2 *__restrict__ tw)
+// two fused radix-4 DIF levels (sub-lengths n and n/4) on 16 register-resident points
+__device__ __forceinline__ void stage_radix16(double *re, double *im, int L, int n,
+                                              const double2 *__restrict__ tw)
 {
-    int n = L;
-    while (n >= 4) n >>= 2;          // n = 2 iff log2(L) is odd
-    int first = 4;
-    if (n == 2) {
-        stage_radix2(re, im, L);
-        first = 8;
-    }
-    for (n = first; n <= L; n <<= 2) {
-        const int q = n >> 2, tstep = L / n;
-        for (int b = threadIdx.x; b < (L >> 2); b += blockDim.x) {
-            const int k = b & (q - 1), g = (b - k) << 2;
-            const int p0 = padi(g + k), p1 = padi(g + k + q), p2 = padi(g + k + 2 * q), p3 = padi(g + k + 3 * q);
-            cplx b0{re[p0], im[p0]}, b1{re[p1], im[p1]}, b2{re[p2], im[p2]}, b3{re[p3], im[p3]};
-            if (k) {
-                b1 = cmul(b1, __ldg(tw + k * tstep));
-                b2 = cmul(b2, __ldg(tw + 2 * k * tstep));
-                b3 = cmul(b3, __ldg(tw + 3 * k * tstep));
-            }
-            cplx t0{b0.x + b2.x, b0.y + b2.y}, t1{b0.x - b2.x, b0.y - b2.y};
-            cplx t2{b1.x + b3.x, b1.y + b3.y}, t3{b1.y - b3.y, -(b1.x - b3.x)};
-            re[p0] = t0.x + t2.x; im[p0] = t0.y + t2.y;
-            re[p1] = t1.x + t3.x; im[p1] = t1.y + t3.y;
-            re[p2] = t0.x - t2.x; im[p2] = t0.y - t2.y;
-            re[p3] = t1.x - t3.x; im[p3] = t1.y - t3.y;
+    const int st = n >> 4;                       // spacing of the 16 points
+    const int ts1 = L / n, ts2 = 4 * ts1;        // twiddle strides of the two levels
+    for (int b = threadIdx.x; b < (L >> 4); b += blockDim.x) {
+        const int k0 = b & (st - 1), base = ((b - k0) << 4) + k0;
+        cplx a[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int p = padi(base + m * st);
+            a[m] = {re[p], im[p]};
         }
-        __syncthreads();
-    }
-}
-
-// --------------------------------------------------------------- DCT-I, rows
-// One CTA transforms rows 2*blockIdx.x and 2*blockIdx.x+1 (unnormalised DCT-I
-// times `scale`).  `partial` (optional) receives the CTA's sum of outputs.
-__global__ void k_dct_rows(const double *__restrict__ in, double *__restrict__ out, int Ny, int Nx,
-                           const double2 *__restrict__ tw, double scale, double *__restrict__ partial)
-{
-    extern __shared__ double sm[];
-    const int M = Nx - 1, L = 2 * M;
-    double *re = sm, *im = sm + padi(L);
-    const int r0 = 2 * blockIdx.x, r1 = r0 + 1;
-    const bool has1 = r1 < Ny;
-    const double *a = in + (size_t)r0 * Nx, *b = in + (size_t)(has1 ? r1 : r0) * Nx;
-    for (int m = threadIdx.x; m <= M; m += blockDim.x) {
-        double va = __ldg(a + m), vb = has1 ? __ldg(b + m) : 0.0;
-        re[padi(m)] = va;
-        im[padi(m)] = vb;
-        if (m > 0 && m < M) {
-            re[padi(L - m)] = va;
-            im[padi(L - m)] = vb;
+        // level n: butterflies over m = r, r+4, r+8, r+12; output q lands at slot 4q + r
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            bfly4(a[r], a[r + 4], a[r + 8], a[r + 12]);
+            const int k = k0 + r * st;           // index inside the length-n transform
+            if (k) {
+                a[r + 4] = cmul(a[r + 4], __ldg(tw + k * ts1));
+                a[r + 8] = cmul(a[r + 8], __ldg(tw + 2 * k * ts1));
+                a[r + 12] = cmul(a[r + 12], __ldg(tw + 3 * k * ts1));
+            }
+        }
+        // level n/4: inside quarter q, butterflies over slots 4q .. 4q+3
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            bfly4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+            if (k0) {
+                a[4 * q + 1] = cmul(a[4 * q + 1], __ldg(tw + k0 * ts2));
+                a[4 * q + 2] = cmul(a[4 * q + 2], __ldg(tw + 2 * k0 * ts2));
+                a[4 * q + 3] = cmul(a[4 * q + 3], __ldg(tw + 3 * k0 * ts2));
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int p = padi(base + m * st);
+            re[p] = a[m].x;
+            im[p] = a[m].y;
         }
     }
     __syncthreads();
-    fft_dif(re, im, L, tw);
+}
+
+// Forward DFT of length L (power of two >= 2), natural order in -> digit-reversed
+// order out (see rev_pos).  tw[m] = exp(-2 pi i m / L).  Caller syncs before.
+__device__ void fft_dif(double *re, double *im, int L, const double2 *__restrict__ tw)
+{
+    int n = L;
+    for (; n >= 16; n >>= 4) stage_radix16(re, im, L, n, tw);
+    for (; n >= 4; n >>= 2) stage_radix4(re, im, L, n, tw);
+    if (n == 2) stage_radix2(re, im, L);
+}
+
+// pack the even extension of a real line x[0..M] (element stride `es`) into M complex points
+__device__ __forceinline__ void pack_even(const double *x, size_t es, double *re, double *im, int M)
+{
+    for (int n = threadIdx.x; n < M; n += blockDim.x) {
+        int i0 = 2 * n, i1 = 2 * n + 1;                    // e[2n], e[2n+1]
+        if (i1 > M) { i0 = 2 * M - i0; i1 = 2 * M - i1; }  // mirrored half: e[m] = x[2M - m]
+        re[padi(n)] = x[(size_t)i0 * es];
+        im[padi(n)] = x[(size_t)i1 * es];
+    }
+}
+
+// DCT-I coefficient k from the digit-reversed packed spectrum; tw2[k] = (cos, sin)(pi k / M)
+__device__ __forceinline__ double unpack_dct(const double *re, const double *im, int k, int M,
+                                             const double2 *__restrict__ tw2)
+{
+    if (k == 0) return re[0] + im[0];
+    if (k == M) return re[0] - im[0];
+    const int pa = padi(rev_pos(k, M)), pb = padi(rev_pos(M - k, M));
+    const double ar = re[pa], ai = im[pa], br = re[pb], bi = im[pb];
+    const double2 w = __ldg(tw2 + k);
+    return 0.5 * ((ar + br) + w.x * (ai + bi) - w.y * (ar - br));
+}
+
+// --------------------------------------------------------------- DCT-I, rows
+// One CTA per row (unnormalised DCT-I times `scale`).  `partial` (optional)
+// receives the CTA's sum of outputs.
+__global__ void __launch_bounds__(512)
+k_dct_rows(const double *in, double *out, int Ny, int Nx,   // in == out allowed (a CTA owns its row)
+                           const double2 *__restrict__ tw, const double2 *__restrict__ tw2, double scale,
+                           double *__restrict__ partial)
+{
+    extern __shared__ double sm[];
+    const int M = Nx - 1;
+    double *re = sm, *im = sm + padi(M) + 1;
+    const int r = blockIdx.x;
+    pack_even(in + (size_t)r * Nx, 1, re, im, M);
+    __syncthreads();
+    fft_dif(re, im, M, tw);
     double s = 0.0;
-    double *oa = out + (size_t)r0 * Nx, *ob = out + (size_t)r1 * Nx;
+    double *o = out + (size_t)r * Nx;
     for (int k = threadIdx.x; k <= M; k += blockDim.x) {
-        int p = padi(rev_pos(k, L));
-        double va = re[p] * scale;
-        oa[k] = va;
-        s += va;
-        if (has1) {
-            double vb = im[p] * scale;
-            ob[k] = vb;
-            s += vb;
-        }
+        double v = unpack_dct(re, im, k, M, tw2) * scale;
+        o[k] = v;
+        s += v;
     }
     if (partial) {
         __shared__ double red[32];
@@ -175,46 +224,26 @@ __global__ void k_dct_rows(const double *__restrict__ in, double *__restrict__ o
 }
 
 // -------------------------------------------- DCT-I, columns: fwd, 1/eig, inverse
-// In place on T (Ny, Nx): columns 2*blockIdx.x and +1.
-__global__ void k_dct_cols_solve(double *__restrict__ T, const double *__restrict__ eig, int Ny, int Nx,
-                                 const double2 *__restrict__ tw, double scale)
+// In place on T (Ny, Nx): one CTA per column.
+__global__ void __launch_bounds__(512)
+k_dct_cols_solve(double *__restrict__ T, const double *__restrict__ eig, int Ny, int Nx,
+                                 const double2 *__restrict__ tw, const double2 *__restrict__ tw2, double scale)
 {
     extern __shared__ double sm[];
-    const int M = Ny - 1, L = 2 * M;
-    double *re = sm, *im = sm + padi(L);
-    const int c0 = 2 * blockIdx.x;
-    const bool has1 = (c0 + 1) < Nx;
-    for (int m = threadIdx.x; m <= M; m += blockDim.x) {
-        const double *row = T + (size_t)m * Nx + c0;
-        double va = row[0], vb = has1 ? row[1] : 0.0;
-        re[padi(m)] = va;
-        im[padi(m)] = vb;
-        if (m > 0 && m < M) {
-            re[padi(L - m)] = va;
-            im[padi(L - m)] = vb;
-        }
-    }
+    const int M = Ny - 1;
+    double *re = sm, *im = sm + padi(M) + 1, *line = sm + 2 * (padi(M) + 1);   // line: M+1 reals
+    const int c = blockIdx.x;
+    pack_even(T + c, (size_t)Nx, re, im, M);
     __syncthreads();
-    fft_dif(re, im, L, tw);
-    for (int k = threadIdx.x; k <= M; k += blockDim.x) {
-        const double *er = eig + (size_t)k * Nx + c0;
-        double fa = scale / __ldg(er), fb = has1 ? scale / __ldg(er + 1) : 0.0;
-        int p = padi(rev_pos(k, L));
-        re[p] *= fa;
-        im[p] *= fb;
-        if (k > 0 && k < M) {
-            int p2 = padi(rev_pos(L - k, L));
-            re[p2] *= fa;
-            im[p2] *= fb;
-        }
-    }
+    fft_dif(re, im, M, tw);
+    for (int k = threadIdx.x; k <= M; k += blockDim.x)
+        line[k] = unpack_dct(re, im, k, M, tw2) * (scale / __ldg(eig + (size_t)k * Nx + c));
     __syncthreads();
-    fft_dit(re, im, L, tw);
-    for (int m = threadIdx.x; m <= M; m += blockDim.x) {
-        double *row = T + (size_t)m * Nx + c0;
-        row[0] = re[padi(m)];
-        if (has1) row[1] = im[padi(m)];
-    }
+    pack_even(line, 1, re, im, M);
+    __syncthreads();
+    fft_dif(re, im, M, tw);
+    for (int k = threadIdx.x; k <= M; k += blockDim.x)
+        T[(size_t)k * Nx + c] = unpack_dct(re, im, k, M, tw2);
 }
 
 __global__ void k_sum_final(const double *__restrict__ part, int n, double *__restrict__ out)
@@ -301,8 +330,9 @@ struct rmt_poisson_plan {
     int Ny, Nx, kind;
     bool fast;
     // fast path
-    double2 *tw_x, *tw_y;      // exp(-2 pi i m / L), L = 2(N-1) (DCT) per direction
-    int Lx, Ly;
+    double2 *tw_x, *tw_y;      // exp(-2 pi i m / M), M = N-1, per direction
+    double2 *tw2_x, *tw2_y;    // (cos, sin)(pi k / M), k = 0..M: the real-FFT unpack twiddles
+    int Lx, Ly;                // complex FFT lengths M
     // dense path
     double *Cx, *Cy, *Sx, *Sy; // cosine (and sine, periodic) matrices
     int nx, ny;                // transform sizes (DCT: N ; periodic: N-1)
@@ -373,7 +403,24 @@ int make_dft_matrices(double **c, double **s, int m)
     return upload(s, hs);
 }
 
-int fft_threads(int L) { return L >= 4096 ? 512 : (L >= 1024 ? 256 : (L >= 256 ? 64 : 32)); }
+int make_half_twiddles(double2 **dst, int M)
+{
+    std::vector<double2> h((size_t)M + 1);
+    const double pi = 3.14159265358979323846;
+    for (int k = 0; k <= M; ++k) {
+        h[k].x = std::cos(pi * (double)k / (double)M);
+        h[k].y = std::sin(pi * (double)k / (double)M);
+    }
+    h[0] = {1.0, 0.0};
+    h[M] = {-1.0, 0.0};
+    if (M % 2 == 0) h[M / 2] = {0.0, 1.0};
+    return upload(dst, h);
+}
+
+// one thread per 16 points (a radix-16 pass is one butterfly per thread)
+int fft_threads(int L) { int t = L / 16; return t < 32 ? 32 : (t > 512 ? 512 : t); }
+int rows_smem(int M) { return 2 * (padi(M) + 1) * (int)sizeof(double); }
+int cols_smem(int M) { return (2 * (padi(M) + 1) + M + 2) * (int)sizeof(double); }
 
 }  // namespace
 
@@ -388,7 +435,7 @@ int rmt_poisson_plan_create(int Ny, int Nx, int kind, rmt_poisson_plan **out)
     int e = RMT_OK;
     const size_t ncell = (size_t)Ny * Nx;
     if (kind == 0) {
-        P->Lx = 2 * (Nx - 1); P->Ly = 2 * (Ny - 1);
+        P->Lx = Nx - 1; P->Ly = Ny - 1;
         P->fast = is_pow2(Nx - 1) && is_pow2(Ny - 1) && P->Lx <= kMaxSmemL && P->Ly <= kMaxSmemL &&
                   P->Lx >= 8 && P->Ly >= 8;
         P->nx = Nx; P->ny = Ny;
@@ -403,10 +450,14 @@ int rmt_poisson_plan_create(int Ny, int Nx, int kind, rmt_poisson_plan **out)
     if (P->fast) {
         e = make_twiddles(&P->tw_x, P->Lx);
         if (!e) e = make_twiddles(&P->tw_y, P->Ly);
-        if (!e) e = (int)cudaMalloc((void **)&P->w[0], ncell * sizeof(double));
-        int smem = 2 * padi(P->Lx > P->Ly ? P->Lx : P->Ly) * (int)sizeof(double);
-        if (!e) e = (int)cudaFuncSetAttribute(k_dct_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (!e) e = (int)cudaFuncSetAttribute(k_dct_cols_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (!e) e = make_half_twiddles(&P->tw2_x, P->Lx);
+        if (!e) e = make_half_twiddles(&P->tw2_y, P->Ly);
+        // opt in to the full 227 KB once (a later, smaller plan must not lower it)
+        const int max_dyn = 227 * 1024 - 1024;
+        if (!e) e = (int)cudaFuncSetAttribute(k_dct_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+        if (!e) e = (int)cudaFuncSetAttribute(k_dct_cols_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              max_dyn);
+        if (!e && (rows_smem(P->Lx) > max_dyn || cols_smem(P->Ly) > max_dyn)) e = -2;
     } else if (kind == 0) {
         e = make_dct_matrix(&P->Cx, Nx);
         if (!e) e = make_dct_matrix(&P->Cy, Ny);
@@ -429,7 +480,7 @@ int rmt_poisson_plan_create(int Ny, int Nx, int kind, rmt_poisson_plan **out)
 void rmt_poisson_plan_destroy(rmt_poisson_plan *P)
 {
     if (!P) return;
-    cudaFree(P->tw_x); cudaFree(P->tw_y);
+    cudaFree(P->tw_x); cudaFree(P->tw_y); cudaFree(P->tw2_x); cudaFree(P->tw2_y);
     cudaFree(P->Cx); cudaFree(P->Cy); cudaFree(P->Sx); cudaFree(P->Sy);
     for (int k = 0; k < 4; ++k) cudaFree(P->w[k]);
     cudaFree(P->red);
@@ -448,15 +499,18 @@ int rmt_poisson_solve_dct(rmt_poisson_plan *P, const double *rhs, const double *
     const double scale = 1.0 / (4.0 * (double)(Nx - 1) * (double)(Ny - 1));
     double *sum_dst = sum_out ? sum_out : P->red + rmt_reduce_workspace_doubles() + Ny + 8;
     if (P->fast) {
-        double *T = P->w[0];
-        double *partial = P->red;                       // ceil(Ny/2) partial sums
-        const int nrow_cta = (Ny + 1) / 2, ncol_cta = (Nx + 1) / 2;
-        const int smx = 2 * padi(P->Lx) * (int)sizeof(double), smy = 2 * padi(P->Ly) * (int)sizeof(double);
-        k_dct_rows<<<nrow_cta, fft_threads(P->Lx), smx, s>>>(rhs, T, Ny, Nx, P->tw_x, 1.0, nullptr);
+        // rows: rhs -> sol ; columns in place on sol ; rows in place on sol (a CTA holds its
+        // whole row in shared memory before it writes, so in-place is safe)
+        double *partial = P->red;                       // Ny partial sums
+        const int nrow_cta = Ny;
+        k_dct_rows<<<Ny, fft_threads(P->Lx), rows_smem(P->Lx), s>>>(rhs, sol, Ny, Nx, P->tw_x, P->tw2_x, 1.0,
+                                                                   nullptr);
         RMT_LAUNCH_CHECK();
-        k_dct_cols_solve<<<ncol_cta, fft_threads(P->Ly), smy, s>>>(T, eig, Ny, Nx, P->tw_y, scale);
+        k_dct_cols_solve<<<Nx, fft_threads(P->Ly), cols_smem(P->Ly), s>>>(sol, eig, Ny, Nx, P->tw_y, P->tw2_y,
+                                                                         scale);
         RMT_LAUNCH_CHECK();
-        k_dct_rows<<<nrow_cta, fft_threads(P->Lx), smx, s>>>(T, sol, Ny, Nx, P->tw_x, 1.0, partial);
+        k_dct_rows<<<Ny, fft_threads(P->Lx), rows_smem(P->Lx), s>>>(sol, sol, Ny, Nx, P->tw_x, P->tw2_x, 1.0,
+                                                                   partial);
         RMT_LAUNCH_CHECK();
         k_sum_final<<<1, 256, 0, s>>>(partial, nrow_cta, sum_dst);
         RMT_LAUNCH_CHECK();

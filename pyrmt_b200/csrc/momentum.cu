@@ -192,7 +192,7 @@ struct RhsArgs {
 };
 
 template <bool FUSED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 k_momentum_rhs(const RhsArgs A)
 {
     __shared__ double sU[UHT * UW], sV[UHT * UW];
@@ -223,6 +223,24 @@ k_momentum_rhs(const RhsArgs A)
     const STile U{sU, j0 - UHALO, i0 - UHALO, UW}, V{sV, j0 - UHALO, i0 - UHALO, UW};
     const double i2dx = 1.0 / (2.0 * A.dx), i2dy = 1.0 / (2.0 * A.dy);
     const double inv_w = FUSED ? 1.0 / A.w_t : 0.0;
+
+    // issue the output phase's streaming loads now, so their latency hides behind the
+    // stress phase (they are consumed after the second barrier)
+    double pf_u0[MTY / 8], pf_v0[MTY / 8], pf_au[MTY / 8], pf_av[MTY / 8];
+#pragma unroll
+    for (int r = 0; r < MTY / 8; ++r) {
+        const int i = i0 + threadIdx.x, j = j0 + threadIdx.y + 8 * r;
+        pf_u0[r] = pf_v0[r] = pf_au[r] = pf_av[r] = 0.0;
+        if (FUSED && i < Nx && j < Ny) {
+            const size_t c = (size_t)j * Nx + i;
+            pf_u0[r] = __ldg(A.u0 + c);
+            pf_v0[r] = __ldg(A.v0 + c);
+            if (A.stage > 1) {
+                pf_au[r] = A.acc_u[c];
+                pf_av[r] = A.acc_v[c];
+            }
+        }
+    }
 
     // ---- blended stress  T = H sigma_f + (1-H) sigma_s  --------------------
     {
@@ -299,21 +317,21 @@ k_momentum_rhs(const RhsArgs A)
             A.out_u[c] = ku;
             A.out_v[c] = kv;
         } else {
-            const double ub = __ldg(A.u0 + c), vb = __ldg(A.v0 + c);
+            const double ub = pf_u0[r], vb = pf_v0[r];
             if (A.stage == 1) {
                 A.acc_u[c] = ku;
                 A.acc_v[c] = kv;
                 A.out_u[c] = ub + (0.5 * A.dt) * ku;
                 A.out_v[c] = vb + (0.5 * A.dt) * kv;
             } else if (A.stage == 2 || A.stage == 3) {
-                A.acc_u[c] = A.acc_u[c] + 2.0 * ku;
-                A.acc_v[c] = A.acc_v[c] + 2.0 * kv;
+                A.acc_u[c] = pf_au[r] + 2.0 * ku;
+                A.acc_v[c] = pf_av[r] + 2.0 * kv;
                 double cdt = (A.stage == 2) ? 0.5 * A.dt : A.dt;
                 A.out_u[c] = ub + cdt * ku;
                 A.out_v[c] = vb + cdt * kv;
             } else {
-                A.out_u[c] = ub + (A.dt / 6.0) * (A.acc_u[c] + ku);
-                A.out_v[c] = vb + (A.dt / 6.0) * (A.acc_v[c] + kv);
+                A.out_u[c] = ub + (A.dt / 6.0) * (pf_au[r] + ku);
+                A.out_v[c] = vb + (A.dt / 6.0) * (pf_av[r] + kv);
             }
         }
     }

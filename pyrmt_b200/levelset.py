@@ -43,7 +43,7 @@ class DiscSDF:
     def _build_bins(self):
         Lx, Ly = map(float, self.domain)
         nd = self.cx.size
-        gb = int(min(256, max(2, round(2.0 * np.sqrt(nd)))))
+        gb = int(min(256, max(2, round(8.0 * np.sqrt(nd)))))
         bw_x, bw_y = Lx / gb, Ly / gb
         diag = np.hypot(bw_x, bw_y)
         start = np.zeros(gb * gb + 1, dtype=np.int32)
