@@ -26,6 +26,7 @@
 #include "../../include/rmt_b200.h"
 #include <cooperative_groups.h>
 #include <limits.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -99,13 +100,27 @@ __global__ void k_ext_seed(const double *__restrict__ X1, const double *__restri
     }
 }
 
-constexpr int XT = 256;                // columns per x-tile of the sweep (multiple of 32)
-constexpr int MRB = 32;                // row blocks a CTA sweeps in sequence (macro-tile = MRB*RB rows x XT columns)
+// Sweep tiling (tunable at start-up through RMT_EXT_XT / RMT_EXT_MRB / RMT_EXT_SLEEP):
+//   XT  columns per x-tile (multiple of 32)
+//   MRB row blocks a CTA sweeps in sequence (macro-tile = MRB*RB rows x XT columns)
+struct ExtTune { int XT, MRB, sleep_ns; };
+static ExtTune ext_tune()
+{
+    static ExtTune t = {0, 0, 0};
+    if (!t.XT) {
+        const char *e;
+        t.XT = 256; t.MRB = 32; t.sleep_ns = 20;
+        if ((e = getenv("RMT_EXT_XT")) && atoi(e) >= 32) t.XT = (atoi(e) / 32) * 32;
+        if ((e = getenv("RMT_EXT_MRB")) && atoi(e) >= 1) t.MRB = atoi(e);
+        if ((e = getenv("RMT_EXT_SLEEP"))) t.sleep_ns = atoi(e);
+    }
+    return t;
+}
 
 // frontier of the current layer: unknown interior cells with a known 3x3
 // neighbour (functions.py:79-90); one warp per row, counts them per x-tile.
 __global__ void k_ext_flag(unsigned char *__restrict__ st, int *__restrict__ seg_cnt, int Ny, int Nx,
-                           int nxt)
+                           int nxt, int XT)
 {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int nwarp = (gridDim.x * blockDim.x) >> 5;
@@ -168,7 +183,7 @@ __global__ void k_ext_scan(const int *__restrict__ seg_cnt, int *__restrict__ se
 // segment's initial progress marker = column of its first target (INT_MAX if
 // none): "segment (j, xt) has dealt with every column < prog[j*nxt+xt]".
 __global__ void k_ext_fill(const unsigned char *__restrict__ st, const int *__restrict__ seg_off,
-                           int *__restrict__ tcol, int *__restrict__ prog, int Ny, int Nx, int nxt)
+                           int *__restrict__ tcol, int *__restrict__ prog, int Ny, int Nx, int nxt, int XT)
 {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int nwarp = (gridDim.x * blockDim.x) >> 5;
@@ -276,7 +291,8 @@ __device__ __forceinline__ void store_products(double *q, double w, double x, do
 __global__ void __launch_bounds__(RB * 32, 1)
 k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__restrict__ st,
             const int *__restrict__ seg_off, const int *__restrict__ tcol, int *__restrict__ prog,
-            int *__restrict__ tile_counter, int Ny, int Nx, int nxt, double dx, double dy, double r2)
+            int *__restrict__ tile_counter, int Ny, int Nx, int nxt, int XT, int MRB, int sleep_ns,
+            double dx, double dy, double r2)
 {
     extern __shared__ unsigned char s_raw[];
     SweepSmem &S = *reinterpret_cast<SweepSmem *>(s_raw);
@@ -378,7 +394,10 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                 else { xq = (xl != xt) ? xl : -1; need = i - 1; }
                 if (jr >= 1 && xq >= 0) {
                     if (xq == xt && jr >= row0) {
-                        if (jr != j) while (sp[jr - row0] <= need) __nanosleep(20);
+                        if (jr != j) {
+                            if (sleep_ns > 0) while (sp[jr - row0] <= need) __nanosleep(sleep_ns);
+                            else while (sp[jr - row0] <= need) { }
+                        }
                     } else {
                         const int *g = prog + jr * nxt + xq;
                         while (ld_relaxed_gpu(g) <= need) __nanosleep(100);
@@ -506,7 +525,7 @@ inline int flat_blocks(long n) { long b = (n + 255) / 256; return (int)(b > 148 
 
 extern "C" {
 
-static inline int ext_nxt(int Nx) { return (Nx + XT - 1) / XT; }
+static inline int ext_nxt(int Nx) { int XT = ext_tune().XT; return (Nx + XT - 1) / XT; }
 
 long rmt_extrapolate_workspace_bytes(int Ny, int Nx)
 {
@@ -527,6 +546,8 @@ int rmt_extrapolate(const double *X1, const double *X2, const double *phi, doubl
     size_t ncell = (size_t)Ny * (size_t)Nx;
     int nxt = ext_nxt(Nx);
     int nseg = Ny * nxt;
+    ExtTune tune = ext_tune();
+    int XT = tune.XT, MRB = tune.MRB, sleep_ns = tune.sleep_ns;
     unsigned char *st = (unsigned char *)workspace;
     size_t st_bytes = (ncell + 255) & ~(size_t)255;
     int *seg_cnt = (int *)((char *)workspace + st_bytes);
@@ -561,17 +582,18 @@ int rmt_extrapolate(const double *X1, const double *X2, const double *phi, doubl
     if (row_warps_blocks > 148 * 8) row_warps_blocks = 148 * 8;
 
     for (int layer = 0; layer < max_layers; ++layer) {
-        k_ext_flag<<<row_warps_blocks, 256, 0, s>>>(st, seg_cnt, Ny, Nx, nxt);
+        k_ext_flag<<<row_warps_blocks, 256, 0, s>>>(st, seg_cnt, Ny, Nx, nxt, XT);
         RMT_LAUNCH_CHECK();
         k_ext_scan<<<1, 1024, 0, s>>>(seg_cnt, seg_off, nseg, tile_counter);
         RMT_LAUNCH_CHECK();
-        k_ext_fill<<<row_warps_blocks, 256, 0, s>>>(st, seg_off, tcol, prog, Ny, Nx, nxt);
+        k_ext_fill<<<row_warps_blocks, 256, 0, s>>>(st, seg_off, tcol, prog, Ny, Nx, nxt, XT);
         RMT_LAUNCH_CHECK();
         // all CTAs must be co-resident (warps wait on each other): cooperative launch
         int blocks = sweep_blocks;
         int need = rmt_cdiv(rmt_cdiv(Ny - 2, RB), MRB) * nxt;
         if (blocks > need) blocks = need;
-        void *args[] = {&X1e, &X2e, &st, &seg_off, &tcol, &prog, &tile_counter, &Ny, &Nx, &nxt, &dx, &dy, &r2};
+        void *args[] = {&X1e, &X2e, &st, &seg_off, &tcol, &prog, &tile_counter, &Ny, &Nx, &nxt, &XT, &MRB,
+                        &sleep_ns, &dx, &dy, &r2};
         RMT_CUDA(cudaLaunchCooperativeKernel((void *)k_ext_sweep, dim3(blocks), dim3(RB * 32), args,
                                              sweep_smem, s));
     }

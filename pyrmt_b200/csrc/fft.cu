@@ -47,17 +47,16 @@ constexpr int kMaxSmemL = 8192;   // longest complex FFT held in one CTA's share
 // half-warp for all the passes.
 __host__ __device__ __forceinline__ int padi(int i) { return i + (i >> 4) + (i >> 8); }
 
-// Storage position of frequency k after the in-place DIF (radices 4,...,4[,2]).
-__device__ __forceinline__ int rev_pos(int k, int L)
+// Storage position of frequency k after the in-place DIF (radices 4,...,4[,2]): the base-4
+// digits of k (least significant first) become the most significant digits of the
+// position; a trailing radix-2 level contributes the lowest bit.  lg = log2(L).
+__device__ __forceinline__ int rev_pos(int k, int lg)
 {
-    int p = 0, n = L;
-    while (n >= 4) {
-        n >>= 2;
-        p += (k & 3) * n;
-        k >>= 2;
-    }
-    if (n == 2) p += (k & 1);
-    return p;
+    const int s2 = lg & ~1;                                   // bits covered by radix-4 digits
+    const unsigned lowk = (unsigned)k & ((1u << s2) - 1u);
+    unsigned r = s2 ? (__brev(lowk) >> (32 - s2)) : 0u;       // bit reversal ...
+    r = ((r & 0x55555555u) << 1) | ((r >> 1) & 0x55555555u);  // ... with the bit pairs kept in order
+    return (lg & 1) ? (int)((r << 1) | ((unsigned)k >> s2)) : (int)r;
 }
 
 struct cplx {
@@ -70,6 +69,16 @@ __device__ __forceinline__ cplx cmul(cplx a, double2 w)
 __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.x + b.x, a.y + b.y}; }
 __device__ __forceinline__ cplx csub(cplx a, cplx b) { return {a.x - b.x, a.y - b.y}; }
 
+// w_16^m = exp(-2 pi i m / 16)
+#define RMT_C8 0.92387953251128673848   /* cos(pi/8) */
+#define RMT_S8 0.38268343236508978178   /* sin(pi/8) */
+#define RMT_R2 0.70710678118654752440   /* sqrt(1/2)  */
+__device__ constexpr double2 kW16[16] = {
+    {1.0, 0.0},      {RMT_C8, -RMT_S8},  {RMT_R2, -RMT_R2},  {RMT_S8, -RMT_C8},
+    {0.0, -1.0},     {-RMT_S8, -RMT_C8}, {-RMT_R2, -RMT_R2}, {-RMT_C8, -RMT_S8},
+    {-1.0, 0.0},     {-RMT_C8, RMT_S8},  {-RMT_R2, RMT_R2},  {-RMT_S8, RMT_C8},
+    {0.0, 1.0},      {RMT_S8, RMT_C8},   {RMT_R2, RMT_R2},   {RMT_C8, RMT_S8}};
+
 // radix-4 forward DFT kernel:  y_q = sum_m a_m (-i)^(q m)
 __device__ __forceinline__ void bfly4(cplx &a0, cplx &a1, cplx &a2, cplx &a3)
 {
@@ -81,26 +90,36 @@ __device__ __forceinline__ void bfly4(cplx &a0, cplx &a1, cplx &a2, cplx &a3)
     a3 = csub(t1, t3);
 }
 
+// A CTA hosts G independent thread groups (one line each); a group synchronises on its
+// own named barrier so the groups drift apart and overlap each other's latencies.
+struct Grp {
+    int tid, nthr, bar;
+    __device__ __forceinline__ void sync() const
+    {
+        asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthr) : "memory");
+    }
+};
+
 // radix-2 level on adjacent pairs (the n = 2 level; no twiddles)
-__device__ __forceinline__ void stage_radix2(double *re, double *im, int L)
+__device__ __forceinline__ void stage_radix2(double *re, double *im, int L, const Grp &g)
 {
-    for (int b = threadIdx.x; b < (L >> 1); b += blockDim.x) {
+    for (int b = g.tid; b < (L >> 1); b += g.nthr) {
         int p0 = padi(2 * b), p1 = padi(2 * b + 1);
         double ar = re[p0], ai = im[p0], br = re[p1], bi = im[p1];
         re[p0] = ar + br; im[p0] = ai + bi;
         re[p1] = ar - br; im[p1] = ai - bi;
     }
-    __syncthreads();
+    g.sync();
 }
 
 // one radix-4 DIF level of sub-length n
 __device__ __forceinline__ void stage_radix4(double *re, double *im, int L, int n,
-                                             const double2 *__restrict__ tw)
+                                             const double2 *__restrict__ tw, const Grp &g)
 {
     const int q = n >> 2, tstep = L / n;
-    for (int b = threadIdx.x; b < (L >> 2); b += blockDim.x) {
-        const int k = b & (q - 1), g = (b - k) << 2;
-        const int p0 = padi(g + k), p1 = padi(g + k + q), p2 = padi(g + k + 2 * q), p3 = padi(g + k + 3 * q);
+    for (int b = g.tid; b < (L >> 2); b += g.nthr) {
+        const int k = b & (q - 1), gb = (b - k) << 2;
+        const int p0 = padi(gb + k), p1 = padi(gb + k + q), p2 = padi(gb + k + 2 * q), p3 = padi(gb + k + 3 * q);
         cplx a0{re[p0], im[p0]}, a1{re[p1], im[p1]}, a2{re[p2], im[p2]}, a3{re[p3], im[p3]};
         bfly4(a0, a1, a2, a3);
         if (k) {
@@ -113,16 +132,16 @@ __device__ __forceinline__ void stage_radix4(double *re, double *im, int L, int 
         re[p2] = a2.x; im[p2] = a2.y;
         re[p3] = a3.x; im[p3] = a3.y;
     }
-    __syncthreads();
+    g.sync();
 }
 
 // two fused radix-4 DIF levels (sub-lengths n and n/4) on 16 register-resident points
 __device__ __forceinline__ void stage_radix16(double *re, double *im, int L, int n,
-                                              const double2 *__restrict__ tw)
+                                              const double2 *__restrict__ tw, const Grp &g)
 {
     const int st = n >> 4;                       // spacing of the 16 points
-    const int ts1 = L / n, ts2 = 4 * ts1;        // twiddle strides of the two levels
-    for (int b = threadIdx.x; b < (L >> 4); b += blockDim.x) {
+    const int ts1 = L / n;                       // twiddle stride: w_n^k = tw[k * ts1]
+    for (int b = g.tid; b < (L >> 4); b += g.nthr) {
         const int k0 = b & (st - 1), base = ((b - k0) << 4) + k0;
         cplx a[16];
 #pragma unroll
@@ -130,26 +149,32 @@ __device__ __forceinline__ void stage_radix16(double *re, double *im, int L, int
             const int p = padi(base + m * st);
             a[m] = {re[p], im[p]};
         }
+        // ONE table lookup per pass: b1 = w_n^k0.  Everything else follows by powers:
+        // w_n^(q (k0 + r n/16)) = b1^q * w_16^(q r)  and  w_(n/4)^(q' k0) = (b1^4)^q'.
+        const double2 b1 = __ldg(tw + k0 * ts1);
+        const cplx B1{b1.x, b1.y};
+        const cplx B2 = cmul(B1, b1), B3 = cmul(B2, b1);
+        const cplx C1 = cmul(B2, double2{B2.x, B2.y});
+        const cplx C2 = cmul(C1, double2{C1.x, C1.y}), C3 = cmul(C2, double2{C1.x, C1.y});
+        const cplx Bq[4] = {{1.0, 0.0}, B1, B2, B3};
         // level n: butterflies over m = r, r+4, r+8, r+12; output q lands at slot 4q + r
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             bfly4(a[r], a[r + 4], a[r + 8], a[r + 12]);
-            const int k = k0 + r * st;           // index inside the length-n transform
-            if (k) {
-                a[r + 4] = cmul(a[r + 4], __ldg(tw + k * ts1));
-                a[r + 8] = cmul(a[r + 8], __ldg(tw + 2 * k * ts1));
-                a[r + 12] = cmul(a[r + 12], __ldg(tw + 3 * k * ts1));
+#pragma unroll
+            for (int q = 1; q < 4; ++q) {
+                cplx t = Bq[q];
+                if (r) t = cmul(t, kW16[(q * r) & 15]);
+                a[r + 4 * q] = cmul(a[r + 4 * q], double2{t.x, t.y});
             }
         }
         // level n/4: inside quarter q, butterflies over slots 4q .. 4q+3
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             bfly4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
-            if (k0) {
-                a[4 * q + 1] = cmul(a[4 * q + 1], __ldg(tw + k0 * ts2));
-                a[4 * q + 2] = cmul(a[4 * q + 2], __ldg(tw + 2 * k0 * ts2));
-                a[4 * q + 3] = cmul(a[4 * q + 3], __ldg(tw + 3 * k0 * ts2));
-            }
+            a[4 * q + 1] = cmul(a[4 * q + 1], double2{C1.x, C1.y});
+            a[4 * q + 2] = cmul(a[4 * q + 2], double2{C2.x, C2.y});
+            a[4 * q + 3] = cmul(a[4 * q + 3], double2{C3.x, C3.y});
         }
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
@@ -158,92 +183,145 @@ __device__ __forceinline__ void stage_radix16(double *re, double *im, int L, int
             im[p] = a[m].y;
         }
     }
-    __syncthreads();
+    g.sync();
 }
 
 // Forward DFT of length L (power of two >= 2), natural order in -> digit-reversed
 // order out (see rev_pos).  tw[m] = exp(-2 pi i m / L).  Caller syncs before.
-__device__ void fft_dif(double *re, double *im, int L, const double2 *__restrict__ tw)
+__device__ void fft_dif(double *re, double *im, int L, const double2 *__restrict__ tw, const Grp &g)
 {
     int n = L;
-    for (; n >= 16; n >>= 4) stage_radix16(re, im, L, n, tw);
-    for (; n >= 4; n >>= 2) stage_radix4(re, im, L, n, tw);
-    if (n == 2) stage_radix2(re, im, L);
+    for (; n >= 16; n >>= 4) stage_radix16(re, im, L, n, tw, g);
+    for (; n >= 4; n >>= 2) stage_radix4(re, im, L, n, tw, g);
+    if (n == 2) stage_radix2(re, im, L, g);
 }
 
-// pack the even extension of a real line x[0..M] (element stride `es`) into M complex points
-__device__ __forceinline__ void pack_even(const double *x, size_t es, double *re, double *im, int M)
+// pack the even extension of the real line x[0..M] (shared memory) into M complex points
+__device__ __forceinline__ void pack_even(const double *x, double *re, double *im, int M, const Grp &g)
 {
-    for (int n = threadIdx.x; n < M; n += blockDim.x) {
+    for (int n = g.tid; n < M; n += g.nthr) {
         int i0 = 2 * n, i1 = 2 * n + 1;                    // e[2n], e[2n+1]
         if (i1 > M) { i0 = 2 * M - i0; i1 = 2 * M - i1; }  // mirrored half: e[m] = x[2M - m]
-        re[padi(n)] = x[(size_t)i0 * es];
-        im[padi(n)] = x[(size_t)i1 * es];
+        re[padi(n)] = x[i0];
+        im[padi(n)] = x[i1];
     }
 }
 
 // DCT-I coefficient k from the digit-reversed packed spectrum; tw2[k] = (cos, sin)(pi k / M)
-__device__ __forceinline__ double unpack_dct(const double *re, const double *im, int k, int M,
+__device__ __forceinline__ double unpack_dct(const double *re, const double *im, int k, int M, int lg,
                                              const double2 *__restrict__ tw2)
 {
     if (k == 0) return re[0] + im[0];
     if (k == M) return re[0] - im[0];
-    const int pa = padi(rev_pos(k, M)), pb = padi(rev_pos(M - k, M));
+    const int pa = padi(rev_pos(k, lg)), pb = padi(rev_pos(M - k, lg));
     const double ar = re[pa], ai = im[pa], br = re[pb], bi = im[pb];
     const double2 w = __ldg(tw2 + k);
     return 0.5 * ((ar + br) + w.x * (ai + bi) - w.y * (ar - br));
 }
 
-// --------------------------------------------------------------- DCT-I, rows
-// One CTA per row (unnormalised DCT-I times `scale`).  `partial` (optional)
-// receives the CTA's sum of outputs.
-__global__ void __launch_bounds__(512)
-k_dct_rows(const double *in, double *out, int Ny, int Nx,   // in == out allowed (a CTA owns its row)
-                           const double2 *__restrict__ tw, const double2 *__restrict__ tw2, double scale,
-                           double *__restrict__ partial)
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+constexpr int kMaxPerThread = 18;   // line points per thread held in registers in solve mode (>= (M+1)/nthr)
+
+// ----------------------------------------------------- DCT-I along rows, persistent
+// Lines are the rows of a (nrows, N) array, N = M + 1.  A CTA hosts `G` groups of
+// `tpg` threads; each group owns one line at a time (planes re/im + a staging copy of
+// the NEXT line, fetched with cp.async while the current one is transformed) and walks
+// lines grp, grp + ngroups, ...  MODE 0: out = scale * DCT-I(in).  MODE 1 (Poisson
+// solve along this axis): out = DCT-I( DCT-I(in) * scale / eig ), eig laid out like in.
+// in == out is allowed (a group holds its whole line on chip before it writes).
+template <int MODE>
+__global__ void __launch_bounds__(512, 1)
+k_dct_lines(const double *in, double *out, const double *__restrict__ eig, int nrows, int N,
+            const double2 *__restrict__ tw, const double2 *__restrict__ tw2, double scale, int tpg,
+            double *__restrict__ partial)
 {
     extern __shared__ double sm[];
-    const int M = Nx - 1;
-    double *re = sm, *im = sm + padi(M) + 1;
-    const int r = blockIdx.x;
-    pack_even(in + (size_t)r * Nx, 1, re, im, M);
-    __syncthreads();
-    fft_dif(re, im, M, tw);
+    const int M = N - 1, lg = 31 - __clz(M);
+    const int G = blockDim.x / tpg, gi = threadIdx.x / tpg;
+    const Grp g{(int)threadIdx.x % tpg, tpg, 1 + gi};
+    const int plane = padi(M) + 1, per_group = 2 * plane + (N + 1);
+    double *re = sm + (size_t)gi * per_group, *im = re + plane, *stage = im + plane;
+    const int ngroups = gridDim.x * G;
+    int r = blockIdx.x * G + gi;
     double s = 0.0;
-    double *o = out + (size_t)r * Nx;
-    for (int k = threadIdx.x; k <= M; k += blockDim.x) {
-        double v = unpack_dct(re, im, k, M, tw2) * scale;
-        o[k] = v;
-        s += v;
+
+    if (r < nrows)
+        for (int k = g.tid; k < N; k += g.nthr) cp_async8(stage + k, in + (size_t)r * N + k);
+    for (; r < nrows; r += ngroups) {
+        cp_async_wait_all();
+        g.sync();                                   // staged line complete; previous unpack done
+        pack_even(stage, re, im, M, g);
+        g.sync();
+        const int rn = r + ngroups;                 // prefetch the next line behind the FFT
+        if (rn < nrows)
+            for (int k = g.tid; k < N; k += g.nthr) cp_async8(stage + k, in + (size_t)rn * N + k);
+        fft_dif(re, im, M, tw, g);
+        if (MODE == 1) {
+            // spectrum -> registers (x scale/eig), then straight back into packed form
+            double y[kMaxPerThread];
+            const double *er = eig + (size_t)r * N;
+#pragma unroll
+            for (int m = 0; m < kMaxPerThread; ++m) {
+                const int k = g.tid + m * g.nthr;
+                y[m] = (k <= M) ? unpack_dct(re, im, k, M, lg, tw2) * (scale / __ldg(er + k)) : 0.0;
+            }
+            g.sync();
+#pragma unroll
+            for (int m = 0; m < kMaxPerThread; ++m) {
+                const int k = g.tid + m * g.nthr;
+                if (k <= M) {
+                    // e[k] = y_k sits at z[k/2] (k < M) and, mirrored as e[2M-k], at z[M - (k+1)/2] (k > 0)
+                    double *pl = (k & 1) ? im : re;
+                    if (k < M) pl[padi(k >> 1)] = y[m];
+                    if (k > 0) pl[padi(M - ((k + 1) >> 1))] = y[m];
+                }
+            }
+            g.sync();
+            fft_dif(re, im, M, tw, g);
+        }
+        double *o = out + (size_t)r * N;
+        const double sc = (MODE == 1) ? 1.0 : scale;
+        for (int k = g.tid; k <= M; k += g.nthr) {
+            double v = unpack_dct(re, im, k, M, lg, tw2) * sc;
+            o[k] = v;
+            s += v;
+        }
     }
     if (partial) {
         __shared__ double red[32];
+        __syncthreads();
         s = block_sum(s, red);
         if (threadIdx.x == 0) partial[blockIdx.x] = s;
     }
 }
 
-// -------------------------------------------- DCT-I, columns: fwd, 1/eig, inverse
-// In place on T (Ny, Nx): one CTA per column.
-__global__ void __launch_bounds__(512)
-k_dct_cols_solve(double *__restrict__ T, const double *__restrict__ eig, int Ny, int Nx,
-                                 const double2 *__restrict__ tw, const double2 *__restrict__ tw2, double scale)
+// out (C, R) = in (R, C)^T, 32x32 tiles through padded shared memory (both sides coalesced)
+__global__ void __launch_bounds__(256)
+k_transpose(const double *__restrict__ in, double *__restrict__ out, int R, int C)
 {
-    extern __shared__ double sm[];
-    const int M = Ny - 1;
-    double *re = sm, *im = sm + padi(M) + 1, *line = sm + 2 * (padi(M) + 1);   // line: M+1 reals
-    const int c = blockIdx.x;
-    pack_even(T + c, (size_t)Nx, re, im, M);
+    __shared__ double t[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int r = r0 + ty + 8 * k, c = c0 + tx;
+        if (r < R && c < C) t[ty + 8 * k][tx] = __ldg(in + (size_t)r * C + c);
+    }
     __syncthreads();
-    fft_dif(re, im, M, tw);
-    for (int k = threadIdx.x; k <= M; k += blockDim.x)
-        line[k] = unpack_dct(re, im, k, M, tw2) * (scale / __ldg(eig + (size_t)k * Nx + c));
-    __syncthreads();
-    pack_even(line, 1, re, im, M);
-    __syncthreads();
-    fft_dif(re, im, M, tw);
-    for (int k = threadIdx.x; k <= M; k += blockDim.x)
-        T[(size_t)k * Nx + c] = unpack_dct(re, im, k, M, tw2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int c = c0 + ty + 8 * k, r = r0 + tx;
+        if (r < R && c < C) out[(size_t)c * R + r] = t[tx][ty + 8 * k];
+    }
 }
 
 __global__ void k_sum_final(const double *__restrict__ part, int n, double *__restrict__ out)
@@ -336,7 +414,8 @@ struct rmt_poisson_plan {
     // dense path
     double *Cx, *Cy, *Sx, *Sy; // cosine (and sine, periodic) matrices
     int nx, ny;                // transform sizes (DCT: N ; periodic: N-1)
-    double *w[4];              // work arrays
+    double *w[4];              // work arrays (fast DCT: w[0] = transposed field, w[1] = transposed eig)
+    const double *eig_src;     // eigenvalue table w[1] was transposed from
     double *red;               // reduction partials / stats
 };
 
@@ -419,8 +498,26 @@ int make_half_twiddles(double2 **dst, int M)
 
 // one thread per 16 points (a radix-16 pass is one butterfly per thread)
 int fft_threads(int L) { int t = L / 16; return t < 32 ? 32 : (t > 512 ? 512 : t); }
-int rows_smem(int M) { return 2 * (padi(M) + 1) * (int)sizeof(double); }
-int cols_smem(int M) { return (2 * (padi(M) + 1) + M + 2) * (int)sizeof(double); }
+int group_doubles(int M) { return 2 * (padi(M) + 1) + (M + 2); }
+constexpr int kMaxDyn = 227 * 1024 - 1024;
+
+// launch geometry of k_dct_lines for line length M+1: groups per CTA and CTAs
+struct LineLaunch { int tpg, G, threads, smem, ctas; };
+LineLaunch line_launch(int M, int nrows)
+{
+    LineLaunch L;
+    L.tpg = fft_threads(M);
+    int by_smem = kMaxDyn / (group_doubles(M) * (int)sizeof(double));
+    int by_thr = 512 / L.tpg;
+    L.G = by_smem < by_thr ? by_smem : by_thr;
+    if (L.G < 1) L.G = 1;
+    if (L.G > 8) L.G = 8;                                  // named barriers 1..8
+    L.threads = L.G * L.tpg;
+    L.smem = L.G * group_doubles(M) * (int)sizeof(double);
+    int want = (nrows + L.G - 1) / L.G;
+    L.ctas = want < 148 ? want : 148;                     // one persistent CTA per SM
+    return L;
+}
 
 }  // namespace
 
@@ -453,11 +550,13 @@ int rmt_poisson_plan_create(int Ny, int Nx, int kind, rmt_poisson_plan **out)
         if (!e) e = make_half_twiddles(&P->tw2_x, P->Lx);
         if (!e) e = make_half_twiddles(&P->tw2_y, P->Ly);
         // opt in to the full 227 KB once (a later, smaller plan must not lower it)
-        const int max_dyn = 227 * 1024 - 1024;
-        if (!e) e = (int)cudaFuncSetAttribute(k_dct_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
-        if (!e) e = (int)cudaFuncSetAttribute(k_dct_cols_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              max_dyn);
-        if (!e && (rows_smem(P->Lx) > max_dyn || cols_smem(P->Ly) > max_dyn)) e = -2;
+        if (!e) e = (int)cudaFuncSetAttribute(k_dct_lines<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+        if (!e) e = (int)cudaFuncSetAttribute(k_dct_lines<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+        const int mxy = P->Lx > P->Ly ? P->Lx : P->Ly;
+        if (!e && group_doubles(mxy) * (int)sizeof(double) > kMaxDyn) e = -2;
+        if (!e && (mxy + 1 + fft_threads(mxy) - 1) / fft_threads(mxy) > kMaxPerThread) e = -2;
+        // transposed work arrays: T2 (Nx, Ny) and the transposed eigenvalue table
+        for (int k = 0; k < 2 && !e; ++k) e = (int)cudaMalloc((void **)&P->w[k], ncell * sizeof(double));
     } else if (kind == 0) {
         e = make_dct_matrix(&P->Cx, Nx);
         if (!e) e = make_dct_matrix(&P->Cy, Ny);
@@ -499,18 +598,31 @@ int rmt_poisson_solve_dct(rmt_poisson_plan *P, const double *rhs, const double *
     const double scale = 1.0 / (4.0 * (double)(Nx - 1) * (double)(Ny - 1));
     double *sum_dst = sum_out ? sum_out : P->red + rmt_reduce_workspace_doubles() + Ny + 8;
     if (P->fast) {
-        // rows: rhs -> sol ; columns in place on sol ; rows in place on sol (a CTA holds its
-        // whole row in shared memory before it writes, so in-place is safe)
-        double *partial = P->red;                       // Ny partial sums
-        const int nrow_cta = Ny;
-        k_dct_rows<<<Ny, fft_threads(P->Lx), rows_smem(P->Lx), s>>>(rhs, sol, Ny, Nx, P->tw_x, P->tw2_x, 1.0,
-                                                                   nullptr);
+        // rows: rhs -> sol | transpose -> T2 | rows of T2 = columns: fwd, x scale/eig, inverse |
+        // transpose back -> sol | rows in place on sol (+ partial sums).  The only FFT kernel is the
+        // row kernel; the two transposes are plain tiled copies.
+        double *T2 = P->w[0], *eigT = P->w[1];
+        dim3 tg_f(rmt_cdiv(Nx, 32), rmt_cdiv(Ny, 32)), tg_b(rmt_cdiv(Ny, 32), rmt_cdiv(Nx, 32));
+        if (P->eig_src != eig) {                         // transposed eigenvalues, once per table
+            k_transpose<<<tg_f, 256, 0, s>>>(eig, eigT, Ny, Nx);
+            RMT_LAUNCH_CHECK();
+            P->eig_src = eig;
+        }
+        const LineLaunch lx = line_launch(P->Lx, Ny), ly = line_launch(P->Ly, Nx);
+        double *partial = P->red;                        // one partial sum per CTA
+        const int nrow_cta = lx.ctas;
+        k_dct_lines<0><<<lx.ctas, lx.threads, lx.smem, s>>>(rhs, sol, nullptr, Ny, Nx, P->tw_x, P->tw2_x, 1.0,
+                                                           lx.tpg, nullptr);
         RMT_LAUNCH_CHECK();
-        k_dct_cols_solve<<<Nx, fft_threads(P->Ly), cols_smem(P->Ly), s>>>(sol, eig, Ny, Nx, P->tw_y, P->tw2_y,
-                                                                         scale);
+        k_transpose<<<tg_f, 256, 0, s>>>(sol, T2, Ny, Nx);
         RMT_LAUNCH_CHECK();
-        k_dct_rows<<<Ny, fft_threads(P->Lx), rows_smem(P->Lx), s>>>(sol, sol, Ny, Nx, P->tw_x, P->tw2_x, 1.0,
-                                                                   partial);
+        k_dct_lines<1><<<ly.ctas, ly.threads, ly.smem, s>>>(T2, T2, eigT, Nx, Ny, P->tw_y, P->tw2_y, scale,
+                                                           ly.tpg, nullptr);
+        RMT_LAUNCH_CHECK();
+        k_transpose<<<tg_b, 256, 0, s>>>(T2, sol, Nx, Ny);
+        RMT_LAUNCH_CHECK();
+        k_dct_lines<0><<<lx.ctas, lx.threads, lx.smem, s>>>(sol, sol, nullptr, Ny, Nx, P->tw_x, P->tw2_x, 1.0,
+                                                           lx.tpg, partial);
         RMT_LAUNCH_CHECK();
         k_sum_final<<<1, 256, 0, s>>>(partial, nrow_cta, sum_dst);
         RMT_LAUNCH_CHECK();
