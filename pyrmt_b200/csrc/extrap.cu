@@ -183,7 +183,8 @@ __global__ void k_ext_scan(const int *__restrict__ seg_cnt, int *__restrict__ se
 // segment's initial progress marker = column of its first target (INT_MAX if
 // none): "segment (j, xt) has dealt with every column < prog[j*nxt+xt]".
 __global__ void k_ext_fill(const unsigned char *__restrict__ st, const int *__restrict__ seg_off,
-                           int *__restrict__ tcol, int *__restrict__ prog, int Ny, int Nx, int nxt, int XT)
+                           int *__restrict__ tcol, int *__restrict__ trow, int *__restrict__ prog, int Ny,
+                           int Nx, int nxt, int XT)
 {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int nwarp = (gridDim.x * blockDim.x) >> 5;
@@ -201,7 +202,11 @@ __global__ void k_ext_fill(const unsigned char *__restrict__ st, const int *__re
                 int i = base + lane;
                 bool tgt = (i < Nx) && (r1[i] == ST_TARGET);
                 unsigned m = __ballot_sync(0xffffffffu, tgt);
-                if (tgt) tcol[off + __popc(m & ((1u << lane) - 1u))] = i;
+                if (tgt) {
+                    const int o = off + __popc(m & ((1u << lane) - 1u));
+                    tcol[o] = i;
+                    trow[o] = j;
+                }
                 if (first && m) {
                     if (lane == 0) prog[j * nxt + xt] = base + __ffs(m) - 1;
                     first = false;
@@ -225,19 +230,37 @@ constexpr int NACC = 12;               // running sums: B1[3], B2[3], A00 A01 A0
 constexpr int RING = 16;               // direct-mapped cache of a row's freshly fitted cells
 constexpr int MAXPEND = 40;            // window cells that precede the target in raster order
 
-struct SweepWarp {
+// Everything about a target that does not depend on this layer's earlier fits ("phase A").
+// Same layout in shared memory (the warp's working buffer) and in global memory (the
+// records k_ext_prepare writes for the whole layer up front).
+struct alignas(16) ExtRec {
     double prod[WIN][NACC];            // per contributing cell (in gather order): the 12 products
     double pw[MAXPEND], px[MAXPEND], py[MAXPEND];   // weight / coordinates of the undecided cells
+    unsigned char pn[MAXPEND], pslot[MAXPEND];      // window index and prod[] slot of the undecided cells
+};
+static_assert(sizeof(ExtRec) % 16 == 0, "ExtRec must be copyable in 16-byte chunks");
+constexpr int REC_PEND_OFF = WIN * NACC * 8;                   // byte offset of pw
+constexpr int REC_PEND_BYTES = (int)sizeof(ExtRec) - REC_PEND_OFF;
+
+struct SweepWarp {
+    ExtRec rec;
     double sums[NACC];                 // the twelve running sums, handed from 12 lanes to all
     double ring_v[RING][2];            // freshly fitted (xi1, xi2) of this row, slot = column & (RING-1)
     int ring_tag[RING];                // column held by the slot (-1: none / being rewritten)
-    unsigned char pn[MAXPEND], pslot[MAXPEND];      // window index and prod[] slot of the undecided cells
 };
 struct SweepSmem {
     SweepWarp w[RB];
+    double prev_v[4][RING][2];         // rings of the last four rows of the previous row block
+    int prev_tag[4][RING];
+    int prev_row0;                     // grid row of prev_*[0] (-100: none)
     int prog[RB];                      // per-row progress marker of the tile being swept
     int tile;                          // tile index handed out by the global counter
 };
+
+__device__ __forceinline__ void st_relaxed_gpu(int *p, int v)
+{
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ int ld_relaxed_gpu(const int *p)
 {
@@ -257,6 +280,107 @@ __device__ __forceinline__ void store_products(double *q, double w, double x, do
     q[3] = w * v2;  q[4] = wx * v2; q[5] = wy * v2;
     q[6] = w;       q[7] = wx;      q[8] = wy;
     q[9] = wx * x;  q[10] = wx * y; q[11] = wy * y;
+}
+
+// Phase A of one target (warp-collective): classify the 81 window cells, weight them,
+// turn the cells known before the layer into their 12 products (compacted in gather
+// order) and list the undecided ones.  Returns nslots | npend << 8.
+__device__ __forceinline__ int ext_phase_a(ExtRec *R, const double *__restrict__ X1e,
+                                           const double *__restrict__ X2e,
+                                           const unsigned char *__restrict__ st, int j, int i, int Ny, int Nx,
+                                           double dx, double dy, double r2, int lane)
+{
+    const unsigned lt = (1u << lane) - 1u;
+    const double x0 = dx * i, y0 = dy * j;
+    int cls[3];                                 // 0 no contribution, 1 known, 2 undecided
+    double cw[3], cx_[3], cy_[3], c1[3], c2[3];
+    unsigned mk[3], mp[3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        const int n = lane + 32 * s;
+        cls[s] = 0;
+        cw[s] = cx_[s] = cy_[s] = c1[s] = c2[s] = 0.0;
+        if (n < WIN) {
+            const int dj = n / 9 - 4, di = n % 9 - 4;
+            const int jj = j + dj, ii = i + di;
+            if (jj >= 0 && jj < Ny && ii >= 0 && ii < Nx) {
+                const size_t cc = (size_t)jj * Nx + ii;
+                const unsigned char sv = st[cc];     // 1 is final; 2/3 decided during the sweep
+                const double v1 = X1e[cc], v2 = X2e[cc];   // only meaningful if sv == 1
+                const double xi = dx * ii, yi = dy * jj;
+                const double ex = xi - x0, ey = yi - y0;
+                const double dist_sq = ex * ex + ey * ey;
+                const bool earlier = (dj < 0) || (dj == 0 && di < 0);
+                if (dist_sq <= r2 && (sv == ST_KNOWN || (sv != ST_UNKNOWN && earlier))) {
+                    cls[s] = (sv == ST_KNOWN) ? 1 : 2;
+                    cw[s] = exp_glibc(-dist_sq / r2);
+                    cx_[s] = xi; cy_[s] = yi; c1[s] = v1; c2[s] = v2;
+                }
+            }
+        }
+        mk[s] = __ballot_sync(0xffffffffu, cls[s] == 1);
+        mp[s] = __ballot_sync(0xffffffffu, cls[s] == 2);
+    }
+    int slot_base = 0, pend_base = 0;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        const unsigned mv = mk[s] | mp[s];
+        const int slot = slot_base + __popc(mv & lt);
+        if (cls[s] == 1) {
+            store_products(R->prod[slot], cw[s], cx_[s], cy_[s], c1[s], c2[s]);
+        } else if (cls[s] == 2) {
+            const int r = pend_base + __popc(mp[s] & lt);
+            R->pw[r] = cw[s]; R->px[r] = cx_[s]; R->py[r] = cy_[s];
+            R->pn[r] = (unsigned char)(lane + 32 * s);
+            R->pslot[r] = (unsigned char)slot;
+        }
+        slot_base += __popc(mv);
+        pend_base += __popc(mp[s]);
+    }
+    // pad the slot list with zero products to a multiple of 8 (exact no-ops in the sums):
+    // the accumulation loop then runs in fixed, fully unrolled chunks of 8
+    const int npad = min((slot_base + 7) & ~7, WIN);
+    for (int e = slot_base * NACC + lane; e < npad * NACC; e += 32) (&R->prod[0][0])[e] = 0.0;
+    return slot_base | (pend_base << 8);
+}
+
+// Phase A for every target of the layer, fully parallel (one warp per target): nothing in
+// it depends on this layer's fits, so it is taken off the serial chain of the sweep.
+__global__ void __launch_bounds__(256)
+k_ext_prepare(const double *__restrict__ X1e, const double *__restrict__ X2e,
+              const unsigned char *__restrict__ st, const int *__restrict__ seg_off, int nseg,
+              const int *__restrict__ tcol, const int *__restrict__ trow, ExtRec *__restrict__ recs,
+              int *__restrict__ tinfo, int cap, int Ny, int Nx, double dx, double dy, double r2)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    const int ntot = min(seg_off[nseg], cap);
+    for (int t = warp; t < ntot; t += nwarp) {
+        const int info = ext_phase_a(recs + t, X1e, X2e, st, trow[t], tcol[t], Ny, Nx, dx, dy, r2, lane);
+        if (lane == 0) tinfo[t] = info;
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// start copying target t's record into the warp's buffer (only the used part)
+__device__ __forceinline__ void ext_fetch(ExtRec *dst, const ExtRec *__restrict__ src, int info, int lane)
+{
+    const int nslots = info & 255, npend = info >> 8;
+    const char *s8 = (const char *)src;
+    char *d8 = (char *)dst;
+    const int npad = min((nslots + 7) & ~7, WIN);
+    for (int c = lane; c < npad * (NACC * 8 / 16); c += 32) cp_async16(d8 + c * 16, s8 + c * 16);
+    if (npend)
+        for (int c = lane; c < REC_PEND_BYTES / 16; c += 32)
+            cp_async16(d8 + REC_PEND_OFF + c * 16, s8 + REC_PEND_OFF + c * 16);
 }
 
 // The row-pipelined sweep (functions.py:95-161).
@@ -291,8 +415,8 @@ __device__ __forceinline__ void store_products(double *q, double w, double x, do
 __global__ void __launch_bounds__(RB * 32, 1)
 k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__restrict__ st,
             const int *__restrict__ seg_off, const int *__restrict__ tcol, int *__restrict__ prog,
-            int *__restrict__ tile_counter, int Ny, int Nx, int nxt, int XT, int MRB, int sleep_ns,
-            double dx, double dy, double r2)
+            int *__restrict__ tile_counter, const ExtRec *__restrict__ recs, const int *__restrict__ tinfo,
+            int cap, int Ny, int Nx, int nxt, int XT, int MRB, int sleep_ns, double dx, double dy, double r2)
 {
     extern __shared__ unsigned char s_raw[];
     SweepSmem &S = *reinterpret_cast<SweepSmem *>(s_raw);
@@ -303,7 +427,6 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
     const int nmrb = (nrb + MRB - 1) / MRB;            // macro row blocks
     const int ntiles = nmrb * nxt;
     const int la = (lane < NACC) ? lane : 0;
-    const unsigned lt = (1u << lane) - 1u;
 
     // A CTA takes a macro-tile (MRB row blocks x one x-tile) and sweeps its row blocks
     // top to bottom itself, so the chain that runs along a flank stays on this SM for
@@ -316,7 +439,9 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
         if (tile >= ntiles) break;
         const int mrb = tile / nxt, xt = tile - mrb * nxt;
         const int xc0 = xt * XT, xc1 = min(xc0 + XT, Nx); // its column range
-      for (int rb = mrb * MRB; rb < min((mrb + 1) * MRB, nrb); ++rb) {
+        const int rb_end = min((mrb + 1) * MRB, nrb);
+        if (threadIdx.x == 0) S.prev_row0 = -100;
+      for (int rb = mrb * MRB; rb < rb_end; ++rb) {
         const int row0 = 1 + rb * RB;                  // first row of this row block
         const int j = row0 + wib;
         const bool live = j < Ny - 1;
@@ -325,6 +450,16 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
         if (lane == 0) sp[wib] = (t1 > t0) ? tcol[t0] : INT_MAX;
         if (lane < RING) W.ring_tag[lane] = -1;
         __syncthreads();
+        const int prow0 = S.prev_row0;                 // rows prow0..prow0+3 were swept by this CTA just before
+        const bool prev_ok = (prow0 == row0 - 4);
+        const bool last_rb = (rb == rb_end - 1);
+        // does another tile possibly read this row's results?  (x-edges, or the macro-tile's last rows)
+        const bool edgy = (t1 > t0) && (tcol[t0] < xc0 + 8 || tcol[t1 - 1] >= xc1 - 8 || (last_rb && wib >= RB - 4));
+
+        // the first target's record is fetched while this warp waits for its dependencies;
+        // every later one right after the previous accumulation has drained the buffer
+        int info_next = (t0 < t1 && t0 < cap) ? tinfo[t0] : 0;
+        if (t0 < t1 && t0 < cap) ext_fetch(&W.rec, recs + t0, info_next, lane);
 
         for (int t = t0; t < t1; ++t) {
             const int i = tcol[t];
@@ -332,53 +467,17 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
 #ifdef RMT_EXT_TIMING
             long long tmark = clock64();
 #endif
-            // ---- phase A (before the wait) ----------------------------------------
-            int cls[3];                                 // 0 no contribution, 1 known, 2 undecided
-            double cw[3], cx_[3], cy_[3], c1[3], c2[3];
-            unsigned mk[3], mp[3];
-#pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const int n = lane + 32 * s;
-                cls[s] = 0;
-                cw[s] = cx_[s] = cy_[s] = c1[s] = c2[s] = 0.0;
-                if (n < WIN) {
-                    const int dj = n / 9 - 4, di = n % 9 - 4;
-                    const int jj = j + dj, ii = i + di;
-                    if (jj >= 0 && jj < Ny && ii >= 0 && ii < Nx) {
-                        const size_t cc = (size_t)jj * Nx + ii;
-                        const unsigned char sv = st[cc];     // 1 is final; 2/3 decided after the wait
-                        const double v1 = X1e[cc], v2 = X2e[cc];   // only meaningful if sv == 1
-                        const double xi = dx * ii, yi = dy * jj;
-                        const double ex = xi - x0, ey = yi - y0;
-                        const double dist_sq = ex * ex + ey * ey;
-                        const bool earlier = (dj < 0) || (dj == 0 && di < 0);
-                        if (dist_sq <= r2 && (sv == ST_KNOWN || (sv != ST_UNKNOWN && earlier))) {
-                            cls[s] = (sv == ST_KNOWN) ? 1 : 2;
-                            cw[s] = exp_glibc(-dist_sq / r2);
-                            cx_[s] = xi; cy_[s] = yi; c1[s] = v1; c2[s] = v2;
-                        }
-                    }
-                }
-                mk[s] = __ballot_sync(0xffffffffu, cls[s] == 1);
-                mp[s] = __ballot_sync(0xffffffffu, cls[s] == 2);
+            // ---- phase A: prepared record (or inline beyond the record capacity) -------
+            int info;
+            if (t < cap) {
+                info = info_next;
+                cp_async_wait_all();
+            } else {
+                info = ext_phase_a(&W.rec, X1e, X2e, st, j, i, Ny, Nx, dx, dy, r2, lane);
             }
-            int slot_base = 0, pend_base = 0;
-#pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const unsigned mv = mk[s] | mp[s];
-                const int slot = slot_base + __popc(mv & lt);
-                if (cls[s] == 1) {
-                    store_products(W.prod[slot], cw[s], cx_[s], cy_[s], c1[s], c2[s]);
-                } else if (cls[s] == 2) {
-                    const int r = pend_base + __popc(mp[s] & lt);
-                    W.pw[r] = cw[s]; W.px[r] = cx_[s]; W.py[r] = cy_[s];
-                    W.pn[r] = (unsigned char)(lane + 32 * s);
-                    W.pslot[r] = (unsigned char)slot;
-                }
-                slot_base += __popc(mv);
-                pend_base += __popc(mp[s]);
-            }
-            const int nslots = slot_base, npend = pend_base;
+            info_next = (t + 1 < t1 && t + 1 < cap) ? tinfo[t + 1] : 0;
+            const int next = (t + 1 < t1) ? tcol[t + 1] : INT_MAX;   // loaded early: it gates the publish
+            const int nslots = info & 255, npend = info >> 8;
             const int nknown = nslots - npend;
             __syncwarp();
             EXT_T(0);
@@ -392,7 +491,7 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                 if (lane < 4) { jr = j - 1 - lane; xq = xr; }
                 else if (lane < 8) { jr = j - 1 - (lane - 4); xq = (xl != xr) ? xl : -1; }
                 else { xq = (xl != xt) ? xl : -1; need = i - 1; }
-                if (jr >= 1 && xq >= 0) {
+                if (jr >= 1 && xq >= 0 && !(xq == xt && prev_ok && jr < row0)) {   // (own previous block: done)
                     if (xq == xt && jr >= row0) {
                         if (jr != j) {
                             if (sleep_ns > 0) while (sp[jr - row0] <= need) __nanosleep(sleep_ns);
@@ -413,14 +512,16 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                 const int r = r0 + lane;
                 bool fail = false;
                 if (r < npend) {
-                    const int n = W.pn[r];
+                    const int n = W.rec.pn[r];
                     const int dj = n / 9 - 4, di = n % 9 - 4;
                     const int jj = j + dj, ii = i + di;
+                    const int slot = ii & (RING - 1);
+                    const bool mine = (ii >= xc0 && ii < xc1);
                     double v1 = 0.0, v2 = 0.0;
-                    bool got = false;
-                    if (jj >= row0 && ii >= xc0 && ii < xc1) {  // a row of this tile: its shared-memory ring
+                    bool got = false, smem_row = false;
+                    if (mine && jj >= row0) {                 // a row of this block: its live ring (seqlock)
+                        smem_row = true;
                         SweepWarp &R = S.w[jj - row0];
-                        const int slot = ii & (RING - 1);
                         volatile int *tag = &R.ring_tag[slot];
                         volatile double *rv = R.ring_v[slot];
                         if (*tag == ii) {
@@ -428,23 +529,28 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                             SMEM_ORDER();
                             got = (*tag == ii);
                         }
-                        if (!got) {                           // slot recycled long ago / target rejected
-                            const size_t cc = (size_t)jj * Nx + ii;
+                    } else if (mine && prev_ok && jj >= prow0) {   // last rows of the previous block: frozen rings
+                        smem_row = true;
+                        if (S.prev_tag[jj - prow0][slot] == ii) {
+                            v1 = S.prev_v[jj - prow0][slot][0]; v2 = S.prev_v[jj - prow0][slot][1];
+                            got = true;
+                        }
+                    }
+                    if (!got) {
+                        const size_t cc = (size_t)jj * Nx + ii;
+                        if (smem_row) {                       // slot recycled long ago / target rejected
                             if (ld_cta_u8(st + cc) == ST_FRESH) {
                                 v1 = ld_cta_f64(X1e + cc); v2 = ld_cta_f64(X2e + cc);
                                 got = true;
                             }
-                        }
-                    } else {                                  // fitted by another tile (L2)
-                        const size_t cc = (size_t)jj * Nx + ii;
-                        if (__ldcg(st + cc) == ST_FRESH) {
+                        } else if (__ldcg(st + cc) == ST_FRESH) {   // fitted by another tile (L2)
                             v1 = __ldcg(X1e + cc); v2 = __ldcg(X2e + cc);
                             got = true;
                         }
                     }
                     // a rejected target contributes exact zeros (weight 0)
-                    store_products(W.prod[W.pslot[r]], got ? W.pw[r] : 0.0, got ? W.px[r] : 0.0,
-                                   got ? W.py[r] : 0.0, v1, v2);
+                    store_products(W.rec.prod[W.rec.pslot[r]], got ? W.rec.pw[r] : 0.0, got ? W.rec.px[r] : 0.0,
+                                   got ? W.rec.py[r] : 0.0, v1, v2);
                     fail = !got;
                 }
                 nfail += __popc(__ballot_sync(0xffffffffu, fail));
@@ -455,9 +561,15 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
             // ---- ordered accumulation: lane a owns running sum a ----------------------
             double acc = 0.0;
             {
-                const double *q = &W.prod[0][la];
-#pragma unroll 8
-                for (int k = 0; k < nslots; ++k) acc += q[k * NACC];
+                const double *q = &W.rec.prod[0][la];
+                int k = 0;
+                for (; k + 8 <= nslots + 7 && k + 8 <= WIN; k += 8) {      // zero-padded chunks of 8
+                    const double q0 = q[(k + 0) * NACC], q1 = q[(k + 1) * NACC], q2 = q[(k + 2) * NACC],
+                                 q3 = q[(k + 3) * NACC], q4 = q[(k + 4) * NACC], q5 = q[(k + 5) * NACC],
+                                 q6 = q[(k + 6) * NACC], q7 = q[(k + 7) * NACC];
+                    acc += q0; acc += q1; acc += q2; acc += q3; acc += q4; acc += q5; acc += q6; acc += q7;
+                }
+                for (; k < nslots; ++k) acc += q[k * NACC];                // (window of 81: last odd slot)
             }
             if (lane < NACC) W.sums[lane] = acc;
             __syncwarp();
@@ -479,7 +591,6 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
             EXT_T(4);
             // ---- publish: shared memory first (that is what the next row waits for) ----
             {
-                const int next = (t + 1 < t1) ? tcol[t + 1] : INT_MAX;
                 const size_t c = (size_t)j * Nx + i;
                 const int slot = i & (RING - 1);
                 if (fitted) {
@@ -496,16 +607,24 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                 }
                 if (lane == 0) sp[wib] = next;                // shared-memory stores retire in order
                 SMEM_ORDER();
+                // the record buffer was drained by the accumulation: fetch the next target's record
+                if (t + 1 < t1 && t + 1 < cap) ext_fetch(&W.rec, recs + t + 1, info_next, lane);
                 if (fitted) {
                     if (lane == 0) X1e[c] = val;
                     if (lane == 1) X2e[c] = val;
                     __syncwarp();
                     if (lane == 0) st[c] = ST_FRESH;
                 }
-                // global marker: only where another tile can be waiting on this row
-                if (lane == 0 && (wib >= RB - 4 || i < xc0 + 8 || i >= xc1 - 8 || next == INT_MAX)) {
-                    __threadfence();
-                    st_release(prog + j * nxt + xt, next);
+                // global marker: only where another tile can be waiting on this row; the fence is
+                // needed only if that tile can also read this row's values
+                if (lane == 0) {
+                    const bool data = (last_rb && wib >= RB - 4) || i < xc0 + 8 || i >= xc1 - 8;
+                    if (data || (next == INT_MAX && edgy)) {
+                        __threadfence();
+                        st_release(prog + j * nxt + xt, next);
+                    } else if (next == INT_MAX) {
+                        st_relaxed_gpu(prog + j * nxt + xt, next);
+                    }
                 }
             }
             __syncwarp();
@@ -513,6 +632,15 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
 #ifdef RMT_EXT_TIMING
             if (lane == 0) atomicAdd(&g_ext_dbg[7], 1ull);
 #endif
+        }
+        __syncthreads();
+        if (wib >= RB - 4) {                                   // freeze the last four rows' rings
+            if (lane < RING) {
+                S.prev_tag[wib - (RB - 4)][lane] = W.ring_tag[lane];
+                S.prev_v[wib - (RB - 4)][lane][0] = W.ring_v[lane][0];
+                S.prev_v[wib - (RB - 4)][lane][1] = W.ring_v[lane][1];
+            }
+            if (wib == RB - 4 && lane == 0) S.prev_row0 = row0 + RB - 4;
         }
         __syncthreads();                                       // shared state is reused by the next row block
       }
@@ -527,15 +655,38 @@ extern "C" {
 
 static inline int ext_nxt(int Nx) { int XT = ext_tune().XT; return (Nx + XT - 1) / XT; }
 
-long rmt_extrapolate_workspace_bytes(int Ny, int Nx)
+// prepared-record capacity (targets per layer); beyond it the sweep computes phase A inline
+static inline long ext_cap(long ncell)
 {
-    size_t ncell = (size_t)Ny * (size_t)Nx;
-    size_t st = (ncell + 255) & ~(size_t)255;
-    size_t nseg = (size_t)Ny * ext_nxt(Nx) + 2;
-    size_t segs = ((size_t)(3 * nseg + 16) * sizeof(int) + 255) & ~(size_t)255;
-    size_t cols = ncell * sizeof(int);
-    return (long)(st + segs + cols);
+    long c = ncell / 48;
+    if (c < 4096) c = 4096;
+    if (c > 300000) c = 300000;
+    return c;
 }
+static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+struct ExtLayout {
+    size_t st, segs, tcol, trow, tinfo, recs, total;
+    long cap;
+};
+static ExtLayout ext_layout(int Ny, int Nx)
+{
+    ExtLayout L;
+    size_t ncell = (size_t)Ny * (size_t)Nx;
+    size_t nseg = (size_t)Ny * ext_nxt(Nx) + 2;
+    L.cap = ext_cap((long)ncell);
+    size_t off = 0;
+    L.st = off;    off += al256(ncell);
+    L.segs = off;  off += al256((3 * nseg + 16) * sizeof(int));
+    L.tcol = off;  off += al256(ncell * sizeof(int));
+    L.trow = off;  off += al256(ncell * sizeof(int));
+    L.tinfo = off; off += al256((size_t)L.cap * sizeof(int));
+    L.recs = off;  off += al256((size_t)L.cap * sizeof(ExtRec));
+    L.total = off;
+    return L;
+}
+
+long rmt_extrapolate_workspace_bytes(int Ny, int Nx) { return (long)ext_layout(Ny, Nx).total; }
 
 int rmt_extrapolate(const double *X1, const double *X2, const double *phi, double *X1e, double *X2e,
                     int Ny, int Nx, double dx, double dy, int max_layers, void *workspace,
@@ -548,14 +699,16 @@ int rmt_extrapolate(const double *X1, const double *X2, const double *phi, doubl
     int nseg = Ny * nxt;
     ExtTune tune = ext_tune();
     int XT = tune.XT, MRB = tune.MRB, sleep_ns = tune.sleep_ns;
-    unsigned char *st = (unsigned char *)workspace;
-    size_t st_bytes = (ncell + 255) & ~(size_t)255;
-    int *seg_cnt = (int *)((char *)workspace + st_bytes);
+    const ExtLayout L = ext_layout(Ny, Nx);
+    char *ws = (char *)workspace;
+    unsigned char *st = (unsigned char *)(ws + L.st);
+    int *seg_cnt = (int *)(ws + L.segs);
     int *seg_off = seg_cnt + (nseg + 2);
     int *prog = seg_off + (nseg + 2);
     int *tile_counter = prog + (nseg + 2);
-    size_t segs_bytes = ((size_t)(3 * ((size_t)nseg + 2) + 16) * sizeof(int) + 255) & ~(size_t)255;
-    int *tcol = (int *)((char *)workspace + st_bytes + segs_bytes);
+    int *tcol = (int *)(ws + L.tcol), *trow = (int *)(ws + L.trow), *tinfo = (int *)(ws + L.tinfo);
+    ExtRec *recs = (ExtRec *)(ws + L.recs);
+    int cap = (int)L.cap;
 
     // stencil_radius_sq = (4*sqrt(dx**2+dy**2))**2, functions.py:76 (no contraction)
     volatile double dx2 = dx * dx, dy2 = dy * dy;
@@ -586,14 +739,17 @@ int rmt_extrapolate(const double *X1, const double *X2, const double *phi, doubl
         RMT_LAUNCH_CHECK();
         k_ext_scan<<<1, 1024, 0, s>>>(seg_cnt, seg_off, nseg, tile_counter);
         RMT_LAUNCH_CHECK();
-        k_ext_fill<<<row_warps_blocks, 256, 0, s>>>(st, seg_off, tcol, prog, Ny, Nx, nxt, XT);
+        k_ext_fill<<<row_warps_blocks, 256, 0, s>>>(st, seg_off, tcol, trow, prog, Ny, Nx, nxt, XT);
+        RMT_LAUNCH_CHECK();
+        k_ext_prepare<<<148 * 8, 256, 0, s>>>(X1e, X2e, st, seg_off, nseg, tcol, trow, recs, tinfo, cap, Ny, Nx,
+                                               dx, dy, r2);
         RMT_LAUNCH_CHECK();
         // all CTAs must be co-resident (warps wait on each other): cooperative launch
         int blocks = sweep_blocks;
         int need = rmt_cdiv(rmt_cdiv(Ny - 2, RB), MRB) * nxt;
         if (blocks > need) blocks = need;
-        void *args[] = {&X1e, &X2e, &st, &seg_off, &tcol, &prog, &tile_counter, &Ny, &Nx, &nxt, &XT, &MRB,
-                        &sleep_ns, &dx, &dy, &r2};
+        void *args[] = {&X1e, &X2e, &st, &seg_off, &tcol, &prog, &tile_counter, &recs, &tinfo, &cap,
+                        &Ny, &Nx, &nxt, &XT, &MRB, &sleep_ns, &dx, &dy, &r2};
         RMT_CUDA(cudaLaunchCooperativeKernel((void *)k_ext_sweep, dim3(blocks), dim3(RB * 32), args,
                                              sweep_smem, s));
     }

@@ -229,8 +229,6 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-constexpr int kMaxPerThread = 18;   // line points per thread held in registers in solve mode (>= (M+1)/nthr)
-
 // ----------------------------------------------------- DCT-I along rows, persistent
 // Lines are the rows of a (nrows, N) array, N = M + 1.  A CTA hosts `G` groups of
 // `tpg` threads; each group owns one line at a time (planes re/im + a staging copy of
@@ -261,31 +259,20 @@ k_dct_lines(const double *in, double *out, const double *__restrict__ eig, int n
         g.sync();                                   // staged line complete; previous unpack done
         pack_even(stage, re, im, M, g);
         g.sync();
-        const int rn = r + ngroups;                 // prefetch the next line behind the FFT
-        if (rn < nrows)
+        const int rn = r + ngroups;                 // prefetch the next line behind the (last) FFT
+        if (MODE == 0 && rn < nrows)
             for (int k = g.tid; k < N; k += g.nthr) cp_async8(stage + k, in + (size_t)rn * N + k);
         fft_dif(re, im, M, tw, g);
         if (MODE == 1) {
-            // spectrum -> registers (x scale/eig), then straight back into packed form
-            double y[kMaxPerThread];
+            // spectrum x scale/eig -> staging buffer (natural order) -> packed again -> second FFT
             const double *er = eig + (size_t)r * N;
-#pragma unroll
-            for (int m = 0; m < kMaxPerThread; ++m) {
-                const int k = g.tid + m * g.nthr;
-                y[m] = (k <= M) ? unpack_dct(re, im, k, M, lg, tw2) * (scale / __ldg(er + k)) : 0.0;
-            }
+            for (int k = g.tid; k <= M; k += g.nthr)
+                stage[k] = unpack_dct(re, im, k, M, lg, tw2) * (scale / __ldg(er + k));
             g.sync();
-#pragma unroll
-            for (int m = 0; m < kMaxPerThread; ++m) {
-                const int k = g.tid + m * g.nthr;
-                if (k <= M) {
-                    // e[k] = y_k sits at z[k/2] (k < M) and, mirrored as e[2M-k], at z[M - (k+1)/2] (k > 0)
-                    double *pl = (k & 1) ? im : re;
-                    if (k < M) pl[padi(k >> 1)] = y[m];
-                    if (k > 0) pl[padi(M - ((k + 1) >> 1))] = y[m];
-                }
-            }
+            pack_even(stage, re, im, M, g);
             g.sync();
+            if (rn < nrows)
+                for (int k = g.tid; k < N; k += g.nthr) cp_async8(stage + k, in + (size_t)rn * N + k);
             fft_dif(re, im, M, tw, g);
         }
         double *o = out + (size_t)r * N;
@@ -554,7 +541,6 @@ int rmt_poisson_plan_create(int Ny, int Nx, int kind, rmt_poisson_plan **out)
         if (!e) e = (int)cudaFuncSetAttribute(k_dct_lines<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
         const int mxy = P->Lx > P->Ly ? P->Lx : P->Ly;
         if (!e && group_doubles(mxy) * (int)sizeof(double) > kMaxDyn) e = -2;
-        if (!e && (mxy + 1 + fft_threads(mxy) - 1) / fft_threads(mxy) > kMaxPerThread) e = -2;
         // transposed work arrays: T2 (Nx, Ny) and the transposed eigenvalue table
         for (int k = 0; k < 2 && !e; ++k) e = (int)cudaMalloc((void **)&P->w[k], ncell * sizeof(double));
     } else if (kind == 0) {

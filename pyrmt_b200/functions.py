@@ -221,7 +221,7 @@ def extrapolate_reference_map(X1, X2, phi, dx, dy, max_layers):
     c = ctx()
     o1, o2 = torch.empty_like(x1), torch.empty_like(x2)
     ws = c.extrap_workspace(Ny, Nx)
-    profiler.launches += 4 * int(max_layers)
+    profiler.launches += 5 * int(max_layers)
     _chk(c.lib.rmt_extrapolate(ptr(x1), ptr(x2), ptr(ph), ptr(o1), ptr(o2), Ny, Nx, float(dx), float(dy),
                                int(max_layers), ptr(ws), stream()), "rmt_extrapolate")
     return to_user(o1, as_np), to_user(o2, as_np)
