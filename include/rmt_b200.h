@@ -190,6 +190,19 @@ int rmt_poisson_solve_dct(rmt_poisson_plan *plan, const double *rhs, const doubl
 int rmt_poisson_solve_fft(rmt_poisson_plan *plan, const double *rhs, const double *eig,
                           const unsigned char *null_mask, double *sol, double *sum_out, void *stream);
 
+/* -------------------------------- building blocks of the slab-decomposed solve */
+/* DCT-I (scipy.fft.dct type 1, the 1-D factor of functions.py:1115-1117) along the rows of
+ * a (nrows, N) array, N - 1 a power of two in [8, 8192]:
+ *   eig == NULL: out = scale * DCT-I(in)
+ *   eig != NULL: out = DCT-I( DCT-I(in) * scale / eig ), eig laid out like in.
+ * in == out is allowed.  Used by pyrmt_b200/slab.py between the all-to-all transposes. */
+int rmt_dct_lines(const double *in, double *out, const double *eig, int nrows, int N, double scale,
+                  void *stream);
+/* out (C, R) = in (R, C)^T */
+int rmt_transpose(const double *in, double *out, int R, int C, void *stream);
+/* dst[r*dst_ld + c] = src[r*src_ld + c], rows x cols block (all-to-all pack / unpack). */
+int rmt_copy2d(const double *src, double *dst, int rows, int cols, long src_ld, long dst_ld, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

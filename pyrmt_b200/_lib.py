@@ -55,6 +55,9 @@ _SIG = {
     "rmt_poisson_plan_is_fast": [vp],
     "rmt_poisson_solve_dct": [vp, vp, vp, vp, vp, vp],
     "rmt_poisson_solve_fft": [vp, vp, vp, vp, vp, vp, vp],
+    "rmt_dct_lines": [vp, vp, vp, i32, i32, dbl, vp],
+    "rmt_transpose": [vp, vp, i32, i32, vp],
+    "rmt_copy2d": [vp, vp, i32, i32, i64, i64, vp],
 }
 _RESTYPE = {"rmt_extrapolate_workspace_bytes": i64, "rmt_poisson_plan_destroy": None}
 

@@ -377,6 +377,14 @@ __global__ void k_tile_overlap(double *__restrict__ s, int Ny, int Nx)
     }
 }
 
+__global__ void k_copy2d(const double *__restrict__ src, double *__restrict__ dst, int rows, int cols,
+                         long src_ld, long dst_ld)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) dst[(size_t)r * dst_ld + c] = src[(size_t)r * src_ld + c];
+}
+
 inline int flat_blocks(long n) { long b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
 inline bool is_pow2(int v) { return v >= 2 && (v & (v - 1)) == 0; }
 
@@ -573,6 +581,64 @@ void rmt_poisson_plan_destroy(rmt_poisson_plan *P)
 }
 
 int rmt_poisson_plan_is_fast(const rmt_poisson_plan *P) { return (P && P->fast) ? 1 : 0; }
+
+// ---- building blocks of the slab-decomposed (multi-GPU) DCT solve ------------------------
+// DCT-I along the rows of a (nrows, N) array, N - 1 a power of two in [8, 8192].
+//   eig == NULL: out = scale * DCT-I(in);   eig != NULL: out = DCT-I(DCT-I(in) * scale / eig).
+// Twiddle tables are cached per line length (per device); in == out is allowed.
+int rmt_dct_lines(const double *in, double *out, const double *eig, int nrows, int N, double scale,
+                  void *stream)
+{
+    if (!in || !out || nrows < 1 || N < 9) return RMT_EINVAL;
+    const int M = N - 1;
+    if (!is_pow2(M) || M > kMaxSmemL) return -2;
+    struct Tab { int M, dev; double2 *tw, *tw2; };
+    static std::vector<Tab> cache;
+    int dev = 0;
+    RMT_CUDA(cudaGetDevice(&dev));
+    const Tab *T = nullptr;
+    for (const Tab &t : cache)
+        if (t.M == M && t.dev == dev) T = &t;
+    if (!T) {
+        Tab t{M, dev, nullptr, nullptr};
+        int e = make_twiddles(&t.tw, M);
+        if (!e) e = make_half_twiddles(&t.tw2, M);
+        if (!e) e = (int)cudaFuncSetAttribute(k_dct_lines<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+        if (!e) e = (int)cudaFuncSetAttribute(k_dct_lines<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+        if (e) return e;
+        cache.push_back(t);
+        T = &cache.back();
+    }
+    const LineLaunch L = line_launch(M, nrows);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (eig)
+        k_dct_lines<1><<<L.ctas, L.threads, L.smem, s>>>(in, out, eig, nrows, N, T->tw, T->tw2, scale, L.tpg, nullptr);
+    else
+        k_dct_lines<0><<<L.ctas, L.threads, L.smem, s>>>(in, out, nullptr, nrows, N, T->tw, T->tw2, scale, L.tpg,
+                                                        nullptr);
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
+
+// out (C, R) = in (R, C)^T
+int rmt_transpose(const double *in, double *out, int R, int C, void *stream)
+{
+    if (!in || !out || R < 1 || C < 1) return RMT_EINVAL;
+    dim3 grd(rmt_cdiv(C, 32), rmt_cdiv(R, 32));
+    k_transpose<<<grd, 256, 0, (cudaStream_t)stream>>>(in, out, R, C);
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
+
+// dst[r*dst_ld + c] = src[r*src_ld + c] for a rows x cols block (pack / unpack of the all-to-all)
+int rmt_copy2d(const double *src, double *dst, int rows, int cols, long src_ld, long dst_ld, void *stream)
+{
+    if (!src || !dst || rows < 1 || cols < 1) return RMT_EINVAL;
+    dim3 grd(rmt_cdiv(cols, 128), rows > 65535 ? 65535 : rows);
+    k_copy2d<<<grd, 128, 0, (cudaStream_t)stream>>>(src, dst, rows, cols, src_ld, dst_ld);
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
 
 int rmt_poisson_solve_dct(rmt_poisson_plan *P, const double *rhs, const double *eig, double *sol,
                           double *sum_out, void *stream)

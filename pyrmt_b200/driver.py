@@ -62,6 +62,20 @@ class LidBC:
     def __call__(self, u, v):
         return no_slip_lid_bc(u, v, self.lid_speed)
 
+    def rmt_table(self, Ny, Nx):
+        """The gather table of this BC written down directly (what bc.classify would find by
+        probing; saves the host-side probe arrays on 8193^2 / 16385^2 grids)."""
+        from .bc import BCTable, _FIELD_BIT
+        j = np.concatenate([np.zeros(Nx, np.int64), np.full(Nx, Ny - 1, np.int64),
+                            np.arange(1, Ny - 1), np.arange(1, Ny - 1)])
+        i = np.concatenate([np.arange(Nx), np.arange(Nx), np.zeros(Ny - 2, np.int64),
+                            np.full(Ny - 2, Nx - 1, np.int64)])
+        cell = j * Nx + i
+        lid = (j == Ny - 1) & (i > 0) & (i < Nx - 1)
+        dst = np.concatenate([cell, cell | _FIELD_BIT]).astype(np.int64)
+        cb = np.concatenate([np.where(lid, self.lid_speed, 0.0), np.zeros(cell.size)])
+        return BCTable(dst, np.full(dst.size, -1, np.int64), np.zeros(dst.size), cb.astype(np.float64), (Ny, Nx))
+
 
 def disc_lattice(k_side, L, R_frac, seed=20240607):
     """K = k_side^2 discs on a jittered lattice."""

@@ -1,0 +1,132 @@
+"""CPU tests of the slab-decomposition host logic: partition arithmetic, the
+per-slab BC table, and -- with two gloo processes -- the halo exchange and the all-to-all
+bookkeeping of the distributed DCT solve (device kernels replaced by SciPy test doubles;
+the same Comm / DistPoissonDCT code runs on NCCL on the GPUs)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def test_split_and_layout():
+    from pyrmt_b200.slab import SlabLayout, split
+    assert split(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    for Ny, P in ((129, 2), (4097, 8), (33, 4)):
+        rows = split(Ny, P)
+        assert rows[0][0] == 0 and rows[-1][1] == Ny and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+        for r in range(P):
+            L = SlabLayout(Ny, 17, P, r, halo=4)
+            assert L.e0 == max(L.r0 - 4, 0) and L.e1 == min(L.r1 + 4, Ny)
+            assert L.o1 - L.o0 == L.r1 - L.r0 and L.nl == L.e1 - L.e0
+    with pytest.raises(ValueError):
+        SlabLayout(16, 16, 8, 0, halo=4)
+
+
+def test_lid_table_matches_classifier():
+    from pyrmt_b200.bc import classify
+    from pyrmt_b200.driver import LidBC
+    bc = LidBC(1.5)
+    for Ny, Nx in ((9, 13), (28, 36)):
+        t1, t2 = bc.rmt_table(Ny, Nx), classify(lambda u, v: bc(u, v), Ny, Nx)
+        rng = np.random.default_rng(0)
+        u, v = rng.standard_normal((Ny, Nx)), rng.standard_normal((Ny, Nx))
+        a1, a2, ref = t1.apply_host(u, v), t2.apply_host(u, v), bc(u, v)
+        assert np.array_equal(a1[0], ref[0]) and np.array_equal(a1[1], ref[1])
+        assert np.array_equal(a2[0], ref[0]) and np.array_equal(a2[1], ref[1])
+
+
+def test_local_bc_table_reproduces_global_bc():
+    from pyrmt_b200.bc import free_slip_box_bc
+    from pyrmt_b200.driver import LidBC
+    from pyrmt_b200.slab import SlabLayout, local_bc_table
+    Ny, Nx, P = 40, 23, 3
+    rng = np.random.default_rng(1)
+    u, v = rng.standard_normal((Ny, Nx)), rng.standard_normal((Ny, Nx))
+    for bc in (LidBC(2.0), free_slip_box_bc):
+        ru, rv = bc(u, v)
+        for r in range(P):
+            L = SlabLayout(Ny, Nx, P, r, halo=4)
+            t = local_bc_table(bc, L)
+            su, sv = t.apply_host(L.take(u).copy(), L.take(v).copy())
+            assert np.array_equal(L.owned(su), ru[L.r0:L.r1]) and np.array_equal(L.owned(sv), rv[L.r0:L.r1])
+
+
+class SciPyOps:
+    """Test doubles of the three device primitives."""
+
+    def dct_lines(self, x, eig=None, scale=1.0):
+        from scipy.fft import dct
+        y = dct(x.numpy(), type=1, axis=1)
+        if eig is not None:
+            y = dct(y * (scale / eig.numpy()), type=1, axis=1)
+        else:
+            y = y * scale
+        x.copy_(torch.from_numpy(np.ascontiguousarray(y)))
+        return x
+
+    def transpose(self, x):
+        return x.t().contiguous()
+
+    def copy2d(self, src, dst):
+        dst.copy_(src)
+
+
+def _worker(rank, world, port, Ny, Nx, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import rmt_oracle as O
+        from pyrmt_b200.slab import Comm, DistPoissonDCT, SlabLayout
+        lay = SlabLayout(Ny, Nx, world, rank, halo=4)
+        comm = Comm()
+        # halo exchange: every rank fills its slab with global row ids, halos poisoned
+        f = torch.full((lay.nl, Nx), -1.0, dtype=torch.float64)
+        g = torch.full((lay.nl, Nx), -1.0, dtype=torch.float64)
+        rows = torch.arange(lay.r0, lay.r1, dtype=torch.float64)[:, None]
+        lay.owned(f).copy_(rows.expand(-1, Nx))
+        lay.owned(g).copy_(1000.0 + rows.expand(-1, Nx))
+        comm.halo_exchange(lay, (f, g))
+        want = torch.arange(lay.e0, lay.e1, dtype=torch.float64)[:, None].expand(-1, Nx)
+        ok_halo = bool(torch.equal(f, want) and torch.equal(g, want + 1000.0))
+        # distributed DCT solve against the serial oracle
+        X, Y, dx, dy = O.create_grid(Nx, Ny, 1.3, 0.7)
+        eig = O._precompute_poisson_eigenvalues(Nx, Ny, dx, dy)
+        rng = np.random.default_rng(7)
+        rhs = rng.standard_normal((Ny, Nx))
+        ref = O._solve_poisson_dct(rhs, eig)
+        solver = DistPoissonDCT(lay, eig, comm, ops=SciPyOps())
+        sol, total = solver.solve(torch.from_numpy(np.ascontiguousarray(rhs[lay.r0:lay.r1])))
+        sol = sol.numpy() - float(total) / (Ny * Nx)
+        err = float(np.max(np.abs(sol - ref[lay.r0:lay.r1])) / np.max(np.abs(ref)))
+        mx = comm.allreduce(torch.tensor([float(rank + 3)]), "max")
+        out[rank] = (ok_halo, err, float(mx))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,Ny,Nx", [(2, 33, 17), (3, 40, 29)])
+def test_halo_exchange_and_distributed_dct_gloo(world, Ny, Nx):
+    ctx_ = mp.get_context("spawn")
+    with ctx_.Manager() as m:
+        out = m.dict()
+        port = 29500 + (os.getpid() % 2000) + world
+        procs = [ctx_.Process(target=_worker, args=(r, world, port, Ny, Nx, out)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+        for r in range(world):
+            ok_halo, err, mx = out[r]
+            assert ok_halo, "halo exchange wrong on rank %d" % r
+            assert err < 1e-12, (r, err)
+            assert mx == world + 2
