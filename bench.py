@@ -21,8 +21,10 @@ operator API (pyrmt_b200.driver.fsi_step).
 
 --impl reference times that CPU oracle alone (the reference itself is pure
 Python + Numba and cannot travel to the GPU box).
-N > 1: the slab-decomposed step is not built yet -- every rank runs an
-independent replica of the workload ("replicas only", weak scaling).
+N > 1: `value` is N independent replicas of the full FSI step ("replicas only", weak
+scaling) -- reference-map advection and extrapolation are not slab-decomposed yet.  The
+part that is (momentum predictor + DCT projection over y-slabs, NCCL halo exchange +
+all-to-all transposes) is timed on one 8193^2 grid and reported as `slab_fluid_step`.
 """
 import argparse
 import json
@@ -57,6 +59,17 @@ ALG_BYTES_PER_CELL_LAUNCH = {
     "rmt_subtract_mean": 8.0 * 2.0,
     "rmt_apply_bc": 0.0,
 }
+
+
+def workload_config(N, scheme, world):
+    cells = N * N
+    return {"workload": "synthetic 64-disc lid-driven FSI at %dx%d nodes (%d^2 cells), %s + SSP-RK3 ref-map "
+                        "advection, 3-layer extrapolation, RK4 momentum, Rhie-Chow + DCT-I projection"
+                        % (N, N, N - 1, scheme),
+            "grid": [N, N], "discs": 64, "scheme": scheme,
+            "cache": "working set ~%.1f GB per step >> 126 MB L2 (no flush needed)" % (25 * cells * 8 / 1e9),
+            "parallelism": ("replicas x%d of the full FSI step (only momentum + projection are slab-decomposed "
+                            "so far: see slab_fluid_step)" % world) if world > 1 else "single GPU"}
 
 
 def peaks():
@@ -147,6 +160,46 @@ def oracle_rate(n_nodes, steps, warmup, scheme):
     return N * N * steps / el / 1e6, el / steps * 1e3
 
 
+def slab_fluid_rate(N, steps, rank, world):
+    """Momentum predictor + DCT projection on y-slabs over all ranks (NCCL halo exchange +
+    all-to-all transposes, pyrmt_b200/slab.py): ms per step, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pyrmt_b200 import functions as F
+    from pyrmt_b200.driver import LidBC
+    from pyrmt_b200.slab import SlabFluidSolver, SlabLayout
+    lay = SlabLayout(N, N, world, rank, halo=4)
+    X, Y, dx, dy = F.create_grid(N, N, 1.0, 1.0)
+    solver = SlabFluidSolver(lay, LidBC(1.0), F._precompute_poisson_eigenvalues(N, N, dx, dy))
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+    z = torch.zeros((lay.nl, N), dtype=torch.float64, device="cuda")
+    a, b, p = z.clone(), z.clone(), z.clone()
+    if rank == world - 1:
+        a[lay.o1 - 1, 1:-1] = 1.0
+    X1, X2, phi = up(lay.take(X)), up(lay.take(Y)), torch.ones_like(z)
+    del X, Y
+    prm = dict(dx=dx, dy=dy, mu_s=0.0, kappa=0.0, eta_s=0.0, rho_s=1.0, rho_f=1.0, mu_f=0.01, w_t=2 * dx)
+    dt = 0.2 * dx * dx / (4 * 0.01)
+    for _ in range(3):
+        a, b, p = solver.fluid_step(a, b, p, X1, X2, phi, prm, dt)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        a, b, p = solver.fluid_step(a, b, p, X1, X2, phi, prm, dt)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    return {"what": "momentum_step_rk4 + Neumann/DCT projection, y-slabs, NCCL halo exchange + all-to-all "
+                    "transposes (strong scaling: one %dx%d grid over %d GPUs)" % (N, N, world),
+            "grid": [N, N], "ms_per_step": ms, "value": N * N / ms / 1e3, "unit": "Mcell-steps/s",
+            "finite": bool(torch.isfinite(a).all().item())}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -161,8 +214,7 @@ def run_reference(args, rank):
             "unit": "Mcell-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 2),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic 64-disc lid-driven FSI, %s + SSP-RK3, DCT Poisson" % args.scheme,
-                       "grid": "%dx%d nodes (bounded sample of the 4097x4097 workload)" % (n, n)},
+            "config": workload_config(args.size, args.scheme, args.gpus),
             "cpu_baseline": {"value": rate, "unit": "Mcell-steps/s", "cores": cores, "kind": "port",
                              "sample": sample},
             "e2e": {"value": rate, "unit": "Mcell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -182,6 +234,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-slab", action="store_true")
+    ap.add_argument("--slab-size", type=int, default=8193, help="nodes per side of the sharded fluid-step timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -203,6 +257,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     N = args.size
@@ -280,6 +336,11 @@ def main():
                "ms_per_step": ems / args.e2e_steps,
                "call": "pyrmt_b200.driver.fsi_step_host (pinned host state -> device -> step -> host)"}
 
+    # ---- N > 1: the part of the step that IS slab-decomposed (momentum + projection) ----
+    slab = None
+    if world > 1 and not args.no_slab:
+        slab = slab_fluid_rate(args.slab_size, 10, rank, world)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         n = args.ref_size
@@ -294,18 +355,11 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": "synthetic 64-disc lid-driven FSI at %dx%d nodes (%d^2 cells), %s + SSP-RK3 "
-                                       "ref-map advection, 3-layer extrapolation, RK4 momentum, Rhie-Chow + "
-                                       "DCT-I projection" % (N, N, N - 1, args.scheme),
-                           "grid": [N, N], "discs": 64, "scheme": args.scheme,
-                           "cache": "working set ~%.1f GB per step >> 126 MB L2 (no flush needed)"
-                                    % (25 * cells * 8 / 1e9),
-                           "parallelism": "replicas x%d (slab decomposition not built yet)" % world
-                           if world > 1 else "single GPU"},
+                "config": workload_config(N, args.scheme, world),
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "step_roofline": {"alg_bytes_per_cell_step": ALG_BYTES_PER_CELL_STEP.get(args.scheme, 512.0),
                                   "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak},
-                "cpu_baseline": cpu, "kernels": breakdown, "finite": finite}
+                "cpu_baseline": cpu, "kernels": breakdown, "finite": finite, "slab_fluid_step": slab}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
