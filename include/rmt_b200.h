@@ -86,6 +86,14 @@ int rmt_advect_sl_rk4(const double *q0, const double *q1, const double *a, const
 int rmt_advect_euler_rk3(const double *q, const double *a, const double *b, const double *phi,
                          double *out, double *work1, double *work2, int Ny, int Nx, double dx,
                          double dy, double dt, double w_cut, int scheme, void *stream);
+/* Both reference-map components in one pass per stage (the drivers advect xi1 and xi2 with the
+ * same a, b, phi, dt: soft_disc_in_lid_driven.py:88-91); mask_solid != 0 also applies the
+ * driver's "* (phi <= 0)" to the result.  Bitwise identical to two rmt_advect_euler_rk3 calls
+ * (+ rmt_mask_mul).  work: 4 fields. */
+int rmt_advect_euler_rk3_pair(const double *q0, const double *q1, const double *a, const double *b,
+                              const double *phi, double *out0, double *out1, double *work, int Ny, int Nx,
+                              double dx, double dy, double dt, double w_cut, int scheme, int mask_solid,
+                              void *stream);
 /* _central2_rhs :420-440 / _weno5_rhs :321-393 / _conservative_rhs :462-486. */
 int rmt_euler_rhs(const double *q, const double *a, const double *b, const double *phi, double *out,
                   int Ny, int Nx, double dx, double dy, double w_cut, int scheme, void *stream);

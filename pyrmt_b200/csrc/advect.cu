@@ -237,43 +237,57 @@ __device__ __forceinline__ double weno5_dq(G g, int k, int n, double vel, double
 //   stage 3: c0=1/3, c1=2/3                  q' = 1/3 q + 2/3 (q2 + dt R(q2))
 // SCHEME: 0 central2, 1 weno5, 2 conservative.  RHS is zero where phi > w_cut
 // or outside the scheme's interior range.
-template <int SCHEME>
-__global__ void __launch_bounds__(256, 4) k_euler_stage(const double *__restrict__ q0, const double *__restrict__ qs,
-                              const double *__restrict__ a, const double *__restrict__ b,
-                              const double *__restrict__ phi, double *__restrict__ out, int Ny,
-                              int Nx, double dx, double dy, double dt, double w_cut, double c0,
-                              double c1, int first)
+struct EulerFields {      // up to two transported fields that share (a, b, phi) -- xi1 and xi2
+    const double *q0[2], *qs[2];
+    double *out[2];
+};
+
+template <int SCHEME, int NQ>
+__global__ void __launch_bounds__(256, 4)
+k_euler_stage(const EulerFields F, const double *__restrict__ a, const double *__restrict__ b,
+              const double *__restrict__ phi, int Ny, int Nx, double dx, double dy, double dt,
+              double w_cut, double c0, double c1, int first, int mask_solid)
 {
     int i = blockIdx.x * TX + threadIdx.x;
     int j = blockIdx.y * TY + threadIdx.y;
     if (i >= Nx || j >= Ny) return;
     size_t c = (size_t)j * Nx + i;
     const int halo = (SCHEME == 1) ? 2 : 1;
-    double qc = qs[c];
-    double rhs = 0.0;
-    bool interior = (i >= halo && i < Nx - halo && j >= halo && j < Ny - halo);
-    if (interior && !(phi[c] > w_cut)) {
-        if (SCHEME == 0) {
-            double dqdx = (__ldg(qs + c + 1) - __ldg(qs + c - 1)) * (0.5 / dx);
-            double dqdy = (__ldg(qs + c + Nx) - __ldg(qs + c - Nx)) * (0.5 / dy);
-            rhs = -(a[c] * dqdx + b[c] * dqdy);
-        } else if (SCHEME == 2) {
-            double fx = (__ldg(a + c + 1) * __ldg(qs + c + 1) - __ldg(a + c - 1) * __ldg(qs + c - 1)) * (0.5 / dx);
-            double fy = (__ldg(b + c + Nx) * __ldg(qs + c + Nx) - __ldg(b + c - Nx) * __ldg(qs + c - Nx)) * (0.5 / dy);
-            rhs = -(fx + fy);
-        } else {
-            double u = a[c], v = b[c];
-            const double *row = qs + (size_t)j * Nx;
-            const double *col = qs + i;
-            double dqdx = weno5_dq([&](int o) { return __ldg(row + i + o); }, i, Nx, u, dx,
-                                   __ldg(row + Nx - 1));
-            double dqdy = weno5_dq([&](int o) { return __ldg(col + (size_t)(j + o) * Nx); }, j, Ny, v,
-                                   dy, __ldg(col + (size_t)(Ny - 1) * Nx));
-            rhs = -(u * dqdx + v * dqdy);
+    const bool interior = (i >= halo && i < Nx - halo && j >= halo && j < Ny - halo);
+    const double ph = phi[c];
+    const bool active = interior && !(ph > w_cut);
+    double u = 0.0, v = 0.0;
+    if (active && SCHEME != 2) { u = a[c]; v = b[c]; }
+    // final stage may apply the driver's "* (phi <= 0)" mask (soft_disc_in_lid_driven.py:88-91)
+    const double m = (mask_solid && !(ph <= 0.0)) ? 0.0 : 1.0;
+#pragma unroll
+    for (int f = 0; f < NQ; ++f) {
+        const double *qs = F.qs[f];
+        const double qc = qs[c];
+        double rhs = 0.0;
+        if (active) {
+            if (SCHEME == 0) {
+                double dqdx = (__ldg(qs + c + 1) - __ldg(qs + c - 1)) * (0.5 / dx);
+                double dqdy = (__ldg(qs + c + Nx) - __ldg(qs + c - Nx)) * (0.5 / dy);
+                rhs = -(u * dqdx + v * dqdy);
+            } else if (SCHEME == 2) {
+                double fx = (__ldg(a + c + 1) * __ldg(qs + c + 1) - __ldg(a + c - 1) * __ldg(qs + c - 1)) * (0.5 / dx);
+                double fy = (__ldg(b + c + Nx) * __ldg(qs + c + Nx) - __ldg(b + c - Nx) * __ldg(qs + c - Nx)) * (0.5 / dy);
+                rhs = -(fx + fy);
+            } else {
+                const double *row = qs + (size_t)j * Nx;
+                const double *col = qs + i;
+                double dqdx = weno5_dq([&](int o) { return __ldg(row + i + o); }, i, Nx, u, dx,
+                                       __ldg(row + Nx - 1));
+                double dqdy = weno5_dq([&](int o) { return __ldg(col + (size_t)(j + o) * Nx); }, j, Ny, v,
+                                       dy, __ldg(col + (size_t)(Ny - 1) * Nx));
+                rhs = -(u * dqdx + v * dqdy);
+            }
         }
+        const double upd = qc + dt * rhs;
+        const double r = first ? upd : (c0 * F.q0[f][c] + c1 * upd);
+        F.out[f][c] = mask_solid ? r * m : r;
     }
-    double upd = qc + dt * rhs;
-    out[c] = first ? upd : (c0 * q0[c] + c1 * upd);
 }
 
 // standalone RHS (API parity for _weno5_rhs/_central2_rhs/_conservative_rhs)
@@ -314,18 +328,24 @@ __global__ void k_euler_rhs(const double *__restrict__ qs, const double *__restr
 
 inline int flat_blocks(long n) { long b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
 
-template <int SCHEME>
-static int euler_rk3(const double *q, const double *a, const double *b, const double *phi, double *out,
-                     double *w1, double *w2, int Ny, int Nx, double dx, double dy, double dt,
-                     double w_cut, cudaStream_t s)
+template <int SCHEME, int NQ>
+static int euler_rk3(const double *const *q, const double *a, const double *b, const double *phi,
+                     double *const *out, double *const *w1, double *const *w2, int Ny, int Nx, double dx,
+                     double dy, double dt, double w_cut, int mask_solid, cudaStream_t s)
 {
     dim3 blk(TX, TY), grd(rmt_cdiv(Nx, TX), rmt_cdiv(Ny, TY));
-    k_euler_stage<SCHEME><<<grd, blk, 0, s>>>(q, q, a, b, phi, w1, Ny, Nx, dx, dy, dt, w_cut, 0.0, 1.0, 1);
+    EulerFields F1{}, F2{}, F3{};
+    for (int f = 0; f < NQ; ++f) {
+        F1.q0[f] = q[f]; F1.qs[f] = q[f];  F1.out[f] = w1[f];
+        F2.q0[f] = q[f]; F2.qs[f] = w1[f]; F2.out[f] = w2[f];
+        F3.q0[f] = q[f]; F3.qs[f] = w2[f]; F3.out[f] = out[f];
+    }
+    k_euler_stage<SCHEME, NQ><<<grd, blk, 0, s>>>(F1, a, b, phi, Ny, Nx, dx, dy, dt, w_cut, 0.0, 1.0, 1, 0);
     RMT_LAUNCH_CHECK();
-    k_euler_stage<SCHEME><<<grd, blk, 0, s>>>(q, w1, a, b, phi, w2, Ny, Nx, dx, dy, dt, w_cut, 0.75, 0.25, 0);
+    k_euler_stage<SCHEME, NQ><<<grd, blk, 0, s>>>(F2, a, b, phi, Ny, Nx, dx, dy, dt, w_cut, 0.75, 0.25, 0, 0);
     RMT_LAUNCH_CHECK();
-    k_euler_stage<SCHEME><<<grd, blk, 0, s>>>(q, w2, a, b, phi, out, Ny, Nx, dx, dy, dt, w_cut,
-                                            1.0 / 3.0, 2.0 / 3.0, 0);
+    k_euler_stage<SCHEME, NQ><<<grd, blk, 0, s>>>(F3, a, b, phi, Ny, Nx, dx, dy, dt, w_cut, 1.0 / 3.0, 2.0 / 3.0,
+                                                 0, mask_solid);
     RMT_LAUNCH_CHECK();
     return RMT_OK;
 }
@@ -370,10 +390,30 @@ int rmt_advect_euler_rk3(const double *q, const double *a, const double *b, cons
 {
     if (!q || !a || !b || !phi || !out || !work1 || !work2 || Nx < 5 || Ny < 5) return RMT_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
+    const double *qq[1] = {q};
+    double *oo[1] = {out}, *w1[1] = {work1}, *w2[1] = {work2};
     switch (scheme) {
-    case 0: return euler_rk3<0>(q, a, b, phi, out, work1, work2, Ny, Nx, dx, dy, dt, w_cut, s);
-    case 1: return euler_rk3<1>(q, a, b, phi, out, work1, work2, Ny, Nx, dx, dy, dt, w_cut, s);
-    case 2: return euler_rk3<2>(q, a, b, phi, out, work1, work2, Ny, Nx, dx, dy, dt, w_cut, s);
+    case 0: return euler_rk3<0, 1>(qq, a, b, phi, oo, w1, w2, Ny, Nx, dx, dy, dt, w_cut, 0, s);
+    case 1: return euler_rk3<1, 1>(qq, a, b, phi, oo, w1, w2, Ny, Nx, dx, dy, dt, w_cut, 0, s);
+    case 2: return euler_rk3<2, 1>(qq, a, b, phi, oo, w1, w2, Ny, Nx, dx, dy, dt, w_cut, 0, s);
+    }
+    return RMT_EINVAL;
+}
+
+int rmt_advect_euler_rk3_pair(const double *q0, const double *q1, const double *a, const double *b,
+                              const double *phi, double *out0, double *out1, double *work /* 4 fields */,
+                              int Ny, int Nx, double dx, double dy, double dt, double w_cut, int scheme,
+                              int mask_solid, void *stream)
+{
+    if (!q0 || !q1 || !a || !b || !phi || !out0 || !out1 || !work || Nx < 5 || Ny < 5) return RMT_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)Ny * Nx;
+    const double *qq[2] = {q0, q1};
+    double *oo[2] = {out0, out1}, *w1[2] = {work, work + n}, *w2[2] = {work + 2 * n, work + 3 * n};
+    switch (scheme) {
+    case 0: return euler_rk3<0, 2>(qq, a, b, phi, oo, w1, w2, Ny, Nx, dx, dy, dt, w_cut, mask_solid, s);
+    case 1: return euler_rk3<1, 2>(qq, a, b, phi, oo, w1, w2, Ny, Nx, dx, dy, dt, w_cut, mask_solid, s);
+    case 2: return euler_rk3<2, 2>(qq, a, b, phi, oo, w1, w2, Ny, Nx, dx, dy, dt, w_cut, mask_solid, s);
     }
     return RMT_EINVAL;
 }

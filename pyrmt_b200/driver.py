@@ -26,8 +26,12 @@ def fsi_step(state, prm, dt=None):
     phi = F.rebuild_phi_from_reference_map(X1, X2, prm["phi_init"])
     phi = F.reinitialize_level_set(phi, dx, dy, "none")
     sch, wc = prm["scheme"], prm.get("w_cut", 0.0)
-    X1 = F.mask_solid(F.advect_reference_map(X1, a, b, prm["X"], prm["Y"], dt, dx, dy, phi, sch, wc), phi)
-    X2 = F.mask_solid(F.advect_reference_map(X2, a, b, prm["X"], prm["Y"], dt, dx, dy, phi, sch, wc), phi)
+    if prm.get("fuse_pair", True):      # xi1, xi2 and the "* solid_mask" in one pass (bitwise identical)
+        X1, X2 = F.advect_reference_map_pair(X1, X2, a, b, prm["X"], prm["Y"], dt, dx, dy, phi, sch, wc,
+                                             mask_solid=True)
+    else:                               # the reference's loop, operator by operator
+        X1 = F.mask_solid(F.advect_reference_map(X1, a, b, prm["X"], prm["Y"], dt, dx, dy, phi, sch, wc), phi)
+        X2 = F.mask_solid(F.advect_reference_map(X2, a, b, prm["X"], prm["Y"], dt, dx, dy, phi, sch, wc), phi)
     X1, X2 = F.extrapolate_reference_map(X1, X2, phi, dx, dy, prm["layers"])
     phi = F.rebuild_phi_from_reference_map(X1, X2, prm["phi_init"])
     a_s, b_s, sxx, sxy, syy, J = F.momentum_step_rk4(

@@ -154,6 +154,34 @@ def advect_conservative_rk3(q, a, b, dx, dy, dt, phi, w_cut=0.0):
     return _euler_rk3(q, a, b, dx, dy, dt, phi, w_cut, 2)
 
 
+def advect_reference_map_pair(q0, q1, a, b, X, Y, dt, dx, dy, phi, scheme='semilagrangian', w_cut=0.0,
+                              mask_solid=False):
+    """Both reference-map components in one call -- bitwise identical to two
+    ``advect_reference_map`` calls (the drivers advect xi1 and xi2 with the same a, b, phi, dt:
+    benchmarks/soft_disc_in_lid_driven.py:88-91) but a, b, phi are read once per stage and the
+    semi-Lagrangian backtrace is shared.  ``mask_solid=True`` also applies the driver's
+    ``* (phi <= 0)`` to both results."""
+    if not _velocity_is_finite(a, b):
+        raise FloatingPointError(
+            "advect_reference_map: non-finite velocity (the simulation diverged)")
+    if scheme in ('semilagrangian', 'semilagrangian_cubic'):
+        r0, r1 = advect_semilagrangian_pair(q0, q1, a, b, X, Y, dt, dx, dy, cubic=scheme.endswith('cubic'))
+        return (mask_solid_(r0, phi), mask_solid_(r1, phi)) if mask_solid else (r0, r1)
+    if scheme not in _SCHEMES:
+        raise ValueError("Unknown advection scheme %r (expected 'semilagrangian', "
+                         "'central2', 'weno5' or 'conservative')" % (scheme,))
+    as_np = is_np(q0)
+    q0d, q1d, ad, bd, pd = (to_dev(t) for t in (q0, q1, a, b, phi))
+    Ny, Nx = shape2(q0d)
+    o0, o1 = torch.empty_like(q0d), torch.empty_like(q0d)
+    work = torch.empty((4, Ny, Nx), dtype=F64, device=q0d.device)
+    _chk(ctx().lib.rmt_advect_euler_rk3_pair(ptr(q0d), ptr(q1d), ptr(ad), ptr(bd), ptr(pd), ptr(o0), ptr(o1),
+                                             ptr(work), Ny, Nx, float(dx), float(dy), float(dt), float(w_cut),
+                                             _SCHEMES[scheme], 1 if mask_solid else 0, stream()),
+         "rmt_advect_euler_rk3_pair")
+    return to_user(o0, as_np), to_user(o1, as_np)
+
+
 def _euler_rhs(q, a, b, dx, dy, phi, w_cut, scheme):
     as_np = is_np(q)
     qd, ad, bd, pd = (to_dev(t) for t in (q, a, b, phi))
@@ -262,6 +290,10 @@ def heaviside_and_density(phi, w_t, rho_s, rho_f):
     _chk(ctx().lib.rmt_heaviside_rho(ptr(pd), ptr(H), ptr(rho), pd.numel(), float(w_t), float(rho_s),
                                      float(rho_f), stream()), "rmt_heaviside_rho")
     return to_user(H, as_np), to_user(rho, as_np)
+
+
+def mask_solid_(q, phi):
+    return mask_solid(q, phi)
 
 
 def mask_solid(q, phi):

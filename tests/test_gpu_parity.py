@@ -177,6 +177,18 @@ def test_sl_identity_on_index_grid(P):
     assert np.max(np.abs(r - q)) < 1e-12
 
 
+@pytest.mark.parametrize("scheme", ["weno5", "central2", "conservative", "semilagrangian"])
+def test_advect_pair_equals_two_calls(P, golden, scheme):
+    g = golden("advect")
+    dx, dy, dt = float(g["dx"]), float(g["dy"]), float(g["dt"])
+    args = (g["a"], g["b"], g["X"], g["Y"], dt, dx, dy, g["phi"], scheme, 0.0)
+    r0, r1 = P.advect_reference_map_pair(g["q"], g["q2"], *args)
+    assert same(r0, P.advect_reference_map(g["q"], *args)) and same(r1, P.advect_reference_map(g["q2"], *args))
+    m0, m1 = P.advect_reference_map_pair(g["q"], g["q2"], *args, mask_solid=True)
+    msk = (g["phi"] <= 0).astype(float)
+    assert same(m0, g["out_" + scheme] * msk) and same(m1, P.advect_reference_map(g["q2"], *args) * msk)
+
+
 def test_sl_pair_equals_two_calls(P, golden):
     g = golden("advect")
     dx, dy, dt = float(g["dx"]), float(g["dy"]), float(g["dt"])
