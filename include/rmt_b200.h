@@ -104,6 +104,12 @@ long rmt_extrapolate_workspace_bytes(int Ny, int Nx);
 int rmt_extrapolate(const double *X1, const double *X2, const double *phi, double *X1e, double *X2e,
                     int Ny, int Nx, double dx, double dy, int max_layers, void *workspace,
                     void *stream);
+/* The same on a block of rows [row_offset, row_offset + Ny) of a taller grid: the fit uses
+ * the GLOBAL absolute coordinates y = dy * (j + row_offset), so a slab reproduces the bits of
+ * the whole-grid sweep (pyrmt_b200/slab.py). */
+int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, double *X1e, double *X2e,
+                         int Ny, int Nx, int row_offset, double dx, double dy, int max_layers,
+                         void *workspace, void *stream);
 /* device exp() used for the weights, exposed so tests can prove bit-equality
  * with the host libm (functions.py:120). */
 int rmt_exp_probe(const double *x, double *y, long n, void *stream);

@@ -37,6 +37,7 @@ _SIG = {
     "rmt_euler_rhs": [vp, vp, vp, vp, vp, i32, i32, dbl, dbl, dbl, i32, vp],
     "rmt_extrapolate_workspace_bytes": [i32, i32],
     "rmt_extrapolate": [vp, vp, vp, vp, vp, i32, i32, dbl, dbl, i32, vp, vp],
+    "rmt_extrapolate_rows": [vp, vp, vp, vp, vp, i32, i32, i32, dbl, dbl, i32, vp, vp],
     "rmt_exp_probe": [vp, vp, i64, vp],
     "rmt_solid_stress": [vp, vp, vp, vp, vp, vp, vp, i32, i32, dbl, dbl, dbl, dbl, dbl, dbl, i32, vp],
     "rmt_curvature": [vp, vp, i32, i32, dbl, dbl, vp],

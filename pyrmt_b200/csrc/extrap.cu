@@ -288,10 +288,10 @@ __device__ __forceinline__ void store_products(double *q, double w, double x, do
 __device__ __forceinline__ int ext_phase_a(ExtRec *R, const double *__restrict__ X1e,
                                            const double *__restrict__ X2e,
                                            const unsigned char *__restrict__ st, int j, int i, int Ny, int Nx,
-                                           double dx, double dy, double r2, int lane)
+                                           int joff, double dx, double dy, double r2, int lane)
 {
     const unsigned lt = (1u << lane) - 1u;
-    const double x0 = dx * i, y0 = dy * j;
+    const double x0 = dx * i, y0 = dy * (j + joff);     // absolute coordinates of the GLOBAL grid (functions.py:105)
     int cls[3];                                 // 0 no contribution, 1 known, 2 undecided
     double cw[3], cx_[3], cy_[3], c1[3], c2[3];
     unsigned mk[3], mp[3];
@@ -307,7 +307,7 @@ __device__ __forceinline__ int ext_phase_a(ExtRec *R, const double *__restrict__
                 const size_t cc = (size_t)jj * Nx + ii;
                 const unsigned char sv = st[cc];     // 1 is final; 2/3 decided during the sweep
                 const double v1 = X1e[cc], v2 = X2e[cc];   // only meaningful if sv == 1
-                const double xi = dx * ii, yi = dy * jj;
+                const double xi = dx * ii, yi = dy * (jj + joff);
                 const double ex = xi - x0, ey = yi - y0;
                 const double dist_sq = ex * ex + ey * ey;
                 const bool earlier = (dj < 0) || (dj == 0 && di < 0);
@@ -350,13 +350,13 @@ __global__ void __launch_bounds__(256)
 k_ext_prepare(const double *__restrict__ X1e, const double *__restrict__ X2e,
               const unsigned char *__restrict__ st, const int *__restrict__ seg_off, int nseg,
               const int *__restrict__ tcol, const int *__restrict__ trow, ExtRec *__restrict__ recs,
-              int *__restrict__ tinfo, int cap, int Ny, int Nx, double dx, double dy, double r2)
+              int *__restrict__ tinfo, int cap, int Ny, int Nx, int joff, double dx, double dy, double r2)
 {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
     const int ntot = min(seg_off[nseg], cap);
     for (int t = warp; t < ntot; t += nwarp) {
-        const int info = ext_phase_a(recs + t, X1e, X2e, st, trow[t], tcol[t], Ny, Nx, dx, dy, r2, lane);
+        const int info = ext_phase_a(recs + t, X1e, X2e, st, trow[t], tcol[t], Ny, Nx, joff, dx, dy, r2, lane);
         if (lane == 0) tinfo[t] = info;
     }
 }
@@ -416,7 +416,8 @@ __global__ void __launch_bounds__(RB * 32, 1)
 k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__restrict__ st,
             const int *__restrict__ seg_off, const int *__restrict__ tcol, int *__restrict__ prog,
             int *__restrict__ tile_counter, const ExtRec *__restrict__ recs, const int *__restrict__ tinfo,
-            int cap, int Ny, int Nx, int nxt, int XT, int MRB, int sleep_ns, double dx, double dy, double r2)
+            int cap, int Ny, int Nx, int joff, int nxt, int XT, int MRB, int sleep_ns, double dx, double dy,
+            double r2)
 {
     extern __shared__ unsigned char s_raw[];
     SweepSmem &S = *reinterpret_cast<SweepSmem *>(s_raw);
@@ -463,7 +464,7 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
 
         for (int t = t0; t < t1; ++t) {
             const int i = tcol[t];
-            const double x0 = dx * i, y0 = dy * j;
+            const double x0 = dx * i, y0 = dy * (j + joff);
 #ifdef RMT_EXT_TIMING
             long long tmark = clock64();
 #endif
@@ -473,7 +474,7 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                 info = info_next;
                 cp_async_wait_all();
             } else {
-                info = ext_phase_a(&W.rec, X1e, X2e, st, j, i, Ny, Nx, dx, dy, r2, lane);
+                info = ext_phase_a(&W.rec, X1e, X2e, st, j, i, Ny, Nx, joff, dx, dy, r2, lane);
             }
             info_next = (t + 1 < t1 && t + 1 < cap) ? tinfo[t + 1] : 0;
             const int next = (t + 1 < t1) ? tcol[t + 1] : INT_MAX;   // loaded early: it gates the publish
@@ -692,7 +693,15 @@ int rmt_extrapolate(const double *X1, const double *X2, const double *phi, doubl
                     int Ny, int Nx, double dx, double dy, int max_layers, void *workspace,
                     void *stream)
 {
+    return rmt_extrapolate_rows(X1, X2, phi, X1e, X2e, Ny, Nx, 0, dx, dy, max_layers, workspace, stream);
+}
+
+int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, double *X1e, double *X2e,
+                         int Ny, int Nx, int row_offset, double dx, double dy, int max_layers,
+                         void *workspace, void *stream)
+{
     if (!X1 || !X2 || !phi || !X1e || !X2e || !workspace || Ny < 3 || Nx < 3) return RMT_EINVAL;
+    int joff = row_offset;
     cudaStream_t s = (cudaStream_t)stream;
     size_t ncell = (size_t)Ny * (size_t)Nx;
     int nxt = ext_nxt(Nx);
@@ -742,14 +751,14 @@ int rmt_extrapolate(const double *X1, const double *X2, const double *phi, doubl
         k_ext_fill<<<row_warps_blocks, 256, 0, s>>>(st, seg_off, tcol, trow, prog, Ny, Nx, nxt, XT);
         RMT_LAUNCH_CHECK();
         k_ext_prepare<<<148 * 8, 256, 0, s>>>(X1e, X2e, st, seg_off, nseg, tcol, trow, recs, tinfo, cap, Ny, Nx,
-                                               dx, dy, r2);
+                                               joff, dx, dy, r2);
         RMT_LAUNCH_CHECK();
         // all CTAs must be co-resident (warps wait on each other): cooperative launch
         int blocks = sweep_blocks;
         int need = rmt_cdiv(rmt_cdiv(Ny - 2, RB), MRB) * nxt;
         if (blocks > need) blocks = need;
         void *args[] = {&X1e, &X2e, &st, &seg_off, &tcol, &prog, &tile_counter, &recs, &tinfo, &cap,
-                        &Ny, &Nx, &nxt, &XT, &MRB, &sleep_ns, &dx, &dy, &r2};
+                        &Ny, &Nx, &joff, &nxt, &XT, &MRB, &sleep_ns, &dx, &dy, &r2};
         RMT_CUDA(cudaLaunchCooperativeKernel((void *)k_ext_sweep, dim3(blocks), dim3(RB * 32), args,
                                              sweep_smem, s));
     }

@@ -241,8 +241,10 @@ def advect_reference_map(q, a, b, X, Y, dt, dx, dy, phi, scheme='semilagrangian'
 # --------------------------------------------------------------------------
 # narrow-band extrapolation
 # --------------------------------------------------------------------------
-def extrapolate_reference_map(X1, X2, phi, dx, dy, max_layers):
-    """pyRMT/functions.py:48-163 -- serial-order-faithful least-squares extrapolation."""
+def extrapolate_reference_map(X1, X2, phi, dx, dy, max_layers, row_offset=0):
+    """pyRMT/functions.py:48-163 -- serial-order-faithful least-squares extrapolation.
+    ``row_offset`` (not upstream; default 0): the arrays are rows [row_offset, ...) of a taller
+    grid -- the fit then uses the global y coordinates, which the slab decomposition needs."""
     as_np = is_np(X1)
     x1, x2, ph = to_dev(X1), to_dev(X2), to_dev(phi)
     Ny, Nx = shape2(x1)
@@ -250,8 +252,9 @@ def extrapolate_reference_map(X1, X2, phi, dx, dy, max_layers):
     o1, o2 = torch.empty_like(x1), torch.empty_like(x2)
     ws = c.extrap_workspace(Ny, Nx)
     profiler.launches += 5 * int(max_layers)
-    _chk(c.lib.rmt_extrapolate(ptr(x1), ptr(x2), ptr(ph), ptr(o1), ptr(o2), Ny, Nx, float(dx), float(dy),
-                               int(max_layers), ptr(ws), stream()), "rmt_extrapolate")
+    _chk(c.lib.rmt_extrapolate_rows(ptr(x1), ptr(x2), ptr(ph), ptr(o1), ptr(o2), Ny, Nx, int(row_offset),
+                                    float(dx), float(dy), int(max_layers), ptr(ws), stream()),
+         "rmt_extrapolate_rows")
     return to_user(o1, as_np), to_user(o2, as_np)
 
 

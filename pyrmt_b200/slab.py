@@ -4,11 +4,15 @@ Poisson solve (local row transforms, all-to-all transpose, local column solve,
 all-to-all back).  One process per GPU, torch.distributed (NCCL over NVLink) for the
 exchanges, the same C-ABI kernels as the single-GPU path on every rank.
 
-What is sharded in this round: the momentum predictor (`momentum_step_rk4`) and the
-constant-density Neumann projection (`pressure_projection_amg`) -- i.e. the pure-fluid
-step of benchmarks/lid_driven_cavity.py:58-80, and the fluid half of the FSI step with
-the solid fields supplied as slabs.  Reference-map advection and extrapolation across
-slab boundaries are the next rows.
+What is sharded: the whole FSI step of benchmarks/soft_disc_in_lid_driven.py:78-106 for
+the Eulerian advection schemes (WENO5 / central2 / conservative) with wall-type BCs and the
+Neumann/DCT projection (`SlabFSISolver`), and its fluid half alone (`SlabFluidSolver`).
+The narrow-band extrapolation is a serial raster sweep whose dependencies run down the
+flank of a body, so it is not cut at slab boundaries: every rank sweeps its own rows plus
+an overlap of `overlap` rows above them (the bodies that reach into its slab, from their
+first row on), which reproduces the serial result bit for bit as long as each such body
+starts inside the overlap -- checked every step by `guard`.  Semi-Lagrangian advection
+(needs a row offset in the sampling kernel) and periodic BCs across ranks are next.
 
 Layout: rank k owns rows [r0, r1) of the (Ny, Nx) grid and stores rows
 [e0, e1) = [r0 - H, r1 + H) clipped to the grid ("extended slab").  Kernels run on the
@@ -293,3 +297,98 @@ class SlabFluidSolver:
                                           prm["dx"], prm["dy"], dt, prm["rho_s"], prm["rho_f"], prm["mu_f"],
                                           prm["w_t"])
         return self.projection(a_s, b_s, p, prm["rho_f"], prm["dx"], prm["dy"], dt)
+
+
+class SlabFSISolver(SlabFluidSolver):
+    """The full FSI step on row slabs (Eulerian advection schemes, wall-type BCs, DCT projection).
+
+    State per rank: extended slabs (lay.nl, Nx) of a, b, p, X1, X2 with valid halos (lay.H >= 12).
+    `overlap`: rows above the slab that the extrapolation re-sweeps (>= tallest body + 16)."""
+
+    def __init__(self, lay, bc, eig, phi_init, overlap=512, layers=3, comm=None):
+        super().__init__(lay, bc, eig, comm)
+        if lay.H < 12:
+            raise ValueError("the FSI slab step needs a halo of >= 12 rows (3 WENO5 stages + margin)")
+        self.phi_init, self.layers, self._overlap = phi_init, layers, overlap
+        self.top = min(overlap, lay.r0)                     # rows available above
+        self.bot = min(4 * layers + 4, lay.Ny - lay.r1)
+        for r in range(1, lay.world):                       # same verdict on every rank (no one-sided raise)
+            above = lay.rows[r - 1][1] - lay.rows[r - 1][0]
+            if above < min(overlap, lay.rows[r][0]) or lay.rows[r][1] - lay.rows[r][0] < 4 * layers + 4:
+                raise ValueError("slabs of %d rows are thinner than the extrapolation overlap (%d rows)"
+                                 % (above, overlap))
+        self.ws = {}
+
+    # rows [r0 - top, r1 + bot) of a field, from the neighbours' owned rows
+    def _gather_big(self, fields):
+        lay, comm = self.lay, self.comm
+        n_own = lay.r1 - lay.r0
+        big = [torch.empty((self.top + n_own + self.bot, lay.Nx), dtype=F64, device=f.device) for f in fields]
+        for B, f in zip(big, fields):
+            B[self.top:self.top + n_own].copy_(lay.owned(f))
+        if comm.world > 1:
+            ops = []
+            # every rank uses the same `overlap`, so the neighbour's top overlap is min(overlap, its r0)
+            for B, f in zip(big, fields):
+                own = lay.owned(f)
+                if lay.rank + 1 < lay.world:
+                    want = min(self._overlap_of(lay.rank + 1), n_own)
+                    ops.append(dist.P2POp(dist.isend, own[n_own - want:], comm.rank + 1, comm.group))
+                    if self.bot:
+                        ops.append(dist.P2POp(dist.irecv, B[self.top + n_own:], comm.rank + 1, comm.group))
+                if lay.rank > 0:
+                    if self.top:
+                        ops.append(dist.P2POp(dist.irecv, B[:self.top], comm.rank - 1, comm.group))
+                    wantb = self._bot_of(lay.rank - 1)
+                    if wantb:
+                        ops.append(dist.P2POp(dist.isend, own[:wantb], comm.rank - 1, comm.group))
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        return big
+
+    def _overlap_of(self, rank):
+        return min(self._overlap, self.lay.rows[rank][0])
+
+    def _bot_of(self, rank):
+        return min(4 * self.layers + 4, self.lay.Ny - self.lay.rows[rank][1])
+
+    def guard(self, phi_big, dx, dy):
+        """True if the extrapolated values of the owned rows cannot depend on the cut at the top
+        of the overlap: four consecutive rows without any band cell between the cut and the slab."""
+        if self.top == 0 or self.lay.r0 == self.top:       # nothing above, or the overlap reaches the domain edge
+            return True
+        thr = (self.layers + 1) * float(np.hypot(dx, dy))
+        band_row = ((phi_big[:self.top] >= 0) & (phi_big[:self.top] <= thr)).any(dim=1)
+        free = (~band_row).to(torch.int32)
+        run4 = free[:-3] * free[1:-2] * free[2:-1] * free[3:]
+        return bool(run4[8:].any().item()) if run4.numel() > 8 else False
+
+    def fsi_step(self, state, prm, dt, check_guard=True):
+        from . import functions as F
+        lay, comm = self.lay, self.comm
+        a, b, p, X1, X2 = state
+        dx, dy = prm["dx"], prm["dy"]
+        phi = F.rebuild_phi_from_reference_map(X1, X2, self.phi_init)
+        # Eulerian SSP-RK3 advection of both components + solid mask on the extended slab (halo 9 consumed)
+        Y0 = prm.get("X"), prm.get("Y")
+        X1, X2 = F.advect_reference_map_pair(X1, X2, a, b, Y0[0], Y0[1], dt, dx, dy, phi, prm["scheme"],
+                                             prm.get("w_cut", 0.0), mask_solid=True)
+        # extrapolation on [r0 - top, r1 + bot): the bodies reaching into this slab, from their first row
+        B1, B2, Bphi = self._gather_big((X1, X2, phi))
+        if check_guard and not self.guard(Bphi, dx, dy):
+            raise RuntimeError("slab extrapolation: a body reaches above the %d-row overlap of rank %d; "
+                               "increase `overlap`" % (self.top, lay.rank))
+        E1, E2 = F.extrapolate_reference_map(B1, B2, Bphi, dx, dy, self.layers, row_offset=lay.r0 - self.top)
+        n_own = lay.r1 - lay.r0
+        X1n, X2n = torch.empty_like(a), torch.empty_like(a)
+        lay.owned(X1n).copy_(E1[self.top:self.top + n_own])
+        lay.owned(X2n).copy_(E2[self.top:self.top + n_own])
+        comm.halo_exchange(lay, (X1n, X2n))
+        # rows of the halo that lie outside every neighbour's ownership do not exist; domain-edge slabs
+        # have no halo there.  (Halo rows are now the neighbours' exact values.)
+        phi = F.rebuild_phi_from_reference_map(X1n, X2n, self.phi_init)
+        a_s, b_s, *_ = self.momentum_step(a, b, p, X1n, X2n, phi, prm["mu_s"], prm["kappa"], prm["eta_s"], dx, dy,
+                                          dt, prm["rho_s"], prm["rho_f"], prm["mu_f"], prm["w_t"])
+        _, rho_local = F.heaviside_and_density(phi, prm["w_t"], prm["rho_s"], prm["rho_f"])
+        a, b, p = self.projection(a_s, b_s, p, rho_local, dx, dy, dt)
+        return (a, b, p, X1n, X2n)

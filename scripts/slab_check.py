@@ -15,6 +15,9 @@ import torch.distributed as dist
 ap = argparse.ArgumentParser()
 ap.add_argument("--check", type=int, default=1025)
 ap.add_argument("--time", type=int, default=0)
+ap.add_argument("--fsi", type=int, default=0, help="check the full slab FSI step against the single-GPU step")
+ap.add_argument("--fsi-time", type=int, default=0, help="time the full slab FSI step at N x N")
+ap.add_argument("--overlap", type=int, default=256)
 ap.add_argument("--steps", type=int, default=10)
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -76,6 +79,91 @@ if args.check:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     out["check"] = {"N": N, "rel_linf_vs_single_gpu": float(t.item())}
     del a, b, p, X1, X2, phi, solver
+    torch.cuda.empty_cache()
+
+if args.fsi:
+    from pyrmt_b200.driver import fsi_step
+    from pyrmt_b200.slab import SlabFSISolver
+    N = args.fsi
+    X, Y, dx, dy = F.create_grid(N, N, 1.0, 1.0)
+    cx, cy, R = disc_lattice(3, 1.0, 0.08)        # the middle lattice row straddles the 2-rank cut
+    sdf = DiscSDF(cx, cy, R, domain=(1.0, 1.0))
+    bc = LidBC(1.0)
+    eig = F._precompute_poisson_eigenvalues(N, N, dx, dy)
+    Xd, Yd = up(X), up(Y)
+    phi0 = sdf(Xd, Yd)
+    X1, X2 = F.extrapolate_reference_map(F.mask_solid(Xd, phi0), F.mask_solid(Yd, phi0), phi0, dx, dy, 3)
+    a0, b0 = bc(np.zeros((N, N)), np.zeros((N, N)))
+    state = (up(a0), up(b0), up(np.zeros((N, N))), X1, X2)
+    prm = dict(dx=dx, dy=dy, CFL=0.2, dt_cap=1e-3, mu_s=0.1, kappa=0.0, rho_s=1.0, rho_f=1.0, eta_s=0.01,
+               mu_f=0.01, w_t=2 * dx, layers=3, scheme="weno5", w_cut=0.0, phi_init=sdf, bc=bc, eig=eig,
+               X=Xd, Y=Yd)
+    lay = SlabLayout(N, N, world, rank, halo=12)
+    solver = SlabFSISolver(lay, bc, eig, sdf, overlap=args.overlap, layers=3)
+    sstate = tuple(lay.take(t).contiguous() for t in state)
+    sprm = dict(prm, X=None, Y=None)
+    worst = {}
+    for n in range(4):
+        state, dt, _ = fsi_step(state, prm)
+        sstate = solver.fsi_step(sstate, sprm, dt)
+        for nm, ref, got in zip(("a", "b", "p", "X1", "X2"), state, sstate):
+            err = float(((got - ref[lay.e0:lay.e1]).abs().max() / ref.abs().max()).item())   # owned rows + halos
+            worst[nm] = max(worst.get(nm, 0.0), err)
+    t = torch.tensor([worst[k] for k in ("a", "b", "p", "X1", "X2")], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out["fsi_check"] = {"N": N, "steps": 4, "rel_linf_vs_single_gpu": dict(zip(("a", "b", "p", "X1", "X2"), t.tolist()))}
+    del state, sstate, solver, X1, X2, Xd, Yd, phi0
+    torch.cuda.empty_cache()
+
+if args.fsi_time:
+    from pyrmt_b200.slab import SlabFSISolver
+    N = args.fsi_time
+    X, Y, dx, dy = F.create_grid(N, N, 1.0, 1.0)
+    k_side = 8 * max(1, (N - 1) // 4096)
+    cx, cy, R = disc_lattice(k_side, 1.0, 0.04 * 4096.0 / (N - 1))
+    sdf = DiscSDF(cx, cy, R, domain=(1.0, 1.0))
+    bc = LidBC(1.0)
+    lay = SlabLayout(N, N, world, rank, halo=12)
+    solver = SlabFSISolver(lay, bc, F._precompute_poisson_eigenvalues(N, N, dx, dy), sdf, overlap=512, layers=3)
+    Xs, Ys = up(lay.take(X)), up(lay.take(Y))
+    del X, Y
+    phi0 = sdf(Xs, Ys)
+    # initial map: identity in the solid, extrapolated locally (every disc of the lattice lies inside one slab
+    # or is re-swept through the overlap during the steps; the initial halo rows are exact copies)
+    X1, X2 = F.mask_solid(Xs, phi0), F.mask_solid(Ys, phi0)
+    B1, B2, Bp = solver._gather_big((X1, X2, phi0))
+    E1, E2 = F.extrapolate_reference_map(B1, B2, Bp, dx, dy, 3, row_offset=lay.r0 - solver.top)
+    n_own = lay.r1 - lay.r0
+    X1, X2 = torch.zeros_like(Xs), torch.zeros_like(Xs)
+    lay.owned(X1).copy_(E1[solver.top:solver.top + n_own]); lay.owned(X2).copy_(E2[solver.top:solver.top + n_own])
+    solver.comm.halo_exchange(lay, (X1, X2))
+    z = torch.zeros_like(Xs)
+    a = z.clone()
+    if rank == world - 1:
+        a[lay.o1 - 1, 1:-1] = 1.0
+    sstate = (a, z.clone(), z.clone(), X1, X2)
+    prm = dict(dx=dx, dy=dy, mu_s=0.1, kappa=0.0, rho_s=1.0, rho_f=1.0, eta_s=0.01, mu_f=0.01, w_t=2 * dx,
+               scheme="weno5", w_cut=0.0, X=None, Y=None)
+    dt = 0.2 * dx * dx / (4 * 0.01)
+    for _ in range(3):
+        sstate = solver.fsi_step(sstate, prm, dt)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sstate = solver.fsi_step(sstate, prm, dt, check_guard=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item()) / args.steps
+    out["fsi_time"] = {"N": N, "discs": int(cx.size), "ms_per_step": ms, "Mcell_steps_per_s": N * N / ms / 1e3,
+                       "finite": bool(torch.isfinite(sstate[0]).all().item())}
+    del sstate, solver
     torch.cuda.empty_cache()
 
 if args.time:

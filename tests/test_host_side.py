@@ -58,7 +58,7 @@ def test_signatures_match_reference_names():
     expect = {
         F.create_grid: "(Nx, Ny, Lx, Ly)",
         F.apply_phi_BCs: "(phi)",
-        F.extrapolate_reference_map: "(X1, X2, phi, dx, dy, max_layers)",
+        F.extrapolate_reference_map: "(X1, X2, phi, dx, dy, max_layers, row_offset=0)",
         F.compute_timestep: "(a, b, dx, dy, CFL, dt_min_cap, mu_s, rho_s, gamma, rho_f, mu_f=0.0, eta_s=0.0, kappa=0.0)",
         F.advect_semilagrangian_rk4: "(q, a, b, X, Y, dt, dx, dy)",
         F.advect_semilagrangian_cubic_rk4: "(q, a, b, X, Y, dt, dx, dy)",
