@@ -21,10 +21,10 @@ operator API (pyrmt_b200.driver.fsi_step).
 
 --impl reference times that CPU oracle alone (the reference itself is pure
 Python + Numba and cannot travel to the GPU box).
-N > 1: `value` is N independent replicas of the full FSI step ("replicas only", weak
-scaling) -- reference-map advection and extrapolation are not slab-decomposed yet.  The
-part that is (momentum predictor + DCT projection over y-slabs, NCCL halo exchange +
-all-to-all transposes) is timed on one 8193^2 grid and reported as `slab_fluid_step`.
+N > 1: the SAME 4097^2 problem is slab-decomposed over the N GPUs (pyrmt_b200/slab.py: y-slabs,
+NCCL halo exchange, all-to-all transposes in the DCT solve, overlap-swept extrapolation) --
+strong scaling; the results equal the single-GPU step (xi bit for bit).  The fluid half of
+the step on one 8193^2 grid is reported beside it as `slab_fluid_step`.
 """
 import argparse
 import json
@@ -68,8 +68,8 @@ def workload_config(N, scheme, world):
                         % (N, N, N - 1, scheme),
             "grid": [N, N], "discs": 64, "scheme": scheme,
             "cache": "working set ~%.1f GB per step >> 126 MB L2 (no flush needed)" % (25 * cells * 8 / 1e9),
-            "parallelism": ("replicas x%d of the full FSI step (only momentum + projection are slab-decomposed "
-                            "so far: see slab_fluid_step)" % world) if world > 1 else "single GPU"}
+            "parallelism": ("one grid in %d y-slabs: NCCL halo exchange, all-to-all transposes in the DCT solve, "
+                            "overlap-swept extrapolation (strong scaling)" % world) if world > 1 else "single GPU"}
 
 
 def peaks():
@@ -235,6 +235,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-slab", action="store_true")
+    ap.add_argument("--overlap", type=int, default=512, help="rows above a slab re-swept by the extrapolation")
     ap.add_argument("--slab-size", type=int, default=8193, help="nodes per side of the sharded fluid-step timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -250,7 +251,7 @@ def main():
     import torch
     import torch.distributed as dist
     from pyrmt_b200._runtime import profiler
-    from pyrmt_b200.driver import fsi_step, fsi_step_host, make_case
+    from pyrmt_b200.driver import fsi_step, make_case
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
@@ -263,8 +264,29 @@ def main():
 
     N = args.size
     state, prm = make_case(N, L=1.0, k_side=8, R_frac=0.04, scheme=args.scheme, bc_kind="lid")
+    if world == 1:
+        def step(st):
+            return fsi_step(st, prm)[0]
+    else:
+        # ONE grid over all ranks: y-slabs, NCCL halo exchange, all-to-all transposes in the DCT solve,
+        # overlap-swept extrapolation (pyrmt_b200/slab.py); strong scaling of the N = 1 workload
+        from pyrmt_b200 import functions as Fn
+        from pyrmt_b200.slab import SlabFSISolver, SlabLayout
+        lay = SlabLayout(N, N, world, rank, halo=12)
+        solver = SlabFSISolver(lay, prm["bc"], prm["eig"], prm["phi_init"], overlap=args.overlap, layers=prm["layers"])
+        state = tuple(lay.take(t).contiguous() for t in state)
+        sprm = dict(prm, X=None, Y=None)
+
+        def step(st):
+            dt = Fn.compute_timestep(lay.owned(st[0]), lay.owned(st[1]), prm["dx"], prm["dy"], prm["CFL"],
+                                     prm["dt_cap"], prm["mu_s"], prm["rho_s"], 0.0, prm["rho_f"], mu_f=prm["mu_f"],
+                                     eta_s=prm["eta_s"], kappa=prm["kappa"])
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return solver.fsi_step(st, sprm, float(t.item()), check_guard=False)
+        solver.fsi_step(state, sprm, 1e-7, check_guard=True)      # validates the overlap once (raises if too small)
     for _ in range(args.warmup):
-        state, dt, _ = fsi_step(state, prm)
+        state = step(state)
     torch.cuda.synchronize()
 
     def barrier():
@@ -280,7 +302,7 @@ def main():
     barrier()
     e0.record()
     for _ in range(args.steps):
-        state, dt, _ = fsi_step(state, prm)
+        state = step(state)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -295,13 +317,13 @@ def main():
     finite = bool(torch.isfinite(state[0]).all().item())
 
     cells = N * N
-    value = cells * args.steps * world / (ms * 1e-3) / 1e6
+    value = cells * args.steps / (ms * 1e-3) / 1e6          # one N x N grid, whatever the number of GPUs
     peak, peak_kind = peaks()
 
     # ---- dominant kernel -> roofline --------------------------------------
     top = max(per_kernel.items(), key=lambda kv: kv[1][1])
     kname, (kcalls, ktotal) = top
-    alg_launch = ALG_BYTES_PER_CELL_LAUNCH.get(kname, 0.0) * cells
+    alg_launch = ALG_BYTES_PER_CELL_LAUNCH.get(kname, 0.0) * (state[0].numel() if world > 1 else cells)
     kavg_ms = ktotal / kcalls
     achieved = alg_launch / (kavg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -316,13 +338,21 @@ def main():
     # ---- end to end: host state in, host state out, every step --------------
     e2e = None
     if not args.no_e2e:
+        def host_step(hs):
+            st = tuple(t.to("cuda", non_blocking=True) for t in hs)
+            new = step(st)
+            out = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in new)
+            for h, d in zip(out, new):
+                h.copy_(d, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out
         hstate = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in state)
-        hstate = fsi_step_host(hstate, prm)            # warm-up
+        hstate = host_step(hstate)            # warm-up
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         for _ in range(args.e2e_steps):
-            hstate = fsi_step_host(hstate, prm)
+            hstate = host_step(hstate)
         f1.record()
         barrier()
         ems = f0.elapsed_time(f1)
@@ -330,11 +360,11 @@ def main():
             t = torch.tensor([ems], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
-        nbytes = 5 * cells * 8
-        e2e = {"value": cells * args.e2e_steps * world / (ems * 1e-3) / 1e6, "unit": "Mcell-steps/s",
+        nbytes = 5 * state[0].numel() * 8 * world
+        e2e = {"value": cells * args.e2e_steps / (ems * 1e-3) / 1e6, "unit": "Mcell-steps/s",
                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": args.e2e_steps,
                "ms_per_step": ems / args.e2e_steps,
-               "call": "pyrmt_b200.driver.fsi_step_host (pinned host state -> device -> step -> host)"}
+               "call": "the five state fields (per rank: its slab) pinned host -> device -> fsi step -> pinned host"}
 
     # ---- N > 1: the part of the step that IS slab-decomposed (momentum + projection) ----
     slab = None
@@ -353,8 +383,8 @@ def main():
     if rank == 0:
         line = {"metric": "Mcell-steps/s full FSI step", "value": value, "unit": "Mcell-steps/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic",
+                "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
                 "config": workload_config(N, args.scheme, world),
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "step_roofline": {"alg_bytes_per_cell_step": ALG_BYTES_PER_CELL_STEP.get(args.scheme, 512.0),

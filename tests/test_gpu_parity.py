@@ -454,3 +454,58 @@ def test_fsi_steps_vs_oracle(P, O, N, scheme):
             err = rel_linf(x, r)
             assert err < TOL, (N, scheme, n, nm, err)
         state = so
+
+
+# ----------------------------------------------------------------- slab decomposition (1 rank)
+def test_slab_solver_world1_equals_single_gpu(P):
+    """The slab-decomposed FSI step with one rank (no halos, the same kernels and the
+    transpose-based DCT building blocks) reproduces the single-GPU step; the 2-GPU
+    comparison is scripts/slab_check.py (profiles/r01f_*)."""
+    import torch
+    from pyrmt_b200.driver import LidBC, disc_lattice, fsi_step
+    from pyrmt_b200.levelset import DiscSDF
+    from pyrmt_b200.slab import SlabFSISolver, SlabLayout
+    N = 257
+    X, Y, dx, dy = P.create_grid(N, N, 1.0, 1.0)
+    cx, cy, R = disc_lattice(3, 1.0, 0.1)
+    sdf, bc = DiscSDF(cx, cy, R, domain=(1.0, 1.0)), LidBC(1.0)
+    eig = P._precompute_poisson_eigenvalues(N, N, dx, dy)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    Xd, Yd = up(X), up(Y)
+    phi0 = sdf(Xd, Yd)
+    X1, X2 = P.extrapolate_reference_map(P.mask_solid(Xd, phi0), P.mask_solid(Yd, phi0), phi0, dx, dy, 3)
+    a0, b0 = bc(np.zeros((N, N)), np.zeros((N, N)))
+    state = (up(a0), up(b0), up(np.zeros((N, N))), X1, X2)
+    prm = dict(dx=dx, dy=dy, CFL=0.2, dt_cap=1e-3, mu_s=0.1, kappa=0.0, rho_s=1.0, rho_f=1.0, eta_s=0.01,
+               mu_f=0.01, w_t=2 * dx, layers=3, scheme="weno5", w_cut=0.0, phi_init=sdf, bc=bc, eig=eig,
+               X=Xd, Y=Yd)
+    lay = SlabLayout(N, N, 1, 0, halo=12)
+    solver = SlabFSISolver(lay, bc, eig, sdf, overlap=64, layers=3)
+    sstate = tuple(t.clone() for t in state)
+    for _ in range(3):
+        state, dt, _ = fsi_step(state, prm)
+        sstate = solver.fsi_step(sstate, dict(prm, X=None, Y=None), dt)
+        for nm, ref, got in zip("abp12", state, sstate):
+            if nm in "12":
+                assert torch.equal(ref, got), nm
+            assert float(((ref - got).abs().max() / ref.abs().max()).item()) < 1e-12, nm
+
+
+def test_dct_lines_building_blocks(P, O):
+    """rmt_dct_lines / rmt_transpose / rmt_copy2d against scipy (through the oracle's imports)."""
+    import torch
+    from scipy.fft import dct
+    from pyrmt_b200.slab import CudaOps
+    ops = CudaOps()
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((37, 129))
+    xd = torch.from_numpy(x.copy()).cuda()
+    assert rel_linf(ops.dct_lines(xd.clone()).cpu().numpy(), dct(x, type=1, axis=1)) < 1e-13
+    eig = 1.0 + rng.random((37, 129))
+    ref = dct(dct(x, type=1, axis=1) * (0.25 / eig), type=1, axis=1)
+    got = ops.dct_lines(xd.clone(), eig=torch.from_numpy(eig).cuda(), scale=0.25).cpu().numpy()
+    assert rel_linf(got, ref) < 1e-13
+    assert same(ops.transpose(xd).cpu().numpy(), x.T)
+    dst = torch.zeros((37, 200), dtype=torch.float64, device="cuda")
+    ops.copy2d(xd[:, 5:60], dst[:, 100:155])
+    assert same(dst[:, 100:155].cpu().numpy(), x[:, 5:60]) and float(dst[:, :100].abs().max()) == 0.0
