@@ -49,7 +49,10 @@ ALG_BYTES_PER_CELL_LAUNCH = {
     "rmt_solid_stress": 8.0 * 7.0,
     "rmt_projection_rhs": 8.0 * 5.0,
     "rmt_projection_correct": 8.0 * 8.0,
-    "rmt_extrapolate": 8.0 * 5.0,
+    "rmt_extrapolate": 8.0 * 5.0,        # a dependency-chain (latency) kernel, not a bandwidth one
+    "rmt_extrapolate_rows": 8.0 * 5.0,
+    "rmt_advect_euler_rk3_pair": 8.0 * 25.0,   # 3 stage kernels per call, two fields: 7 + 9 + 9
+    "rmt_dct_lines": 8.0 * 2.0,
     "rmt_disc_sdf": 8.0 * 3.0,
     "rmt_mask_mul": 8.0 * 3.0,
     "rmt_heaviside_rho": 8.0 * 3.0,
@@ -93,7 +96,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -331,6 +334,16 @@ def main():
                 "launches_timed": kcalls, "avg_launch_ms": kavg_ms,
                 "share_of_step": ktotal / ms,
                 "alg_bytes_per_launch": alg_launch}
+    ncell_rank = state[0].numel() if world > 1 else cells
+    roofline["note"] = ("dominant entry point by summed CUDA-event time; rmt_extrapolate* is bound by the serial "
+                        "dependency chain of the reference's raster sweep (latency), not by HBM -- see DESIGN.md 5; "
+                        "`kernels_roofline` lists every entry point")
+    kernels_roofline = []
+    for k, (c, t) in sorted(per_kernel.items(), key=lambda kv: -kv[1][1]):
+        ab = ALG_BYTES_PER_CELL_LAUNCH.get(k, 0.0) * ncell_rank
+        kernels_roofline.append({"kernel": k, "share_of_step": t / ms, "avg_launch_ms": t / c,
+                                 "achieved_GBps": ab / (t / c * 1e-3) / 1e9 if t > 0 else None,
+                                 "frac": ab / (t / c * 1e-3) / 1e9 / peak if t > 0 else None})
     step_gbs = cells * ALG_BYTES_PER_CELL_STEP.get(args.scheme, 512.0) * args.steps / (ms * 1e-3) / 1e9
     breakdown = {k: {"calls": c, "ms_per_step": t / args.steps} for k, (c, t) in
                  sorted(per_kernel.items(), key=lambda kv: -kv[1][1])}
@@ -389,7 +402,8 @@ def main():
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "step_roofline": {"alg_bytes_per_cell_step": ALG_BYTES_PER_CELL_STEP.get(args.scheme, 512.0),
                                   "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak},
-                "cpu_baseline": cpu, "kernels": breakdown, "finite": finite, "slab_fluid_step": slab}
+                "cpu_baseline": cpu, "kernels": breakdown, "kernels_roofline": kernels_roofline[:8],
+                "finite": finite, "slab_fluid_step": slab}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
