@@ -152,15 +152,18 @@ __global__ void k_ext_flag(unsigned char *__restrict__ st, int *__restrict__ seg
     }
 }
 
-// exclusive scan of the per-(row, x-tile) counts -> seg_off[0..n]; resets the tile counter
-__global__ void k_ext_scan(const int *__restrict__ seg_cnt, int *__restrict__ seg_off, int n,
+// exclusive scan of the per-(row, x-tile) counts -> seg_off[0..Ny*nxt]; resets the tile counter.
+// One thread per row sums its nxt segments, the row totals are scanned in shared memory, each
+// thread then writes its row's segment offsets.
+__global__ void k_ext_scan(const int *__restrict__ seg_cnt, int *__restrict__ seg_off, int Ny, int nxt,
                            int *__restrict__ tile_counter)
 {
     __shared__ int sh[1024];
-    int per = (n + blockDim.x - 1) / blockDim.x;
-    int lo = min((int)threadIdx.x * per, n), hi = min(lo + per, n);
+    const int per = (Ny + blockDim.x - 1) / blockDim.x;       // rows per thread (contiguous)
+    const int lo = min((int)threadIdx.x * per, Ny), hi = min(lo + per, Ny);
     int s = 0;
-    for (int k = lo; k < hi; ++k) s += seg_cnt[k];
+    for (int j = lo; j < hi; ++j)
+        for (int x = 0; x < nxt; ++x) s += seg_cnt[j * nxt + x];
     sh[threadIdx.x] = s;
     __syncthreads();
     for (int o = 1; o < blockDim.x; o <<= 1) {
@@ -170,11 +173,12 @@ __global__ void k_ext_scan(const int *__restrict__ seg_cnt, int *__restrict__ se
         __syncthreads();
     }
     int run = sh[threadIdx.x] - s;
-    for (int k = lo; k < hi; ++k) {
-        seg_off[k] = run;
-        run += seg_cnt[k];
-    }
-    if (threadIdx.x == blockDim.x - 1) seg_off[n] = sh[threadIdx.x];
+    for (int j = lo; j < hi; ++j)
+        for (int x = 0; x < nxt; ++x) {
+            seg_off[j * nxt + x] = run;
+            run += seg_cnt[j * nxt + x];
+        }
+    if (threadIdx.x == blockDim.x - 1) seg_off[Ny * nxt] = sh[threadIdx.x];
     if (threadIdx.x == 0) *tile_counter = 0;
 }
 
@@ -481,6 +485,14 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
             const int nslots = info & 255, npend = info >> 8;
             const int nknown = nslots - npend;
             __syncwarp();
+            // this lane's undecided cell (the first 32; a second round is rare): everything that does
+            // not depend on the wait is read now
+            int p_n = 0, p_slot = 0;
+            double p_w = 0.0, p_x = 0.0, p_y = 0.0;
+            if (lane < npend) {
+                p_n = W.rec.pn[lane]; p_slot = W.rec.pslot[lane];
+                p_w = W.rec.pw[lane]; p_x = W.rec.px[lane]; p_y = W.rec.py[lane];
+            }
             EXT_T(0);
             // ---- wait: rows j-4..j-1 past column i+4, own row past column i-1 ---------
             //   lanes 0-3: the tile holding column i+4 (normally this one), rows j-1-lane
@@ -513,7 +525,8 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                 const int r = r0 + lane;
                 bool fail = false;
                 if (r < npend) {
-                    const int n = W.rec.pn[r];
+                    const bool pre = (r0 == 0);
+                    const int n = pre ? p_n : W.rec.pn[r];
                     const int dj = n / 9 - 4, di = n % 9 - 4;
                     const int jj = j + dj, ii = i + di;
                     const int slot = ii & (RING - 1);
@@ -550,8 +563,10 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                         }
                     }
                     // a rejected target contributes exact zeros (weight 0)
-                    store_products(W.rec.prod[W.rec.pslot[r]], got ? W.rec.pw[r] : 0.0, got ? W.rec.px[r] : 0.0,
-                                   got ? W.rec.py[r] : 0.0, v1, v2);
+                    const double cw = pre ? p_w : W.rec.pw[r], cx = pre ? p_x : W.rec.px[r],
+                                 cy = pre ? p_y : W.rec.py[r];
+                    store_products(W.rec.prod[pre ? p_slot : W.rec.pslot[r]], got ? cw : 0.0, got ? cx : 0.0,
+                                   got ? cy : 0.0, v1, v2);
                     fail = !got;
                 }
                 nfail += __popc(__ballot_sync(0xffffffffu, fail));
@@ -746,11 +761,11 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
     for (int layer = 0; layer < max_layers; ++layer) {
         k_ext_flag<<<row_warps_blocks, 256, 0, s>>>(st, seg_cnt, Ny, Nx, nxt, XT);
         RMT_LAUNCH_CHECK();
-        k_ext_scan<<<1, 1024, 0, s>>>(seg_cnt, seg_off, nseg, tile_counter);
+        k_ext_scan<<<1, 1024, 0, s>>>(seg_cnt, seg_off, Ny, nxt, tile_counter);
         RMT_LAUNCH_CHECK();
         k_ext_fill<<<row_warps_blocks, 256, 0, s>>>(st, seg_off, tcol, trow, prog, Ny, Nx, nxt, XT);
         RMT_LAUNCH_CHECK();
-        k_ext_prepare<<<148 * 8, 256, 0, s>>>(X1e, X2e, st, seg_off, nseg, tcol, trow, recs, tinfo, cap, Ny, Nx,
+        k_ext_prepare<<<148 * 12, 256, 0, s>>>(X1e, X2e, st, seg_off, nseg, tcol, trow, recs, tinfo, cap, Ny, Nx,
                                                joff, dx, dy, r2);
         RMT_LAUNCH_CHECK();
         // all CTAs must be co-resident (warps wait on each other): cooperative launch
