@@ -64,6 +64,20 @@ ALG_BYTES_PER_CELL_LAUNCH = {
 }
 
 
+# DRAM bytes per call (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full` capture of
+# this workload at 4097^2 on one B200 (profiles/r01e_ncu_full_summary.txt); per-call = sum over the
+# kernels the entry point launches.  Only reported for N = 1 at the default size.
+NCU_TRAFFIC_BYTES_4097 = {
+    "rmt_momentum_stage": 1.603e9,         # mean of the four stages (1.46 / 1.74 / 1.74 / 1.48 GB)
+    "rmt_advect_euler_rk3_pair": 2.82e9,   # three stage kernels: 0.75 + 1.04 + 1.03 GB
+    "rmt_poisson_solve_dct": 1.31e9,       # 2 x lines<0> (0.22) + lines<1> (0.36) + 2 x transpose (0.22) + sum
+    "rmt_projection_correct": 1.04e9,
+    "rmt_projection_rhs": 0.66e9,
+    "rmt_solid_stress": 0.71e9,
+    "rmt_disc_sdf": 0.38e9,
+}
+
+
 def workload_config(N, scheme, world):
     cells = N * N
     return {"workload": "synthetic 64-disc lid-driven FSI at %dx%d nodes (%d^2 cells), %s + SSP-RK3 ref-map "
@@ -335,6 +349,8 @@ def main():
                 "share_of_step": ktotal / ms,
                 "alg_bytes_per_launch": alg_launch}
     ncell_rank = state[0].numel() if world > 1 else cells
+    if world == 1 and N == 4097:
+        roofline["traffic"] = NCU_TRAFFIC_BYTES_4097.get(kname)
     roofline["note"] = ("dominant entry point by summed CUDA-event time; rmt_extrapolate* is bound by the serial "
                         "dependency chain of the reference's raster sweep (latency), not by HBM -- see DESIGN.md 5; "
                         "`kernels_roofline` lists every entry point")
@@ -343,7 +359,9 @@ def main():
         ab = ALG_BYTES_PER_CELL_LAUNCH.get(k, 0.0) * ncell_rank
         kernels_roofline.append({"kernel": k, "share_of_step": t / ms, "avg_launch_ms": t / c,
                                  "achieved_GBps": ab / (t / c * 1e-3) / 1e9 if t > 0 else None,
-                                 "frac": ab / (t / c * 1e-3) / 1e9 / peak if t > 0 else None})
+                                 "frac": ab / (t / c * 1e-3) / 1e9 / peak if t > 0 else None,
+                                 "alg_bytes_per_launch": ab,
+                                 "traffic": NCU_TRAFFIC_BYTES_4097.get(k) if (world == 1 and N == 4097) else None})
     step_gbs = cells * ALG_BYTES_PER_CELL_STEP.get(args.scheme, 512.0) * args.steps / (ms * 1e-3) / 1e9
     breakdown = {k: {"calls": c, "ms_per_step": t / args.steps} for k, (c, t) in
                  sorted(per_kernel.items(), key=lambda kv: -kv[1][1])}

@@ -192,7 +192,7 @@ struct RhsArgs {
 };
 
 template <bool FUSED>
-__global__ void __launch_bounds__(256, 5)
+__global__ void __launch_bounds__(256, 4)
 k_momentum_rhs(const RhsArgs A)
 {
     __shared__ double sU[UHT * UW], sV[UHT * UW];
@@ -206,26 +206,39 @@ k_momentum_rhs(const RhsArgs A)
     const bool rim = (i0 == 0) || (j0 == 0) || (i1 == Nx) || (j1 == Ny);
     const int th = rim ? 2 : 1, uh = th + 1;
 
-    // ---- stage velocities with halo ----------------------------------------
-    {
-        const int ja = max(j0 - uh, 0), jb = min(j1 + uh, Ny);
-        const int ia = max(i0 - uh, 0), ib = min(i1 + uh, Nx);
-        const int w = ib - ia, n = (jb - ja) * w;
-        for (int e = tid; e < n; e += 256) {
-            int jj = ja + e / w, ii = ia + e % w;
-            size_t g = (size_t)jj * Nx + ii;
-            int s = (jj - (j0 - UHALO)) * UW + (ii - (i0 - UHALO));
-            sU[s] = __ldg(A.us + g);
-            sV[s] = __ldg(A.vs + g);
+    // Every global load whose address is known up front is issued HERE, before the first barrier:
+    // the velocity tile (<= 4 points per thread), the level set / Heaviside at this thread's stress
+    // nodes (<= 3), and the output phase's streaming fields -- ~19 loads in flight per thread, so the
+    // kernel pays the HBM latency once instead of once per loop iteration and per phase.
+    const int uja = max(j0 - uh, 0), ujb = min(j1 + uh, Ny), uia = max(i0 - uh, 0), uib = min(i1 + uh, Nx);
+    const int uw = uib - uia, un = (ujb - uja) * uw;
+    double ru[4], rv[4];
+    int us_idx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = tid + 256 * k;
+        us_idx[k] = -1;
+        ru[k] = rv[k] = 0.0;
+        if (e < un) {
+            const int jj = uja + e / uw, ii = uia + e % uw;
+            const size_t g = (size_t)jj * Nx + ii;
+            us_idx[k] = (jj - (j0 - UHALO)) * UW + (ii - (i0 - UHALO));
+            ru[k] = __ldg(A.us + g);
+            rv[k] = __ldg(A.vs + g);
         }
     }
-    __syncthreads();
-    const STile U{sU, j0 - UHALO, i0 - UHALO, UW}, V{sV, j0 - UHALO, i0 - UHALO, UW};
-    const double i2dx = 1.0 / (2.0 * A.dx), i2dy = 1.0 / (2.0 * A.dy);
-    const double inv_w = FUSED ? 1.0 / A.w_t : 0.0;
-
-    // issue the output phase's streaming loads now, so their latency hides behind the
-    // stress phase (they are consumed after the second barrier)
+    const int tja = max(j0 - th, 0), tjb = min(j1 + th, Ny), tia = max(i0 - th, 0), tib = min(i1 + th, Nx);
+    const int tw_ = tib - tia, tn = (tjb - tja) * tw_;
+    double rh[3];                                  // phi (FUSED) or H at this thread's stress nodes
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int e = tid + 256 * k;
+        rh[k] = 1.0;
+        if (e < tn) {
+            const size_t g = (size_t)(tja + e / tw_) * Nx + (tia + e % tw_);
+            rh[k] = FUSED ? __ldg(A.phi + g) : __ldg(A.H + g);
+        }
+    }
     double pf_u0[MTY / 8], pf_v0[MTY / 8], pf_au[MTY / 8], pf_av[MTY / 8];
 #pragma unroll
     for (int r = 0; r < MTY / 8; ++r) {
@@ -241,40 +254,58 @@ k_momentum_rhs(const RhsArgs A)
             }
         }
     }
+    // ---- stage velocities with halo -> shared memory ------------------------
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (us_idx[k] >= 0) {
+            sU[us_idx[k]] = ru[k];
+            sV[us_idx[k]] = rv[k];
+        }
+    __syncthreads();
+    const STile U{sU, j0 - UHALO, i0 - UHALO, UW}, V{sV, j0 - UHALO, i0 - UHALO, UW};
+    const double i2dx = 1.0 / (2.0 * A.dx), i2dy = 1.0 / (2.0 * A.dy);
+    const double inv_w = FUSED ? 1.0 / A.w_t : 0.0;
 
     // ---- blended stress  T = H sigma_f + (1-H) sigma_s  --------------------
     {
-        const int ja = max(j0 - th, 0), jb = min(j1 + th, Ny);
-        const int ia = max(i0 - th, 0), ib = min(i1 + th, Nx);
-        const int w = ib - ia, n = (jb - ja) * w;
-        for (int e = tid; e < n; e += 256) {
-            int jj = ja + e / w, ii = ia + e % w;
-            size_t g = (size_t)jj * Nx + ii;
-            double ux = ddx2(U, jj, ii, Nx, i2dx), vy = ddy2(V, jj, ii, Ny, i2dy);
-            double uy = ddy2(U, jj, ii, Ny, i2dy), vx = ddx2(V, jj, ii, Nx, i2dx);
-            double h, ph = 1.0;
-            if (FUSED) {
-                ph = __ldg(A.phi + g);
-                h = heaviside_sin(ph, A.w_t, inv_w);
-            } else {
-                h = __ldg(A.H + g);
+        // solid stress only where (1-H) != 0: issue those loads for all of this thread's nodes first
+        double hh[3], sx[3], sy[3], sq[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int e = tid + 256 * k;
+            hh[k] = FUSED ? heaviside_sin(rh[k], A.w_t, inv_w) : rh[k];
+            sx[k] = sy[k] = sq[k] = 0.0;
+            if (e < tn && hh[k] != 1.0) {
+                const size_t g = (size_t)(tja + e / tw_) * Nx + (tia + e % tw_);
+                sx[k] = __ldg(A.sxx + g);
+                sy[k] = __ldg(A.syy + g);
+                sq[k] = __ldg(A.sxy + g);
             }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int e = tid + 256 * k;
+            if (e >= tn) continue;
+            const int jj = tja + e / tw_, ii = tia + e % tw_;
+            const double ux = ddx2(U, jj, ii, Nx, i2dx), vy = ddy2(V, jj, ii, Ny, i2dy);
+            const double uy = ddy2(U, jj, ii, Ny, i2dy), vx = ddx2(V, jj, ii, Nx, i2dx);
+            const double h = hh[k];
             double txx = h * (2.0 * A.mu_f * ux);
             double tyy = h * (2.0 * A.mu_f * vy);
             double txy = h * (A.mu_f * (uy + vx));
             if (h != 1.0) {   // (1-H)*sigma_s vanishes identically in the pure fluid
-                double sx = __ldg(A.sxx + g), sy = __ldg(A.syy + g), sxy = __ldg(A.sxy + g);
-                if (FUSED && A.eta_s > 0.0 && ph <= 0.0) {   // Kelvin-Voigt, :717-730
-                    sx += A.eta_s * ux;
-                    sy += A.eta_s * vy;
-                    sxy += A.eta_s * 0.5 * (uy + vx);
+                double ex = sx[k], ey = sy[k], exy = sq[k];
+                if (FUSED && A.eta_s > 0.0 && rh[k] <= 0.0) {   // Kelvin-Voigt, :717-730 (rh = phi)
+                    ex += A.eta_s * ux;
+                    ey += A.eta_s * vy;
+                    exy += A.eta_s * 0.5 * (uy + vx);
                 }
-                double omh = 1.0 - h;
-                txx += omh * sx;
-                tyy += omh * sy;
-                txy += omh * sxy;
+                const double omh = 1.0 - h;
+                txx += omh * ex;
+                tyy += omh * ey;
+                txy += omh * exy;
             }
-            int s = (jj - (j0 - THALO)) * TW + (ii - (i0 - THALO));
+            const int s = (jj - (j0 - THALO)) * TW + (ii - (i0 - THALO));
             sTxx[s] = txx;
             sTxy[s] = txy;
             sTyy[s] = tyy;
