@@ -120,8 +120,9 @@ static ExtTune ext_tune()
 // frontier of the current layer: unknown interior cells with a known 3x3
 // neighbour (functions.py:79-90); one warp per row, counts them per x-tile.
 __global__ void k_ext_flag(unsigned char *__restrict__ st, int *__restrict__ seg_cnt, int Ny, int Nx,
-                           int nxt, int XT)
+                           int nxt, int XT, const int *__restrict__ mode)
 {
+    if (mode && *mode == 1) return;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int nwarp = (gridDim.x * blockDim.x) >> 5;
     for (int j = warp; j < Ny; j += nwarp) {
@@ -156,8 +157,9 @@ __global__ void k_ext_flag(unsigned char *__restrict__ st, int *__restrict__ seg
 // One thread per row sums its nxt segments, the row totals are scanned in shared memory, each
 // thread then writes its row's segment offsets.
 __global__ void k_ext_scan(const int *__restrict__ seg_cnt, int *__restrict__ seg_off, int Ny, int nxt,
-                           int *__restrict__ tile_counter)
+                           int *__restrict__ tile_counter, const int *__restrict__ mode)
 {
+    if (mode && *mode == 1) return;
     __shared__ int sh[1024];
     const int per = (Ny + blockDim.x - 1) / blockDim.x;       // rows per thread (contiguous)
     const int lo = min((int)threadIdx.x * per, Ny), hi = min(lo + per, Ny);
@@ -188,8 +190,9 @@ __global__ void k_ext_scan(const int *__restrict__ seg_cnt, int *__restrict__ se
 // none): "segment (j, xt) has dealt with every column < prog[j*nxt+xt]".
 __global__ void k_ext_fill(const unsigned char *__restrict__ st, const int *__restrict__ seg_off,
                            int *__restrict__ tcol, int *__restrict__ trow, int *__restrict__ prog, int Ny,
-                           int Nx, int nxt, int XT)
+                           int Nx, int nxt, int XT, const int *__restrict__ mode)
 {
+    if (mode && *mode == 1) return;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int nwarp = (gridDim.x * blockDim.x) >> 5;
     for (int j = warp; j < Ny; j += nwarp) {
@@ -289,10 +292,15 @@ __device__ __forceinline__ void store_products(double *q, double w, double x, do
 // Phase A of one target (warp-collective): classify the 81 window cells, weight them,
 // turn the cells known before the layer into their 12 products (compacted in gather
 // order) and list the undecided ones.  Returns nslots | npend << 8.
+// FUSED = false: per-layer launches -- known == state 1, undecided == marked 2/3 and raster-earlier.
+// FUSED = true : all layers in one launch -- state 2l+3 = fitted by layer l; "known" is any odd state
+// below this layer's code `fresh`; every raster-earlier cell that is not known is a candidate (there
+// are no target marks); all reads go to L2 (other SMs wrote the previous layers).
+template <bool FUSED>
 __device__ __forceinline__ int ext_phase_a(ExtRec *R, const double *__restrict__ X1e,
                                            const double *__restrict__ X2e,
                                            const unsigned char *__restrict__ st, int j, int i, int Ny, int Nx,
-                                           int joff, double dx, double dy, double r2, int lane)
+                                           int joff, double dx, double dy, double r2, int lane, int fresh = ST_FRESH)
 {
     const unsigned lt = (1u << lane) - 1u;
     const double x0 = dx * i, y0 = dy * (j + joff);     // absolute coordinates of the GLOBAL grid (functions.py:105)
@@ -309,14 +317,17 @@ __device__ __forceinline__ int ext_phase_a(ExtRec *R, const double *__restrict__
             const int jj = j + dj, ii = i + di;
             if (jj >= 0 && jj < Ny && ii >= 0 && ii < Nx) {
                 const size_t cc = (size_t)jj * Nx + ii;
-                const unsigned char sv = st[cc];     // 1 is final; 2/3 decided during the sweep
-                const double v1 = X1e[cc], v2 = X2e[cc];   // only meaningful if sv == 1
+                const unsigned char sv = FUSED ? __ldcg(st + cc) : st[cc];   // known cells are final
+                const double v1 = FUSED ? __ldcg(X1e + cc) : X1e[cc];         // only meaningful if known
+                const double v2 = FUSED ? __ldcg(X2e + cc) : X2e[cc];
                 const double xi = dx * ii, yi = dy * (jj + joff);
                 const double ex = xi - x0, ey = yi - y0;
                 const double dist_sq = ex * ex + ey * ey;
                 const bool earlier = (dj < 0) || (dj == 0 && di < 0);
-                if (dist_sq <= r2 && (sv == ST_KNOWN || (sv != ST_UNKNOWN && earlier))) {
-                    cls[s] = (sv == ST_KNOWN) ? 1 : 2;
+                const bool known = FUSED ? ((sv & 1) && sv < fresh) : (sv == ST_KNOWN);
+                const bool cand = FUSED ? (!known && earlier) : (sv != ST_UNKNOWN && sv != ST_KNOWN && earlier);
+                if (dist_sq <= r2 && (known || cand)) {
+                    cls[s] = known ? 1 : 2;
                     cw[s] = exp_glibc(-dist_sq / r2);
                     cx_[s] = xi; cy_[s] = yi; c1[s] = v1; c2[s] = v2;
                 }
@@ -354,13 +365,15 @@ __global__ void __launch_bounds__(256)
 k_ext_prepare(const double *__restrict__ X1e, const double *__restrict__ X2e,
               const unsigned char *__restrict__ st, const int *__restrict__ seg_off, int nseg,
               const int *__restrict__ tcol, const int *__restrict__ trow, ExtRec *__restrict__ recs,
-              int *__restrict__ tinfo, int cap, int Ny, int Nx, int joff, double dx, double dy, double r2)
+              int *__restrict__ tinfo, int cap, int Ny, int Nx, int joff, double dx, double dy, double r2,
+              const int *__restrict__ mode)
 {
+    if (mode && *mode == 1) return;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
     const int ntot = min(seg_off[nseg], cap);
     for (int t = warp; t < ntot; t += nwarp) {
-        const int info = ext_phase_a(recs + t, X1e, X2e, st, trow[t], tcol[t], Ny, Nx, joff, dx, dy, r2, lane);
+        const int info = ext_phase_a<false>(recs + t, X1e, X2e, st, trow[t], tcol[t], Ny, Nx, joff, dx, dy, r2, lane);
         if (lane == 0) tinfo[t] = info;
     }
 }
@@ -421,8 +434,9 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
             const int *__restrict__ seg_off, const int *__restrict__ tcol, int *__restrict__ prog,
             int *__restrict__ tile_counter, const ExtRec *__restrict__ recs, const int *__restrict__ tinfo,
             int cap, int Ny, int Nx, int joff, int nxt, int XT, int MRB, int sleep_ns, double dx, double dy,
-            double r2)
+            double r2, const int *__restrict__ mode)
 {
+    if (mode && *mode == 1) return;
     extern __shared__ unsigned char s_raw[];
     SweepSmem &S = *reinterpret_cast<SweepSmem *>(s_raw);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -478,7 +492,7 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                 info = info_next;
                 cp_async_wait_all();
             } else {
-                info = ext_phase_a(&W.rec, X1e, X2e, st, j, i, Ny, Nx, joff, dx, dy, r2, lane);
+                info = ext_phase_a<false>(&W.rec, X1e, X2e, st, j, i, Ny, Nx, joff, dx, dy, r2, lane);
             }
             info_next = (t + 1 < t1 && t + 1 < cap) ? tinfo[t + 1] : 0;
             const int next = (t + 1 < t1) ? tcol[t + 1] : INT_MAX;   // loaded early: it gates the publish
@@ -663,6 +677,392 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
     }
 }
 
+// ===========================================================================================
+// All layers in ONE launch.
+//
+// Layer l+1 may trail layer l by a few rows: a layer-(l+1) fit at row j needs layer l complete
+// on rows j-4..j+4 (its window) and rows j-1..j+1 (to know whether it is a target at all).  So
+// the three sweeps run as three wavefronts a few rows apart, on different SMs, and the serial
+// chain along a body costs ~one layer instead of the sum of all layers.  Because a rejected fit
+// (|det| <= 1e-10, count < 3) changes which cells the NEXT layer fits, targets cannot be listed
+// up front: every (layer, row, x-tile) warp discovers its own targets from the state bytes once
+// the previous layer has passed, prepares their phase-A records (to its own global scratch
+// slots), and then sweeps them exactly like k_ext_sweep.  State byte: 0 unknown, 1 known at
+// entry, 2l+3 fitted by layer l.
+//
+// Tasks = (macro-row m, layer l, x-tile xt), handed out in that lexicographic order by a global
+// counter to co-resident CTAs.  A task waits only on tasks handed out before it, or at most
+// (2L-1) groups of nxt tasks after it (layer l-1 of the next macro-row, for its last four rows);
+// the launcher keeps (2L-1)*nxt below the number of resident CTAs, so every awaited task is
+// resident or done: no deadlock.
+constexpr int CAPW = 8;                // phase-A records prepared per row warp (beyond: inline)
+constexpr int LMAX = 512;              // targets listed per (row, x-tile)
+
+struct FusedSmem {
+    SweepWarp w[RB];
+    double prev_v[4][RING][2];
+    int prev_tag[4][RING];
+    int prev_row0;
+    int prog[RB];
+    int tile;
+    int tinf[RB][CAPW];
+    unsigned short tl[RB][LMAX];
+};
+
+__global__ void __launch_bounds__(RB * 32, 1)
+k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__restrict__ st,
+            const int *__restrict__ cnt0 /* layer-0 target counts per (row, x-tile) */,
+            int *__restrict__ prog /* [L][Ny*nxt] */, int *__restrict__ tile_counter,
+            ExtRec *__restrict__ scratch /* [gridDim][RB][CAPW] */, const int *__restrict__ mode, int L, int Ny,
+            int Nx, int joff, int nxt, int XT, int MRB, double dx, double dy, double r2)
+{
+    if (*mode != 1) return;
+    extern __shared__ unsigned char s_raw[];
+    FusedSmem &S = *reinterpret_cast<FusedSmem *>(s_raw);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    SweepWarp &W = S.w[wib];
+    volatile int *sp = S.prog;
+    const int nseg = Ny * nxt;
+    const int nrb = (Ny - 2 + RB - 1) / RB, nmrb = (nrb + MRB - 1) / MRB;
+    const int ntasks = nmrb * L * nxt;
+    const int la = (lane < NACC) ? lane : 0;
+    ExtRec *myrecs = scratch + ((size_t)blockIdx.x * RB + wib) * CAPW;
+
+    for (;;) {
+        if (threadIdx.x == 0) S.tile = atomicAdd(tile_counter, 1);
+        __syncthreads();
+        const int task = S.tile;
+        if (task >= ntasks) break;
+        const int xt = task % nxt, grp = task / nxt, layer = grp % L, mrb = grp / L;
+        const int fresh = 2 * layer + 3;
+        int *progL = prog + (size_t)layer * nseg;
+        const int *progP = prog + (size_t)(layer - 1) * nseg;       // previous layer (layer > 0)
+        const int xc0 = xt * XT, xc1 = min(xc0 + XT, Nx);
+        const int rb_end = min((mrb + 1) * MRB, nrb);
+        if (threadIdx.x == 0) S.prev_row0 = -100;
+      for (int rb = mrb * MRB; rb < rb_end; ++rb) {
+        const int row0 = 1 + rb * RB;
+        const int j = row0 + wib;
+        const bool live = j < Ny - 1;
+        // ---- can this block hold targets of this layer at all?  (layer-l targets lie within l cells of
+        //      layer-0 targets; cnt0 is exact for layer 0 and conservative beyond)
+        int any = 0;
+        for (int e = threadIdx.x; e < (RB + 2 * layer + 2) * 3; e += blockDim.x) {
+            const int jr = row0 - layer - 1 + e / 3, xq = xt - 1 + e % 3;
+            if (jr >= 0 && jr < Ny && xq >= 0 && xq < nxt) any |= cnt0[jr * nxt + xq];
+        }
+        if (__syncthreads_or(any) == 0) {
+            if (live && lane == 0) st_relaxed_gpu(progL + j * nxt + xt, INT_MAX);   // nothing here, ever
+            continue;
+        }
+        if (lane == 0) sp[wib] = 0;                                 // 0 = list not built yet
+        if (lane < RING) W.ring_tag[lane] = -1;
+        __syncthreads();
+        const int prow0 = S.prev_row0;
+        const bool prev_ok = (prow0 == row0 - 4);
+        const bool last_rb = (rb == rb_end - 1);
+        int nt = 0;
+        if (live) {
+            // ---- (1) previous layer complete on rows j-4..j+4, tiles xt-1..xt+1 ---------------
+            if (layer > 0 && lane < 27) {
+                const int jr = j - 4 + lane / 3, xq = xt - 1 + lane % 3;
+                if (jr >= 1 && jr < Ny - 1 && xq >= 0 && xq < nxt)
+                    while (ld_relaxed_gpu(progP + jr * nxt + xq) != INT_MAX) __nanosleep(200);
+            }
+            __syncwarp();
+            // ---- (2) discover this row's targets: not known before this layer, with a known neighbour
+            const unsigned char *rowc = st + (size_t)j * Nx, *rowa = rowc - Nx, *rowb = rowc + Nx;
+            for (int base = xc0; base < xc1; base += 32) {
+                const int i = base + lane;
+                bool tgt = false;
+                if (i < xc1 && i >= 1 && i < Nx - 1) {
+                    const unsigned me = __ldcg(rowc + i);
+                    if (!((me & 1) && me < fresh)) {
+                        unsigned kb = 0;
+#pragma unroll
+                        for (int d = -1; d <= 1; ++d) {
+                            const unsigned a = __ldcg(rowa + i + d), c = __ldcg(rowb + i + d);
+                            kb |= ((a & 1) && a < fresh) | ((c & 1) && c < fresh);
+                            if (d) { const unsigned b = __ldcg(rowc + i + d); kb |= ((b & 1) && b < fresh); }
+                        }
+                        tgt = kb != 0;
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, tgt);
+                if (tgt) {
+                    const int o = nt + __popc(m & ((1u << lane) - 1u));
+                    if (o < LMAX) S.tl[wib][o] = (unsigned short)(i - xc0);
+                }
+                nt += __popc(m);
+            }
+            // (more than LMAX targets in one row segment cannot be listed: treated as an error state --
+            //  the launcher keeps XT <= LMAX so this cannot happen)
+            __syncwarp();
+            // ---- (3) announce the list: the row is now "at" its first target -----------------
+            const int first = nt ? xc0 + S.tl[wib][0] : INT_MAX;
+            if (lane == 0) {
+                sp[wib] = first;
+                st_relaxed_gpu(progL + j * nxt + xt, first);
+            }
+            // ---- (4) phase A of the first CAPW targets into this warp's scratch records -------
+            const int nprep = min(nt, CAPW);
+            for (int k = 0; k < nprep; ++k) {
+                const int info = ext_phase_a<true>(myrecs + k, X1e, X2e, st, j, xc0 + S.tl[wib][k], Ny, Nx, joff,
+                                                   dx, dy, r2, lane, fresh);
+                if (lane == 0) S.tinf[wib][k] = info;
+            }
+            if (nprep) __threadfence();                            // records readable by this warp's cp.async
+            __syncwarp();
+        } else if (lane == 0) {
+            sp[wib] = INT_MAX;
+        }
+        const bool edgy = nt && (xc0 + S.tl[wib][0] < xc0 + 8 || xc0 + S.tl[wib][nt - 1] >= xc1 - 8 ||
+                                 (last_rb && wib >= RB - 4));
+        (void)edgy;
+
+        // ---- (5) the sweep of this row, as in k_ext_sweep -----------------------------------------
+        int info_next = nt ? (0 < CAPW ? S.tinf[wib][0] : 0) : 0;
+        if (nt) ext_fetch(&W.rec, myrecs, info_next, lane);
+        for (int t = 0; t < nt; ++t) {
+            const int i = xc0 + S.tl[wib][t];
+            const double x0 = dx * i, y0 = dy * (j + joff);
+            int info;
+            if (t < CAPW) {
+                info = info_next;
+                cp_async_wait_all();
+            } else {
+                info = ext_phase_a<true>(&W.rec, X1e, X2e, st, j, i, Ny, Nx, joff, dx, dy, r2, lane, fresh);
+            }
+            info_next = (t + 1 < nt && t + 1 < CAPW) ? S.tinf[wib][t + 1] : 0;
+            const int next = (t + 1 < nt) ? xc0 + S.tl[wib][t + 1] : INT_MAX;
+            const int nslots = info & 255, npend = info >> 8;
+            const int nknown = nslots - npend;
+            __syncwarp();
+            // ---- wait: rows j-4..j-1 past column i+4, own row past column i-1 (same layer) ---------
+            if (lane < 9) {
+                const int xr = min(i + 4, Nx - 1) / XT, xl = max(i - 4, 0) / XT;
+                int jr = j, xq = -1, need = i + 4;
+                if (lane < 4) { jr = j - 1 - lane; xq = xr; }
+                else if (lane < 8) { jr = j - 1 - (lane - 4); xq = (xl != xr) ? xl : -1; }
+                else { xq = (xl != xt) ? xl : -1; need = i - 1; }
+                if (jr >= 1 && xq >= 0 && !(xq == xt && prev_ok && jr < row0)) {
+                    if (xq == xt && jr >= row0) {
+                        if (jr != j) while (sp[jr - row0] <= need) __nanosleep(20);
+                    } else {
+                        const int *g = progL + jr * nxt + xq;
+                        while (ld_relaxed_gpu(g) <= need) __nanosleep(100);
+                    }
+                }
+            }
+            __syncwarp();
+            SMEM_ORDER();
+            // ---- phase C: one lane per undecided cell ----------------------------------
+            int nfail = 0;
+            for (int q0 = 0; q0 < npend; q0 += 32) {
+                const int r = q0 + lane;
+                bool fail = false;
+                if (r < npend) {
+                    const int n = W.rec.pn[r];
+                    const int dj = n / 9 - 4, di = n % 9 - 4;
+                    const int jj = j + dj, ii = i + di;
+                    const int slot = ii & (RING - 1);
+                    const bool mine = (ii >= xc0 && ii < xc1);
+                    double v1 = 0.0, v2 = 0.0;
+                    bool got = false, smem_row = false;
+                    if (mine && jj >= row0) {
+                        smem_row = true;
+                        SweepWarp &R = S.w[jj - row0];
+                        volatile int *tag = &R.ring_tag[slot];
+                        volatile double *rv = R.ring_v[slot];
+                        if (*tag == ii) {
+                            v1 = rv[0]; v2 = rv[1];
+                            SMEM_ORDER();
+                            got = (*tag == ii);
+                        }
+                    } else if (mine && prev_ok && jj >= prow0) {
+                        smem_row = true;
+                        if (S.prev_tag[jj - prow0][slot] == ii) {
+                            v1 = S.prev_v[jj - prow0][slot][0]; v2 = S.prev_v[jj - prow0][slot][1];
+                            got = true;
+                        }
+                    }
+                    if (!got) {
+                        const size_t cc = (size_t)jj * Nx + ii;
+                        if (smem_row) {
+                            if (ld_cta_u8(st + cc) == fresh) {
+                                v1 = ld_cta_f64(X1e + cc); v2 = ld_cta_f64(X2e + cc);
+                                got = true;
+                            }
+                        } else if (__ldcg(st + cc) == fresh) {
+                            v1 = __ldcg(X1e + cc); v2 = __ldcg(X2e + cc);
+                            got = true;
+                        }
+                    }
+                    store_products(W.rec.prod[W.rec.pslot[r]], got ? W.rec.pw[r] : 0.0, got ? W.rec.px[r] : 0.0,
+                                   got ? W.rec.py[r] : 0.0, v1, v2);
+                    fail = !got;
+                }
+                nfail += __popc(__ballot_sync(0xffffffffu, fail));
+            }
+            const int count = nknown + npend - nfail;
+            __syncwarp();
+            // ---- ordered accumulation ----------------------------------------------------
+            double acc = 0.0;
+            {
+                const double *q = &W.rec.prod[0][la];
+                int k = 0;
+                for (; k + 8 <= nslots + 7 && k + 8 <= WIN; k += 8) {
+                    const double q0 = q[(k + 0) * NACC], q1 = q[(k + 1) * NACC], q2 = q[(k + 2) * NACC],
+                                 q3 = q[(k + 3) * NACC], q4 = q[(k + 4) * NACC], q5 = q[(k + 5) * NACC],
+                                 q6 = q[(k + 6) * NACC], q7 = q[(k + 7) * NACC];
+                    acc += q0; acc += q1; acc += q2; acc += q3; acc += q4; acc += q5; acc += q6; acc += q7;
+                }
+                for (; k < nslots; ++k) acc += q[k * NACC];
+            }
+            if (lane < NACC) W.sums[lane] = acc;
+            __syncwarp();
+            const volatile double *sm = W.sums;
+            const int h = (lane & 1) * 3;
+            const double b0 = sm[h], b1 = sm[h + 1], b2 = sm[h + 2];
+            const double A00 = sm[6], A01 = sm[7], A02 = sm[8], A11 = sm[9], A12 = sm[10], A22 = sm[11];
+            const double A10 = A01, A20 = A02, A21 = A12;
+            const double m00 = A11 * A22 - A12 * A21, m01 = A10 * A22 - A12 * A20, m02 = A10 * A21 - A11 * A20;
+            const double det = (A00 * m00 - A01 * m01 + A02 * m02);
+            const bool fitted = (count >= 3) && (fabs(det) > 1e-10);
+            const double inv_det = 1.0 / det;
+            const double cx = (b0 * m00 - A01 * (b1 * A22 - A12 * b2) + A02 * (b1 * A21 - A11 * b2)) * inv_det;
+            const double cy = (A00 * (b1 * A22 - A12 * b2) - b0 * m01 + A02 * (A10 * b2 - b1 * A20)) * inv_det;
+            const double cz = (A00 * (A11 * b2 - b1 * A21) - A01 * (A10 * b2 - b1 * A20) + b0 * m02) * inv_det;
+            const double val = cx + cy * x0 + cz * y0;
+            // ---- publish ---------------------------------------------------------------------
+            {
+                const size_t c = (size_t)j * Nx + i;
+                const int slot = i & (RING - 1);
+                if (fitted) {
+                    if (lane == 0) {
+                        if (W.ring_tag[slot] >= 0) __threadfence_block();
+                        *((volatile int *)&W.ring_tag[slot]) = -1;
+                    }
+                    SMEM_ORDER();
+                    if (lane < 2) *((volatile double *)&W.ring_v[slot][lane]) = val;
+                    SMEM_ORDER();
+                    if (lane == 0) *((volatile int *)&W.ring_tag[slot]) = i;
+                    SMEM_ORDER();
+                }
+                if (lane == 0) sp[wib] = next;
+                SMEM_ORDER();
+                if (t + 1 < nt && t + 1 < CAPW) ext_fetch(&W.rec, myrecs + t + 1, info_next, lane);
+                if (fitted) {
+                    if (lane == 0) X1e[c] = val;
+                    if (lane == 1) X2e[c] = val;
+                    __syncwarp();
+                    if (lane == 0) st[c] = (unsigned char)fresh;
+                }
+                // global marker: the next layer reads every row (fence at the row's end); this layer's
+                // other tiles read the rows/columns next to them
+                if (lane == 0) {
+                    const bool data = (last_rb && wib >= RB - 4) || i < xc0 + 8 || i >= xc1 - 8;
+                    if (data || next == INT_MAX) {
+                        __threadfence();
+                        st_release(progL + j * nxt + xt, next);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        if (wib >= RB - 4) {
+            if (lane < RING) {
+                S.prev_tag[wib - (RB - 4)][lane] = W.ring_tag[lane];
+                S.prev_v[wib - (RB - 4)][lane][0] = W.ring_v[lane][0];
+                S.prev_v[wib - (RB - 4)][lane][1] = W.ring_v[lane][1];
+            }
+            if (wib == RB - 4 && lane == 0) S.prev_row0 = row0 + RB - 4;
+        }
+        __syncthreads();
+      }
+    }
+}
+
+// Which variant sweeps this call?  The all-layers kernel keeps one CTA (SM) per (layer, macro-tile) for
+// the whole length of a chain, so it wins while there are fewer such tasks than SMs and loses when bodies
+// outnumber the SMs (then the per-layer launches pack the SMs better).  Decided on the device from the
+// layer-0 counts -- no host round trip; the kernels of the variant not chosen return at once.
+// Cost model (microseconds, measured at 4097^2 on B200): a chain advances one target row in ~3.4 us within
+// one layer; the all-layers kernel runs the L layers of a tile side by side and needs ~7.1 us per row of its
+// longest macro-tile, the per-layer launches L * (0.36 ms + 3.4 us per row of the longest 512-row band).
+// longest chain of target rows through vertically adjacent tiles of x-tile xt (a body crossing a tile
+// boundary chains the two tiles); also counts the non-empty tiles
+__device__ inline int ext_longest_chain(const int *__restrict__ cnt0, const int *__restrict__ rows, int ntile_rows,
+                                        int height, int nxt, int xt, int Ny, int *nonempty)
+{
+    int chain = 0, longest = 0;
+    for (int m = 0; m < ntile_rows; ++m) {
+        const int r = rows[m * nxt + xt], jb = m * height;               // jb: last row of the tile above
+        const bool linked = m > 0 && jb + 1 < Ny && cnt0[jb * nxt + xt] && cnt0[(jb + 1) * nxt + xt];
+        chain = r + (linked ? chain : 0);
+        *nonempty += r != 0;
+        longest = max(longest, chain);
+    }
+    return longest;
+}
+
+__global__ void k_ext_decide(const int *__restrict__ cnt0, const int *__restrict__ rows_macro, int nmrb,
+                             int macro, const int *__restrict__ rows_band, int nbands, int band, int nxt,
+                             int Ny, int L, int limit, int *__restrict__ mode)
+{
+    __shared__ int busy, longest_macro, longest_band;
+    if (threadIdx.x == 0) busy = longest_macro = longest_band = 0;
+    __syncthreads();
+    for (int xt = threadIdx.x; xt < nxt; xt += blockDim.x) {
+        int nb = 0, dummy = 0;
+        const int lm = ext_longest_chain(cnt0, rows_macro, nmrb, macro, nxt, xt, Ny, &nb);
+        const int lb = ext_longest_chain(cnt0, rows_band, nbands, band, nxt, xt, Ny, &dummy);
+        atomicAdd(&busy, nb);
+        atomicMax(&longest_macro, lm);
+        atomicMax(&longest_band, lb);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float fused = 7.1f * longest_macro, layered = L * (360.f + 3.4f * longest_band);
+        *mode = (busy * L <= limit && fused < layered) ? 1 : 0;
+    }
+}
+
+// layer-0 target counts per (row, x-tile), without touching the state bytes
+__global__ void k_ext_count0(const unsigned char *__restrict__ st, int *__restrict__ cnt0,
+                             int *__restrict__ rows_macro /* [macro-row][x-tile], zeroed */, int macro,
+                             int *__restrict__ rows_band /* [row band][x-tile], zeroed */, int band, int Ny,
+                             int Nx, int nxt, int XT)
+{
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int j = warp; j < Ny; j += nwarp) {
+        const unsigned char *r1 = st + (size_t)j * Nx;
+        const bool inner = (j >= 1 && j < Ny - 1);
+        const unsigned char *r0 = inner ? r1 - Nx : r1, *r2 = inner ? r1 + Nx : r1;
+        for (int xt = 0; xt < nxt; ++xt) {
+            int cnt = 0;
+            const int cend = min((xt + 1) * XT, Nx);
+            for (int base = xt * XT; base < cend; base += 32) {
+                int i = base + lane;
+                bool tgt = false;
+                if (inner && i >= 1 && i < Nx - 1 && i < cend && !(r1[i] & 1))
+                    tgt = ((r0[i - 1] | r0[i] | r0[i + 1] | r1[i - 1] | r1[i + 1] | r2[i - 1] | r2[i] |
+                            r2[i + 1]) & 1) != 0;
+                cnt += __popc(__ballot_sync(0xffffffffu, tgt));
+            }
+            if (lane == 0) {
+                cnt0[j * nxt + xt] = cnt;
+                if (cnt) {       // rows with targets per tile: the length of the dependency chain through it
+                    atomicAdd(&rows_macro[((j - 1) / macro) * nxt + xt], 1);
+                    atomicAdd(&rows_band[((j - 1) / band) * nxt + xt], 1);
+                }
+            }
+        }
+    }
+}
+
 inline int flat_blocks(long n) { long b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
 
 }  // namespace
@@ -691,6 +1091,11 @@ static ExtLayout ext_layout(int Ny, int Nx)
     size_t ncell = (size_t)Ny * (size_t)Nx;
     size_t nseg = (size_t)Ny * ext_nxt(Nx) + 2;
     L.cap = ext_cap((long)ncell);
+    {   // the all-layers kernel keeps CAPW records per row warp of every resident CTA
+        long nmrb = ((Ny - 2 + RB - 1) / RB + 31) / 32, tasks = nmrb * 8 * ext_nxt(Nx);
+        long fused = (tasks < 148 ? tasks : 148) * RB * CAPW;
+        if (L.cap < fused) L.cap = fused;
+    }
     size_t off = 0;
     L.st = off;    off += al256(ncell);
     L.segs = off;  off += al256((3 * nseg + 16) * sizeof(int));
@@ -743,6 +1148,69 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
     k_ext_seed<<<flat_blocks((long)ncell), 256, 0, s>>>(X1, X2, phi, X1e, X2e, st, (long)ncell);
     RMT_LAUNCH_CHECK();
 
+    // ---- all layers in one launch when the bodies are few enough (RMT_EXT_FUSED=0: never) ----
+    int *mode = nullptr;        // device flag: 1 = the all-layers kernel did the work, 0 = per-layer launches do
+    {
+        static int fused_on = -1, fused_blocks = 0;
+        if (fused_on < 0) {
+            const char *e = getenv("RMT_EXT_FUSED");
+            fused_on = (e && atoi(e) == 0) ? 0 : 1;
+        }
+        const int Lyr = max_layers;
+        if (fused_on && Lyr >= 1 && Lyr <= 8) {
+            if (!fused_blocks) {
+                int dev = 0, sms = 0, per_sm = 0;
+                RMT_CUDA(cudaGetDevice(&dev));
+                RMT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+                RMT_CUDA(cudaFuncSetAttribute(k_ext_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)sizeof(FusedSmem)));
+                RMT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_fused, RB * 32,
+                                                                       sizeof(FusedSmem)));
+                if (per_sm < 1) return RMT_EINVAL;
+                fused_blocks = sms * per_sm;
+            }
+            // x-tiles wide enough that a task never waits on a task more than ~3/4 of the resident CTAs ahead
+            int max_tiles = (fused_blocks * 3 / 4) / (2 * Lyr - 1);
+            if (max_tiles < 1) max_tiles = 1;
+            int XTf = (Nx > 1024) ? 512 : XT;             // both flanks of a body in one tile: fewer tasks
+            const int need_xt = ((Nx + max_tiles - 1) / max_tiles + 31) / 32 * 32;
+            if (need_xt > XTf) XTf = need_xt;
+            const int nxtf = (Nx + XTf - 1) / XTf, nsegf = Ny * nxtf;
+            const long prog_ints = (long)Lyr * nsegf;
+            const int MRBf = 64;                           // macro-rows of 64 * RB rows
+            const int nmrb = rmt_cdiv(rmt_cdiv(Ny - 2, RB), MRBf);
+            const int band = 32 * RB;                      // the per-layer path's macro-tile height
+            const int nmac = nmrb * nxtf, nbnd = rmt_cdiv(Ny - 2, band) * nxtf, nbusy = nmac + nbnd;
+            if (XTf <= LMAX && prog_ints + nsegf + nbusy + 8 <= (long)ncell) {
+                int *progF = trow;                         // [L][nsegf] ints, then chain lengths, then cnt0 (trow
+                int *busy = trow + prog_ints;              //  holds ncell ints; the per-layer path rewrites it
+                int *cnt0 = busy + nbusy;                  //  afterwards if it is the one that runs)
+                mode = tile_counter + 2;
+                RMT_CUDA(cudaMemsetAsync(progF, 0, (size_t)(prog_ints + nbusy) * sizeof(int), s));
+                RMT_CUDA(cudaMemsetAsync(tile_counter, 0, sizeof(int), s));
+                int rwb = rmt_cdiv((long)Ny * 32, 256);
+                if (rwb > 148 * 8) rwb = 148 * 8;
+                k_ext_count0<<<rwb, 256, 0, s>>>(st, cnt0, busy, MRBf * RB, busy + nmac, band, Ny, Nx, nxtf, XTf);
+                RMT_LAUNCH_CHECK();
+                const long ntasks = (long)nmrb * Lyr * nxtf;
+                int blocks = fused_blocks;
+                if ((long)blocks > ntasks) blocks = (int)ntasks;
+                if ((long)blocks * RB * CAPW <= (long)cap) {
+                    k_ext_decide<<<1, 64, 0, s>>>(cnt0, busy, nmrb, MRBf * RB, busy + nmac, nbnd / nxtf, band, nxtf, Ny, Lyr,
+                                                  fused_blocks * 9 / 10, mode);
+                    RMT_LAUNCH_CHECK();
+                    int Lv = Lyr, nxv = nxtf, xtv = XTf, mrbv = MRBf;
+                    void *args[] = {&X1e, &X2e, &st, &cnt0, &progF, &tile_counter, &recs, &mode, &Lv, &Ny, &Nx,
+                                    &joff, &nxv, &xtv, &mrbv, &dx, &dy, &r2};
+                    RMT_CUDA(cudaLaunchCooperativeKernel((void *)k_ext_fused, dim3(blocks), dim3(RB * 32), args,
+                                                         sizeof(FusedSmem), s));
+                } else {
+                    mode = nullptr;
+                }
+            }
+        }
+    }
+
     const size_t sweep_smem = sizeof(SweepSmem);
     static int sweep_blocks = 0;
     if (!sweep_blocks) {
@@ -759,21 +1227,21 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
     if (row_warps_blocks > 148 * 8) row_warps_blocks = 148 * 8;
 
     for (int layer = 0; layer < max_layers; ++layer) {
-        k_ext_flag<<<row_warps_blocks, 256, 0, s>>>(st, seg_cnt, Ny, Nx, nxt, XT);
+        k_ext_flag<<<row_warps_blocks, 256, 0, s>>>(st, seg_cnt, Ny, Nx, nxt, XT, mode);
         RMT_LAUNCH_CHECK();
-        k_ext_scan<<<1, 1024, 0, s>>>(seg_cnt, seg_off, Ny, nxt, tile_counter);
+        k_ext_scan<<<1, 1024, 0, s>>>(seg_cnt, seg_off, Ny, nxt, tile_counter, mode);
         RMT_LAUNCH_CHECK();
-        k_ext_fill<<<row_warps_blocks, 256, 0, s>>>(st, seg_off, tcol, trow, prog, Ny, Nx, nxt, XT);
+        k_ext_fill<<<row_warps_blocks, 256, 0, s>>>(st, seg_off, tcol, trow, prog, Ny, Nx, nxt, XT, mode);
         RMT_LAUNCH_CHECK();
         k_ext_prepare<<<148 * 12, 256, 0, s>>>(X1e, X2e, st, seg_off, nseg, tcol, trow, recs, tinfo, cap, Ny, Nx,
-                                               joff, dx, dy, r2);
+                                               joff, dx, dy, r2, mode);
         RMT_LAUNCH_CHECK();
         // all CTAs must be co-resident (warps wait on each other): cooperative launch
         int blocks = sweep_blocks;
         int need = rmt_cdiv(rmt_cdiv(Ny - 2, RB), MRB) * nxt;
         if (blocks > need) blocks = need;
         void *args[] = {&X1e, &X2e, &st, &seg_off, &tcol, &prog, &tile_counter, &recs, &tinfo, &cap,
-                        &Ny, &Nx, &joff, &nxt, &XT, &MRB, &sleep_ns, &dx, &dy, &r2};
+                        &Ny, &Nx, &joff, &nxt, &XT, &MRB, &sleep_ns, &dx, &dy, &r2, &mode};
         RMT_CUDA(cudaLaunchCooperativeKernel((void *)k_ext_sweep, dim3(blocks), dim3(RB * 32), args,
                                              sweep_smem, s));
     }
