@@ -212,6 +212,14 @@ int rmt_poisson_solve_fft(rmt_poisson_plan *plan, const double *rhs, const doubl
  * in == out is allowed.  Used by pyrmt_b200/slab.py between the all-to-all transposes. */
 int rmt_dct_lines(const double *in, double *out, const double *eig, int nrows, int N, double scale,
                   void *stream);
+/* Discrete Hartley transform H_k = sum_n x_n (cos + sin)(2 pi k n / m) along the rows (length m, a
+ * power of two in [16, 16384], row strides ldi / ldo doubles) of a real array:
+ *   out[r][k] = H(in[r])[k] * (mul ? mul[r*m + k] : scale).
+ * The separable 2-D Hartley transform diagonalises the periodic Poisson operator of
+ * functions.py:1177-1233 (its symbol is even in each wavenumber), so it stands in for
+ * numpy.fft.fft2/ifft2 (:1227,:1230) on real fields.  in == out is allowed. */
+int rmt_dht_lines(const double *in, double *out, const double *mul, int nrows, int m, long ldi, long ldo,
+                  double scale, void *stream);
 /* out (C, R) = in (R, C)^T */
 int rmt_transpose(const double *in, double *out, int R, int C, void *stream);
 /* dst[r*dst_ld + c] = src[r*src_ld + c], rows x cols block (all-to-all pack / unpack). */

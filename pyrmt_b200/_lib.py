@@ -58,6 +58,7 @@ _SIG = {
     "rmt_poisson_solve_dct": [vp, vp, vp, vp, vp, vp],
     "rmt_poisson_solve_fft": [vp, vp, vp, vp, vp, vp, vp],
     "rmt_dct_lines": [vp, vp, vp, i32, i32, dbl, vp],
+    "rmt_dht_lines": [vp, vp, vp, i32, i32, i64, i64, dbl, vp],
     "rmt_transpose": [vp, vp, i32, i32, vp],
     "rmt_copy2d": [vp, vp, i32, i32, i64, i64, vp],
 }

@@ -25,6 +25,14 @@
 //            are the same transform; functions.py:1117 idctn = dctn / (2M))
 // so the 2-D solve is three passes over HBM.  4096^2 is fp64-pipe and
 // shared-memory bound at about the same level as HBM.
+// Periodic solve (fast path, reduced grid lengths m a power of two): the symbol of
+// functions.py:1177-1202 is even in each wavenumber separately, so fft2 -> /eig -> ifft2 of a
+// REAL field equals  DHT2 -> /eig -> DHT2 / (mx my)  with the separable discrete Hartley
+// transform  H_k = sum_n x_n (cos + sin)(2 pi k n / m) = Re X_k - Im X_k  (cas(k.) and
+// cas(-k.) span the same eigenspace as exp(+-ik.)).  A Hartley line is real -> real, so the
+// 2-D solve has the same row / transpose / column structure as the DCT one and never stores
+// a complex plane: the m-point real line is packed into m/2 complex points, transformed with
+// the same radix-16 kernel and unpacked to (H_k, H_{m-k}).
 // Other sizes (N <= RMT_DENSE_MAX) use dense cosine/sine matrices and a small
 // fp64 GEMM kernel -- O(N^3) but exact to rounding and only used on the small
 // awkward grids of the reference's benchmarks (N = 128 -> 2*127 and 127).
@@ -291,6 +299,97 @@ k_dct_lines(const double *in, double *out, const double *__restrict__ eig, int n
     }
 }
 
+
+// ----------------------------------------------------- DHT along rows, persistent
+// Lines are the rows (length m = 2M, stride ldi) of a real array; out row stride ldo.
+//   out[k] = DHT(in)[k] * (mul ? mul[r * m + k] : scale)
+// The packing z[n] = x[2n] + i x[2n+1] is the load itself (straight into the planes), so a
+// group needs no staging copy: more groups per CTA hide each other's load latency instead.
+// in == out is allowed (a group holds its whole line on chip before it writes).
+__global__ void __launch_bounds__(512, 1)
+k_dht_lines(const double *in, double *out, const double *__restrict__ mul, int nrows, int m, long ldi,
+            long ldo, const double2 *__restrict__ tw, const double2 *__restrict__ tw2, double scale, int tpg)
+{
+    extern __shared__ double sm[];
+    const int M = m >> 1, lg = 31 - __clz(M);
+    const int G = blockDim.x / tpg, gi = threadIdx.x / tpg;
+    const Grp g{(int)threadIdx.x % tpg, tpg, 1 + gi};
+    const int plane = padi(M) + 1;
+    double *re = sm + (size_t)gi * 2 * plane, *im = re + plane;
+    const int ngroups = gridDim.x * G;
+    for (int r = blockIdx.x * G + gi; r < nrows; r += ngroups) {
+        const double *x = in + (size_t)r * ldi;
+        g.sync();                                   // previous line's unpack has finished with the planes
+        for (int k = g.tid; k < m; k += g.nthr) {
+            const double v = __ldg(x + k);
+            ((k & 1) ? im : re)[padi(k >> 1)] = v;
+        }
+        g.sync();
+        fft_dif(re, im, M, tw, g);
+        double *o = out + (size_t)r * ldo;
+        const double *f = mul ? mul + (size_t)r * m : nullptr;
+        for (int k = g.tid; k <= M; k += g.nthr) {
+            if (k == 0 || k == M) {
+                const double v = (k == 0) ? re[0] + im[0] : re[0] - im[0];     // X_0, X_M are real
+                o[k] = v * (f ? __ldg(f + k) : scale);
+                continue;
+            }
+            const int pa = padi(rev_pos(k, lg)), pb = padi(rev_pos(M - k, lg));
+            const double ar = re[pa], ai = im[pa], br = re[pb], bi = im[pb];
+            const double2 w = __ldg(tw2 + k);                                   // (cos, sin)(2 pi k / m)
+            const double er = 0.5 * (ar + br), ei = 0.5 * (ai - bi);            // even-sample spectrum
+            const double pr = 0.5 * (ai + bi), pi_ = -0.5 * (ar - br);          // odd-sample spectrum
+            const double xr = er + w.x * pr + w.y * pi_, xi = ei + w.x * pi_ - w.y * pr;
+            o[k] = (xr - xi) * (f ? __ldg(f + k) : scale);
+            o[m - k] = (xr + xi) * (f ? __ldg(f + m - k) : scale);
+        }
+    }
+}
+
+// out (C, R; row stride ldo) = in (R, C; row stride ldi)^T
+__global__ void __launch_bounds__(256)
+k_transpose_ld(const double *__restrict__ in, double *__restrict__ out, int R, int C, long ldi, long ldo)
+{
+    __shared__ double t[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int r = r0 + ty + 8 * k, c = c0 + tx;
+        if (r < R && c < C) t[ty + 8 * k][tx] = __ldg(in + (size_t)r * ldi + c);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int c = c0 + ty + 8 * k, r = r0 + tx;
+        if (r < R && c < C) out[(size_t)c * ldo + r] = t[tx][ty + 8 * k];
+    }
+}
+
+// transposed multiplier table of the periodic solve: fT[i][j] = null[j][i] ? 0 : scale / eig[j][i]
+__global__ void __launch_bounds__(256)
+k_inv_symbol_T(const double *__restrict__ eig, const unsigned char *__restrict__ null_mask,
+               double *__restrict__ fT, int R, int C, double scale)
+{
+    __shared__ double t[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int r = r0 + ty + 8 * k, c = c0 + tx;
+        if (r < R && c < C) {
+            const size_t q = (size_t)r * C + c;
+            t[ty + 8 * k][tx] = null_mask[q] ? 0.0 : scale / eig[q];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int c = c0 + ty + 8 * k, r = r0 + tx;
+        if (r < R && c < C) fT[(size_t)c * R + r] = t[tx][ty + 8 * k];
+    }
+}
+
 // out (C, R) = in (R, C)^T, 32x32 tiles through padded shared memory (both sides coalesced)
 __global__ void __launch_bounds__(256)
 k_transpose(const double *__restrict__ in, double *__restrict__ out, int R, int C)
@@ -514,6 +613,45 @@ LineLaunch line_launch(int M, int nrows)
     return L;
 }
 
+// k_dht_lines for line length m = 2M: no staging copy, so more groups fit
+LineLaunch dht_launch(int M, int nrows)
+{
+    LineLaunch L;
+    L.tpg = fft_threads(M);
+    const int per_group = 2 * (padi(M) + 1) * (int)sizeof(double);
+    int by_smem = kMaxDyn / per_group, by_thr = 512 / L.tpg;
+    L.G = by_smem < by_thr ? by_smem : by_thr;
+    if (L.G < 1) L.G = 1;
+    if (L.G > 8) L.G = 8;
+    L.threads = L.G * L.tpg;
+    L.smem = L.G * per_group;
+    int want = (nrows + L.G - 1) / L.G;
+    L.ctas = want < 148 ? want : 148;
+    return L;
+}
+
+// twiddle tables per complex FFT length (per device), shared by the line entry points
+struct LineTab { int M, dev; double2 *tw, *tw2; };
+int line_tables(int M, const LineTab **out)
+{
+    static std::vector<LineTab> cache;
+    int dev = 0;
+    RMT_CUDA(cudaGetDevice(&dev));
+    for (const LineTab &t : cache)
+        if (t.M == M && t.dev == dev) { *out = &t; return RMT_OK; }
+    LineTab t{M, dev, nullptr, nullptr};
+    int e = make_twiddles(&t.tw, M);
+    if (!e) e = make_half_twiddles(&t.tw2, M);
+    if (!e) e = (int)cudaFuncSetAttribute(k_dct_lines<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+    if (!e) e = (int)cudaFuncSetAttribute(k_dct_lines<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+    if (!e) e = (int)cudaFuncSetAttribute(k_dht_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+    if (e) return e;
+    cache.reserve(64);
+    cache.push_back(t);
+    *out = &cache.back();
+    return RMT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -532,14 +670,20 @@ int rmt_poisson_plan_create(int Ny, int Nx, int kind, rmt_poisson_plan **out)
                   P->Lx >= 8 && P->Ly >= 8;
         P->nx = Nx; P->ny = Ny;
     } else {
-        P->fast = false;   // periodic shared-memory path: see rmt_poisson_solve_fft
         P->nx = Nx - 1; P->ny = Ny - 1;
+        P->Lx = P->nx / 2; P->Ly = P->ny / 2;         // a real line of m points is m/2 packed complex points
+        P->fast = is_pow2(P->nx) && is_pow2(P->ny) && P->Lx <= kMaxSmemL && P->Ly <= kMaxSmemL &&
+                  P->Lx >= 8 && P->Ly >= 8;
     }
     if (!P->fast && (P->nx > RMT_DENSE_MAX || P->ny > RMT_DENSE_MAX)) {
         delete P;
         return -2;
     }
-    if (P->fast) {
+    if (P->fast && kind == 1) {
+        // Hartley path: transposed work array + transposed multiplier table
+        for (int k = 0; k < 2 && !e; ++k)
+            e = (int)cudaMalloc((void **)&P->w[k], (size_t)P->nx * P->ny * sizeof(double));
+    } else if (P->fast) {
         e = make_twiddles(&P->tw_x, P->Lx);
         if (!e) e = make_twiddles(&P->tw_y, P->Ly);
         if (!e) e = make_half_twiddles(&P->tw2_x, P->Lx);
@@ -592,23 +736,8 @@ int rmt_dct_lines(const double *in, double *out, const double *eig, int nrows, i
     if (!in || !out || nrows < 1 || N < 9) return RMT_EINVAL;
     const int M = N - 1;
     if (!is_pow2(M) || M > kMaxSmemL) return -2;
-    struct Tab { int M, dev; double2 *tw, *tw2; };
-    static std::vector<Tab> cache;
-    int dev = 0;
-    RMT_CUDA(cudaGetDevice(&dev));
-    const Tab *T = nullptr;
-    for (const Tab &t : cache)
-        if (t.M == M && t.dev == dev) T = &t;
-    if (!T) {
-        Tab t{M, dev, nullptr, nullptr};
-        int e = make_twiddles(&t.tw, M);
-        if (!e) e = make_half_twiddles(&t.tw2, M);
-        if (!e) e = (int)cudaFuncSetAttribute(k_dct_lines<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
-        if (!e) e = (int)cudaFuncSetAttribute(k_dct_lines<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
-        if (e) return e;
-        cache.push_back(t);
-        T = &cache.back();
-    }
+    const LineTab *T = nullptr;
+    if (int e = line_tables(M, &T)) return e;
     const LineLaunch L = line_launch(M, nrows);
     cudaStream_t s = (cudaStream_t)stream;
     if (eig)
@@ -616,6 +745,23 @@ int rmt_dct_lines(const double *in, double *out, const double *eig, int nrows, i
     else
         k_dct_lines<0><<<L.ctas, L.threads, L.smem, s>>>(in, out, nullptr, nrows, N, T->tw, T->tw2, scale, L.tpg,
                                                         nullptr);
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
+
+// Discrete Hartley transform along the rows (length m, a power of two in [16, 16384]) of a real array:
+//   out[r][k] = DHT(in[r])[k] * (mul ? mul[r*m + k] : scale);  row strides ldi / ldo doubles.
+int rmt_dht_lines(const double *in, double *out, const double *mul, int nrows, int m, long ldi, long ldo,
+                  double scale, void *stream)
+{
+    if (!in || !out || nrows < 1 || m < 16 || ldi < m || ldo < m) return RMT_EINVAL;
+    const int M = m / 2;
+    if (!is_pow2(m) || M > kMaxSmemL) return -2;
+    const LineTab *T = nullptr;
+    if (int e = line_tables(M, &T)) return e;
+    const LineLaunch L = dht_launch(M, nrows);
+    k_dht_lines<<<L.ctas, L.threads, L.smem, (cudaStream_t)stream>>>(in, out, mul, nrows, m, ldi, ldo, T->tw,
+                                                                       T->tw2, scale, L.tpg);
     RMT_LAUNCH_CHECK();
     return RMT_OK;
 }
@@ -706,6 +852,36 @@ int rmt_poisson_solve_fft(rmt_poisson_plan *P, const double *rhs, const double *
     const double scale = 1.0 / ((double)mx * (double)my);
     // The mean removal before the transform (functions.py:1226) only changes the
     // DC mode, which the null mask zeroes (eig[0,0] = 0 exactly) -- skipped.
+    if (P->fast) {
+        // rows DHT: rhs[:-1,:-1] -> sol[:-1,:-1] | transpose -> T2 (mx, my) | columns: DHT x fT, DHT |
+        // transpose back | rows DHT in place | overlap row / column
+        double *T2 = P->w[0], *fT = P->w[1];
+        dim3 tg_f(rmt_cdiv(mx, 32), rmt_cdiv(my, 32)), tg_b(rmt_cdiv(my, 32), rmt_cdiv(mx, 32));
+        if (P->eig_src != eig) {
+            k_inv_symbol_T<<<tg_f, 256, 0, s>>>(eig, null_mask, fT, my, mx, scale);
+            RMT_LAUNCH_CHECK();
+            P->eig_src = eig;
+        }
+        int e;
+        if ((e = rmt_dht_lines(rhs, sol, nullptr, my, mx, Nx, Nx, 1.0, stream))) return e;
+        k_transpose_ld<<<tg_f, 256, 0, s>>>(sol, T2, my, mx, Nx, my);
+        RMT_LAUNCH_CHECK();
+        if ((e = rmt_dht_lines(T2, T2, fT, mx, my, my, my, 1.0, stream))) return e;
+        if ((e = rmt_dht_lines(T2, T2, nullptr, mx, my, my, my, 1.0, stream))) return e;
+        k_transpose_ld<<<tg_b, 256, 0, s>>>(T2, sol, mx, my, my, Nx);
+        RMT_LAUNCH_CHECK();
+        if ((e = rmt_dht_lines(sol, sol, nullptr, my, mx, Nx, Nx, 1.0, stream))) return e;
+        int nt = Ny > Nx ? Ny : Nx;
+        k_tile_overlap<<<rmt_cdiv(nt, 256), 256, 0, s>>>(sol, Ny, Nx);
+        RMT_LAUNCH_CHECK();
+        double *stats = P->red + rmt_reduce_workspace_doubles();
+        if ((e = rmt_field_stats(sol, ncell, P->red, stats, stream))) return e;
+        if (sum_out) {
+            RMT_CUDA(cudaMemcpyAsync(sum_out, stats, sizeof(double), cudaMemcpyDeviceToDevice, s));
+            return RMT_OK;
+        }
+        return rmt_subtract_mean(sol, stats, ncell, stream);
+    }
     double *Zr = P->w[0], *Zi = P->w[1], *Yr = P->w[2], *Yi = P->w[3];
     int e;
     // rows:  Z = r (Cx - i Sx)        (the DFT matrices are symmetric)

@@ -126,6 +126,12 @@ class CudaOps:
                    "rmt_dct_lines")
         return x
 
+    def dht_lines(self, x, out, m, mul=None, scale=1.0):
+        """out[r, :m] = DHT(x[r, :m]) * (mul[r] or scale) for 2-D views with unit column stride."""
+        _lib.check(ctx().lib.rmt_dht_lines(x.data_ptr(), out.data_ptr(), ptr(mul), x.shape[0], m, x.stride(0),
+                                           out.stride(0), float(scale), stream()), "rmt_dht_lines")
+        return out
+
     def transpose(self, x):
         R, C = x.shape
         out = torch.empty((C, R), dtype=x.dtype, device=x.device)

@@ -387,6 +387,40 @@ def test_dct_nonsquare_vs_oracle(P, O):
     assert rel_linf(P._solve_poisson_dct(rhs, eig), O._solve_poisson_dct(rhs, eig)) < 1e-11
 
 
+@pytest.mark.parametrize("Ny,Nx", [(129, 129), (1025, 1025), (65, 513), (2049, 33)])
+def test_periodic_fast_solve_vs_oracle(P, O, Ny, Nx):
+    """Power-of-two reduced grids: separable Hartley transforms in shared memory against numpy's
+    fft2/ifft2 through the oracle (functions.py:1216-1233)."""
+    rng = np.random.default_rng(Ny + Nx)
+    X, Y, dx, dy = O.create_grid(Nx, Ny, 2.0, 0.5)
+    eig = O._precompute_poisson_eigenvalues_periodic(Nx, Ny, dx, dy)
+    rhs = np.sin(2 * np.pi * X / 2.0) * np.cos(4 * np.pi * Y / 0.5) * 40 + rng.standard_normal((Ny, Nx))
+    from pyrmt_b200._runtime import ctx
+    assert ctx().lib.rmt_poisson_plan_is_fast(ctx().plan(Ny, Nx, 1)) == 1
+    assert rel_linf(P._solve_poisson_fft(rhs, eig), O._solve_poisson_fft(rhs, eig)) < 1e-11
+
+
+def test_dht_lines_building_block(P):
+    """rmt_dht_lines against numpy: H = Re(fft) - Im(fft)."""
+    import torch
+    from pyrmt_b200.slab import CudaOps
+    ops = CudaOps()
+    rng = np.random.default_rng(4)
+    for m in (16, 64, 4096, 16384):
+        x = rng.standard_normal((5, m + 3))
+        F = np.fft.fft(x[:, :m], axis=1)
+        ref = F.real - F.imag
+        xd = torch.from_numpy(x.copy()).cuda()
+        out = torch.zeros((5, m + 1), dtype=torch.float64, device="cuda")
+        ops.dht_lines(xd, out, m, scale=0.5)
+        assert rel_linf(out[:, :m].cpu().numpy(), 0.5 * ref) < 1e-13, m
+        assert float(out[:, m].abs().max()) == 0.0
+        mul = rng.random((5, m))
+        ops.dht_lines(xd, xd, m, mul=torch.from_numpy(mul).cuda())          # in place, strided rows
+        assert rel_linf(xd[:, :m].cpu().numpy(), mul * ref) < 1e-13, m
+        assert same(xd[:, m:].cpu().numpy(), x[:, m:])
+
+
 # ----------------------------------------------------------------- full steps
 def _fsi_prm(P, g, scheme, tensors):
     import torch
