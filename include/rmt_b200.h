@@ -164,7 +164,11 @@ int rmt_pressure_gradient_periodic(const double *p, double *gx, double *gy, int 
 /* Fused projection front end (:1292-1295,:1331 / :1286-1290):
  *   rhs = rho * div / dt      (Neumann: rho elementwise; rho==NULL -> rho_scalar)
  *   rhs = rho_bar * div / dt  (periodic: rho_bar = rho_sum[0]/(Ny*Nx))
- * div is Rhie-Chow when p_prev != NULL (Neumann only), else plain / periodic. */
+ * div is Rhie-Chow when p_prev != NULL (Neumann only), else plain / periodic.
+ * periodic: 0 Neumann; 1 periodic in x and y on the reduced (Ny-1, Nx-1) grid; 2 row slab of a
+ * periodic grid: periodic in x, the y neighbours are the stored rows above / below (the caller has
+ * exchanged the wrap rows; rows 0 and Ny-1 of the slab are halo rows whose outputs are meaningless).
+ * The same values apply to rmt_projection_correct. */
 int rmt_projection_rhs(const double *a, const double *b, const double *p_prev, const double *rho,
                        double rho_scalar, const double *rho_sum, double *rhs, int Ny, int Nx,
                        double dx, double dy, double dt, int periodic, void *stream);

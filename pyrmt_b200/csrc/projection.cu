@@ -65,7 +65,9 @@ __device__ __forceinline__ double div_periodic(const GField &A, const GField &B,
     return (A(j, ip) - A(j, im)) * i2dx + (B(jp, i) - B(jm, i)) * i2dy;
 }
 
-// mode 0 plain, 1 Rhie-Chow, 2 periodic.  scale: 0 none (API divergence),
+// mode 0 plain, 1 Rhie-Chow, 2 periodic, 3 periodic in x with the y neighbours taken from the rows
+// above / below as stored (a row slab whose wrap rows were exchanged; rows 0 and Ny-1 are halo rows).
+// scale: 0 none (API divergence),
 // 1 rho[c]*div/dt, 2 rho_scalar*div/dt, 3 (rho_sum/n)*div/dt.
 __global__ void __launch_bounds__(256)
 k_divergence(const double *__restrict__ a, const double *__restrict__ b,
@@ -82,6 +84,12 @@ k_divergence(const double *__restrict__ a, const double *__restrict__ b,
     if (mode == 2) {
         int jr = (j == Ny - 1) ? 0 : j, ir = (i == Nx - 1) ? 0 : i;   // _tile_overlap :1205-1213
         d = div_periodic(A, B, jr, ir, Ny - 1, Nx - 1, 0.5 / dx, 0.5 / dy);
+    } else if (mode == 3) {
+        if (j >= 1 && j < Ny - 1) {
+            const int mx = Nx - 1, ir = (i == mx) ? 0 : i;
+            const int ip = (ir + 1 == mx) ? 0 : ir + 1, im = (ir == 0) ? mx - 1 : ir - 1;
+            d = (A(j, ip) - A(j, im)) * (0.5 / dx) + (B(j + 1, ir) - B(j - 1, ir)) * (0.5 / dy);
+        }
     } else if (i >= 1 && i < Nx - 1 && j >= 1 && j < Ny - 1) {
         if (mode == 1) {
             const GField P{p_prev, Nx};
@@ -128,6 +136,18 @@ __device__ __forceinline__ void pgrad_periodic(const F &P, int j, int i, int Ny,
     gy = (P(jp, ir) - P(jm, ir)) * i2dy;
 }
 
+// periodic in x, stored rows in y (slab with exchanged wrap rows; rows 0 and Ny-1 are halo rows)
+template <class F>
+__device__ __forceinline__ void pgrad_slab(const F &P, int j, int i, int Ny, int Nx, double i2dx,
+                                           double i2dy, double &gx, double &gy)
+{
+    const int mx = Nx - 1, ir = (i == mx) ? 0 : i;
+    const int ip = (ir + 1 == mx) ? 0 : ir + 1, im = (ir == 0) ? mx - 1 : ir - 1;
+    const int jp = min(j + 1, Ny - 1), jm = max(j - 1, 0);
+    gx = (P(j, ip) - P(j, im)) * i2dx;
+    gy = (P(jp, ir) - P(jm, ir)) * i2dy;
+}
+
 __global__ void __launch_bounds__(256)
 k_pressure_gradient(const double *__restrict__ p, double *__restrict__ gx, double *__restrict__ gy,
                     int Ny, int Nx, double dx, double dy, int periodic)
@@ -158,7 +178,8 @@ k_projection_correct(const double *__restrict__ sol, const double *__restrict__ 
     const size_t c = (size_t)j * Nx + i;
     const Shifted PC{sol, Nx, sol_sum ? sol_sum[0] / ((double)Ny * (double)Nx) : 0.0};
     double gx, gy;
-    if (periodic) pgrad_periodic(PC, j, i, Ny, Nx, 0.5 / dx, 0.5 / dy, gx, gy);
+    if (periodic == 2) pgrad_slab(PC, j, i, Ny, Nx, 0.5 / dx, 0.5 / dy, gx, gy);
+    else if (periodic) pgrad_periodic(PC, j, i, Ny, Nx, 0.5 / dx, 0.5 / dy, gx, gy);
     else pgrad_neumann(PC, j, i, Ny, Nx, 0.5 / dx, 0.5 / dy, gx, gy);
     const double r = rho ? rho[c] : rho_scalar;
     const double dtr = dt / r;
@@ -240,7 +261,8 @@ int rmt_projection_rhs(const double *a, const double *b, const double *p_prev, c
     if (!a || !b || !rhs || Ny < 4 || Nx < 4) return RMT_EINVAL;
     if (periodic) {
         if (!rho_sum) return RMT_EINVAL;
-        return launch_div(a, b, nullptr, nullptr, 0.0, rho_sum, rhs, Ny, Nx, dx, dy, dt, 2, 3, stream);
+        return launch_div(a, b, nullptr, nullptr, 0.0, rho_sum, rhs, Ny, Nx, dx, dy, dt, periodic == 2 ? 3 : 2, 3,
+                          stream);
     }
     if (p_prev && !rho_sum) return RMT_EINVAL;
     return launch_div(a, b, p_prev, rho, rho_scalar, rho_sum, rhs, Ny, Nx, dx, dy, dt, p_prev ? 1 : 0,

@@ -81,6 +81,25 @@ class LidBC:
         return BCTable(dst, np.full(dst.size, -1, np.int64), np.zeros(dst.size), cb.astype(np.float64), (Ny, Nx))
 
 
+class PeriodicBC:
+    """tests/test_poisson.py:60-64 (`_periodic_bc`) as a callable that also writes its gather table down
+    directly (bc.classify probes with full host arrays: too much at 16385^2)."""
+
+    def __call__(self, u, v):
+        from .bc import periodic_bc
+        return periodic_bc(u, v)
+
+    def rmt_table(self, Ny, Nx):
+        from .bc import BCTable, _FIELD_BIT
+        j = np.arange(Ny - 1)
+        i = np.arange(Nx - 1)
+        dst = np.concatenate([j * Nx + (Nx - 1), (Ny - 1) * Nx + i, [(Ny - 1) * Nx + Nx - 1]]).astype(np.int64)
+        src = np.concatenate([j * Nx, i, [0]]).astype(np.int64)
+        dst = np.concatenate([dst, dst | _FIELD_BIT])
+        src = np.concatenate([src, src | _FIELD_BIT])
+        return BCTable(dst, src, np.ones(dst.size), np.zeros(dst.size), (Ny, Nx))
+
+
 def disc_lattice(k_side, L, R_frac, seed=20240607):
     """K = k_side^2 discs on a jittered lattice."""
     rng = np.random.default_rng(seed)

@@ -42,17 +42,32 @@ def split(n, parts):
 
 
 class SlabLayout:
-    def __init__(self, Ny, Nx, world, rank, halo=4):
+    """periodic=True: the rows of the REDUCED (Ny-1, Nx-1) grid of functions.py:1216-1233 are split
+    evenly (`red_rows`), the overlap row Ny-1 rides with the last rank, and `cols` splits the
+    reduced grid's columns (the lines of the distributed transform)."""
+
+    def __init__(self, Ny, Nx, world, rank, halo=4, periodic=False):
         self.Ny, self.Nx, self.world, self.rank, self.H = Ny, Nx, world, rank, halo
-        self.rows = split(Ny, world)
-        self.cols = split(Nx, world)
+        self.periodic = periodic
+        if periodic:
+            self.red_rows = split(Ny - 1, world)
+            self.rows = self.red_rows[:-1] + [(self.red_rows[-1][0], Ny)]
+            self.cols = split(Nx - 1, world)
+        else:
+            self.rows = split(Ny, world)
+            self.cols = split(Nx, world)
         self.r0, self.r1 = self.rows[rank]
         self.c0, self.c1 = self.cols[rank]
         if min(e - s for s, e in self.rows) < halo:
             raise ValueError("slabs of %d rows are thinner than the halo (%d)" % (Ny // world, halo))
-        self.e0, self.e1 = max(self.r0 - halo, 0), min(self.r1 + halo, Ny)
+        self.e0, self.e1 = self.stored(rank)
         self.nl = self.e1 - self.e0                 # rows stored
         self.o0, self.o1 = self.r0 - self.e0, self.r1 - self.e0   # owned rows inside the slab
+
+    def stored(self, rank):
+        """Rows [e0, e1) that `rank` stores (its own plus the halo, clipped to the grid)."""
+        s, e = self.rows[rank]
+        return max(s - self.H, 0), min(e + self.H, self.Ny)
 
     def take(self, full):
         """Extended slab of a full (Ny, Nx) host/device array."""
@@ -87,6 +102,32 @@ class Comm:
             if lay.rank > 0:                                  # lower neighbour
                 ops.append(dist.P2POp(dist.isend, f[lay.o0:lay.o0 + H], self.rank - 1, self.group))
                 ops.append(dist.P2POp(dist.irecv, f[lay.o0 - H:lay.o0], self.rank - 1, self.group))
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+
+    def ring_exchange(self, items):
+        """Periodic neighbour exchange.  items: list of (send_to_next, send_to_prev, recv_from_prev,
+        recv_from_next) row blocks (any may be None).  next/prev wrap around; with one rank the blocks
+        are copied locally.  Sends to next are posted before sends to prev and receives from prev before
+        receives from next, so the two messages between the same pair (world == 2) match in order."""
+        if self.world == 1:
+            for to_next, to_prev, from_prev, from_next in items:
+                if from_prev is not None:
+                    from_prev.copy_(to_next)
+                if from_next is not None:
+                    from_next.copy_(to_prev)
+            return
+        nxt, prv = (self.rank + 1) % self.world, (self.rank - 1) % self.world
+        ops = []
+        for to_next, to_prev, from_prev, from_next in items:
+            if to_next is not None:
+                ops.append(dist.P2POp(dist.isend, to_next, nxt, self.group))
+            if to_prev is not None:
+                ops.append(dist.P2POp(dist.isend, to_prev, prv, self.group))
+            if from_prev is not None:
+                ops.append(dist.P2POp(dist.irecv, from_prev, prv, self.group))
+            if from_next is not None:
+                ops.append(dist.P2POp(dist.irecv, from_next, nxt, self.group))
         for r in dist.batch_isend_irecv(ops):
             r.wait()
 
@@ -194,11 +235,145 @@ class DistPoissonDCT:
         return sol, total
 
 
+class DistPoissonFFT:
+    """_solve_poisson_fft (functions.py:1216-1233) over row slabs of the reduced (Ny-1, Nx-1) grid.
+
+    The symbol is even in each wavenumber, so fft2 -> /eig -> ifft2 of a real field equals the separable
+    Hartley transform pair (csrc/fft.cu) -- real lines only, same exchange pattern as the DCT solve:
+        rows DHT (local) -> transpose -> all-to-all -> columns: DHT x 1/(mx my eig) (0 on null modes),
+        DHT (local) -> all-to-all back -> transpose -> rows DHT (local); x overlap column; sum by all-reduce.
+    `eig`: the (eig, null_mask) pair of _precompute_poisson_eigenvalues_periodic, or None with
+    `spacing=(dx, dy)` to build only this rank's columns (the full table is 2 GB at 16385^2)."""
+
+    def __init__(self, lay, eig=None, spacing=None, comm=None, ops=None, device=None):
+        if not lay.periodic:
+            raise ValueError("DistPoissonFFT needs SlabLayout(..., periodic=True)")
+        self.lay, self.comm, self.ops = lay, comm or Comm(), ops or CudaOps()
+        my, mx = lay.Ny - 1, lay.Nx - 1
+        c0, c1 = lay.c0, lay.c1
+        if eig is not None:
+            e, null = eig
+            e, null = np.asarray(e, dtype=np.float64)[:, c0:c1], np.asarray(null, dtype=bool)[:, c0:c1]
+            if e.shape[0] != my or np.asarray(eig[0]).shape != (my, mx):
+                raise ValueError("periodic eigenvalues do not match the reduced grid %s" % ((my, mx),))
+        else:
+            dx, dy = spacing                                           # functions.py:1177-1202, my columns only
+            lam_x = -(np.sin(2.0 * np.pi * np.arange(mx) / mx) / dx) ** 2
+            lam_y = -(np.sin(2.0 * np.pi * np.arange(my) / my) / dy) ** 2
+            e = lam_x[np.newaxis, c0:c1] + lam_y[:, np.newaxis]
+            null = np.abs(e) < 1e-12
+            e = np.where(null, 1.0, e)
+        f = np.where(null, 0.0, (1.0 / (float(mx) * float(my))) / e)
+        fT = np.ascontiguousarray(f.T)                                 # (nc_me, my): my columns as lines
+        self.fT = torch.from_numpy(fT).to(device) if device is not None else torch.from_numpy(fT)
+        self.nr = [e_ - s_ for s_, e_ in lay.red_rows]
+        self.nc = [e_ - s_ for s_, e_ in lay.cols]
+
+    def solve(self, rhs_rows, sol_rows):
+        """rhs_rows / sol_rows: this rank's reduced rows, (nr_me, Nx) views with unit column stride.
+        Fills sol_rows[:, :Nx] (overlap column included); returns the sum of the tile-overlapped global
+        solution (functions.py:1231-1232 takes the mean over the full (Ny, Nx) array) as a 1-element tensor."""
+        lay, ops, comm = self.lay, self.ops, self.comm
+        me, P = lay.rank, lay.world
+        my, mx = lay.Ny - 1, lay.Nx - 1
+        nr_me, nc_me = self.nr[me], self.nc[me]
+        kw = dict(dtype=rhs_rows.dtype, device=rhs_rows.device)
+        A = ops.dht_lines(rhs_rows, torch.empty((nr_me, mx), **kw), mx)
+        At = ops.transpose(A)                                          # (mx, nr_me)
+        send_counts = [self.nc[q] * nr_me for q in range(P)]
+        recv_counts = [nc_me * self.nr[q] for q in range(P)]
+        rbuf = torch.empty(nc_me * my, **kw)
+        comm.all_to_all(At.reshape(-1), send_counts, rbuf, recv_counts)
+        B = torch.empty((nc_me, my), **kw)
+        off = 0
+        for q, (s, e) in enumerate(lay.red_rows):
+            ops.copy2d(rbuf[off:off + nc_me * (e - s)].view(nc_me, e - s), B[:, s:e])
+            off += nc_me * (e - s)
+        ops.dht_lines(B, B, my, mul=self.fT)                           # columns: forward x multiplier
+        ops.dht_lines(B, B, my)                                        # ... and back
+        sbuf = torch.empty(nc_me * my, **kw)
+        off = 0
+        for q, (s, e) in enumerate(lay.red_rows):
+            ops.copy2d(B[:, s:e], sbuf[off:off + nc_me * (e - s)].view(nc_me, e - s))
+            off += nc_me * (e - s)
+        At2 = torch.empty(mx * nr_me, **kw)
+        comm.all_to_all(sbuf, recv_counts, At2, send_counts)
+        ops.dht_lines(ops.transpose(At2.view(mx, nr_me)), sol_rows, mx)
+        ops.copy2d(sol_rows[:, 0:1], sol_rows[:, mx:mx + 1])           # _tile_overlap, x direction
+        part = sol_rows.sum().reshape(1)
+        if me == 0:
+            part = part + sol_rows[0].sum()                            # the overlap row Ny-1 repeats row 0
+        return comm.allreduce(part)
+
+
 # ------------------------------------------------------------------ BC table per slab
+class RemoteCopies:
+    """BC entries whose source cell is stored on another rank (the row wrap of a periodic BC:
+    u[-1, :] = u[0, :] is rank 0 -> rank P-1).  Every rank derives both sides from the same global
+    table, so no set-up communication is needed.  Per application: gather the source values, one
+    message per peer, scatter ca * value + cb into the destinations."""
+
+    def __init__(self, lay, dst, src, ca, cb, dst_rank, src_rank):
+        from .bc import _FIELD_BIT
+        Nx, me = lay.Nx, lay.rank
+        cell = lambda k: k & (_FIELD_BIT - 1)
+        isv = lambda k: (k & _FIELD_BIT) != 0
+        order = np.lexsort((np.arange(dst.size), isv(src)))            # u-sourced entries first, table order within
+        dst, src, ca, cb, dst_rank, src_rank = (x[order] for x in (dst, src, ca, cb, dst_rank, src_rank))
+        self.give, self.need = {}, {}
+        for q in range(lay.world):
+            if q == me:
+                continue
+            g = (dst_rank == q) & (src_rank == me)                     # q needs these values of mine
+            if g.any():
+                rel = cell(src[g]) - lay.e0 * Nx
+                self.give[q] = (rel[~isv(src[g])], rel[isv(src[g])])
+            n = (dst_rank == me) & (src_rank == q)
+            if n.any():
+                rel = cell(dst[n]) - lay.e0 * Nx
+                self.need[q] = (rel, isv(dst[n]), ca[n], cb[n])
+        self.n = sum(v[0].size for v in self.need.values()) + sum(v[0].size + v[1].size for v in self.give.values())
+        self._dev = None
+
+    def _on(self, dev):
+        if self._dev is None:
+            up = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+            give = {q: (up(iu), up(iv)) for q, (iu, iv) in self.give.items()}
+            need = {}
+            for q, (rel, dv, ca, cb) in self.need.items():
+                need[q] = (up(rel[~dv]), up(rel[dv]), up(np.nonzero(~dv)[0]), up(np.nonzero(dv)[0]), up(ca), up(cb))
+            self._dev = (give, need)
+        return self._dev
+
+    def apply_(self, u, v, comm):
+        if self.n == 0:
+            return
+        give, need = self._on(u.device)
+        fu, fv = u.reshape(-1), v.reshape(-1)
+        ops, keep = [], []
+        for q in sorted(give):
+            iu, iv = give[q]
+            buf = torch.cat([fu[iu], fv[iv]])
+            keep.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, q, comm.group))
+        rbufs = {}
+        for q in sorted(need):
+            rbufs[q] = torch.empty(need[q][4].numel(), dtype=u.dtype, device=u.device)
+            ops.append(dist.P2POp(dist.irecv, rbufs[q], q, comm.group))
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        for q, buf in rbufs.items():
+            du, dv, pu, pv, ca, cb = need[q]
+            vals = ca * buf + cb
+            fu[du] = vals[pu]
+            fv[dv] = vals[pv]
+
+
 def local_bc_table(bc, lay):
-    """The global gather table of a BC callable restricted to the rows this rank owns,
-    re-indexed into the extended slab.  Sources must live in the same slab (true for
-    wall / lid / free-slip BCs; a periodic wrap across ranks is not supported here)."""
+    """The global gather table of a BC callable restricted to the rows this rank owns, re-indexed
+    into the extended slab -> (BCTable, RemoteCopies or None).  Sources stored in the same slab
+    (wall / lid / free-slip BCs, the column wrap of a periodic BC) go into the table; sources on
+    another rank (the row wrap of a periodic BC) into the RemoteCopies."""
     from .bc import BCTable, _FIELD_BIT, table_for
     full = table_for(bc, lay.Ny, lay.Nx)
     if full is None:
@@ -206,33 +381,48 @@ def local_bc_table(bc, lay):
     dst, src, ca, cb = full.host
     Nx = lay.Nx
     cell = lambda k: k & (_FIELD_BIT - 1)
-    keep = (cell(dst) // Nx >= lay.r0) & (cell(dst) // Nx < lay.r1)
-    dst, src, ca, cb = dst[keep], src[keep], ca[keep], cb[keep]
+    starts = np.array([r[0] for r in lay.rows])
+    owner = lambda rows: np.searchsorted(starts, rows, side="right") - 1
+    drank = owner(cell(dst) // Nx)
     has = src >= 0
-    srow = cell(src[has]) // Nx
-    if np.any((srow < lay.e0) | (srow >= lay.e1)):
-        raise NotImplementedError("BC copies across slab boundaries (e.g. a periodic wrap) are not supported")
+    srow = np.where(has, cell(np.where(has, src, 0)) // Nx, 0)
+    stored = np.array([lay.stored(r) for r in range(lay.world)])
+    remote = has & ((srow < stored[drank, 0]) | (srow >= stored[drank, 1]))
+    rem = None
+    if remote.any():
+        rem = RemoteCopies(lay, dst[remote], src[remote], ca[remote], cb[remote], drank[remote], owner(srow[remote]))
+    keep = (drank == lay.rank) & ~remote
+    dst, src, ca, cb, has = dst[keep], src[keep], ca[keep], cb[keep], has[keep]
     shift = lay.e0 * Nx
     rel = lambda k: (k & _FIELD_BIT) | (cell(k) - shift)
     src2 = src.copy()
     src2[has] = rel(src[has])
-    return BCTable(rel(dst).astype(np.int64), src2.astype(np.int64), ca, cb, (lay.nl, Nx))
+    return BCTable(rel(dst).astype(np.int64), src2.astype(np.int64), ca, cb, (lay.nl, Nx)), rem
 
 
 class SlabFluidSolver:
     """momentum_step_rk4 + pressure_projection_amg (Neumann, constant density) on row slabs.
     All field arguments and results are extended slabs (lay.nl, Nx) with valid halos."""
 
-    def __init__(self, lay, bc, eig, comm=None):
+    def __init__(self, lay, bc, eig, comm=None, spacing=None):
         self.lay, self.comm = lay, comm or Comm()
-        self.table = local_bc_table(bc, lay)
+        self.table, self.remote = local_bc_table(bc, lay)
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.poisson = DistPoissonDCT(lay, eig, self.comm, device=dev)
+        if lay.periodic:      # bc_type='periodic' (functions.py:1277-1290): FFT solve on the reduced grid
+            self.poisson = DistPoissonFFT(lay, eig, spacing, self.comm, device=dev)
+        else:
+            self.poisson = DistPoissonDCT(lay, eig, self.comm, device=dev)
         self.lib = ctx().lib
+        self.ops = CudaOps()
 
     # -- helpers -----------------------------------------------------------------
-    def _bc_and_halo(self, u, v):
+    def _apply_bc(self, u, v):
         self.table.apply_(u, v)
+        if self.remote is not None:
+            self.remote.apply_(u, v, self.comm)
+
+    def _bc_and_halo(self, u, v):
+        self._apply_bc(u, v)
         self.comm.halo_exchange(self.lay, (u, v))
 
     def max_speed(self, a, b):
@@ -268,6 +458,8 @@ class SlabFluidSolver:
 
     # -- functions.py:1255-1364 (Neumann, constant density) ---------------------------------
     def projection(self, a_star, b_star, p_prev, rho, dx, dy, dt):
+        if self.lay.periodic:
+            return self.projection_periodic(a_star, b_star, p_prev, rho, dx, dy, dt)
         lay, lib, st, comm = self.lay, self.lib, stream(), self.comm
         nl, Nx, ncell = lay.nl, lay.Nx, lay.Ny * lay.Nx
         if isinstance(rho, torch.Tensor):
@@ -291,8 +483,63 @@ class SlabFluidSolver:
         _lib.check(lib.rmt_projection_correct(ptr(sol), ptr(ssum_local), ptr(a_star), ptr(b_star), ptr(rd),
                                               rscalar, ptr(p_prev), ptr(a), ptr(b), ptr(p), nl, Nx, dx, dy, dt,
                                               0, st), "rmt_projection_correct")
-        self.table.apply_(a, b)
+        self._apply_bc(a, b)
         psum = comm.allreduce(lay.owned(p).sum().reshape(1)) * (float(nl * Nx) / float(ncell))
+        _lib.check(lib.rmt_subtract_mean(ptr(p), ptr(psum), p.numel(), st), "rmt_subtract_mean")
+        comm.halo_exchange(lay, (a, b, p))
+        return a, b, p
+
+    # -- functions.py:1277-1290 (bc_type='periodic') ---------------------------------------
+    def projection_periodic(self, a_star, b_star, p_prev, rho, dx, dy, dt):
+        """Work arrays hold [wrap row below | this rank's reduced rows (| overlap row Ny-1 on the last
+        rank) | wrap row(s) above]; the kernels run in their slab mode (periodic in x, stored rows in y)."""
+        lay, lib, st, comm, ops = self.lay, self.lib, stream(), self.comm, self.ops
+        Nx, ncell, last = lay.Nx, lay.Ny * lay.Nx, lay.rank == lay.world - 1
+        n_red = lay.red_rows[lay.rank][1] - lay.red_rows[lay.rank][0]
+        n_cmp = n_red + (1 if last else 0)             # rows whose (a, b, p) this rank produces
+        ne = n_cmp + 2
+        kw = dict(dtype=F64, device=a_star.device)
+
+        def ext(f):
+            E = torch.empty((ne, Nx), **kw)
+            ops.copy2d(lay.owned(f), E[1:1 + n_cmp])
+            return E
+
+        Ea, Eb = ext(a_star), ext(b_star)
+        # divergence: row above the last reduced row is reduced row 0 (on the last rank it lands in the
+        # overlap row's slot, restored afterwards)
+        comm.ring_exchange([(E[n_red:n_red + 1], E[1:2], E[0:1], E[1 + n_red:2 + n_red]) for E in (Ea, Eb)])
+        if isinstance(rho, torch.Tensor):
+            rsum = comm.allreduce(lay.owned(rho).sum().reshape(1))
+            Er, rscalar = ext(rho), 0.0
+        else:
+            Er, rscalar = None, float(rho)
+            rsum = torch.full((1,), rscalar * ncell, **kw)
+        scale = float(ne * Nx) / float(ncell)          # the kernels divide device sums by THEIR grid size
+        rsum_local = rsum * scale
+        Erhs = torch.empty((ne, Nx), **kw)
+        _lib.check(lib.rmt_projection_rhs(ptr(Ea), ptr(Eb), None, None, 0.0, ptr(rsum_local), ptr(Erhs), ne, Nx,
+                                          dx, dy, dt, 2, st), "rmt_projection_rhs")
+        if last:
+            ops.copy2d(lay.owned(a_star)[n_red:], Ea[1 + n_red:2 + n_red])
+            ops.copy2d(lay.owned(b_star)[n_red:], Eb[1 + n_red:2 + n_red])
+        Esol = torch.empty((ne, Nx), **kw)
+        total = self.poisson.solve(Erhs[1:1 + n_red], Esol[1:1 + n_red])
+        up = 2 if last else 1                          # rows I need from the next rank ...
+        up_prev = 2 if lay.rank == 0 else 1            # ... and the previous rank from me (rank 0 feeds the last)
+        comm.ring_exchange([(Esol[n_red:n_red + 1], Esol[1:1 + up_prev], Esol[0:1],
+                             Esol[1 + n_red:1 + n_red + up])])
+        ssum_local = total * scale
+        Ep = ext(p_prev) if p_prev is not None else None
+        oa, ob, op = (torch.empty((ne, Nx), **kw) for _ in range(3))
+        _lib.check(lib.rmt_projection_correct(ptr(Esol), ptr(ssum_local), ptr(Ea), ptr(Eb), ptr(Er), rscalar,
+                                              ptr(Ep), ptr(oa), ptr(ob), ptr(op), ne, Nx, dx, dy, dt, 2, st),
+                   "rmt_projection_correct")
+        a, b, p = (torch.empty_like(a_star) for _ in range(3))
+        for o, f in ((oa, a), (ob, b), (op, p)):
+            ops.copy2d(o[1:1 + n_cmp], lay.owned(f))
+        self._apply_bc(a, b)
+        psum = comm.allreduce(lay.owned(p).sum().reshape(1)) * (float(lay.nl * Nx) / float(ncell))
         _lib.check(lib.rmt_subtract_mean(ptr(p), ptr(psum), p.numel(), st), "rmt_subtract_mean")
         comm.halo_exchange(lay, (a, b, p))
         return a, b, p
@@ -311,8 +558,8 @@ class SlabFSISolver(SlabFluidSolver):
     State per rank: extended slabs (lay.nl, Nx) of a, b, p, X1, X2 with valid halos (lay.H >= 12).
     `overlap`: rows above the slab that the extrapolation re-sweeps (>= tallest body + 16)."""
 
-    def __init__(self, lay, bc, eig, phi_init, overlap=512, layers=3, comm=None):
-        super().__init__(lay, bc, eig, comm)
+    def __init__(self, lay, bc, eig, phi_init, overlap=512, layers=3, comm=None, spacing=None):
+        super().__init__(lay, bc, eig, comm, spacing)
         if lay.H < 12:
             raise ValueError("the FSI slab step needs a halo of >= 12 rows (3 WENO5 stages + margin)")
         self.phi_init, self.layers, self._overlap = phi_init, layers, overlap
@@ -398,3 +645,36 @@ class SlabFSISolver(SlabFluidSolver):
         _, rho_local = F.heaviside_and_density(phi, prm["w_t"], prm["rho_s"], prm["rho_f"])
         a, b, p = self.projection(a_s, b_s, p, rho_local, dx, dy, dt)
         return (a, b, p, X1n, X2n)
+
+
+def slab_initial_state(solver, L, sdf, velocity=None):
+    """Extended-slab state (a, b, p, X1, X2) of a synthetic multi-disc case, built per slab without ever
+    forming a full-grid array: node coordinates as create_grid makes them
+    (functions.py:25-31), xi = x inside the bodies and 0 outside, extrapolated `solver.layers` layers
+    through the overlap sweep, velocity(X, Y) -> (a0, b0) on host rows (None: at rest) followed by the
+    BC.  Returns (state, dx, dy)."""
+    from . import functions as F
+    lay = solver.lay
+    x = np.linspace(0.0, L, lay.Nx)
+    y = np.linspace(0.0, L, lay.Ny)
+    dx, dy = float(x[1] - x[0]), float(y[1] - y[0])
+    Xh, Yh = np.meshgrid(x, y[lay.e0:lay.e1])
+    dev = torch.device("cuda", torch.cuda.current_device())
+    up = lambda arr: torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(dev)
+    Xs, Ys = up(Xh), up(Yh)
+    phi0 = sdf(Xs, Ys)
+    X1, X2 = F.mask_solid(Xs, phi0), F.mask_solid(Ys, phi0)
+    B1, B2, Bp = solver._gather_big((X1, X2, phi0))
+    E1, E2 = F.extrapolate_reference_map(B1, B2, Bp, dx, dy, solver.layers, row_offset=lay.r0 - solver.top)
+    n_own = lay.r1 - lay.r0
+    X1, X2 = torch.zeros_like(Xs), torch.zeros_like(Xs)
+    lay.owned(X1).copy_(E1[solver.top:solver.top + n_own])
+    lay.owned(X2).copy_(E2[solver.top:solver.top + n_own])
+    solver.comm.halo_exchange(lay, (X1, X2))
+    if velocity is None:
+        a, b = torch.zeros_like(Xs), torch.zeros_like(Xs)
+    else:
+        a0, b0 = velocity(Xh, Yh)
+        a, b = up(a0), up(b0)
+    solver._bc_and_halo(a, b)
+    return (a, b, torch.zeros_like(Xs), X1, X2), dx, dy

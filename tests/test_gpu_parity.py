@@ -525,6 +525,44 @@ def test_slab_solver_world1_equals_single_gpu(P):
             assert float(((ref - got).abs().max() / ref.abs().max()).item()) < 1e-12, nm
 
 
+def test_slab_solver_periodic_world1_equals_single_gpu(P):
+    """Periodic Taylor-Green + discs (SURVEY 8d config 5 physics) with one rank: the slab path's wrap
+    rows, slab-mode projection kernels and transpose-based Hartley solve against the single-GPU step."""
+    import torch
+    from pyrmt_b200.driver import PeriodicBC, disc_lattice, fsi_step
+    from pyrmt_b200.levelset import DiscSDF
+    from pyrmt_b200.slab import SlabFSISolver, SlabLayout, slab_initial_state
+    N, L, U0 = 257, 2.0, 0.05
+    X, Y, dx, dy = P.create_grid(N, N, L, L)
+    cx, cy, R = disc_lattice(3, L, 0.1)
+    sdf, bc = DiscSDF(cx, cy, R, domain=(L, L)), PeriodicBC()
+    eig = P._precompute_poisson_eigenvalues_periodic(N, N, dx, dy)
+    k = 2.0 * np.pi / L
+    vel = lambda X, Y: (U0 * k * np.sin(k * X) * np.cos(k * Y), -U0 * k * np.cos(k * X) * np.sin(k * Y))
+    lay = SlabLayout(N, N, 1, 0, halo=12, periodic=True)
+    solver = SlabFSISolver(lay, bc, eig, sdf, overlap=64, layers=3)
+    sstate, sdx, sdy = slab_initial_state(solver, L, sdf, vel)
+    assert sdx == dx and sdy == dy
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    Xd, Yd = up(X), up(Y)
+    phi0 = sdf(Xd, Yd)
+    X1, X2 = P.extrapolate_reference_map(P.mask_solid(Xd, phi0), P.mask_solid(Yd, phi0), phi0, dx, dy, 3)
+    a0, b0 = bc(*vel(X, Y))
+    state = (up(a0), up(b0), up(np.zeros((N, N))), X1, X2)
+    for nm, ref, got in zip("abp12", state, sstate):
+        assert torch.equal(ref, got), nm
+    prm = dict(dx=dx, dy=dy, CFL=0.2, dt_cap=1e-3, mu_s=0.1, kappa=0.0, rho_s=1.0, rho_f=1.0, eta_s=0.01,
+               mu_f=0.01, w_t=2 * dx, layers=3, scheme="weno5", w_cut=0.0, phi_init=sdf, bc=bc, eig=eig,
+               bc_type="periodic", X=Xd, Y=Yd)
+    for _ in range(3):
+        state, dt, _ = fsi_step(state, prm)
+        sstate = solver.fsi_step(sstate, dict(prm, X=None, Y=None), dt)
+        for nm, ref, got in zip("abp12", state, sstate):
+            if nm in "12":
+                assert torch.equal(ref, got), nm
+            assert float(((ref - got).abs().max() / ref.abs().max()).item()) < 1e-12, nm
+
+
 def test_dct_lines_building_blocks(P, O):
     """rmt_dct_lines / rmt_transpose / rmt_copy2d against scipy (through the oracle's imports)."""
     import torch

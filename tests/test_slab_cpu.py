@@ -43,6 +43,17 @@ def test_lid_table_matches_classifier():
         assert np.array_equal(a2[0], ref[0]) and np.array_equal(a2[1], ref[1])
 
 
+def test_periodic_table_matches_callable():
+    from pyrmt_b200.bc import periodic_bc
+    from pyrmt_b200.driver import PeriodicBC
+    for Ny, Nx in ((9, 13), (28, 36)):
+        t = PeriodicBC().rmt_table(Ny, Nx)
+        rng = np.random.default_rng(2)
+        u, v = rng.standard_normal((Ny, Nx)), rng.standard_normal((Ny, Nx))
+        got, ref = t.apply_host(u, v), periodic_bc(u, v)
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+
+
 def test_local_bc_table_reproduces_global_bc():
     from pyrmt_b200.bc import free_slip_box_bc
     from pyrmt_b200.driver import LidBC
@@ -54,7 +65,8 @@ def test_local_bc_table_reproduces_global_bc():
         ru, rv = bc(u, v)
         for r in range(P):
             L = SlabLayout(Ny, Nx, P, r, halo=4)
-            t = local_bc_table(bc, L)
+            t, rem = local_bc_table(bc, L)
+            assert rem is None
             su, sv = t.apply_host(L.take(u).copy(), L.take(v).copy())
             assert np.array_equal(L.owned(su), ru[L.r0:L.r1]) and np.array_equal(L.owned(sv), rv[L.r0:L.r1])
 
@@ -71,6 +83,13 @@ class SciPyOps:
             y = y * scale
         x.copy_(torch.from_numpy(np.ascontiguousarray(y)))
         return x
+
+    def dht_lines(self, x, out, m, mul=None, scale=1.0):
+        Fx = np.fft.fft(x.numpy()[:, :m], axis=1)
+        h = Fx.real - Fx.imag
+        h = h * (mul.numpy() if mul is not None else scale)
+        out[:, :m].copy_(torch.from_numpy(np.ascontiguousarray(h)))
+        return out
 
     def transpose(self, x):
         return x.t().contiguous()
@@ -130,3 +149,80 @@ def test_halo_exchange_and_distributed_dct_gloo(world, Ny, Nx):
             assert ok_halo, "halo exchange wrong on rank %d" % r
             assert err < 1e-12, (r, err)
             assert mx == world + 2
+
+
+def test_periodic_layout():
+    from pyrmt_b200.slab import SlabLayout
+    for Ny, Nx, P in ((33, 17, 2), (65, 33, 4), (41, 29, 3)):
+        for r in range(P):
+            L = SlabLayout(Ny, Nx, P, r, halo=4, periodic=True)
+            assert L.rows[-1][1] == Ny and L.red_rows[-1][1] == Ny - 1 and L.cols[-1][1] == Nx - 1
+            assert all(a == b for a, b in zip(L.rows[:-1], L.red_rows[:-1]))
+
+
+def _periodic_worker(rank, world, port, Ny, Nx, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import rmt_oracle as O
+        from pyrmt_b200.bc import periodic_bc
+        from pyrmt_b200.slab import Comm, DistPoissonFFT, SlabLayout, local_bc_table
+        lay = SlabLayout(Ny, Nx, world, rank, halo=4, periodic=True)
+        comm = Comm()
+        # the periodic BC: column wrap from the local table, row wrap (rank 0 -> last rank) by message
+        rng = np.random.default_rng(11)
+        u, v = rng.standard_normal((Ny, Nx)), rng.standard_normal((Ny, Nx))
+        ru, rv = periodic_bc(u, v)
+        table, rem = local_bc_table(periodic_bc, lay)
+        su, sv = table.apply_host(lay.take(u).copy(), lay.take(v).copy())
+        su, sv = torch.from_numpy(su.copy()), torch.from_numpy(sv.copy())
+        assert (rem is not None) == (world > 1)
+        if rem is not None:
+            rem.apply_(su, sv, comm)
+        ok_bc = bool(np.array_equal(lay.owned(su).numpy(), ru[lay.r0:lay.r1])
+                     and np.array_equal(lay.owned(sv).numpy(), rv[lay.r0:lay.r1]))
+        # ring exchange: global row ids travel with wrap-around
+        n_red = lay.red_rows[rank][1] - lay.red_rows[rank][0]
+        E = torch.full((n_red + 3, 3), -1.0, dtype=torch.float64)
+        E[1:1 + n_red] = torch.arange(lay.red_rows[rank][0], lay.red_rows[rank][1], dtype=torch.float64)[:, None]
+        comm.ring_exchange([(E[n_red:n_red + 1], E[1:3], E[0:1], E[1 + n_red:3 + n_red])])
+        my = Ny - 1
+        want = [(lay.red_rows[rank][0] - 1) % my] + list(range(lay.red_rows[rank][0], lay.red_rows[rank][1])) + \
+               [lay.red_rows[rank][1] % my, (lay.red_rows[rank][1] + 1) % my]
+        ok_ring = bool(torch.equal(E[:, 0], torch.tensor(want, dtype=torch.float64)))
+        # distributed Hartley solve against numpy's fft2 through the oracle, table and separable set-up
+        X, Y, dx, dy = O.create_grid(Nx, Ny, 1.3, 0.7)
+        eig = O._precompute_poisson_eigenvalues_periodic(Nx, Ny, dx, dy)
+        rhs = rng.standard_normal((Ny, Nx))
+        ref = O._solve_poisson_fft(rhs, eig)
+        errs = []
+        for kw in (dict(eig=eig), dict(spacing=(dx, dy))):
+            solver = DistPoissonFFT(lay, comm=comm, ops=SciPyOps(), **kw)
+            r0, r1 = lay.red_rows[rank]
+            sol = torch.zeros((r1 - r0, Nx), dtype=torch.float64)
+            total = solver.solve(torch.from_numpy(np.ascontiguousarray(rhs[r0:r1])), sol)
+            got = sol.numpy() - float(total) / (Ny * Nx)
+            errs.append(float(np.max(np.abs(got - ref[r0:r1])) / np.max(np.abs(ref))))
+        out[rank] = (ok_bc, ok_ring, max(errs))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,Ny,Nx", [(2, 33, 17), (3, 40, 29), (1, 17, 33)])
+def test_periodic_wrap_and_distributed_fft_gloo(world, Ny, Nx):
+    ctx_ = mp.get_context("spawn")
+    with ctx_.Manager() as m:
+        out = m.dict()
+        port = 31500 + (os.getpid() % 2000) + world
+        procs = [ctx_.Process(target=_periodic_worker, args=(r, world, port, Ny, Nx, out)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+        for r in range(world):
+            ok_bc, ok_ring, err = out[r]
+            assert ok_bc, "periodic BC wrong on rank %d" % r
+            assert ok_ring, "ring exchange wrong on rank %d" % r
+            assert err < 1e-12, (r, err)
