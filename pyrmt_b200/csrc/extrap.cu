@@ -1074,6 +1074,9 @@ static inline int ext_nxt(int Nx) { int XT = ext_tune().XT; return (Nx + XT - 1)
 // prepared-record capacity (targets per layer); beyond it the sweep computes phase A inline
 static inline long ext_cap(long ncell)
 {
+    static long forced = -1;                     // RMT_EXT_CAP: test hook (exercises the inline path)
+    if (forced < 0) { const char *e = getenv("RMT_EXT_CAP"); forced = e ? atol(e) : 0; }
+    if (forced > 0) return forced;
     long c = ncell / 48;
     if (c < 4096) c = 4096;
     if (c > 300000) c = 300000;

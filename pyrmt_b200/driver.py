@@ -100,12 +100,13 @@ class PeriodicBC:
         return BCTable(dst, src, np.ones(dst.size), np.zeros(dst.size), (Ny, Nx))
 
 
-def disc_lattice(k_side, L, R_frac, seed=20240607):
-    """K = k_side^2 discs on a jittered lattice."""
+def disc_lattice(k_side, L, R_frac, seed=20240607, jitter=0.01):
+    """K = k_side^2 discs on a jittered lattice (jitter 0.01 L on the 8 x 8
+    lattice; finer lattices scale it with the spacing so the discs stay disjoint)."""
     rng = np.random.default_rng(seed)
     m, n = np.meshgrid(np.arange(k_side), np.arange(k_side))
-    jx = rng.uniform(-0.01, 0.01, size=m.shape)
-    jy = rng.uniform(-0.01, 0.01, size=m.shape)
+    jx = rng.uniform(-jitter, jitter, size=m.shape)
+    jy = rng.uniform(-jitter, jitter, size=m.shape)
     cx = ((m + 0.5) / k_side + jx) * L
     cy = ((n + 0.5) / k_side + jy) * L
     return cx.ravel(), cy.ravel(), np.full(cx.size, R_frac * L)

@@ -616,22 +616,31 @@ class SlabFSISolver(SlabFluidSolver):
         run4 = free[:-3] * free[1:-2] * free[2:-1] * free[3:]
         return bool(run4[8:].any().item()) if run4.numel() > 8 else False
 
+    def _dbg(self, tag, *fields):
+        import os
+        if os.environ.get("RMT_SLAB_DEBUG"):
+            print("[rank %d] %s max|.|: %s" % (self.lay.rank, tag, ["%.3e" % float(f.abs().max().item()) for f in fields]),
+                  flush=True)
+
     def fsi_step(self, state, prm, dt, check_guard=True):
         from . import functions as F
         lay, comm = self.lay, self.comm
         a, b, p, X1, X2 = state
+        self._dbg("state", a, b, p, X1, X2)
         dx, dy = prm["dx"], prm["dy"]
         phi = F.rebuild_phi_from_reference_map(X1, X2, self.phi_init)
         # Eulerian SSP-RK3 advection of both components + solid mask on the extended slab (halo 9 consumed)
         Y0 = prm.get("X"), prm.get("Y")
         X1, X2 = F.advect_reference_map_pair(X1, X2, a, b, Y0[0], Y0[1], dt, dx, dy, phi, prm["scheme"],
                                              prm.get("w_cut", 0.0), mask_solid=True)
+        self._dbg("advected", X1, X2, phi)
         # extrapolation on [r0 - top, r1 + bot): the bodies reaching into this slab, from their first row
         B1, B2, Bphi = self._gather_big((X1, X2, phi))
         if check_guard and not self.guard(Bphi, dx, dy):
             raise RuntimeError("slab extrapolation: a body reaches above the %d-row overlap of rank %d; "
                                "increase `overlap`" % (self.top, lay.rank))
         E1, E2 = F.extrapolate_reference_map(B1, B2, Bphi, dx, dy, self.layers, row_offset=lay.r0 - self.top)
+        self._dbg("extrapolated", E1, E2)
         n_own = lay.r1 - lay.r0
         X1n, X2n = torch.empty_like(a), torch.empty_like(a)
         lay.owned(X1n).copy_(E1[self.top:self.top + n_own])
@@ -642,8 +651,10 @@ class SlabFSISolver(SlabFluidSolver):
         phi = F.rebuild_phi_from_reference_map(X1n, X2n, self.phi_init)
         a_s, b_s, *_ = self.momentum_step(a, b, p, X1n, X2n, phi, prm["mu_s"], prm["kappa"], prm["eta_s"], dx, dy,
                                           dt, prm["rho_s"], prm["rho_f"], prm["mu_f"], prm["w_t"])
+        self._dbg("predictor", a_s, b_s)
         _, rho_local = F.heaviside_and_density(phi, prm["w_t"], prm["rho_s"], prm["rho_f"])
         a, b, p = self.projection(a_s, b_s, p, rho_local, dx, dy, dt)
+        self._dbg("projected", a, b, p)
         return (a, b, p, X1n, X2n)
 
 

@@ -17,6 +17,10 @@ ap.add_argument("--check", type=int, default=1025)
 ap.add_argument("--time", type=int, default=0)
 ap.add_argument("--fsi", type=int, default=0, help="check the full slab FSI step against the single-GPU step")
 ap.add_argument("--fsi-time", type=int, default=0, help="time the full slab FSI step at N x N")
+ap.add_argument("--pfsi", type=int, default=0, help="check the periodic (config 5) slab FSI step against the single-GPU step")
+ap.add_argument("--pfsi-time", type=int, default=0, help="time the periodic Taylor-Green multi-disc slab FSI step at N x N")
+ap.add_argument("--pfluid-time", type=int, default=0, help="time the periodic pure-fluid slab step (momentum + FFT projection) at N x N")
+ap.add_argument("--L", type=float, default=0.0, help="domain side for --pfsi-time (default (N-1)/128, i.e. dx = 1/128)")
 ap.add_argument("--overlap", type=int, default=256)
 ap.add_argument("--steps", type=int, default=10)
 args = ap.parse_args()
@@ -164,6 +168,128 @@ if args.fsi_time:
     out["fsi_time"] = {"N": N, "discs": int(cx.size), "ms_per_step": ms, "Mcell_steps_per_s": N * N / ms / 1e3,
                        "finite": bool(torch.isfinite(sstate[0]).all().item())}
     del sstate, solver
+    torch.cuda.empty_cache()
+
+def tg_velocity(L, U0=0.05):
+    k = 2.0 * np.pi / L
+    return lambda X, Y: (U0 * k * np.sin(k * X) * np.cos(k * Y), -U0 * k * np.cos(k * X) * np.sin(k * Y))
+
+
+if args.pfsi:
+    from pyrmt_b200.driver import PeriodicBC, fsi_step
+    from pyrmt_b200.slab import SlabFSISolver, slab_initial_state
+    N, L = args.pfsi, 8.0
+    X, Y, dx, dy = F.create_grid(N, N, L, L)
+    cx, cy, R = disc_lattice(3, L, 0.08)          # the middle lattice row straddles the 2-rank cut
+    sdf, bc = DiscSDF(cx, cy, R, domain=(L, L)), PeriodicBC()
+    eig = F._precompute_poisson_eigenvalues_periodic(N, N, dx, dy)
+    Xd, Yd = up(X), up(Y)
+    phi0 = sdf(Xd, Yd)
+    X1, X2 = F.extrapolate_reference_map(F.mask_solid(Xd, phi0), F.mask_solid(Yd, phi0), phi0, dx, dy, 3)
+    a0, b0 = bc(*tg_velocity(L)(X, Y))
+    state = (up(a0), up(b0), up(np.zeros((N, N))), X1, X2)
+    prm = dict(dx=dx, dy=dy, CFL=0.2, dt_cap=1e-3, mu_s=0.1, kappa=0.0, rho_s=1.0, rho_f=1.0, eta_s=0.01,
+               mu_f=0.01, w_t=2 * dx, layers=3, scheme="weno5", w_cut=0.0, phi_init=sdf, bc=bc, eig=eig,
+               bc_type="periodic", X=Xd, Y=Yd)
+    lay = SlabLayout(N, N, world, rank, halo=12, periodic=True)
+    solver = SlabFSISolver(lay, bc, None, sdf, overlap=args.overlap, layers=3, spacing=(dx, dy))
+    sstate, _, _ = slab_initial_state(solver, L, sdf, tg_velocity(L))
+    worst = {}
+    for nm, ref, got in zip(("a", "b", "p", "X1", "X2"), state, sstate):
+        worst[nm] = float(((got - ref[lay.e0:lay.e1]).abs().max() / max(float(ref.abs().max()), 1e-300)).item())
+    sprm = dict(prm, X=None, Y=None)
+    for n in range(4):
+        state, dt, _ = fsi_step(state, prm)
+        sstate = solver.fsi_step(sstate, sprm, dt)
+        for nm, ref, got in zip(("a", "b", "p", "X1", "X2"), state, sstate):
+            err = float(((got - ref[lay.e0:lay.e1]).abs().max() / ref.abs().max()).item())   # owned rows + halos
+            worst[nm] = max(worst.get(nm, 0.0), err)
+    t = torch.tensor([worst[k] for k in ("a", "b", "p", "X1", "X2")], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out["periodic_fsi_check"] = {"N": N, "steps": 4,
+                                 "rel_linf_vs_single_gpu": dict(zip(("a", "b", "p", "X1", "X2"), t.tolist()))}
+    del state, sstate, solver, X1, X2, Xd, Yd, phi0, eig, X, Y
+    torch.cuda.empty_cache()
+
+if args.pfsi_time:
+    from pyrmt_b200.driver import PeriodicBC
+    from pyrmt_b200.slab import SlabFSISolver, slab_initial_state
+    N = args.pfsi_time
+    # default dx = 1/128 keeps the absolute |det| > 1e-10 gate of the LSQ open; on the unit box
+    # (--L 1) at 16385^2 the gate rejects every band cell, as it does in the reference
+    L = args.L if args.L > 0 else (N - 1) / 128.0
+    k_side = max(2, (N - 1) // 512)                # 32 x 32 discs at 16385, R = 0.01 L = 164 cells
+    cx, cy, R = disc_lattice(k_side, L, 0.32 / k_side, jitter=0.08 / k_side)
+    sdf, bc = DiscSDF(cx, cy, R, domain=(L, L)), PeriodicBC()
+    lay = SlabLayout(N, N, world, rank, halo=12, periodic=True)
+    t0 = time.time()
+    solver = SlabFSISolver(lay, bc, None, sdf, overlap=512, layers=3, spacing=(L / (N - 1), L / (N - 1)))
+    sstate, dx, dy = slab_initial_state(solver, L, sdf, tg_velocity(L))
+    prm = dict(dx=dx, dy=dy, mu_s=1.0, kappa=0.0, rho_s=1.0, rho_f=1.0, eta_s=0.0, mu_f=1e-3, w_t=2 * dx,
+               scheme="weno5", w_cut=0.0, X=None, Y=None)
+    dt = min(0.2 * dx / np.sqrt(4.0 / 3.0), 0.2 * dx * dx / (4 * 1e-3), 1e-4)    # compute_timestep at rest
+    torch.cuda.synchronize()
+    setup_s = time.time() - t0
+    for _ in range(3):
+        sstate = solver.fsi_step(sstate, prm, dt)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sstate = solver.fsi_step(sstate, prm, dt, check_guard=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item()) / args.steps
+    out["periodic_fsi_time"] = {"N": N, "L": L, "dt": dt, "discs": int(cx.size), "max_abs_xi": float(max(sstate[3].abs().max(), sstate[4].abs().max()).item()), "ms_per_step": ms, "Mcell_steps_per_s": N * N / ms / 1e3,
+                                "setup_s": setup_s, "finite": bool(torch.isfinite(sstate[0]).all().item()),
+                                "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30}
+    del sstate, solver
+    torch.cuda.empty_cache()
+
+if args.pfluid_time:
+    from pyrmt_b200.driver import PeriodicBC
+    N = args.pfluid_time
+    L = 1.0
+    lay = SlabLayout(N, N, world, rank, halo=4, periodic=True)
+    dx = L / (N - 1)
+    solver = SlabFluidSolver(lay, PeriodicBC(), None, spacing=(dx, dx))
+    x = np.linspace(0.0, L, N)
+    Xh, Yh = np.meshgrid(x, x[lay.e0:lay.e1])
+    a0, b0 = tg_velocity(L)(Xh, Yh)
+    sa, sb = up(a0), up(b0)
+    del Xh, Yh, a0, b0
+    solver._bc_and_halo(sa, sb)
+    sp = torch.zeros_like(sa)
+    s1, s2, sph = sa, sb, torch.ones_like(sa)       # phi > 0 everywhere: the reference map is never read
+    prm = dict(dx=dx, dy=dx, mu_s=0.0, kappa=0.0, eta_s=0.0, rho_s=1.0, rho_f=1.0, mu_f=1e-3, w_t=2 * dx)
+    dt = min(0.2 * dx / 0.32, 0.2 * dx * dx / (4 * 1e-3))
+    e_first = None
+    for _ in range(3):
+        sa, sb, sp = solver.fluid_step(sa, sb, sp, s1, s2, sph, prm, dt)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sa, sb, sp = solver.fluid_step(sa, sb, sp, s1, s2, sph, prm, dt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item()) / args.steps
+    out["periodic_fluid_time"] = {"N": N, "ms_per_fluid_step": ms, "Mcell_steps_per_s": N * N / ms / 1e3,
+                                  "max_abs_u": float(sa.abs().max().item()),
+                                  "finite": bool(torch.isfinite(sa).all().item()),
+                                  "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30}
+    del sa, sb, sp, s1, s2, sph, solver
     torch.cuda.empty_cache()
 
 if args.time:
