@@ -20,6 +20,7 @@ ap.add_argument("--fsi-time", type=int, default=0, help="time the full slab FSI 
 ap.add_argument("--pfsi", type=int, default=0, help="check the periodic (config 5) slab FSI step against the single-GPU step")
 ap.add_argument("--pfsi-time", type=int, default=0, help="time the periodic Taylor-Green multi-disc slab FSI step at N x N")
 ap.add_argument("--pfluid-time", type=int, default=0, help="time the periodic pure-fluid slab step (momentum + FFT projection) at N x N")
+ap.add_argument("--pfsi-k", type=int, default=3, help="lattice side of the --pfsi check (discs of radius 0.24/k of the box)")
 ap.add_argument("--L", type=float, default=0.0, help="domain side for --pfsi-time (default (N-1)/128, i.e. dx = 1/128)")
 ap.add_argument("--overlap", type=int, default=256)
 ap.add_argument("--steps", type=int, default=10)
@@ -180,7 +181,7 @@ if args.pfsi:
     from pyrmt_b200.slab import SlabFSISolver, slab_initial_state
     N, L = args.pfsi, 8.0
     X, Y, dx, dy = F.create_grid(N, N, L, L)
-    cx, cy, R = disc_lattice(3, L, 0.08)          # the middle lattice row straddles the 2-rank cut
+    cx, cy, R = disc_lattice(args.pfsi_k, L, 0.24 / args.pfsi_k, jitter=0.03 / args.pfsi_k)   # odd k: a lattice row straddles the middle cut
     sdf, bc = DiscSDF(cx, cy, R, domain=(L, L)), PeriodicBC()
     eig = F._precompute_poisson_eigenvalues_periodic(N, N, dx, dy)
     Xd, Yd = up(X), up(Y)
