@@ -254,6 +254,8 @@ def main():
     ap.add_argument("--no-slab", action="store_true")
     ap.add_argument("--overlap", type=int, default=512, help="rows above a slab re-swept by the extrapolation")
     ap.add_argument("--slab-size", type=int, default=8193, help="nodes per side of the sharded fluid-step timing")
+    ap.add_argument("--cfg5-fsi-size", type=int, default=8193, help="nodes per side of the periodic FSI timing (N > 1)")
+    ap.add_argument("--cfg5-fluid-size", type=int, default=16385, help="nodes per side of the periodic fluid timing (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -398,9 +400,19 @@ def main():
                "call": "the five state fields (per rank: its slab) pinned host -> device -> fsi step -> pinned host"}
 
     # ---- N > 1: the part of the step that IS slab-decomposed (momentum + projection) ----
-    slab = None
+    slab = cfg5 = None
     if world > 1 and not args.no_slab:
         slab = slab_fluid_rate(args.slab_size, 10, rank, world)
+        # SURVEY 8d config 5 (periodic Taylor-Green, distributed FFT solve): the full FSI step at the largest
+        # size where the reference's absolute-coordinate LSQ is still meaningful, the fluid half at 16385^2
+        from pyrmt_b200.slab import time_periodic_fluid, time_periodic_fsi
+        torch.cuda.empty_cache()
+        cfg5 = {"fsi_step": time_periodic_fsi(args.cfg5_fsi_size, world, rank, steps=5, warmup=3)}
+        torch.cuda.empty_cache()
+        cfg5["fluid_step"] = time_periodic_fluid(args.cfg5_fluid_size, world, rank, steps=5, warmup=3)
+        cfg5["note"] = ("full FSI at 16385^2 is not runnable with the reference's own algorithm (absolute-coordinate "
+                        "normal equations lose all significance at index ~16384, see DESIGN.md 6): 8193^2 is the "
+                        "FSI size, 16385^2 the fluid-half size")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -421,7 +433,7 @@ def main():
                 "step_roofline": {"alg_bytes_per_cell_step": ALG_BYTES_PER_CELL_STEP.get(args.scheme, 512.0),
                                   "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak},
                 "cpu_baseline": cpu, "kernels": breakdown, "kernels_roofline": kernels_roofline[:8],
-                "finite": finite, "slab_fluid_step": slab}
+                "finite": finite, "slab_fluid_step": slab, "config5_periodic": cfg5}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -714,9 +714,10 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
             const int *__restrict__ cnt0 /* layer-0 target counts per (row, x-tile) */,
             int *__restrict__ prog /* [L][Ny*nxt] */, int *__restrict__ tile_counter,
             ExtRec *__restrict__ scratch /* [gridDim][RB][CAPW] */, const int *__restrict__ mode, int L, int Ny,
-            int Nx, int joff, int nxt, int XT, int MRB, double dx, double dy, double r2)
+            int Nx, int joff, int nxt, int XT, double dx, double dy, double r2)
 {
-    if (*mode != 1) return;
+    if (mode[0] != 1) return;
+    const int MRB = mode[1];                    // macro-tile height in row blocks, chosen by k_ext_decide
     extern __shared__ unsigned char s_raw[];
     FusedSmem &S = *reinterpret_cast<FusedSmem *>(s_raw);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1011,21 +1012,29 @@ __global__ void k_ext_decide(const int *__restrict__ cnt0, const int *__restrict
                              int macro, const int *__restrict__ rows_band, int nbands, int band, int nxt,
                              int Ny, int L, int limit, int *__restrict__ mode)
 {
-    __shared__ int busy, longest_macro, longest_band;
-    if (threadIdx.x == 0) busy = longest_macro = longest_band = 0;
+    __shared__ int busy, busy_band, longest_macro, longest_band;
+    if (threadIdx.x == 0) busy = busy_band = longest_macro = longest_band = 0;
     __syncthreads();
     for (int xt = threadIdx.x; xt < nxt; xt += blockDim.x) {
         int nb = 0, dummy = 0;
         const int lm = ext_longest_chain(cnt0, rows_macro, nmrb, macro, nxt, xt, Ny, &nb);
         const int lb = ext_longest_chain(cnt0, rows_band, nbands, band, nxt, xt, Ny, &dummy);
         atomicAdd(&busy, nb);
+        atomicAdd(&busy_band, dummy);
         atomicMax(&longest_macro, lm);
         atomicMax(&longest_band, lb);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const float fused = 7.1f * longest_macro, layered = L * (360.f + 3.4f * longest_band);
-        *mode = (busy * L <= limit && fused < layered) ? 1 : 0;
+        // all-layers kernel with macro-tiles of `macro` rows or of `band` rows (more, shorter tasks: bodies
+        // stacked in one macro-tile run side by side), or the per-layer launches
+        const float big = 3.0e38f;
+        const float fused_macro = (busy * L <= limit) ? 7.1f * longest_macro : big;
+        const float fused_band = (busy_band * L <= limit) ? 7.1f * longest_band : big;
+        const float layered = L * (360.f + 3.4f * longest_band);
+        const float fused = fminf(fused_macro, fused_band);
+        mode[0] = (fused < layered) ? 1 : 0;
+        mode[1] = ((fused_band < fused_macro) ? band : macro) / RB;
     }
 }
 
@@ -1195,16 +1204,16 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
                 if (rwb > 148 * 8) rwb = 148 * 8;
                 k_ext_count0<<<rwb, 256, 0, s>>>(st, cnt0, busy, MRBf * RB, busy + nmac, band, Ny, Nx, nxtf, XTf);
                 RMT_LAUNCH_CHECK();
-                const long ntasks = (long)nmrb * Lyr * nxtf;
+                const long ntasks = (long)rmt_cdiv(Ny - 2, band) * Lyr * nxtf;   // with the smaller macro-tile
                 int blocks = fused_blocks;
                 if ((long)blocks > ntasks) blocks = (int)ntasks;
                 if ((long)blocks * RB * CAPW <= (long)cap) {
                     k_ext_decide<<<1, 64, 0, s>>>(cnt0, busy, nmrb, MRBf * RB, busy + nmac, nbnd / nxtf, band, nxtf, Ny, Lyr,
                                                   fused_blocks * 9 / 10, mode);
                     RMT_LAUNCH_CHECK();
-                    int Lv = Lyr, nxv = nxtf, xtv = XTf, mrbv = MRBf;
+                    int Lv = Lyr, nxv = nxtf, xtv = XTf;
                     void *args[] = {&X1e, &X2e, &st, &cnt0, &progF, &tile_counter, &recs, &mode, &Lv, &Ny, &Nx,
-                                    &joff, &nxv, &xtv, &mrbv, &dx, &dy, &r2};
+                                    &joff, &nxv, &xtv, &dx, &dy, &r2};
                     RMT_CUDA(cudaLaunchCooperativeKernel((void *)k_ext_fused, dim3(blocks), dim3(RB * 32), args,
                                                          sizeof(FusedSmem), s));
                 } else {

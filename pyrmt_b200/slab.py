@@ -689,3 +689,98 @@ def slab_initial_state(solver, L, sdf, velocity=None):
         a, b = up(a0), up(b0)
     solver._bc_and_halo(a, b)
     return (a, b, torch.zeros_like(Xs), X1, X2), dx, dy
+
+
+# ------------------------------------------------------------------ config 5 timing drivers
+def _timed(step, steps, warmup, comm):
+    """ms per call of `step()` after `warmup` calls: CUDA events, barrier on both sides, max over ranks."""
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if comm.world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=F64, device="cuda")
+    comm.allreduce(ms, "max")
+    return float(ms.item()) / steps
+
+
+def taylor_green(L, U0=0.05):
+    """benchmarks/disc_in_taylor_green.py initial velocity (stream function U0 cos(kx) cos(ky), k = 2 pi / L)."""
+    k = 2.0 * np.pi / L
+    return lambda X, Y: (U0 * k * np.sin(k * X) * np.cos(k * Y), -U0 * k * np.cos(k * X) * np.sin(k * Y))
+
+
+def time_periodic_fsi(N, world, rank, steps=5, warmup=3, L=None, overlap=512, scheme="weno5"):
+    """periodic Taylor-Green flow with (N-1)/512 squared soft discs (R = 164 cells, the
+    config-4 geometry per disc) on an N x N node grid, y-slabs over `world` ranks, FFT projection.
+    L defaults to (N-1)/128, i.e. dx = 1/128 keeps the absolute |det| gate of the LSQ open."""
+    from .driver import PeriodicBC, disc_lattice
+    from .levelset import DiscSDF
+    L = float(L) if L else (N - 1) / 128.0
+    k_side = max(2, (N - 1) // 512)
+    cx, cy, R = disc_lattice(k_side, L, 0.32 / k_side, jitter=0.08 / k_side)
+    sdf = DiscSDF(cx, cy, R, domain=(L, L))
+    lay = SlabLayout(N, N, world, rank, halo=12, periodic=True)
+    h = L / (N - 1)
+    solver = SlabFSISolver(lay, PeriodicBC(), None, sdf, overlap=overlap, layers=3, spacing=(h, h))
+    box = {"state": None}
+    box["state"], dx, dy = slab_initial_state(solver, L, sdf, taylor_green(L))
+    prm = dict(dx=dx, dy=dy, mu_s=1.0, kappa=0.0, rho_s=1.0, rho_f=1.0, eta_s=0.0, mu_f=1e-3, w_t=2 * dx,
+               scheme=scheme, w_cut=0.0, X=None, Y=None)
+    dt = min(0.2 * dx / np.sqrt(4.0 / 3.0), 0.2 * dx * dx / (4 * 1e-3), 1e-4)     # compute_timestep at rest
+    guard = {"on": True}
+
+    def step():
+        box["state"] = solver.fsi_step(box["state"], prm, dt, check_guard=guard["on"])
+
+    step()
+    guard["on"] = False
+    ms = _timed(step, steps, max(warmup - 1, 0), solver.comm)
+    st = box["state"]
+    return {"what": "periodic Taylor-Green multi-disc FSI step (%s + SSP-RK3, 3-layer extrapolation, RK4 momentum, "
+                    "periodic FFT projection), y-slabs over %d GPUs: NCCL halo / wrap exchange + two all-to-all "
+                    "transposes per solve; strong scaling of one %dx%d grid" % (scheme, world, N, N),
+            "grid": [N, N], "L": L, "discs": int(cx.size), "dt": dt, "ms_per_step": ms,
+            "value": N * N / ms / 1e3, "unit": "Mcell-steps/s",
+            "finite": bool(all(torch.isfinite(t).all().item() for t in st)),
+            "max_abs_xi": float(max(st[3].abs().max(), st[4].abs().max()).item()),
+            "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}
+
+
+def time_periodic_fluid(N, world, rank, steps=5, warmup=3, L=1.0):
+    """The fluid half of config 5 at full size: momentum RK4 + periodic FFT projection of a Taylor-Green
+    flow on an N x N node grid (N = 16385: the 16384^2 reduced grid), y-slabs over `world` ranks."""
+    from .driver import PeriodicBC
+    lay = SlabLayout(N, N, world, rank, halo=4, periodic=True)
+    dx = L / (N - 1)
+    solver = SlabFluidSolver(lay, PeriodicBC(), None, spacing=(dx, dx))
+    x = np.linspace(0.0, L, N)
+    Xh, Yh = np.meshgrid(x, x[lay.e0:lay.e1])
+    a0, b0 = taylor_green(L)(Xh, Yh)
+    up = lambda arr: torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).cuda()
+    box = {"s": (up(a0), up(b0))}
+    del Xh, Yh, a0, b0
+    solver._bc_and_halo(*box["s"])
+    box["s"] = box["s"] + (torch.zeros_like(box["s"][0]),)
+    ones = torch.ones_like(box["s"][0])              # phi > 0 everywhere: the reference map is never read
+    prm = dict(dx=dx, dy=dx, mu_s=0.0, kappa=0.0, eta_s=0.0, rho_s=1.0, rho_f=1.0, mu_f=1e-3, w_t=2 * dx)
+    dt = min(0.2 * dx / 0.32, 0.2 * dx * dx / (4 * 1e-3))
+
+    def step():
+        a, b, p = box["s"]
+        box["s"] = solver.fluid_step(a, b, p, a, b, ones, prm, dt)
+
+    ms = _timed(step, steps, warmup, solver.comm)
+    a = box["s"][0]
+    return {"what": "momentum_step_rk4 + periodic FFT projection of a Taylor-Green flow, y-slabs over %d GPUs "
+                    "(NCCL halo / wrap exchange + two all-to-all transposes per solve); strong scaling of one "
+                    "%dx%d grid" % (world, N, N),
+            "grid": [N, N], "ms_per_step": ms, "value": N * N / ms / 1e3, "unit": "Mcell-steps/s",
+            "finite": bool(torch.isfinite(a).all().item()), "max_abs_u": float(a.abs().max().item()),
+            "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}

@@ -171,9 +171,7 @@ if args.fsi_time:
     del sstate, solver
     torch.cuda.empty_cache()
 
-def tg_velocity(L, U0=0.05):
-    k = 2.0 * np.pi / L
-    return lambda X, Y: (U0 * k * np.sin(k * X) * np.cos(k * Y), -U0 * k * np.cos(k * X) * np.sin(k * Y))
+from pyrmt_b200.slab import taylor_green as tg_velocity
 
 
 if args.pfsi:
@@ -214,83 +212,13 @@ if args.pfsi:
     torch.cuda.empty_cache()
 
 if args.pfsi_time:
-    from pyrmt_b200.driver import PeriodicBC
-    from pyrmt_b200.slab import SlabFSISolver, slab_initial_state
-    N = args.pfsi_time
-    # default dx = 1/128 keeps the absolute |det| > 1e-10 gate of the LSQ open; on the unit box
-    # (--L 1) at 16385^2 the gate rejects every band cell, as it does in the reference
-    L = args.L if args.L > 0 else (N - 1) / 128.0
-    k_side = max(2, (N - 1) // 512)                # 32 x 32 discs at 16385, R = 0.01 L = 164 cells
-    cx, cy, R = disc_lattice(k_side, L, 0.32 / k_side, jitter=0.08 / k_side)
-    sdf, bc = DiscSDF(cx, cy, R, domain=(L, L)), PeriodicBC()
-    lay = SlabLayout(N, N, world, rank, halo=12, periodic=True)
-    t0 = time.time()
-    solver = SlabFSISolver(lay, bc, None, sdf, overlap=512, layers=3, spacing=(L / (N - 1), L / (N - 1)))
-    sstate, dx, dy = slab_initial_state(solver, L, sdf, tg_velocity(L))
-    prm = dict(dx=dx, dy=dy, mu_s=1.0, kappa=0.0, rho_s=1.0, rho_f=1.0, eta_s=0.0, mu_f=1e-3, w_t=2 * dx,
-               scheme="weno5", w_cut=0.0, X=None, Y=None)
-    dt = min(0.2 * dx / np.sqrt(4.0 / 3.0), 0.2 * dx * dx / (4 * 1e-3), 1e-4)    # compute_timestep at rest
-    torch.cuda.synchronize()
-    setup_s = time.time() - t0
-    for _ in range(3):
-        sstate = solver.fsi_step(sstate, prm, dt)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        sstate = solver.fsi_step(sstate, prm, dt, check_guard=False)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item()) / args.steps
-    out["periodic_fsi_time"] = {"N": N, "L": L, "dt": dt, "discs": int(cx.size), "max_abs_xi": float(max(sstate[3].abs().max(), sstate[4].abs().max()).item()), "ms_per_step": ms, "Mcell_steps_per_s": N * N / ms / 1e3,
-                                "setup_s": setup_s, "finite": bool(torch.isfinite(sstate[0]).all().item()),
-                                "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30}
-    del sstate, solver
+    from pyrmt_b200.slab import time_periodic_fsi
+    out["periodic_fsi_time"] = time_periodic_fsi(args.pfsi_time, world, rank, steps=args.steps, L=args.L or None)
     torch.cuda.empty_cache()
 
 if args.pfluid_time:
-    from pyrmt_b200.driver import PeriodicBC
-    N = args.pfluid_time
-    L = 1.0
-    lay = SlabLayout(N, N, world, rank, halo=4, periodic=True)
-    dx = L / (N - 1)
-    solver = SlabFluidSolver(lay, PeriodicBC(), None, spacing=(dx, dx))
-    x = np.linspace(0.0, L, N)
-    Xh, Yh = np.meshgrid(x, x[lay.e0:lay.e1])
-    a0, b0 = tg_velocity(L)(Xh, Yh)
-    sa, sb = up(a0), up(b0)
-    del Xh, Yh, a0, b0
-    solver._bc_and_halo(sa, sb)
-    sp = torch.zeros_like(sa)
-    s1, s2, sph = sa, sb, torch.ones_like(sa)       # phi > 0 everywhere: the reference map is never read
-    prm = dict(dx=dx, dy=dx, mu_s=0.0, kappa=0.0, eta_s=0.0, rho_s=1.0, rho_f=1.0, mu_f=1e-3, w_t=2 * dx)
-    dt = min(0.2 * dx / 0.32, 0.2 * dx * dx / (4 * 1e-3))
-    e_first = None
-    for _ in range(3):
-        sa, sb, sp = solver.fluid_step(sa, sb, sp, s1, s2, sph, prm, dt)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        sa, sb, sp = solver.fluid_step(sa, sb, sp, s1, s2, sph, prm, dt)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item()) / args.steps
-    out["periodic_fluid_time"] = {"N": N, "ms_per_fluid_step": ms, "Mcell_steps_per_s": N * N / ms / 1e3,
-                                  "max_abs_u": float(sa.abs().max().item()),
-                                  "finite": bool(torch.isfinite(sa).all().item()),
-                                  "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30}
-    del sa, sb, sp, s1, s2, sph, solver
+    from pyrmt_b200.slab import time_periodic_fluid
+    out["periodic_fluid_time"] = time_periodic_fluid(args.pfluid_time, world, rank, steps=args.steps)
     torch.cuda.empty_cache()
 
 if args.time:
