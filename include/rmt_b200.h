@@ -144,6 +144,23 @@ int rmt_momentum_stage(const double *us, const double *vs, const double *p, cons
                        double *acc_v, double *out_u, double *out_v, int Ny, int Nx, double dx,
                        double dy, double dt, double mu_f, double eta_s, double w_t, double rho_s,
                        double rho_f, int stage, void *stream);
+/* One classical-RK4 stage of momentum_step_rk4_2solids (functions.py:765-835): two solid stresses and
+ * two level sets, n = 2 mixture  sigma = (Ha+Hb-1) sigma_f + (1-Ha) sigma_A + (1-Hb) sigma_B,
+ * rho = (Ha+Hb-1) rho_f + (1-Ha) rho_s + (1-Hb) rho_s, body force (fcx, fcy) (NULL = 0).  Stage
+ * bookkeeping as in rmt_momentum_stage. */
+int rmt_momentum_stage_2solids(const double *us, const double *vs, const double *p, const double *sAxx,
+                               const double *sAxy, const double *sAyy, const double *sBxx, const double *sBxy,
+                               const double *sByy, const double *phi_a, const double *phi_b, const double *fcx,
+                               const double *fcy, const double *u0, const double *v0, double *acc_u,
+                               double *acc_v, double *out_u, double *out_v, int Ny, int Nx, double dx, double dy,
+                               double dt, double mu_f, double w_t, double rho_s, double rho_f, int stage,
+                               void *stream);
+/* pyRMT/functions.py:864-895 compute_contact_force: k_rep * delta_s(phi12) * sign(phi12) * n12 inside
+ * either solid, phi12 = (phi1 - phi2)/2, delta_s(x) = (1 + cos(pi x / w_c)) / (2 w_c) for |x| < w_c. */
+int rmt_contact_force(const double *phi1, const double *phi2, double *fx, double *fy, int Ny, int Nx, double dx,
+                      double dy, double k_rep, double w_c, void *stream);
+/* out = min(a, b) elementwise (functions.py:835, np.minimum(Ja, Jb)). */
+int rmt_min2(const double *a, const double *b, double *out, long n, void *stream);
 
 /* ------------------------------------------------------ projection (a14-a17) */
 /* _compute_divergence (functions.py:1005-1014). */

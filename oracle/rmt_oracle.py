@@ -411,6 +411,70 @@ def momentum_step_rk4(u, v, p, X1, X2, velocity_bc, mu_s, kappa, eta_s, dx, dy, 
     return un, vn, exx, exy, eyy, J
 
 
+def compute_contact_force(phi1, phi2, k_rep, w_c, dx, dy):      # functions.py:864-895
+    """Repulsion across the mid-surface phi12 = (phi1 - phi2)/2 inside either solid."""
+    phi12 = 0.5 * (phi1 - phi2)
+    aphi = np.abs(phi12)
+    delta = np.where(aphi < w_c, (1.0 + np.cos(np.pi * phi12 / w_c)) / (2.0 * w_c), 0.0)
+    g12x = grad_central_x_2nd(phi12, dx)
+    g12y = grad_central_y_2nd(phi12, dy)
+    gmag = np.sqrt(g12x ** 2 + g12y ** 2) + 1e-12
+    n12x = g12x / gmag
+    n12y = g12y / gmag
+    active = ((phi1 < 0.0) | (phi2 < 0.0)).astype(float)
+    sgn = np.sign(phi12)
+    return k_rep * delta * sgn * n12x * active, k_rep * delta * sgn * n12y * active
+
+
+def momentum_step_rk4_2solids(u, v, p, X1a, X2a, X1b, X2b, velocity_bc, mu_s, kappa, eta_s, dx, dy, dt,
+                              rho_s, rho_f, phi_a, phi_b, mu_f, w_t, k_rep=0.0, w_c=None,
+                              detg_clamp=4.0):
+    """Two neo-Hookean solids in one velocity field, functions.py:765-835 (eta_s is accepted and
+    unused upstream as well).  Returns (u_new, v_new, min(Ja, Jb))."""
+    if w_c is None:
+        w_c = 2.0 * w_t
+    sAxx, sAxy, sAyy, Ja = solid_cauchy_stress(X1a, X2a, dx, dy, mu_s, kappa, phi_a, detg_clamp=detg_clamp)
+    sBxx, sBxy, sByy, Jb = solid_cauchy_stress(X1b, X2b, dx, dy, mu_s, kappa, phi_b, detg_clamp=detg_clamp)
+    Ha = smoothed_heaviside(phi_a, w_t)
+    Hb = smoothed_heaviside(phi_b, w_t)
+    Hf = Ha + Hb - 1.0
+    rho_local = Hf * rho_f + (1.0 - Ha) * rho_s + (1.0 - Hb) * rho_s
+    if k_rep > 0.0:
+        fcx, fcy = compute_contact_force(phi_a, phi_b, k_rep, w_c, dx, dy)
+    else:
+        fcx = fcy = 0.0
+
+    def rhs(us, vs):
+        us, vs = velocity_bc(us, vs)
+        ux = grad_central_x_2nd(us, dx)
+        vy = grad_central_y_2nd(vs, dy)
+        uy = grad_central_y_2nd(us, dy)
+        vx = grad_central_x_2nd(vs, dx)
+        sfxx = 2.0 * mu_f * ux
+        sfyy = 2.0 * mu_f * vy
+        sfxy = mu_f * (uy + vx)
+        sig_xx = Hf * sfxx + (1.0 - Ha) * sAxx + (1.0 - Hb) * sBxx
+        sig_yy = Hf * sfyy + (1.0 - Ha) * sAyy + (1.0 - Hb) * sByy
+        sig_xy = Hf * sfxy + (1.0 - Ha) * sAxy + (1.0 - Hb) * sBxy
+        div_x = grad_central_x_2nd(sig_xx, dx) + grad_central_y_2nd(sig_xy, dy)
+        div_y = grad_central_x_2nd(sig_xy, dx) + grad_central_y_2nd(sig_yy, dy)
+        u_adv = -us * diff_upwind_3rd(us, us, dx, 1) - vs * diff_upwind_3rd(us, vs, dy, 0)
+        v_adv = -us * diff_upwind_3rd(vs, us, dx, 1) - vs * diff_upwind_3rd(vs, vs, dy, 0)
+        px = grad_central_x_2nd(p, dx)
+        py = grad_central_y_2nd(p, dy)
+        return (u_adv + (div_x + fcx - px) / (rho_local + 1e-12),
+                v_adv + (div_y + fcy - py) / (rho_local + 1e-12))
+
+    k1u, k1v = rhs(u, v)
+    k2u, k2v = rhs(u + 0.5 * dt * k1u, v + 0.5 * dt * k1v)
+    k3u, k3v = rhs(u + 0.5 * dt * k2u, v + 0.5 * dt * k2v)
+    k4u, k4v = rhs(u + dt * k3u, v + dt * k3v)
+    un = u + (dt / 6.0) * (k1u + 2 * k2u + 2 * k3u + k4u)
+    vn = v + (dt / 6.0) * (k1v + 2 * k2v + 2 * k3v + k4v)
+    un, vn = velocity_bc(un, vn)
+    return un, vn, np.minimum(Ja, Jb)
+
+
 # --------------------------------------------------------------------------
 # functions.py -- pressure projection (constant-density branches)
 # --------------------------------------------------------------------------

@@ -163,6 +163,48 @@ k_curvature(const double *__restrict__ phi, double *__restrict__ out0, double *_
     }
 }
 
+// ------------------------------------------------------- contact force (functions.py:864-895)
+struct MidSurface {     // phi12 = (phi1 - phi2) / 2
+    const double *a, *b;
+    int Nx;
+    __device__ __forceinline__ double operator()(int j, int i) const
+    {
+        const size_t c = (size_t)j * Nx + i;
+        return 0.5 * (__ldg(a + c) - __ldg(b + c));
+    }
+};
+
+__global__ void __launch_bounds__(256)
+k_contact_force(const double *__restrict__ phi1, const double *__restrict__ phi2, double *__restrict__ fx,
+                double *__restrict__ fy, int Ny, int Nx, double dx, double dy, double k_rep, double w_c)
+{
+    int i = blockIdx.x * TX + threadIdx.x;
+    int j = blockIdx.y * TY + threadIdx.y;
+    if (i >= Nx || j >= Ny) return;
+    const size_t c = (size_t)j * Nx + i;
+    const MidSurface P{phi1, phi2, Nx};
+    const double p12 = P(j, i);
+    double ox = 0.0, oy = 0.0;
+    const bool active = (phi1[c] < 0.0) || (phi2[c] < 0.0);
+    if (fabs(p12) < w_c && active && p12 != 0.0) {
+        const double pi = 3.141592653589793;
+        const double delta = (1.0 + cos(pi * p12 / w_c)) / (2.0 * w_c);
+        const double gx = ddx2(P, j, i, Nx, 1.0 / (2.0 * dx)), gy = ddy2(P, j, i, Ny, 1.0 / (2.0 * dy));
+        const double gmag = sqrt(gx * gx + gy * gy) + 1e-12;
+        const double sg = (p12 > 0.0) ? 1.0 : -1.0;
+        ox = k_rep * delta * sg * (gx / gmag);
+        oy = k_rep * delta * sg * (gy / gmag);
+    }
+    fx[c] = ox;
+    fy[c] = oy;
+}
+
+__global__ void k_min2(const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out, long n)
+{
+    for (long k = blockIdx.x * (long)blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x)
+        out[k] = fmin(a[k], b[k]);
+}
+
 // ------------------------------------------------------- momentum RHS / stage
 constexpr int MTX = 32, MTY = 16;            // output tile
 constexpr int UHALO = 3, THALO = 2;          // shared-memory halos (rim tiles use all of it)
@@ -180,6 +222,7 @@ struct STile {   // shared-memory tile addressed with global (j, i)
 
 struct RhsArgs {
     const double *us, *vs, *p, *sxx, *sxy, *syy;
+    const double *sbxx, *sbxy, *sbyy, *phi_b;   // MODE 2: the second solid (functions.py:765-835)
     const double *phi;          // FUSED: level set (H, rho, solid mask derived in-kernel)
     const double *H, *rho;      // !FUSED: arrays as passed to velocity_rhs_blended_optimized
     const double *fsx, *fsy;    // optional surface-tension force
@@ -191,12 +234,17 @@ struct RhsArgs {
     int stage;
 };
 
-template <bool FUSED>
+// MODE 0: velocity_rhs_blended_optimized on caller-supplied H / rho arrays; 1: one RK4 stage of
+// momentum_step_rk4 (one solid); 2: one RK4 stage of momentum_step_rk4_2solids (n = 2 mixture
+// sigma = (Ha+Hb-1) sigma_f + (1-Ha) sigma_A + (1-Hb) sigma_B, no Kelvin-Voigt term).
+template <int MODE>
 __global__ void __launch_bounds__(256, 4)
 k_momentum_rhs(const RhsArgs A)
 {
+    constexpr bool FUSED = (MODE != 0), TWO = (MODE == 2);
     __shared__ double sU[UHT * UW], sV[UHT * UW];
     __shared__ double sTxx[THT * TW], sTxy[THT * TW], sTyy[THT * TW], sH[THT * TW];
+    __shared__ double sHb[TWO ? THT * TW : 1];
 
     const int Ny = A.Ny, Nx = A.Nx;
     const int i0 = blockIdx.x * MTX, j0 = blockIdx.y * MTY;
@@ -230,13 +278,16 @@ k_momentum_rhs(const RhsArgs A)
     const int tja = max(j0 - th, 0), tjb = min(j1 + th, Ny), tia = max(i0 - th, 0), tib = min(i1 + th, Nx);
     const int tw_ = tib - tia, tn = (tjb - tja) * tw_;
     double rh[3];                                  // phi (FUSED) or H at this thread's stress nodes
+    double rhb[TWO ? 3 : 1];                       // phi of the second solid
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int e = tid + 256 * k;
         rh[k] = 1.0;
+        if (TWO) rhb[k] = 1.0;
         if (e < tn) {
             const size_t g = (size_t)(tja + e / tw_) * Nx + (tia + e % tw_);
             rh[k] = FUSED ? __ldg(A.phi + g) : __ldg(A.H + g);
+            if (TWO) rhb[k] = __ldg(A.phi_b + g);
         }
     }
     double pf_u0[MTY / 8], pf_v0[MTY / 8], pf_au[MTY / 8], pf_av[MTY / 8];
@@ -275,7 +326,7 @@ k_momentum_rhs(const RhsArgs A)
             const int e = tid + 256 * k;
             hh[k] = FUSED ? heaviside_sin(rh[k], A.w_t, inv_w) : rh[k];
             sx[k] = sy[k] = sq[k] = 0.0;
-            if (e < tn && hh[k] != 1.0) {
+            if (!TWO && e < tn && hh[k] != 1.0) {
                 const size_t g = (size_t)(tja + e / tw_) * Nx + (tia + e % tw_);
                 sx[k] = __ldg(A.sxx + g);
                 sy[k] = __ldg(A.syy + g);
@@ -290,12 +341,24 @@ k_momentum_rhs(const RhsArgs A)
             const double ux = ddx2(U, jj, ii, Nx, i2dx), vy = ddy2(V, jj, ii, Ny, i2dy);
             const double uy = ddy2(U, jj, ii, Ny, i2dy), vx = ddx2(V, jj, ii, Nx, i2dx);
             const double h = hh[k];
+            if (TWO) {      // functions.py:806-810
+                const size_t g = (size_t)jj * Nx + ii;
+                const double hb = heaviside_sin(rhb[k], A.w_t, inv_w), hf = h + hb - 1.0;
+                const double oma = 1.0 - h, omb = 1.0 - hb;
+                const int s = (jj - (j0 - THALO)) * TW + (ii - (i0 - THALO));
+                sTxx[s] = hf * (2.0 * A.mu_f * ux) + oma * __ldg(A.sxx + g) + omb * __ldg(A.sbxx + g);
+                sTyy[s] = hf * (2.0 * A.mu_f * vy) + oma * __ldg(A.syy + g) + omb * __ldg(A.sbyy + g);
+                sTxy[s] = hf * (A.mu_f * (uy + vx)) + oma * __ldg(A.sxy + g) + omb * __ldg(A.sbxy + g);
+                sH[s] = h;
+                sHb[s] = hb;
+                continue;
+            }
             double txx = h * (2.0 * A.mu_f * ux);
             double tyy = h * (2.0 * A.mu_f * vy);
             double txy = h * (A.mu_f * (uy + vx));
             if (h != 1.0) {   // (1-H)*sigma_s vanishes identically in the pure fluid
                 double ex = sx[k], ey = sy[k], exy = sq[k];
-                if (FUSED && A.eta_s > 0.0 && rh[k] <= 0.0) {   // Kelvin-Voigt, :717-730 (rh = phi)
+                if (MODE == 1 && A.eta_s > 0.0 && rh[k] <= 0.0) {   // Kelvin-Voigt, :717-730 (rh = phi)
                     ex += A.eta_s * ux;
                     ey += A.eta_s * vy;
                     exy += A.eta_s * 0.5 * (uy + vx);
@@ -335,7 +398,11 @@ k_momentum_rhs(const RhsArgs A)
         double adv_v = -u * dvx - v * dvy;
         double px = ddx2(P, j, i, Nx, i2dx), py = ddy2(P, j, i, Ny, i2dy);
         double rho;
-        if (FUSED) {
+        if (TWO) {          // functions.py:793
+            const int s = (j - (j0 - THALO)) * TW + (i - (i0 - THALO));
+            const double ha = sH[s], hb = sHb[s];
+            rho = (ha + hb - 1.0) * A.rho_f + (1.0 - ha) * A.rho_s + (1.0 - hb) * A.rho_s;
+        } else if (FUSED) {
             double h = Hs(j, i);
             rho = (1.0 - h) * A.rho_s + h * A.rho_f;
         } else {
@@ -417,7 +484,7 @@ int rmt_velocity_rhs(const double *u, const double *v, const double *p, const do
     A.H = H; A.rho = rho; A.fsx = fsx; A.fsy = fsy; A.out_u = ru; A.out_v = rv;
     A.Ny = Ny; A.Nx = Nx; A.dx = dx; A.dy = dy; A.mu_f = mu_f;
     dim3 blk(32, 8), grd(rmt_cdiv(Nx, MTX), rmt_cdiv(Ny, MTY));
-    k_momentum_rhs<false><<<grd, blk, 0, (cudaStream_t)stream>>>(A);
+    k_momentum_rhs<0><<<grd, blk, 0, (cudaStream_t)stream>>>(A);
     RMT_LAUNCH_CHECK();
     return RMT_OK;
 }
@@ -438,7 +505,50 @@ int rmt_momentum_stage(const double *us, const double *vs, const double *p, cons
     A.out_u = out_u; A.out_v = out_v; A.Ny = Ny; A.Nx = Nx; A.dx = dx; A.dy = dy; A.dt = dt;
     A.mu_f = mu_f; A.eta_s = eta_s; A.w_t = w_t; A.rho_s = rho_s; A.rho_f = rho_f; A.stage = stage;
     dim3 blk(32, 8), grd(rmt_cdiv(Nx, MTX), rmt_cdiv(Ny, MTY));
-    k_momentum_rhs<true><<<grd, blk, 0, (cudaStream_t)stream>>>(A);
+    k_momentum_rhs<1><<<grd, blk, 0, (cudaStream_t)stream>>>(A);
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
+
+int rmt_momentum_stage_2solids(const double *us, const double *vs, const double *p, const double *sAxx,
+                               const double *sAxy, const double *sAyy, const double *sBxx, const double *sBxy,
+                               const double *sByy, const double *phi_a, const double *phi_b, const double *fcx,
+                               const double *fcy, const double *u0, const double *v0, double *acc_u,
+                               double *acc_v, double *out_u, double *out_v, int Ny, int Nx, double dx, double dy,
+                               double dt, double mu_f, double w_t, double rho_s, double rho_f, int stage,
+                               void *stream)
+{
+    if (!us || !vs || !p || !sAxx || !sAxy || !sAyy || !sBxx || !sBxy || !sByy || !phi_a || !phi_b || !u0 ||
+        !v0 || !acc_u || !acc_v || !out_u || !out_v || Ny < 4 || Nx < 4 || stage < 1 || stage > 4)
+        return RMT_EINVAL;
+    RhsArgs A{};
+    A.us = us; A.vs = vs; A.p = p; A.sxx = sAxx; A.sxy = sAxy; A.syy = sAyy;
+    A.sbxx = sBxx; A.sbxy = sBxy; A.sbyy = sByy; A.phi = phi_a; A.phi_b = phi_b;
+    A.fsx = fcx; A.fsy = fcy; A.u0 = u0; A.v0 = v0; A.acc_u = acc_u; A.acc_v = acc_v;
+    A.out_u = out_u; A.out_v = out_v; A.Ny = Ny; A.Nx = Nx; A.dx = dx; A.dy = dy; A.dt = dt;
+    A.mu_f = mu_f; A.eta_s = 0.0; A.w_t = w_t; A.rho_s = rho_s; A.rho_f = rho_f; A.stage = stage;
+    dim3 blk(32, 8), grd(rmt_cdiv(Nx, MTX), rmt_cdiv(Ny, MTY));
+    k_momentum_rhs<2><<<grd, blk, 0, (cudaStream_t)stream>>>(A);
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
+
+int rmt_contact_force(const double *phi1, const double *phi2, double *fx, double *fy, int Ny, int Nx, double dx,
+                      double dy, double k_rep, double w_c, void *stream)
+{
+    if (!phi1 || !phi2 || !fx || !fy || Ny < 3 || Nx < 3 || !(w_c > 0.0)) return RMT_EINVAL;
+    dim3 blk(TX, TY), grd(rmt_cdiv(Nx, TX), rmt_cdiv(Ny, TY));
+    k_contact_force<<<grd, blk, 0, (cudaStream_t)stream>>>(phi1, phi2, fx, fy, Ny, Nx, dx, dy, k_rep, w_c);
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
+
+int rmt_min2(const double *a, const double *b, double *out, long n, void *stream)
+{
+    if (!a || !b || !out || n <= 0) return RMT_EINVAL;
+    long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_min2<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
     RMT_LAUNCH_CHECK();
     return RMT_OK;
 }

@@ -397,14 +397,64 @@ def momentum_step_rk4(u, v, p, X1, X2, velocity_bc, mu_s, kappa, eta_s, dx, dy, 
     return tuple(to_user(t, as_np) for t in (un, vn, sxx, sxy, syy, J))
 
 
-def momentum_step_rk4_2solids(*args, **kwargs):
-    """pyRMT/functions.py:765-835 -- two-solid predictor: SURVEY 8(f) "next" row, not built yet."""
-    raise NotImplementedError("momentum_step_rk4_2solids is not part of the B200 hot path yet")
+def momentum_step_rk4_2solids(u, v, p, X1a, X2a, X1b, X2b, velocity_bc, mu_s, kappa, eta_s, dx, dy, dt,
+                              rho_s, rho_f, phi_a, phi_b, mu_f, w_t, k_rep=0.0, w_c=None, detg_clamp=4.0):
+    """pyRMT/functions.py:765-835 -- RK4 predictor for TWO neo-Hookean solids sharing one velocity
+    field, with the repulsive contact force of compute_contact_force as a body force.
+
+    Two stress kernels (detG clamped), the contact-force kernel, then four fused stage kernels
+    (n = 2 mixture stress + stage update; Ha, Hb and rho_local evaluated from the level sets
+    in-kernel) with the BC table applied between them.  eta_s is accepted and unused, as upstream.
+    Returns (u_new, v_new, min(Ja, Jb))."""
+    as_np = is_np(u)
+    ud, vd, pd, xa1, xa2, xb1, xb2, pa, pb = (to_dev(t) for t in (u, v, p, X1a, X2a, X1b, X2b, phi_a, phi_b))
+    Ny, Nx = shape2(ud)
+    lib, st = ctx().lib, stream()
+    dx, dy, dt = float(dx), float(dy), float(dt)
+    if w_c is None:
+        w_c = 2.0 * w_t
+    sA = [torch.empty_like(ud) for _ in range(4)]
+    sB = [torch.empty_like(ud) for _ in range(4)]
+    for (x1, x2, ph, out) in ((xa1, xa2, pa, sA), (xb1, xb2, pb, sB)):
+        _chk(lib.rmt_solid_stress(ptr(x1), ptr(x2), ptr(ph), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]),
+                                  Ny, Nx, dx, dy, float(mu_s), float(kappa), 0.0, float(detg_clamp), 0, st),
+             "rmt_solid_stress")
+    fcx = fcy = None
+    if k_rep > 0.0:
+        fcx, fcy = torch.empty_like(ud), torch.empty_like(ud)
+        _chk(lib.rmt_contact_force(ptr(pa), ptr(pb), ptr(fcx), ptr(fcy), Ny, Nx, dx, dy, float(k_rep), float(w_c),
+                                   st), "rmt_contact_force")
+    sa_u, sa_v = apply_bc_(velocity_bc, ud.clone(), vd.clone())
+    sb_u, sb_v = torch.empty_like(ud), torch.empty_like(ud)
+    acc_u, acc_v = torch.empty_like(ud), torch.empty_like(ud)
+    un, vn = torch.empty_like(ud), torch.empty_like(ud)
+
+    def stage(k, iu, iv, ou, ov):
+        _chk(lib.rmt_momentum_stage_2solids(ptr(iu), ptr(iv), ptr(pd), ptr(sA[0]), ptr(sA[1]), ptr(sA[2]),
+                                            ptr(sB[0]), ptr(sB[1]), ptr(sB[2]), ptr(pa), ptr(pb), ptr(fcx),
+                                            ptr(fcy), ptr(ud), ptr(vd), ptr(acc_u), ptr(acc_v), ptr(ou), ptr(ov),
+                                            Ny, Nx, dx, dy, dt, float(mu_f), float(w_t), float(rho_s),
+                                            float(rho_f), k, st), "rmt_momentum_stage_2solids")
+        return apply_bc_(velocity_bc, ou, ov)
+
+    sb_u, sb_v = stage(1, sa_u, sa_v, sb_u, sb_v)
+    sa_u, sa_v = stage(2, sb_u, sb_v, sa_u, sa_v)
+    sb_u, sb_v = stage(3, sa_u, sa_v, sb_u, sb_v)
+    un, vn = stage(4, sb_u, sb_v, un, vn)
+    Jmin = torch.empty_like(ud)
+    _chk(lib.rmt_min2(ptr(sA[3]), ptr(sB[3]), ptr(Jmin), Jmin.numel(), st), "rmt_min2")
+    return tuple(to_user(t, as_np) for t in (un, vn, Jmin))
 
 
-def compute_contact_force(*args, **kwargs):
-    """pyRMT/functions.py:864-895 -- SURVEY 8(f) "next" row, not built yet."""
-    raise NotImplementedError("compute_contact_force is not part of the B200 hot path yet")
+def compute_contact_force(phi1, phi2, k_rep, w_c, dx, dy):
+    """pyRMT/functions.py:864-895 -- repulsive solid-solid contact body force (fx, fy)."""
+    as_np = is_np(phi1)
+    p1, p2 = to_dev(phi1), to_dev(phi2)
+    Ny, Nx = shape2(p1)
+    fx, fy = torch.empty_like(p1), torch.empty_like(p1)
+    _chk(ctx().lib.rmt_contact_force(ptr(p1), ptr(p2), ptr(fx), ptr(fy), Ny, Nx, float(dx), float(dy),
+                                     float(k_rep), float(w_c), stream()), "rmt_contact_force")
+    return to_user(fx, as_np), to_user(fy, as_np)
 
 
 # --------------------------------------------------------------------------

@@ -274,6 +274,54 @@ def test_momentum_step_golden(P, golden, case, bcn):
     assert rel_linf(r[5], g[case + "_J"]) < 1e-11
 
 
+def test_contact_force_and_two_solid_step_golden(P, golden):
+    """functions.py:765-895 against the vectors recorded from the reference."""
+    from test_oracle_golden import CONTACT_CASES, contact_args
+    g = golden("contact")
+    dx, dy = float(g["dx"]), float(g["dy"])
+    for tag in ("c1", "c2"):
+        fx, fy = P.compute_contact_force(g["phi_a"], g["phi_b"], float(g[tag + "_k"]), float(g[tag + "_w"]), dx, dy)
+        assert rel_linf(fx, g[tag + "_fx"]) < TIGHT and rel_linf(fy, g[tag + "_fy"]) < TIGHT
+    for case in CONTACT_CASES:
+        pos, kw = contact_args(g, case)
+        un, vn, Jm = P.momentum_step_rk4_2solids(*pos, **kw)
+        assert rel_linf(un, g[case + "_u"]) < TOL * 1e-2, case
+        assert rel_linf(vn, g[case + "_v"]) < TOL * 1e-2, case
+        assert rel_linf(Jm, g[case + "_J"]) < TIGHT, case
+
+
+def test_two_solid_step_vs_oracle(P, O):
+    """The reference's own smoke case (tests/test_contact.py:45-64) enlarged, and the contact-force
+    properties it checks (repulsive direction, locality)."""
+    N = 161
+    X, Y, dx, dy = O.create_grid(N, N, 1.0, 1.0)
+    disc = lambda x0, y0, R: np.sqrt((X - x0) ** 2 + (Y - y0) ** 2) - R
+    p1, p2 = disc(0.40, 0.5, 0.105), disc(0.60, 0.5, 0.105)
+    w_c = 4 * dx
+    fx, fy = P.compute_contact_force(p1, p2, 1.0, w_c, dx, dy)
+    rx, ry = O.compute_contact_force(p1, p2, 1.0, w_c, dx, dy)
+    assert rel_linf(fx, rx) < TIGHT and rel_linf(fy, ry) < TIGHT
+    jm = N // 2
+    assert fx[jm, np.argmin(np.abs(X[jm] - 0.485))] < 0.0 < fx[jm, np.argmin(np.abs(X[jm] - 0.515))]
+    far = np.abs(0.5 * (p1 - p2)) > w_c
+    assert np.all(fx[far] == 0.0) and np.all(fy[far] == 0.0)
+    fx, fy = P.compute_contact_force(disc(0.25, 0.5, 0.12), disc(0.75, 0.5, 0.12), 1.0, 2 * dx, dx, dy)
+    assert not fx.any() and not fy.any()
+    pa, pb = O.apply_phi_BCs(disc(0.35, 0.5, 0.15)), O.apply_phi_BCs(disc(0.65, 0.5, 0.15))
+    ma, mb = (pa <= 0).astype(float), (pb <= 0).astype(float)
+    X1a, X2a = O.extrapolate_reference_map(X * ma, Y * ma * 0.98, pa, dx, dy, 3)
+    X1b, X2b = O.extrapolate_reference_map(X * mb * 1.02, Y * mb, pb, dx, dy, 3)
+    rng = np.random.default_rng(8)
+    u, v = 0.2 * np.sin(2 * np.pi * X) * np.cos(np.pi * Y), 0.1 * rng.standard_normal((N, N))
+    bc = _bcs()["lid"]
+    args = (u, v, 0.05 * np.cos(np.pi * X), X1a, X2a, X1b, X2b, bc, 1.0, 0.5, 0.0, dx, dy, 1e-3, 1.2, 1.0,
+            pa, pb, 0.01, 2 * dx)
+    got = P.momentum_step_rk4_2solids(*args, k_rep=2.0, w_c=3 * dx)
+    ref = O.momentum_step_rk4_2solids(*args, k_rep=2.0, w_c=3 * dx)
+    for nm, x, r in zip(("u", "v", "Jmin"), got, ref):
+        assert rel_linf(x, r) < TOL * 1e-2, nm
+
+
 def test_curvature_golden(P, golden):
     g = golden("momentum")
     assert rel_linf(P.compute_curvature(g["phi"], float(g["dx"]), float(g["dy"])), g["curv"]) < 1e-10

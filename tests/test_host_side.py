@@ -70,6 +70,8 @@ def test_signatures_match_reference_names():
         F.smoothed_heaviside: "(x, w_t)",
         F.momentum_step_rk4: "(u, v, p, X1, X2, velocity_bc, mu_s, kappa, eta_s, dx, dy, dt, rho_s, rho_f, phi, mu_f, w_t, gamma=0.0, stress_band=False, detg_clamp=3.0)",
         F.compute_curvature: "(phi, dx, dy)",
+        F.momentum_step_rk4_2solids: "(u, v, p, X1a, X2a, X1b, X2b, velocity_bc, mu_s, kappa, eta_s, dx, dy, dt, rho_s, rho_f, phi_a, phi_b, mu_f, w_t, k_rep=0.0, w_c=None, detg_clamp=4.0)",
+        F.compute_contact_force: "(phi1, phi2, k_rep, w_c, dx, dy)",
         F.velocity_rhs_blended_optimized: "(u, v, p, sigma_sxx, sigma_sxy, sigma_syy, dx, dy, phi, mu_f, H, dH_dx, dH_dy, rho_local, st_force_x, st_force_y)",
         F.apply_velocity_BCs: "(bc, u, v)",
         F.build_poisson_matrix: "(Nx, Ny, dx, dy)",
@@ -119,8 +121,6 @@ def test_reinit_and_unbuilt_rows():
         F.reinitialize_level_set(phi, 0.1, 0.1, "bogus")
     with pytest.raises(ImportError):
         F.reinitialize_level_set(phi, 0.1, 0.1, "fmm")
-    with pytest.raises(NotImplementedError):
-        F.momentum_step_rk4_2solids()
     A = F.build_poisson_matrix(129, 129, 0.1, 0.1)         # lazy placeholder
     assert A.shape == (129 * 129, 129 * 129)
 

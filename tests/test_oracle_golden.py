@@ -139,6 +139,37 @@ def test_velocity_rhs_and_curvature(golden):
     assert same(O.compute_curvature(phi, dx, dy), g["curv"])
 
 
+CONTACT_CASES = {"m_lid": ("lid", 2.0, 3.0, 4.0), "m_free": ("identity", 0.0, None, 4.0),
+                 "m_clamp": ("lid", 1.5, None, 1.2)}        # bc, k_rep, w_c / dx, detg_clamp
+
+
+def contact_args(g, case):
+    from oracle.rmt_oracle import no_slip_lid_bc
+    bcn, k_rep, wc, clamp = CONTACT_CASES[case]
+    bc = (lambda u, v: no_slip_lid_bc(u, v, 1.0)) if bcn == "lid" else (lambda u, v: (u.copy(), v.copy()))
+    dx, dy = float(g["dx"]), float(g["dy"])
+    mu_s, kappa, eta_s, dt, rho_s, rho_f, mu_f, w_t = (float(x) for x in g["prm"])
+    pos = (g["u"], g["v"], g["p"], g["X1a"], g["X2a"], g["X1b"], g["X2b"], bc, mu_s, kappa, eta_s, dx, dy, dt,
+           rho_s, rho_f, g["phi_a"], g["phi_b"], mu_f, w_t)
+    return pos, dict(k_rep=k_rep, w_c=None if wc is None else wc * dx, detg_clamp=clamp)
+
+
+def test_contact_force_and_two_solid_step(golden):
+    """functions.py:765-895 against the vectors of tests/golden/make_golden_contact.py."""
+    g = golden("contact")
+    dx, dy = float(g["dx"]), float(g["dy"])
+    for tag in ("c1", "c2"):
+        fx, fy = O.compute_contact_force(g["phi_a"], g["phi_b"], float(g[tag + "_k"]), float(g[tag + "_w"]), dx, dy)
+        assert rel_linf(fx, g[tag + "_fx"]) < 1e-13 and rel_linf(fy, g[tag + "_fy"]) < 1e-13
+        assert np.abs(g[tag + "_fx"]).max() > 0
+    for case in CONTACT_CASES:
+        pos, kw = contact_args(g, case)
+        un, vn, Jm = O.momentum_step_rk4_2solids(*pos, **kw)
+        assert rel_linf(un, g[case + "_u"]) < 1e-13, case
+        assert rel_linf(vn, g[case + "_v"]) < 1e-13, case
+        assert same(Jm, g[case + "_J"]), case
+
+
 def test_projection_neumann(golden):
     g = golden("projection")
     dx, dy, dt = float(g["dx"]), float(g["dy"]), float(g["dt"])
