@@ -43,6 +43,13 @@ int rmt_heaviside(const double *x, double *H, long n, double w_t, void *stream);
  * driver glue benchmarks/soft_disc_in_lid_driven.py:102-103).  H may be NULL. */
 int rmt_heaviside_rho(const double *phi, double *H, double *rho, long n, double w_t, double rho_s,
                       double rho_f, void *stream);
+/* pyRMT/functions.py:1369-1411 reinitialize_phi_PDE, one kernel per piece:
+ *   rmt_reinit_sign: s0 = phi0 / sqrt(phi0^2 + dx^2)                       (:1371)
+ *   rmt_reinit_step: out = phi - dtau * s0 * (|grad phi|_Godunov - 1)      (:1375-1404), out != phi.
+ * The caller applies the optional phi BC callback between steps (:1406-1407). */
+int rmt_reinit_sign(const double *phi0, double *s0, long n, double dx, void *stream);
+int rmt_reinit_step(const double *phi, const double *s0, double *out, int Ny, int Nx, double dx, double dy,
+                    double dtau, void *stream);
 /* out = q * (phi <= 0): the "* solid_mask" glue, soft_disc_in_lid_driven.py:88-91. */
 int rmt_mask_mul(const double *q, const double *phi, double *out, long n, void *stream);
 

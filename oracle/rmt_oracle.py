@@ -618,6 +618,33 @@ def pressure_projection_amg(a_star, b_star, dx, dy, dt, rho, velocity_bc, A=None
     return a, b, p, A, ml
 
 
+def reinitialize_phi_PDE(phi_in, dx, dy, num_iters, apply_phi_BCs_func, dt_reinit_factor=0.5):
+    """Sussman-Smereka-Osher pseudo-time reinitialisation, functions.py:1369-1411: forward Euler on
+    phi_tau = -S0 (|grad phi|_upwind - 1), S0 = phi0 / sqrt(phi0^2 + dx^2), one-sided differences with
+    the edge value repeated outside the grid, Godunov choice by the sign of S0 (zero where S0 == 0)."""
+    phi = np.array(phi_in, dtype=np.float64, copy=True)
+    s0 = phi_in / np.sqrt(phi_in ** 2 + dx ** 2)
+    dtau = dt_reinit_factor * min(dx, dy)
+    zero = np.zeros_like(phi)
+    for _ in range(num_iters):
+        left = np.concatenate([phi[:, :1], phi[:, :-1]], axis=1)
+        right = np.concatenate([phi[:, 1:], phi[:, -1:]], axis=1)
+        down = np.concatenate([phi[:1, :], phi[:-1, :]], axis=0)
+        up = np.concatenate([phi[1:, :], phi[-1:, :]], axis=0)
+        bx, fx = (phi - left) / dx, (right - phi) / dx
+        by, fy = (phi - down) / dy, (up - phi) / dy
+        pos_x = np.maximum(np.maximum(bx, 0.0) ** 2, np.minimum(fx, 0.0) ** 2)
+        pos_y = np.maximum(np.maximum(by, 0.0) ** 2, np.minimum(fy, 0.0) ** 2)
+        neg_x = np.maximum(np.minimum(bx, 0.0) ** 2, np.maximum(fx, 0.0) ** 2)
+        neg_y = np.maximum(np.minimum(by, 0.0) ** 2, np.maximum(fy, 0.0) ** 2)
+        gx2 = np.where(s0 > 0, pos_x, np.where(s0 < 0, neg_x, zero))
+        gy2 = np.where(s0 > 0, pos_y, np.where(s0 < 0, neg_y, zero))
+        phi = phi - dtau * (s0 * (np.sqrt(gx2 + gy2) - 1.0))
+        if apply_phi_BCs_func is not None:
+            phi = apply_phi_BCs_func(phi)
+    return phi
+
+
 # --------------------------------------------------------------------------
 # caller-side contract (benchmarks/common.py) used by drivers and tests
 # --------------------------------------------------------------------------

@@ -24,6 +24,8 @@ _SIG = {
     "rmt_diff_upwind_3rd": [vp, vp, vp, i32, i32, dbl, i32, vp],
     "rmt_heaviside": [vp, vp, i64, dbl, vp],
     "rmt_heaviside_rho": [vp, vp, vp, i64, dbl, dbl, dbl, vp],
+    "rmt_reinit_sign": [vp, vp, i64, dbl, vp],
+    "rmt_reinit_step": [vp, vp, vp, i32, i32, dbl, dbl, dbl, vp],
     "rmt_mask_mul": [vp, vp, vp, i64, vp],
     "rmt_reduce_workspace_doubles": [],
     "rmt_max_speed": [vp, vp, i64, vp, vp, vp],

@@ -92,6 +92,44 @@ __global__ void k_heaviside(const double *__restrict__ x, double *__restrict__ H
         H[k] = heaviside_sin(x[k], w_t, inv_w);
 }
 
+// ---- reinitialize_phi_PDE (functions.py:1369-1411) ------------------------------------------
+// S0 = phi0 / sqrt(phi0^2 + dx^2), fixed for all pseudo-time steps
+__global__ void k_reinit_sign(const double *__restrict__ phi0, double *__restrict__ s0, long n, double dx)
+{
+    const double dx2 = dx * dx;
+    for (long k = blockIdx.x * (long)blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x) {
+        const double p = phi0[k];
+        s0[k] = p / sqrt(p * p + dx2);
+    }
+}
+
+// one forward-Euler step: Godunov upwind |grad phi| from one-sided differences (edge value repeated
+// outside the grid, np.pad mode='edge'), chosen by the sign of S0
+__global__ void __launch_bounds__(256)
+k_reinit_step(const double *__restrict__ phi, const double *__restrict__ s0, double *__restrict__ out, int Ny,
+              int Nx, double dx, double dy, double dtau)
+{
+    int i = blockIdx.x * TX + threadIdx.x;
+    int j = blockIdx.y * TY + threadIdx.y;
+    if (i >= Nx || j >= Ny) return;
+    const size_t c = (size_t)j * Nx + i;
+    const double p = phi[c], s = s0[c];
+    const double pl = (i > 0) ? __ldg(phi + c - 1) : p, pr = (i < Nx - 1) ? __ldg(phi + c + 1) : p;
+    const double pd = (j > 0) ? __ldg(phi + c - Nx) : p, pu = (j < Ny - 1) ? __ldg(phi + c + Nx) : p;
+    const double bx = (p - pl) / dx, fx = (pr - p) / dx, by = (p - pd) / dy, fy = (pu - p) / dy;
+    double gx2 = 0.0, gy2 = 0.0;
+    if (s > 0.0) {
+        const double a = fmax(bx, 0.0), b = fmin(fx, 0.0), e = fmax(by, 0.0), f = fmin(fy, 0.0);
+        gx2 = fmax(a * a, b * b);
+        gy2 = fmax(e * e, f * f);
+    } else if (s < 0.0) {
+        const double a = fmin(bx, 0.0), b = fmax(fx, 0.0), e = fmin(by, 0.0), f = fmax(fy, 0.0);
+        gx2 = fmax(a * a, b * b);
+        gy2 = fmax(e * e, f * f);
+    }
+    out[c] = p - dtau * (s * (sqrt(gx2 + gy2) - 1.0));
+}
+
 // H and rho_local = (1-H)*rho_s + H*rho_f in one pass (driver glue,
 // soft_disc_in_lid_driven.py:102-103).
 __global__ void k_heaviside_rho(const double *__restrict__ phi, double *__restrict__ H,
@@ -313,6 +351,24 @@ int rmt_heaviside(const double *x, double *H, long n, double w_t, void *stream)
 {
     if (!x || !H || n <= 0) return RMT_EINVAL;
     k_heaviside<<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, H, n, w_t);
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
+
+int rmt_reinit_sign(const double *phi0, double *s0, long n, double dx, void *stream)
+{
+    if (!phi0 || !s0 || n <= 0) return RMT_EINVAL;
+    k_reinit_sign<<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(phi0, s0, n, dx);
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
+
+int rmt_reinit_step(const double *phi, const double *s0, double *out, int Ny, int Nx, double dx, double dy,
+                    double dtau, void *stream)
+{
+    if (!phi || !s0 || !out || phi == out || Ny < 2 || Nx < 2) return RMT_EINVAL;
+    dim3 blk(TX, TY), grd(rmt_cdiv(Nx, TX), rmt_cdiv(Ny, TY));
+    k_reinit_step<<<grd, blk, 0, (cudaStream_t)stream>>>(phi, s0, out, Ny, Nx, dx, dy, dtau);
     RMT_LAUNCH_CHECK();
     return RMT_OK;
 }

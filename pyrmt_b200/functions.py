@@ -686,8 +686,32 @@ def pressure_projection_amg(a_star, b_star, dx, dy, dt, rho, velocity_bc, A=None
 # level-set reinitialisation (only the default 'none' is on the hot path)
 # --------------------------------------------------------------------------
 def reinitialize_phi_PDE(phi_in, dx, dy, num_iters, apply_phi_BCs_func, dt_reinit_factor=0.5):
-    """pyRMT/functions.py:1369-1411 -- non-default option, SURVEY 8(f) rank 4."""
-    raise NotImplementedError("reinitialize_phi_PDE is not part of the B200 hot path yet")
+    """pyRMT/functions.py:1369-1411 -- Sussman-Smereka-Osher pseudo-time reinitialisation: one sign
+    kernel, then one Godunov-upwind step kernel per iteration (ping-pong buffers).  The optional
+    phi BC callback runs between steps as upstream: this module's apply_phi_BCs works on the device
+    tensor in place; any other callable receives what the caller passed in (an ndarray costs a
+    host round trip per iteration)."""
+    as_np = is_np(phi_in)
+    cur = to_dev(phi_in).clone()
+    Ny, Nx = shape2(cur)
+    lib, st = ctx().lib, stream()
+    dx, dy = float(dx), float(dy)
+    s0 = torch.empty_like(cur)
+    _chk(lib.rmt_reinit_sign(ptr(cur), ptr(s0), cur.numel(), dx, st), "rmt_reinit_sign")
+    dtau = float(dt_reinit_factor) * min(dx, dy)
+    nxt = torch.empty_like(cur)
+    for _ in range(int(num_iters)):
+        _chk(lib.rmt_reinit_step(ptr(cur), ptr(s0), ptr(nxt), Ny, Nx, dx, dy, dtau, st), "rmt_reinit_step")
+        cur, nxt = nxt, cur
+        if apply_phi_BCs_func is None:
+            continue
+        if apply_phi_BCs_func is apply_phi_BCs or not as_np:
+            cur = to_dev(apply_phi_BCs_func(cur))
+        else:
+            cur = to_dev(np.ascontiguousarray(apply_phi_BCs_func(cur.cpu().numpy()), dtype=np.float64))
+        if cur.data_ptr() == nxt.data_ptr():
+            nxt = torch.empty_like(cur)
+    return to_user(cur, as_np)
 
 
 def reinitialize_phi_fmm(phi, dx, dy):

@@ -322,6 +322,23 @@ def test_two_solid_step_vs_oracle(P, O):
         assert rel_linf(x, r) < TOL * 1e-2, nm
 
 
+def test_reinitialize_phi_pde_golden(P, golden):
+    """functions.py:1369-1411: IEEE operations only, so bit-exact."""
+    import torch
+    g = golden("reinit")
+    dx, dy = float(g["dx"]), float(g["dy"])
+    assert same(P.reinitialize_phi_PDE(g["phi"], dx, dy, 7, None, 0.5), g["r_none_7"])
+    assert same(P.reinitialize_phi_PDE(g["phi"], dx, dy, 20, P.apply_phi_BCs, 0.2), g["r_bc_20"])
+    assert same(P.reinitialize_level_set(g["phi"], dx, dy, method="pde", num_iters=5, dt_reinit_factor=0.3),
+                g["r_level_set"])
+    host_bc = lambda f: P.apply_phi_BCs(np.array(f))                 # an arbitrary callable: host round trip
+    assert same(P.reinitialize_phi_PDE(g["phi"], dx, dy, 20, host_bc, 0.2), g["r_bc_20"])
+    t = torch.from_numpy(g["phi"].copy()).cuda()
+    out = P.reinitialize_phi_PDE(t, dx, dy, 20, P.apply_phi_BCs, 0.2)
+    assert isinstance(out, torch.Tensor) and same(out.cpu().numpy(), g["r_bc_20"])
+    assert same(t.cpu().numpy(), g["phi"])                            # input not mutated
+
+
 def test_curvature_golden(P, golden):
     g = golden("momentum")
     assert rel_linf(P.compute_curvature(g["phi"], float(g["dx"]), float(g["dy"])), g["curv"]) < 1e-10

@@ -84,6 +84,7 @@ def test_signatures_match_reference_names():
         F._solve_poisson_fft: "(rhs_full, eigenvalues_periodic)",
         F.pressure_projection_amg: "(a_star, b_star, dx, dy, dt, rho, velocity_bc, A=None, ml=None, p_prev=None, eigenvalues=None, bc_type='neumann')",
         F.rebuild_phi_from_reference_map: "(X1, X2, phi_init_func)",
+        F.reinitialize_phi_PDE: "(phi_in, dx, dy, num_iters, apply_phi_BCs_func, dt_reinit_factor=0.5)",
         F.reinitialize_level_set: "(phi, dx, dy, method='none', num_iters=20, dt_reinit_factor=0.2, apply_phi_BCs_func=None)",
         I.bilinear_interpolate: "(u, xq, yq, dx, dy, Nx, Ny)",
         I.bicubic_interpolate: "(u, xq, yq, dx, dy, Nx, Ny)",

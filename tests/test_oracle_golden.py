@@ -170,6 +170,15 @@ def test_contact_force_and_two_solid_step(golden):
         assert same(Jm, g[case + "_J"]), case
 
 
+def test_reinitialize_phi_pde(golden):
+    """functions.py:1369-1411 against tests/golden/make_golden_reinit.py (bit-exact: IEEE ops only)."""
+    g = golden("reinit")
+    dx, dy = float(g["dx"]), float(g["dy"])
+    assert same(O.reinitialize_phi_PDE(g["phi"], dx, dy, 7, None, 0.5), g["r_none_7"])
+    assert same(O.reinitialize_phi_PDE(g["phi"], dx, dy, 20, O.apply_phi_BCs, 0.2), g["r_bc_20"])
+    assert same(O.reinitialize_phi_PDE(g["phi"], dx, dy, 5, None, 0.3), g["r_level_set"])
+
+
 def test_projection_neumann(golden):
     g = golden("projection")
     dx, dy, dt = float(g["dx"]), float(g["dy"]), float(g["dt"])
