@@ -122,7 +122,7 @@ static ExtTune ext_tune()
 __global__ void k_ext_flag(unsigned char *__restrict__ st, int *__restrict__ seg_cnt, int Ny, int Nx,
                            int nxt, int XT, const int *__restrict__ mode)
 {
-    if (mode && *mode == 1) return;
+    if (mode && *mode != 0) return;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int nwarp = (gridDim.x * blockDim.x) >> 5;
     for (int j = warp; j < Ny; j += nwarp) {
@@ -159,7 +159,7 @@ __global__ void k_ext_flag(unsigned char *__restrict__ st, int *__restrict__ seg
 __global__ void k_ext_scan(const int *__restrict__ seg_cnt, int *__restrict__ seg_off, int Ny, int nxt,
                            int *__restrict__ tile_counter, const int *__restrict__ mode)
 {
-    if (mode && *mode == 1) return;
+    if (mode && *mode != 0) return;
     __shared__ int sh[1024];
     const int per = (Ny + blockDim.x - 1) / blockDim.x;       // rows per thread (contiguous)
     const int lo = min((int)threadIdx.x * per, Ny), hi = min(lo + per, Ny);
@@ -192,7 +192,7 @@ __global__ void k_ext_fill(const unsigned char *__restrict__ st, const int *__re
                            int *__restrict__ tcol, int *__restrict__ trow, int *__restrict__ prog, int Ny,
                            int Nx, int nxt, int XT, const int *__restrict__ mode)
 {
-    if (mode && *mode == 1) return;
+    if (mode && *mode != 0) return;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int nwarp = (gridDim.x * blockDim.x) >> 5;
     for (int j = warp; j < Ny; j += nwarp) {
@@ -368,7 +368,7 @@ k_ext_prepare(const double *__restrict__ X1e, const double *__restrict__ X2e,
               int *__restrict__ tinfo, int cap, int Ny, int Nx, int joff, double dx, double dy, double r2,
               const int *__restrict__ mode)
 {
-    if (mode && *mode == 1) return;
+    if (mode && *mode != 0) return;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
     const int ntot = min(seg_off[nseg], cap);
@@ -436,7 +436,7 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
             int cap, int Ny, int Nx, int joff, int nxt, int XT, int MRB, int sleep_ns, double dx, double dy,
             double r2, const int *__restrict__ mode)
 {
-    if (mode && *mode == 1) return;
+    if (mode && *mode != 0) return;
     extern __shared__ unsigned char s_raw[];
     SweepSmem &S = *reinterpret_cast<SweepSmem *>(s_raw);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -698,36 +698,40 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
 constexpr int CAPW = 8;                // phase-A records prepared per row warp (beyond: inline)
 constexpr int LMAX = 512;              // targets listed per (row, x-tile)
 
-struct FusedSmem {
-    SweepWarp w[RB];
+template <int RBT>
+struct FusedSmemT {
+    SweepWarp w[RBT];
     double prev_v[4][RING][2];
     int prev_tag[4][RING];
     int prev_row0;
-    int prog[RB];
+    int prog[RBT];
     int tile;
-    int tinf[RB][CAPW];
-    unsigned short tl[RB][LMAX];
+    int tinf[RBT][CAPW];
+    unsigned short tl[RBT][LMAX];
 };
 
-__global__ void __launch_bounds__(RB * 32, 1)
+// RBT = 16: one CTA per SM; RBT = 8: two per SM (half the rows per block, half the shared memory) --
+// twice as many chains in flight for grids with more bodies than SMs, at a higher per-block overhead.
+template <int RBT>
+__global__ void __launch_bounds__(RBT * 32, 16 / RBT)
 k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__restrict__ st,
             const int *__restrict__ cnt0 /* layer-0 target counts per (row, x-tile) */,
             int *__restrict__ prog /* [L][Ny*nxt] */, int *__restrict__ tile_counter,
-            ExtRec *__restrict__ scratch /* [gridDim][RB][CAPW] */, const int *__restrict__ mode, int L, int Ny,
+            ExtRec *__restrict__ scratch /* [gridDim][RBT][CAPW] */, const int *__restrict__ mode, int L, int Ny,
             int Nx, int joff, int nxt, int XT, double dx, double dy, double r2)
 {
-    if (mode[0] != 1) return;
-    const int MRB = mode[1];                    // macro-tile height in row blocks, chosen by k_ext_decide
+    if (mode[0] != RBT) return;                 // k_ext_decide picked another variant
+    const int MRB = mode[1] / RBT;              // macro-tile height (rows, chosen by k_ext_decide) in row blocks
     extern __shared__ unsigned char s_raw[];
-    FusedSmem &S = *reinterpret_cast<FusedSmem *>(s_raw);
+    FusedSmemT<RBT> &S = *reinterpret_cast<FusedSmemT<RBT> *>(s_raw);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     SweepWarp &W = S.w[wib];
     volatile int *sp = S.prog;
     const int nseg = Ny * nxt;
-    const int nrb = (Ny - 2 + RB - 1) / RB, nmrb = (nrb + MRB - 1) / MRB;
+    const int nrb = (Ny - 2 + RBT - 1) / RBT, nmrb = (nrb + MRB - 1) / MRB;
     const int ntasks = nmrb * L * nxt;
     const int la = (lane < NACC) ? lane : 0;
-    ExtRec *myrecs = scratch + ((size_t)blockIdx.x * RB + wib) * CAPW;
+    ExtRec *myrecs = scratch + ((size_t)blockIdx.x * RBT + wib) * CAPW;
 
     for (;;) {
         if (threadIdx.x == 0) S.tile = atomicAdd(tile_counter, 1);
@@ -742,13 +746,13 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
         const int rb_end = min((mrb + 1) * MRB, nrb);
         if (threadIdx.x == 0) S.prev_row0 = -100;
       for (int rb = mrb * MRB; rb < rb_end; ++rb) {
-        const int row0 = 1 + rb * RB;
+        const int row0 = 1 + rb * RBT;
         const int j = row0 + wib;
         const bool live = j < Ny - 1;
         // ---- can this block hold targets of this layer at all?  (layer-l targets lie within l cells of
         //      layer-0 targets; cnt0 is exact for layer 0 and conservative beyond)
         int any = 0;
-        for (int e = threadIdx.x; e < (RB + 2 * layer + 2) * 3; e += blockDim.x) {
+        for (int e = threadIdx.x; e < (RBT + 2 * layer + 2) * 3; e += blockDim.x) {
             const int jr = row0 - layer - 1 + e / 3, xq = xt - 1 + e % 3;
             if (jr >= 0 && jr < Ny && xq >= 0 && xq < nxt) any |= cnt0[jr * nxt + xq];
         }
@@ -818,7 +822,7 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
             sp[wib] = INT_MAX;
         }
         const bool edgy = nt && (xc0 + S.tl[wib][0] < xc0 + 8 || xc0 + S.tl[wib][nt - 1] >= xc1 - 8 ||
-                                 (last_rb && wib >= RB - 4));
+                                 (last_rb && wib >= RBT - 4));
         (void)edgy;
 
         // ---- (5) the sweep of this row, as in k_ext_sweep -----------------------------------------
@@ -962,7 +966,7 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                 // global marker: the next layer reads every row (fence at the row's end); this layer's
                 // other tiles read the rows/columns next to them
                 if (lane == 0) {
-                    const bool data = (last_rb && wib >= RB - 4) || i < xc0 + 8 || i >= xc1 - 8;
+                    const bool data = (last_rb && wib >= RBT - 4) || i < xc0 + 8 || i >= xc1 - 8;
                     if (data || next == INT_MAX) {
                         __threadfence();
                         st_release(progL + j * nxt + xt, next);
@@ -972,13 +976,13 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
             __syncwarp();
         }
         __syncthreads();
-        if (wib >= RB - 4) {
+        if (wib >= RBT - 4) {
             if (lane < RING) {
-                S.prev_tag[wib - (RB - 4)][lane] = W.ring_tag[lane];
-                S.prev_v[wib - (RB - 4)][lane][0] = W.ring_v[lane][0];
-                S.prev_v[wib - (RB - 4)][lane][1] = W.ring_v[lane][1];
+                S.prev_tag[wib - (RBT - 4)][lane] = W.ring_tag[lane];
+                S.prev_v[wib - (RBT - 4)][lane][0] = W.ring_v[lane][0];
+                S.prev_v[wib - (RBT - 4)][lane][1] = W.ring_v[lane][1];
             }
-            if (wib == RB - 4 && lane == 0) S.prev_row0 = row0 + RB - 4;
+            if (wib == RBT - 4 && lane == 0) S.prev_row0 = row0 + RBT - 4;
         }
         __syncthreads();
       }
@@ -995,13 +999,14 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
 // longest chain of target rows through vertically adjacent tiles of x-tile xt (a body crossing a tile
 // boundary chains the two tiles); also counts the non-empty tiles
 __device__ inline int ext_longest_chain(const int *__restrict__ cnt0, const int *__restrict__ rows, int ntile_rows,
-                                        int height, int nxt, int xt, int Ny, int *nonempty)
+                                        int height, int nxt, int xt, int Ny, int *nonempty, int *links)
 {
     int chain = 0, longest = 0;
     for (int m = 0; m < ntile_rows; ++m) {
         const int r = rows[m * nxt + xt], jb = m * height;               // jb: last row of the tile above
         const bool linked = m > 0 && jb + 1 < Ny && cnt0[jb * nxt + xt] && cnt0[(jb + 1) * nxt + xt];
         chain = r + (linked ? chain : 0);
+        *links += linked;
         *nonempty += r != 0;
         longest = max(longest, chain);
     }
@@ -1010,31 +1015,46 @@ __device__ inline int ext_longest_chain(const int *__restrict__ cnt0, const int 
 
 __global__ void k_ext_decide(const int *__restrict__ cnt0, const int *__restrict__ rows_macro, int nmrb,
                              int macro, const int *__restrict__ rows_band, int nbands, int band, int nxt,
-                             int Ny, int L, int limit, int *__restrict__ mode)
+                             int Ny, int L, int limit16, int limit8, int force, int *__restrict__ mode)
 {
-    __shared__ int busy, busy_band, longest_macro, longest_band;
-    if (threadIdx.x == 0) busy = busy_band = longest_macro = longest_band = 0;
+    __shared__ int busy, busy_band, longest_macro, longest_band, links_macro, links_band;
+    if (threadIdx.x == 0) busy = busy_band = longest_macro = longest_band = links_macro = links_band = 0;
     __syncthreads();
     for (int xt = threadIdx.x; xt < nxt; xt += blockDim.x) {
-        int nb = 0, dummy = 0;
-        const int lm = ext_longest_chain(cnt0, rows_macro, nmrb, macro, nxt, xt, Ny, &nb);
-        const int lb = ext_longest_chain(cnt0, rows_band, nbands, band, nxt, xt, Ny, &dummy);
+        int nb = 0, nbb = 0, km = 0, kb = 0;
+        const int lm = ext_longest_chain(cnt0, rows_macro, nmrb, macro, nxt, xt, Ny, &nb, &km);
+        const int lb = ext_longest_chain(cnt0, rows_band, nbands, band, nxt, xt, Ny, &nbb, &kb);
         atomicAdd(&busy, nb);
-        atomicAdd(&busy_band, dummy);
+        atomicAdd(&busy_band, nbb);
+        atomicAdd(&links_macro, km);
+        atomicAdd(&links_band, kb);
         atomicMax(&longest_macro, lm);
         atomicMax(&longest_band, lb);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        // all-layers kernel with macro-tiles of `macro` rows or of `band` rows (more, shorter tasks: bodies
-        // stacked in one macro-tile run side by side), or the per-layer launches
-        const float big = 3.0e38f;
-        const float fused_macro = (busy * L <= limit) ? 7.1f * longest_macro : big;
-        const float fused_band = (busy_band * L <= limit) ? 7.1f * longest_band : big;
-        const float layered = L * (360.f + 3.4f * longest_band);
-        const float fused = fminf(fused_macro, fused_band);
-        mode[0] = (fused < layered) ? 1 : 0;
-        mode[1] = ((fused_band < fused_macro) ? band : macro) / RB;
+        // all-layers kernel (16 or 8 rows per block; macro-tiles of `macro` or of `band` rows: shorter
+        // tasks let bodies stacked in one macro-tile run side by side) or the per-layer launches.
+        // us per chained row: 7.1 with 16-row blocks, 8.1 with 8-row blocks (twice the CTAs per SM).  A body
+        // cut by a task boundary costs the 8-row variant far more than its row count says (measured: 36
+        // discs on a 6 x 6 lattice, 6.3 ms against 4.9 ms per-layer), so it only runs when nothing is cut.
+        const float kRow16 = 7.1f, kRow8 = 8.1f, big = 3.0e38f;
+        const int cut[2] = {links_macro, links_band};
+        float best = L * (360.f + 3.4f * longest_band);
+        int variant = 0, rows = macro;
+        const int nb[2] = {busy, busy_band}, ln[2] = {longest_macro, longest_band}, ht[2] = {macro, band};
+        for (int g = 0; g < 2; ++g) {
+            const float c16 = (nb[g] * L <= limit16) ? kRow16 * ln[g] : big;
+            const float c8 = (nb[g] * L <= limit8 && cut[g] == 0) ? kRow8 * ln[g] : big;
+            if (c16 < best) { best = c16; variant = 16; rows = ht[g]; }
+            if (c8 < best) { best = c8; variant = 8; rows = ht[g]; }
+        }
+        if (force >= 0) {                        // RMT_EXT_FORCE: tuning hook (variant * 10000 + rows)
+            variant = force / 10000;
+            rows = force % 10000 ? force % 10000 : rows;
+        }
+        mode[0] = variant;
+        mode[1] = rows;
     }
 }
 
@@ -1105,7 +1125,7 @@ static ExtLayout ext_layout(int Ny, int Nx)
     L.cap = ext_cap((long)ncell);
     {   // the all-layers kernel keeps CAPW records per row warp of every resident CTA
         long nmrb = ((Ny - 2 + RB - 1) / RB + 31) / 32, tasks = nmrb * 8 * ext_nxt(Nx);
-        long fused = (tasks < 148 ? tasks : 148) * RB * CAPW;
+        long fused = (tasks < 148 ? tasks : 148) * 16 * CAPW;   // = 296 CTAs x 8 warps of the 8-row variant
         if (L.cap < fused) L.cap = fused;
     }
     size_t off = 0;
@@ -1160,64 +1180,72 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
     k_ext_seed<<<flat_blocks((long)ncell), 256, 0, s>>>(X1, X2, phi, X1e, X2e, st, (long)ncell);
     RMT_LAUNCH_CHECK();
 
-    // ---- all layers in one launch when the bodies are few enough (RMT_EXT_FUSED=0: never) ----
-    int *mode = nullptr;        // device flag: 1 = the all-layers kernel did the work, 0 = per-layer launches do
-    {
-        static int fused_on = -1, fused_blocks = 0;
+    // ---- all layers in one launch when that is faster (RMT_EXT_FUSED=0: never) ----
+    int *mode = nullptr;   // device: mode[0] = 0 per-layer launches, 16 / 8 all-layers kernel with that many rows
+    {                      // per block; mode[1] = its macro-tile height in rows
+        static int fused_on = -1, resident16 = 0, resident8 = 0, force = -1;
         if (fused_on < 0) {
             const char *e = getenv("RMT_EXT_FUSED");
             fused_on = (e && atoi(e) == 0) ? 0 : 1;
+            if ((e = getenv("RMT_EXT_FORCE"))) force = atoi(e);
         }
         const int Lyr = max_layers;
         if (fused_on && Lyr >= 1 && Lyr <= 8) {
-            if (!fused_blocks) {
+            if (!resident16) {
                 int dev = 0, sms = 0, per_sm = 0;
                 RMT_CUDA(cudaGetDevice(&dev));
                 RMT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-                RMT_CUDA(cudaFuncSetAttribute(k_ext_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)sizeof(FusedSmem)));
-                RMT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_fused, RB * 32,
-                                                                       sizeof(FusedSmem)));
+                RMT_CUDA(cudaFuncSetAttribute(k_ext_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)sizeof(FusedSmemT<16>)));
+                RMT_CUDA(cudaFuncSetAttribute(k_ext_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)sizeof(FusedSmemT<8>)));
+                RMT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_fused<16>, 16 * 32,
+                                                                       sizeof(FusedSmemT<16>)));
                 if (per_sm < 1) return RMT_EINVAL;
-                fused_blocks = sms * per_sm;
+                resident16 = sms * per_sm;
+                RMT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_fused<8>, 8 * 32,
+                                                                       sizeof(FusedSmemT<8>)));
+                if (per_sm < 1) return RMT_EINVAL;
+                resident8 = sms * per_sm;
             }
             // x-tiles wide enough that a task never waits on a task more than ~3/4 of the resident CTAs ahead
-            int max_tiles = (fused_blocks * 3 / 4) / (2 * Lyr - 1);
+            int max_tiles = (resident16 * 3 / 4) / (2 * Lyr - 1);
             if (max_tiles < 1) max_tiles = 1;
             int XTf = (Nx > 1024) ? 512 : XT;             // both flanks of a body in one tile: fewer tasks
             const int need_xt = ((Nx + max_tiles - 1) / max_tiles + 31) / 32 * 32;
             if (need_xt > XTf) XTf = need_xt;
             const int nxtf = (Nx + XTf - 1) / XTf, nsegf = Ny * nxtf;
             const long prog_ints = (long)Lyr * nsegf;
-            const int MRBf = 64;                           // macro-rows of 64 * RB rows
-            const int nmrb = rmt_cdiv(rmt_cdiv(Ny - 2, RB), MRBf);
-            const int band = 32 * RB;                      // the per-layer path's macro-tile height
+            const int macro = 1024, band = 512;            // candidate macro-tile heights (rows)
+            const int nmrb = rmt_cdiv(Ny - 2, macro);
             const int nmac = nmrb * nxtf, nbnd = rmt_cdiv(Ny - 2, band) * nxtf, nbusy = nmac + nbnd;
             if (XTf <= LMAX && prog_ints + nsegf + nbusy + 8 <= (long)ncell) {
                 int *progF = trow;                         // [L][nsegf] ints, then chain lengths, then cnt0 (trow
                 int *busy = trow + prog_ints;              //  holds ncell ints; the per-layer path rewrites it
                 int *cnt0 = busy + nbusy;                  //  afterwards if it is the one that runs)
-                mode = tile_counter + 2;
-                RMT_CUDA(cudaMemsetAsync(progF, 0, (size_t)(prog_ints + nbusy) * sizeof(int), s));
-                RMT_CUDA(cudaMemsetAsync(tile_counter, 0, sizeof(int), s));
-                int rwb = rmt_cdiv((long)Ny * 32, 256);
-                if (rwb > 148 * 8) rwb = 148 * 8;
-                k_ext_count0<<<rwb, 256, 0, s>>>(st, cnt0, busy, MRBf * RB, busy + nmac, band, Ny, Nx, nxtf, XTf);
-                RMT_LAUNCH_CHECK();
                 const long ntasks = (long)rmt_cdiv(Ny - 2, band) * Lyr * nxtf;   // with the smaller macro-tile
-                int blocks = fused_blocks;
-                if ((long)blocks > ntasks) blocks = (int)ntasks;
-                if ((long)blocks * RB * CAPW <= (long)cap) {
-                    k_ext_decide<<<1, 64, 0, s>>>(cnt0, busy, nmrb, MRBf * RB, busy + nmac, nbnd / nxtf, band, nxtf, Ny, Lyr,
-                                                  fused_blocks * 9 / 10, mode);
+                int blocks16 = resident16, blocks8 = resident8;
+                if ((long)blocks16 > ntasks) blocks16 = (int)ntasks;
+                if ((long)blocks8 > ntasks) blocks8 = (int)ntasks;
+                const long need_recs = (long)(blocks16 * 16 > blocks8 * 8 ? blocks16 * 16 : blocks8 * 8) * CAPW;
+                if (need_recs <= (long)cap) {
+                    mode = tile_counter + 2;
+                    RMT_CUDA(cudaMemsetAsync(progF, 0, (size_t)(prog_ints + nbusy) * sizeof(int), s));
+                    RMT_CUDA(cudaMemsetAsync(tile_counter, 0, sizeof(int), s));
+                    int rwb = rmt_cdiv((long)Ny * 32, 256);
+                    if (rwb > 148 * 8) rwb = 148 * 8;
+                    k_ext_count0<<<rwb, 256, 0, s>>>(st, cnt0, busy, macro, busy + nmac, band, Ny, Nx, nxtf, XTf);
+                    RMT_LAUNCH_CHECK();
+                    k_ext_decide<<<1, 64, 0, s>>>(cnt0, busy, nmrb, macro, busy + nmac, nbnd / nxtf, band, nxtf, Ny,
+                                                  Lyr, resident16 * 9 / 10, resident8 * 9 / 10, force, mode);
                     RMT_LAUNCH_CHECK();
                     int Lv = Lyr, nxv = nxtf, xtv = XTf;
                     void *args[] = {&X1e, &X2e, &st, &cnt0, &progF, &tile_counter, &recs, &mode, &Lv, &Ny, &Nx,
                                     &joff, &nxv, &xtv, &dx, &dy, &r2};
-                    RMT_CUDA(cudaLaunchCooperativeKernel((void *)k_ext_fused, dim3(blocks), dim3(RB * 32), args,
-                                                         sizeof(FusedSmem), s));
-                } else {
-                    mode = nullptr;
+                    RMT_CUDA(cudaLaunchCooperativeKernel((void *)k_ext_fused<16>, dim3(blocks16), dim3(16 * 32),
+                                                         args, sizeof(FusedSmemT<16>), s));
+                    RMT_CUDA(cudaLaunchCooperativeKernel((void *)k_ext_fused<8>, dim3(blocks8), dim3(8 * 32), args,
+                                                         sizeof(FusedSmemT<8>), s));
                 }
             }
         }
