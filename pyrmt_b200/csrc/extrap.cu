@@ -715,7 +715,8 @@ struct FusedSmemT {
 template <int RBT>
 __global__ void __launch_bounds__(RBT * 32, 16 / RBT)
 k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__restrict__ st,
-            const int *__restrict__ cnt0 /* layer-0 target counts per (row, x-tile) */,
+            const int *__restrict__ cnt0 /* layer-0 target counts per (row, x-tile), then their first and last
+                                            columns ([Ny*nxt] each) */,
             int *__restrict__ prog /* [L][Ny*nxt] */, int *__restrict__ tile_counter,
             ExtRec *__restrict__ scratch /* [gridDim][RBT][CAPW] */, const int *__restrict__ mode, int L, int Ny,
             int Nx, int joff, int nxt, int XT, double dx, double dy, double r2)
@@ -769,10 +770,28 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
         int nt = 0;
         if (live) {
             // ---- (1) previous layer complete on rows j-4..j+4, tiles xt-1..xt+1 ---------------
+            //      A neighbouring tile matters only through the few columns next to the shared boundary
+            //      (window: 4, discovery: 1).  Targets of layer l-1 lie within l-1 cells of layer-0 targets,
+            //      so the static first / last layer-0 target columns tell when it cannot have any there
+            //      -- then its progress (its body may sit dozens of rows lower) is not waited for.
             if (layer > 0 && lane < 27) {
                 const int jr = j - 4 + lane / 3, xq = xt - 1 + lane % 3;
-                if (jr >= 1 && jr < Ny - 1 && xq >= 0 && xq < nxt)
-                    while (ld_relaxed_gpu(progP + jr * nxt + xq) != INT_MAX) __nanosleep(200);
+                if (jr >= 1 && jr < Ny - 1 && xq >= 0 && xq < nxt) {
+                    bool need = true;
+                    if (xq != xt) {
+                        const int *cmin0 = cnt0 + nseg, *cmax0 = cnt0 + 2 * nseg;
+                        const int reach = (layer - 1) + 6, bnd = (xq < xt) ? xc0 : xc1;
+                        need = false;
+                        for (int r = max(jr - (layer - 1), 0); r <= min(jr + (layer - 1), Ny - 1) && !need; ++r) {
+                            const int far_lo = cmin0[r * nxt + xq], far_hi = cmax0[r * nxt + xq];
+                            const int own_lo = cmin0[r * nxt + xt], own_hi = cmax0[r * nxt + xt];
+                            need = (xq < xt) ? (far_hi + reach >= bnd || own_lo - reach < bnd)
+                                             : (far_lo - reach < bnd || own_hi + reach >= bnd);
+                        }
+                    }
+                    if (need)
+                        while (ld_relaxed_gpu(progP + jr * nxt + xq) != INT_MAX) __nanosleep(200);
+                }
             }
             __syncwarp();
             // ---- (2) discover this row's targets: not known before this layer, with a known neighbour
@@ -1061,8 +1080,9 @@ __global__ void k_ext_decide(const int *__restrict__ cnt0, const int *__restrict
 // layer-0 target counts per (row, x-tile), without touching the state bytes
 __global__ void k_ext_count0(const unsigned char *__restrict__ st, int *__restrict__ cnt0,
                              int *__restrict__ rows_macro /* [macro-row][x-tile], zeroed */, int macro,
-                             int *__restrict__ rows_band /* [row band][x-tile], zeroed */, int band, int Ny,
-                             int Nx, int nxt, int XT)
+                             int *__restrict__ rows_band /* [row band][x-tile], zeroed */, int band,
+                             int *__restrict__ cmin0, int *__restrict__ cmax0 /* first / last target column */,
+                             int Ny, int Nx, int nxt, int XT)
 {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int nwarp = (gridDim.x * blockDim.x) >> 5;
@@ -1071,7 +1091,7 @@ __global__ void k_ext_count0(const unsigned char *__restrict__ st, int *__restri
         const bool inner = (j >= 1 && j < Ny - 1);
         const unsigned char *r0 = inner ? r1 - Nx : r1, *r2 = inner ? r1 + Nx : r1;
         for (int xt = 0; xt < nxt; ++xt) {
-            int cnt = 0;
+            int cnt = 0, cmin = INT_MAX, cmax = -1;
             const int cend = min((xt + 1) * XT, Nx);
             for (int base = xt * XT; base < cend; base += 32) {
                 int i = base + lane;
@@ -1079,10 +1099,17 @@ __global__ void k_ext_count0(const unsigned char *__restrict__ st, int *__restri
                 if (inner && i >= 1 && i < Nx - 1 && i < cend && !(r1[i] & 1))
                     tgt = ((r0[i - 1] | r0[i] | r0[i + 1] | r1[i - 1] | r1[i + 1] | r2[i - 1] | r2[i] |
                             r2[i + 1]) & 1) != 0;
-                cnt += __popc(__ballot_sync(0xffffffffu, tgt));
+                const unsigned m = __ballot_sync(0xffffffffu, tgt);
+                cnt += __popc(m);
+                if (m) {
+                    cmin = min(cmin, base + __ffs(m) - 1);
+                    cmax = base + 31 - __clz(m);
+                }
             }
             if (lane == 0) {
                 cnt0[j * nxt + xt] = cnt;
+                cmin0[j * nxt + xt] = cmin;
+                cmax0[j * nxt + xt] = cmax;
                 if (cnt) {       // rows with targets per tile: the length of the dependency chain through it
                     atomicAdd(&rows_macro[((j - 1) / macro) * nxt + xt], 1);
                     atomicAdd(&rows_band[((j - 1) / band) * nxt + xt], 1);
@@ -1219,7 +1246,7 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
             const int macro = 1024, band = 512;            // candidate macro-tile heights (rows)
             const int nmrb = rmt_cdiv(Ny - 2, macro);
             const int nmac = nmrb * nxtf, nbnd = rmt_cdiv(Ny - 2, band) * nxtf, nbusy = nmac + nbnd;
-            if (XTf <= LMAX && prog_ints + nsegf + nbusy + 8 <= (long)ncell) {
+            if (XTf <= LMAX && prog_ints + 3L * nsegf + nbusy + 8 <= (long)ncell) {
                 int *progF = trow;                         // [L][nsegf] ints, then chain lengths, then cnt0 (trow
                 int *busy = trow + prog_ints;              //  holds ncell ints; the per-layer path rewrites it
                 int *cnt0 = busy + nbusy;                  //  afterwards if it is the one that runs)
@@ -1234,7 +1261,8 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
                     RMT_CUDA(cudaMemsetAsync(tile_counter, 0, sizeof(int), s));
                     int rwb = rmt_cdiv((long)Ny * 32, 256);
                     if (rwb > 148 * 8) rwb = 148 * 8;
-                    k_ext_count0<<<rwb, 256, 0, s>>>(st, cnt0, busy, macro, busy + nmac, band, Ny, Nx, nxtf, XTf);
+                    k_ext_count0<<<rwb, 256, 0, s>>>(st, cnt0, busy, macro, busy + nmac, band, cnt0 + nsegf,
+                                                     cnt0 + 2 * nsegf, Ny, Nx, nxtf, XTf);
                     RMT_LAUNCH_CHECK();
                     k_ext_decide<<<1, 64, 0, s>>>(cnt0, busy, nmrb, macro, busy + nmac, nbnd / nxtf, band, nxtf, Ny,
                                                   Lyr, resident16 * 9 / 10, resident8 * 9 / 10, force, mode);
