@@ -318,14 +318,16 @@ def main():
         sampler.start()
     profiler.reset(timing=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    from pyrmt_b200 import _lib as _rmt_lib
     barrier()
+    launches0 = _rmt_lib.load().rmt_launch_count()
     e0.record()
     for _ in range(args.steps):
         state = step(state)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = profiler.launches
+    launches = int(_rmt_lib.load().rmt_launch_count() - launches0)   # counted inside librmt_b200.so
     per_kernel = profiler.summary()
     profiler.reset(timing=False)
     clocks = sampler.stop() if sampler else None

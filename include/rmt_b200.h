@@ -28,6 +28,8 @@ extern "C" {
 #endif
 
 int rmt_abi_version(void);
+/* Number of CUDA kernels this library has launched since it was loaded (bench.py: gpu_launches). */
+unsigned long long rmt_launch_count(void);
 
 /* ------------------------------------------------------------------ utils */
 /* pyRMT/utils.py:4-59,116-131.  op: 0 grad_central_x_2nd, 1 grad_central_y_2nd,

@@ -20,6 +20,7 @@ vp, dbl, i32, i64 = C.c_void_p, C.c_double, C.c_int, C.c_long
 # name -> argtypes   (restype is int unless listed in _RESTYPE)
 _SIG = {
     "rmt_abi_version": [],
+    "rmt_launch_count": [],
     "rmt_stencil_op": [vp, vp, i32, i32, dbl, dbl, i32, vp],
     "rmt_diff_upwind_3rd": [vp, vp, vp, i32, i32, dbl, i32, vp],
     "rmt_heaviside": [vp, vp, i64, dbl, vp],
@@ -67,7 +68,7 @@ _SIG = {
     "rmt_transpose": [vp, vp, i32, i32, vp],
     "rmt_copy2d": [vp, vp, i32, i32, i64, i64, vp],
 }
-_RESTYPE = {"rmt_extrapolate_workspace_bytes": i64, "rmt_poisson_plan_destroy": None}
+_RESTYPE = {"rmt_launch_count": C.c_ulonglong, "rmt_extrapolate_workspace_bytes": i64, "rmt_poisson_plan_destroy": None}
 
 EXPORTS = tuple(_SIG)
 

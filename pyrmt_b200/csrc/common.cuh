@@ -10,9 +10,13 @@
 #define RMT_OK 0
 #define RMT_EINVAL (-1)
 
-// Launch epilogue: report launch-time errors through the C ABI as an int.
+// Kernels launched by this library since load (rmt_launch_count; single host thread, no atomics).
+extern "C" unsigned long long g_rmt_launches;
+
+// Launch epilogue: count the launch and report launch-time errors through the C ABI as an int.
 #define RMT_LAUNCH_CHECK()                         \
     do {                                           \
+        ++g_rmt_launches;                          \
         cudaError_t e__ = cudaGetLastError();      \
         if (e__ != cudaSuccess) return (int)e__;   \
     } while (0)

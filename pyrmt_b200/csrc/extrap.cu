@@ -1270,8 +1270,10 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
                     int Lv = Lyr, nxv = nxtf, xtv = XTf;
                     void *args[] = {&X1e, &X2e, &st, &cnt0, &progF, &tile_counter, &recs, &mode, &Lv, &Ny, &Nx,
                                     &joff, &nxv, &xtv, &dx, &dy, &r2};
+                    ++g_rmt_launches;
                     RMT_CUDA(cudaLaunchCooperativeKernel((void *)k_ext_fused<16>, dim3(blocks16), dim3(16 * 32),
                                                          args, sizeof(FusedSmemT<16>), s));
+                    ++g_rmt_launches;
                     RMT_CUDA(cudaLaunchCooperativeKernel((void *)k_ext_fused<8>, dim3(blocks8), dim3(8 * 32), args,
                                                          sizeof(FusedSmemT<8>), s));
                 }
@@ -1310,6 +1312,7 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
         if (blocks > need) blocks = need;
         void *args[] = {&X1e, &X2e, &st, &seg_off, &tcol, &prog, &tile_counter, &recs, &tinfo, &cap,
                         &Ny, &Nx, &joff, &nxt, &XT, &MRB, &sleep_ns, &dx, &dy, &r2, &mode};
+        ++g_rmt_launches;
         RMT_CUDA(cudaLaunchCooperativeKernel((void *)k_ext_sweep, dim3(blocks), dim3(RB * 32), args,
                                              sweep_smem, s));
     }

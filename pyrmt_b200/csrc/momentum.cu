@@ -440,6 +440,8 @@ k_momentum_rhs(const RhsArgs A)
 extern "C" {
 
 int rmt_abi_version(void) { return 1; }
+unsigned long long g_rmt_launches = 0;
+unsigned long long rmt_launch_count(void) { return g_rmt_launches; }
 
 int rmt_solid_stress(const double *X1, const double *X2, const double *phi, double *sxx, double *sxy,
                      double *syy, double *J, int Ny, int Nx, double dx, double dy, double mu_s,
