@@ -237,29 +237,53 @@ struct RhsArgs {
 // MODE 0: velocity_rhs_blended_optimized on caller-supplied H / rho arrays; 1: one RK4 stage of
 // momentum_step_rk4 (one solid); 2: one RK4 stage of momentum_step_rk4_2solids (n = 2 mixture
 // sigma = (Ha+Hb-1) sigma_f + (1-Ha) sigma_A + (1-Hb) sigma_B, no Kelvin-Voigt term).
-template <int MODE>
-__global__ void __launch_bounds__(256, 4)
-k_momentum_rhs(const RhsArgs A)
+// Differences for tiles that cannot touch a rim formula (RIM = false): the interior branch of
+// ddx2 / ddy2 / upwind3 without the position tests -- the kernel is instruction-issue bound.
+template <bool RIM, class F>
+__device__ __forceinline__ double tdx2(F f, int j, int i, int Nx, double inv2h)
+{
+    if (!RIM) return (f(j, i + 1) - f(j, i - 1)) * inv2h;
+    return ddx2(f, j, i, Nx, inv2h);
+}
+template <bool RIM, class F>
+__device__ __forceinline__ double tdy2(F f, int j, int i, int Ny, double inv2h)
+{
+    if (!RIM) return (f(j + 1, i) - f(j - 1, i)) * inv2h;
+    return ddy2(f, j, i, Ny, inv2h);
+}
+template <bool RIM, class G>
+__device__ __forceinline__ double tup3(G g, int k, int n, double vel, double invh)
+{
+    if (!RIM) {
+        if (vel > 0.0)
+            return (2.0 * g(k + 1) + 3.0 * g(k) - 6.0 * g(k - 1) + g(k - 2)) * (invh * (1.0 / 6.0));
+        return (-g(k + 2) + 6.0 * g(k + 1) - 3.0 * g(k) - 2.0 * g(k - 1)) * (invh * (1.0 / 6.0));
+    }
+    return upwind3(g, k, n, vel, invh);
+}
+
+// One 32 x 16 output tile.  RIM = true: the tile touches (or comes within two nodes of) the domain
+// edge -- clamped halos of run-time extent, one-sided formulas.  RIM = false: full tile, halo
+// extents known at compile time (no run-time divisions in the index maps), interior formulas only.
+template <int MODE, bool RIM>
+__device__ __forceinline__ void momentum_tile(const RhsArgs &A, double *sU, double *sV, double *sTxx,
+                                              double *sTxy, double *sTyy, double *sH, double *sHb)
 {
     constexpr bool FUSED = (MODE != 0), TWO = (MODE == 2);
-    __shared__ double sU[UHT * UW], sV[UHT * UW];
-    __shared__ double sTxx[THT * TW], sTxy[THT * TW], sTyy[THT * TW], sH[THT * TW];
-    __shared__ double sHb[TWO ? THT * TW : 1];
-
     const int Ny = A.Ny, Nx = A.Nx;
     const int i0 = blockIdx.x * MTX, j0 = blockIdx.y * MTY;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    const int i1 = min(i0 + MTX, Nx), j1 = min(j0 + MTY, Ny);   // tile end (exclusive)
+    const int i1 = RIM ? min(i0 + MTX, Nx) : i0 + MTX, j1 = RIM ? min(j0 + MTY, Ny) : j0 + MTY;   // tile end
     // rim tiles need the blended stress two nodes away (one-sided divergence)
-    const bool rim = (i0 == 0) || (j0 == 0) || (i1 == Nx) || (j1 == Ny);
-    const int th = rim ? 2 : 1, uh = th + 1;
+    constexpr int th = RIM ? 2 : 1, uh = th + 1;
 
     // Every global load whose address is known up front is issued HERE, before the first barrier:
     // the velocity tile (<= 4 points per thread), the level set / Heaviside at this thread's stress
     // nodes (<= 3), and the output phase's streaming fields -- ~19 loads in flight per thread, so the
     // kernel pays the HBM latency once instead of once per loop iteration and per phase.
-    const int uja = max(j0 - uh, 0), ujb = min(j1 + uh, Ny), uia = max(i0 - uh, 0), uib = min(i1 + uh, Nx);
-    const int uw = uib - uia, un = (ujb - uja) * uw;
+    const int uja = RIM ? max(j0 - uh, 0) : j0 - uh, ujb = RIM ? min(j1 + uh, Ny) : j1 + uh;
+    const int uia = RIM ? max(i0 - uh, 0) : i0 - uh, uib = RIM ? min(i1 + uh, Nx) : i1 + uh;
+    const int uw = RIM ? uib - uia : MTX + 2 * uh, un = RIM ? (ujb - uja) * uw : (MTY + 2 * uh) * (MTX + 2 * uh);
     double ru[4], rv[4];
     int us_idx[4];
 #pragma unroll
@@ -275,8 +299,9 @@ k_momentum_rhs(const RhsArgs A)
             rv[k] = __ldg(A.vs + g);
         }
     }
-    const int tja = max(j0 - th, 0), tjb = min(j1 + th, Ny), tia = max(i0 - th, 0), tib = min(i1 + th, Nx);
-    const int tw_ = tib - tia, tn = (tjb - tja) * tw_;
+    const int tja = RIM ? max(j0 - th, 0) : j0 - th, tjb = RIM ? min(j1 + th, Ny) : j1 + th;
+    const int tia = RIM ? max(i0 - th, 0) : i0 - th, tib = RIM ? min(i1 + th, Nx) : i1 + th;
+    const int tw_ = RIM ? tib - tia : MTX + 2 * th, tn = RIM ? (tjb - tja) * tw_ : (MTY + 2 * th) * (MTX + 2 * th);
     double rh[3];                                  // phi (FUSED) or H at this thread's stress nodes
     double rhb[TWO ? 3 : 1];                       // phi of the second solid
 #pragma unroll
@@ -295,7 +320,7 @@ k_momentum_rhs(const RhsArgs A)
     for (int r = 0; r < MTY / 8; ++r) {
         const int i = i0 + threadIdx.x, j = j0 + threadIdx.y + 8 * r;
         pf_u0[r] = pf_v0[r] = pf_au[r] = pf_av[r] = 0.0;
-        if (FUSED && i < Nx && j < Ny) {
+        if (FUSED && (!RIM || (i < Nx && j < Ny))) {
             const size_t c = (size_t)j * Nx + i;
             pf_u0[r] = __ldg(A.u0 + c);
             pf_v0[r] = __ldg(A.v0 + c);
@@ -338,8 +363,8 @@ k_momentum_rhs(const RhsArgs A)
             const int e = tid + 256 * k;
             if (e >= tn) continue;
             const int jj = tja + e / tw_, ii = tia + e % tw_;
-            const double ux = ddx2(U, jj, ii, Nx, i2dx), vy = ddy2(V, jj, ii, Ny, i2dy);
-            const double uy = ddy2(U, jj, ii, Ny, i2dy), vx = ddx2(V, jj, ii, Nx, i2dx);
+            const double ux = tdx2<RIM>(U, jj, ii, Nx, i2dx), vy = tdy2<RIM>(V, jj, ii, Ny, i2dy);
+            const double uy = tdy2<RIM>(U, jj, ii, Ny, i2dy), vx = tdx2<RIM>(V, jj, ii, Nx, i2dx);
             const double h = hh[k];
             if (TWO) {      // functions.py:806-810
                 const size_t g = (size_t)jj * Nx + ii;
@@ -385,18 +410,18 @@ k_momentum_rhs(const RhsArgs A)
 #pragma unroll
     for (int r = 0; r < MTY / 8; ++r) {
         const int i = i0 + threadIdx.x, j = j0 + threadIdx.y + 8 * r;
-        if (i >= Nx || j >= Ny) continue;
+        if (RIM && (i >= Nx || j >= Ny)) continue;
         const size_t c = (size_t)j * Nx + i;
         const double u = U(j, i), v = V(j, i);
-        double div_x = ddx2(Txx, j, i, Nx, i2dx) + ddy2(Txy, j, i, Ny, i2dy);
-        double div_y = ddx2(Txy, j, i, Nx, i2dx) + ddy2(Tyy, j, i, Ny, i2dy);
-        double dux = upwind3([&](int k) { return U(j, k); }, i, Nx, u, invdx);
-        double duy = upwind3([&](int k) { return U(k, i); }, j, Ny, v, invdy);
-        double dvx = upwind3([&](int k) { return V(j, k); }, i, Nx, u, invdx);
-        double dvy = upwind3([&](int k) { return V(k, i); }, j, Ny, v, invdy);
+        double div_x = tdx2<RIM>(Txx, j, i, Nx, i2dx) + tdy2<RIM>(Txy, j, i, Ny, i2dy);
+        double div_y = tdx2<RIM>(Txy, j, i, Nx, i2dx) + tdy2<RIM>(Tyy, j, i, Ny, i2dy);
+        double dux = tup3<RIM>([&](int k) { return U(j, k); }, i, Nx, u, invdx);
+        double duy = tup3<RIM>([&](int k) { return U(k, i); }, j, Ny, v, invdy);
+        double dvx = tup3<RIM>([&](int k) { return V(j, k); }, i, Nx, u, invdx);
+        double dvy = tup3<RIM>([&](int k) { return V(k, i); }, j, Ny, v, invdy);
         double adv_u = -u * dux - v * duy;
         double adv_v = -u * dvx - v * dvy;
-        double px = ddx2(P, j, i, Nx, i2dx), py = ddy2(P, j, i, Ny, i2dy);
+        double px = tdx2<RIM>(P, j, i, Nx, i2dx), py = tdy2<RIM>(P, j, i, Ny, i2dy);
         double rho;
         if (TWO) {          // functions.py:793
             const int s = (j - (j0 - THALO)) * TW + (i - (i0 - THALO));
@@ -433,6 +458,20 @@ k_momentum_rhs(const RhsArgs A)
             }
         }
     }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 4)
+k_momentum_rhs(const RhsArgs A)
+{
+    __shared__ double sU[UHT * UW], sV[UHT * UW];
+    __shared__ double sTxx[THT * TW], sTxy[THT * TW], sTyy[THT * TW], sH[THT * TW];
+    __shared__ double sHb[MODE == 2 ? THT * TW : 1];
+    const int i0 = blockIdx.x * MTX, j0 = blockIdx.y * MTY;
+    // the one-sided / first-order formulas reach two nodes in from the edge (upwind3: k < 2, k >= n - 2)
+    const bool rim = (i0 == 0) || (j0 == 0) || (i0 + MTX >= A.Nx - 1) || (j0 + MTY >= A.Ny - 1);
+    if (rim) momentum_tile<MODE, true>(A, sU, sV, sTxx, sTxy, sTyy, sH, sHb);
+    else momentum_tile<MODE, false>(A, sU, sV, sTxx, sTxy, sTyy, sH, sHb);
 }
 
 }  // namespace
