@@ -270,7 +270,7 @@ def main():
     import torch
     import torch.distributed as dist
     from pyrmt_b200._runtime import profiler
-    from pyrmt_b200.driver import fsi_step, make_case
+    from pyrmt_b200.driver import fsi_step, fsi_step_host, make_case
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
@@ -374,6 +374,8 @@ def main():
     e2e = None
     if not args.no_e2e:
         def host_step(hs):
+            if world == 1:                    # the package's host-state entry point (copies overlapped with the step)
+                return fsi_step_host(hs, prm)
             st = tuple(t.to("cuda", non_blocking=True) for t in hs)
             new = step(st)
             out = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in new)
@@ -399,7 +401,10 @@ def main():
         e2e = {"value": cells * args.e2e_steps / (ems * 1e-3) / 1e6, "unit": "Mcell-steps/s",
                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": args.e2e_steps,
                "ms_per_step": ems / args.e2e_steps,
-               "call": "the five state fields (per rank: its slab) pinned host -> device -> fsi step -> pinned host"}
+               "call": ("pyrmt_b200.driver.fsi_step_host: the five state fields pinned host -> device -> fsi step -> "
+                        "pinned host every step, uploads ordered by first use and xi downloads overlapped with "
+                        "the predictor/projection on copy streams") if world == 1 else
+                       "the five state fields (per rank: its slab) pinned host -> device -> slab fsi step -> pinned host"}
 
     # ---- N > 1: the part of the step that IS slab-decomposed (momentum + projection) ----
     slab = cfg5 = None

@@ -555,6 +555,21 @@ def test_fsi_steps_vs_oracle(P, O, N, scheme):
         state = so
 
 
+def test_host_state_step_equals_device_step(P):
+    """driver.fsi_step_host (pinned host state, copies overlapped on side streams) returns exactly the
+    state of driver.fsi_step -- the end-to-end path bench.py times."""
+    import torch
+    from pyrmt_b200.driver import fsi_step, fsi_step_host, make_case
+    state, prm = make_case(257, k_side=2, R_frac=0.15)
+    hstate = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in state)
+    for _ in range(3):
+        state, _, _ = fsi_step(state, prm)
+        hstate = fsi_step_host(hstate, prm)
+        assert all(h.is_pinned() for h in hstate)
+        for nm, d, h in zip("abp12", state, hstate):
+            assert torch.equal(d.cpu(), h), nm
+
+
 # ----------------------------------------------------------------- slab decomposition (1 rank)
 def test_slab_solver_world1_equals_single_gpu(P):
     """The slab-decomposed FSI step with one rank (no halos, the same kernels and the
