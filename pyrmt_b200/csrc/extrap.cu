@@ -706,8 +706,8 @@ struct FusedSmemT {
     int prev_row0;
     int prog[RBT];
     int tile;
-    int tinf[RBT][CAPW];
-    unsigned short tl[RBT][LMAX];
+    int tinf[2][RBT][CAPW];            // double-buffered: a warp prepares its next row block's list and
+    unsigned short tl[2][RBT][LMAX];   // records while the warps below it are still sweeping the current one
 };
 
 // RBT = 16: one CTA per SM; RBT = 8: two per SM (half the rows per block, half the shared memory) --
@@ -716,7 +716,7 @@ template <int RBT>
 __global__ void __launch_bounds__(RBT * 32, 16 / RBT)
 k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__restrict__ st,
             const int *__restrict__ cnt0 /* layer-0 target counts per (row, x-tile), then their first and last
-                                            columns ([Ny*nxt] each) */,
+                                            columns and their 32-column chunk masks ([Ny*nxt] each) */,
             int *__restrict__ prog /* [L][Ny*nxt] */, int *__restrict__ tile_counter,
             ExtRec *__restrict__ scratch /* [gridDim][RBT][CAPW] */, const int *__restrict__ mode, int L, int Ny,
             int Nx, int joff, int nxt, int XT, double dx, double dy, double r2)
@@ -732,7 +732,7 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
     const int nrb = (Ny - 2 + RBT - 1) / RBT, nmrb = (nrb + MRB - 1) / MRB;
     const int ntasks = nmrb * L * nxt;
     const int la = (lane < NACC) ? lane : 0;
-    ExtRec *myrecs = scratch + ((size_t)blockIdx.x * RBT + wib) * CAPW;
+    ExtRec *myrecs2 = scratch + ((size_t)blockIdx.x * RBT + wib) * 2 * CAPW;   // two buffers of CAPW records
 
     for (;;) {
         if (threadIdx.x == 0) S.tile = atomicAdd(tile_counter, 1);
@@ -746,6 +746,8 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
         const int xc0 = xt * XT, xc1 = min(xc0 + XT, Nx);
         const int rb_end = min((mrb + 1) * MRB, nrb);
         if (threadIdx.x == 0) S.prev_row0 = -100;
+        int cur = 0, pre_rb = -1, pre_nt = 0;                       // list / record buffer in use; block prepared ahead
+        const int pre_warps = mode[2] ? mode[2] : RBT / 2;
       for (int rb = mrb * MRB; rb < rb_end; ++rb) {
         const int row0 = 1 + rb * RBT;
         const int j = row0 + wib;
@@ -767,15 +769,19 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
         const int prow0 = S.prev_row0;
         const bool prev_ok = (prow0 == row0 - 4);
         const bool last_rb = (rb == rb_end - 1);
-        int nt = 0;
-        if (live) {
-            // ---- (1) previous layer complete on rows j-4..j+4, tiles xt-1..xt+1 ---------------
-            //      A neighbouring tile matters only through the few columns next to the shared boundary
-            //      (window: 4, discovery: 1).  Targets of layer l-1 lie within l-1 cells of layer-0 targets,
-            //      so the static first / last layer-0 target columns tell when it cannot have any there
-            //      -- then its progress (its body may sit dozens of rows lower) is not waited for.
+        // ---- per-row preparation (steps 1, 2, 4 below) for row jr into list / record buffer bf; returns
+        //      the number of targets.  Depends only on EARLIER layers, so a warp also runs it for its row
+        //      of the next block as soon as its own sweep is done (the chain is then further down).
+        auto prepare_row = [&](int jrow, int bf) -> int {
+            int cnt = 0;
+            unsigned short *tl = S.tl[bf][wib];
+            // (1) previous layer complete on rows jrow-4..jrow+4, tiles xt-1..xt+1.
+            //     A neighbouring tile matters only through the few columns next to the shared boundary
+            //     (window: 4, discovery: 1).  Targets of layer l-1 lie within l-1 cells of layer-0 targets,
+            //     so the static first / last layer-0 target columns tell when it cannot have any there
+            //     -- then its progress (its body may sit dozens of rows lower) is not waited for.
             if (layer > 0 && lane < 27) {
-                const int jr = j - 4 + lane / 3, xq = xt - 1 + lane % 3;
+                const int jr = jrow - 4 + lane / 3, xq = xt - 1 + lane % 3;
                 if (jr >= 1 && jr < Ny - 1 && xq >= 0 && xq < nxt) {
                     bool need = true;
                     if (xq != xt) {
@@ -794,9 +800,26 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                 }
             }
             __syncwarp();
-            // ---- (2) discover this row's targets: not known before this layer, with a known neighbour
-            const unsigned char *rowc = st + (size_t)j * Nx, *rowa = rowc - Nx, *rowb = rowc + Nx;
+            // (2) discover the row's targets: not known before this layer, with a known neighbour.  They lie
+            //     within `layer` cells of layer-0 targets, so only the 32-column chunks that the layer-0 chunk
+            //     masks of rows jrow-layer..jrow+layer (dilated by one chunk, plus the neighbouring tiles'
+            //     edge columns) mark are scanned.
+            unsigned chunks;
+            {
+                unsigned m = 0;
+                const int r = jrow - layer + lane;
+                if (lane <= 2 * layer && r >= 0 && r < Ny) {
+                    const int *cmin0 = cnt0 + nseg, *cmax0 = cnt0 + 2 * nseg, *chunk0 = cnt0 + 3 * nseg;
+                    m = (unsigned)chunk0[r * nxt + xt];
+                    if (xt > 0 && cmax0[r * nxt + xt - 1] + layer + 1 >= xc0) m |= 1u;
+                    if (xt + 1 < nxt && cmin0[r * nxt + xt + 1] - layer - 1 < xc1) m |= 1u << ((xc1 - 1 - xc0) >> 5);
+                }
+                m = __reduce_or_sync(0xffffffffu, m);
+                chunks = m | (m << 1) | (m >> 1);
+            }
+            const unsigned char *rowc = st + (size_t)jrow * Nx, *rowa = rowc - Nx, *rowb = rowc + Nx;
             for (int base = xc0; base < xc1; base += 32) {
+                if (!((chunks >> ((base - xc0) >> 5)) & 1u)) continue;
                 const int i = base + lane;
                 bool tgt = false;
                 if (i < xc1 && i >= 1 && i < Nx - 1) {
@@ -814,41 +837,49 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, tgt);
                 if (tgt) {
-                    const int o = nt + __popc(m & ((1u << lane) - 1u));
-                    if (o < LMAX) S.tl[wib][o] = (unsigned short)(i - xc0);
+                    const int o = cnt + __popc(m & ((1u << lane) - 1u));
+                    if (o < LMAX) tl[o] = (unsigned short)(i - xc0);
                 }
-                nt += __popc(m);
+                cnt += __popc(m);
             }
-            // (more than LMAX targets in one row segment cannot be listed: treated as an error state --
-            //  the launcher keeps XT <= LMAX so this cannot happen)
+            // (more than LMAX targets in one row segment cannot be listed: the launcher keeps XT <= LMAX)
             __syncwarp();
+            // (4) phase A of the first CAPW targets into this warp's scratch records
+            const int nprep = min(cnt, CAPW);
+            for (int k = 0; k < nprep; ++k) {
+                const int info = ext_phase_a<true>(myrecs2 + bf * CAPW + k, X1e, X2e, st, jrow, xc0 + tl[k], Ny, Nx,
+                                                   joff, dx, dy, r2, lane, fresh);
+                if (lane == 0) S.tinf[bf][wib][k] = info;
+            }
+            if (nprep) __threadfence();                            // records readable by this warp's cp.async
+            __syncwarp();
+            return cnt;
+        };
+        int nt = 0;
+        if (live) {
+            if (pre_rb == rb) {                                    // prepared while the previous block was swept
+                nt = pre_nt;
+            } else {
+                nt = prepare_row(j, cur);
+            }
             // ---- (3) announce the list: the row is now "at" its first target -----------------
-            const int first = nt ? xc0 + S.tl[wib][0] : INT_MAX;
+            const int first = nt ? xc0 + S.tl[cur][wib][0] : INT_MAX;
             if (lane == 0) {
                 sp[wib] = first;
                 st_relaxed_gpu(progL + j * nxt + xt, first);
             }
-            // ---- (4) phase A of the first CAPW targets into this warp's scratch records -------
-            const int nprep = min(nt, CAPW);
-            for (int k = 0; k < nprep; ++k) {
-                const int info = ext_phase_a<true>(myrecs + k, X1e, X2e, st, j, xc0 + S.tl[wib][k], Ny, Nx, joff,
-                                                   dx, dy, r2, lane, fresh);
-                if (lane == 0) S.tinf[wib][k] = info;
-            }
-            if (nprep) __threadfence();                            // records readable by this warp's cp.async
-            __syncwarp();
         } else if (lane == 0) {
             sp[wib] = INT_MAX;
         }
-        const bool edgy = nt && (xc0 + S.tl[wib][0] < xc0 + 8 || xc0 + S.tl[wib][nt - 1] >= xc1 - 8 ||
-                                 (last_rb && wib >= RBT - 4));
-        (void)edgy;
+        const unsigned short *tlw = S.tl[cur][wib];
+        const int *tinfw = S.tinf[cur][wib];
+        ExtRec *myrecs = myrecs2 + cur * CAPW;
 
         // ---- (5) the sweep of this row, as in k_ext_sweep -----------------------------------------
-        int info_next = nt ? (0 < CAPW ? S.tinf[wib][0] : 0) : 0;
+        int info_next = nt ? (0 < CAPW ? tinfw[0] : 0) : 0;
         if (nt) ext_fetch(&W.rec, myrecs, info_next, lane);
         for (int t = 0; t < nt; ++t) {
-            const int i = xc0 + S.tl[wib][t];
+            const int i = xc0 + tlw[t];
             const double x0 = dx * i, y0 = dy * (j + joff);
             int info;
             if (t < CAPW) {
@@ -857,8 +888,8 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
             } else {
                 info = ext_phase_a<true>(&W.rec, X1e, X2e, st, j, i, Ny, Nx, joff, dx, dy, r2, lane, fresh);
             }
-            info_next = (t + 1 < nt && t + 1 < CAPW) ? S.tinf[wib][t + 1] : 0;
-            const int next = (t + 1 < nt) ? xc0 + S.tl[wib][t + 1] : INT_MAX;
+            info_next = (t + 1 < nt && t + 1 < CAPW) ? tinfw[t + 1] : 0;
+            const int next = (t + 1 < nt) ? xc0 + tlw[t + 1] : INT_MAX;
             const int nslots = info & 255, npend = info >> 8;
             const int nknown = nslots - npend;
             __syncwarp();
@@ -994,6 +1025,30 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
             }
             __syncwarp();
         }
+        // ---- (6) this warp's row is done: prepare its row of the NEXT block while the warps below sweep.
+        //      The emptiness test is the block-wide one of the loop head, evaluated per warp (static data).
+        //      Only the upper half of the warps: they finish first (slack until the chain has run down the
+        //      block) and their rows are needed first in the next block; the lower half prepares at the next
+        //      block's start, behind the chain's passage through the upper rows.
+        pre_rb = -1;
+        if (rb + 1 < rb_end && wib < pre_warps) {
+            const int jn = j + RBT, rown = row0 + RBT;
+            int anyn = 0;
+            for (int e = lane; e < (RBT + 2 * layer + 2) * 3; e += 32) {
+                const int jr = rown - layer - 1 + e / 3, xq = xt - 1 + e % 3;
+                if (jr >= 0 && jr < Ny && xq >= 0 && xq < nxt) anyn |= cnt0[jr * nxt + xq];
+            }
+            if (__any_sync(0xffffffffu, anyn != 0)) {
+                pre_rb = rb + 1;
+                pre_nt = 0;
+                if (jn < Ny - 1) {
+                    pre_nt = prepare_row(jn, cur ^ 1);
+                    // the marker may run ahead: "every column before the first target is dealt with"
+                    if (lane == 0)
+                        st_relaxed_gpu(progL + jn * nxt + xt, pre_nt ? xc0 + S.tl[cur ^ 1][wib][0] : INT_MAX);
+                }
+            }
+        }
         __syncthreads();
         if (wib >= RBT - 4) {
             if (lane < RING) {
@@ -1004,6 +1059,7 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
             if (wib == RBT - 4 && lane == 0) S.prev_row0 = row0 + RBT - 4;
         }
         __syncthreads();
+        if (pre_rb == rb + 1) cur ^= 1;
       }
     }
 }
@@ -1034,7 +1090,7 @@ __device__ inline int ext_longest_chain(const int *__restrict__ cnt0, const int 
 
 __global__ void k_ext_decide(const int *__restrict__ cnt0, const int *__restrict__ rows_macro, int nmrb,
                              int macro, const int *__restrict__ rows_band, int nbands, int band, int nxt,
-                             int Ny, int L, int limit16, int limit8, int force, int *__restrict__ mode)
+                             int Ny, int L, int limit16, int limit8, int force, int pre_warps, int *__restrict__ mode)
 {
     __shared__ int busy, busy_band, longest_macro, longest_band, links_macro, links_band;
     if (threadIdx.x == 0) busy = busy_band = longest_macro = longest_band = links_macro = links_band = 0;
@@ -1054,10 +1110,10 @@ __global__ void k_ext_decide(const int *__restrict__ cnt0, const int *__restrict
     if (threadIdx.x == 0) {
         // all-layers kernel (16 or 8 rows per block; macro-tiles of `macro` or of `band` rows: shorter
         // tasks let bodies stacked in one macro-tile run side by side) or the per-layer launches.
-        // us per chained row: 7.1 with 16-row blocks, 8.1 with 8-row blocks (twice the CTAs per SM).  A body
+        // us per chained row: 6.6 with 16-row blocks, 7.4 with 8-row blocks (twice the CTAs per SM).  A body
         // cut by a task boundary costs the 8-row variant far more than its row count says (measured: 36
         // discs on a 6 x 6 lattice, 6.3 ms against 4.9 ms per-layer), so it only runs when nothing is cut.
-        const float kRow16 = 7.1f, kRow8 = 8.1f, big = 3.0e38f;
+        const float kRow16 = 6.6f, kRow8 = 7.4f, big = 3.0e38f;
         const int cut[2] = {links_macro, links_band};
         float best = L * (360.f + 3.4f * longest_band);
         int variant = 0, rows = macro;
@@ -1074,6 +1130,7 @@ __global__ void k_ext_decide(const int *__restrict__ cnt0, const int *__restrict
         }
         mode[0] = variant;
         mode[1] = rows;
+        mode[2] = pre_warps;
     }
 }
 
@@ -1082,6 +1139,7 @@ __global__ void k_ext_count0(const unsigned char *__restrict__ st, int *__restri
                              int *__restrict__ rows_macro /* [macro-row][x-tile], zeroed */, int macro,
                              int *__restrict__ rows_band /* [row band][x-tile], zeroed */, int band,
                              int *__restrict__ cmin0, int *__restrict__ cmax0 /* first / last target column */,
+                             int *__restrict__ chunk0 /* bit k: targets in columns [32k, 32k+32) of the tile */,
                              int Ny, int Nx, int nxt, int XT)
 {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -1091,7 +1149,7 @@ __global__ void k_ext_count0(const unsigned char *__restrict__ st, int *__restri
         const bool inner = (j >= 1 && j < Ny - 1);
         const unsigned char *r0 = inner ? r1 - Nx : r1, *r2 = inner ? r1 + Nx : r1;
         for (int xt = 0; xt < nxt; ++xt) {
-            int cnt = 0, cmin = INT_MAX, cmax = -1;
+            int cnt = 0, cmin = INT_MAX, cmax = -1, chunks = 0;
             const int cend = min((xt + 1) * XT, Nx);
             for (int base = xt * XT; base < cend; base += 32) {
                 int i = base + lane;
@@ -1104,12 +1162,14 @@ __global__ void k_ext_count0(const unsigned char *__restrict__ st, int *__restri
                 if (m) {
                     cmin = min(cmin, base + __ffs(m) - 1);
                     cmax = base + 31 - __clz(m);
+                    chunks |= 1 << ((base - xt * XT) >> 5);
                 }
             }
             if (lane == 0) {
                 cnt0[j * nxt + xt] = cnt;
                 cmin0[j * nxt + xt] = cmin;
                 cmax0[j * nxt + xt] = cmax;
+                chunk0[j * nxt + xt] = chunks;
                 if (cnt) {       // rows with targets per tile: the length of the dependency chain through it
                     atomicAdd(&rows_macro[((j - 1) / macro) * nxt + xt], 1);
                     atomicAdd(&rows_band[((j - 1) / band) * nxt + xt], 1);
@@ -1152,7 +1212,7 @@ static ExtLayout ext_layout(int Ny, int Nx)
     L.cap = ext_cap((long)ncell);
     {   // the all-layers kernel keeps CAPW records per row warp of every resident CTA
         long nmrb = ((Ny - 2 + RB - 1) / RB + 31) / 32, tasks = nmrb * 8 * ext_nxt(Nx);
-        long fused = (tasks < 148 ? tasks : 148) * 16 * CAPW;   // = 296 CTAs x 8 warps of the 8-row variant
+        long fused = 2 * (tasks < 148 ? tasks : 148) * 16 * CAPW;   // two buffers; = 296 CTAs x 8 warps of the 8-row variant
         if (L.cap < fused) L.cap = fused;
     }
     size_t off = 0;
@@ -1210,11 +1270,12 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
     // ---- all layers in one launch when that is faster (RMT_EXT_FUSED=0: never) ----
     int *mode = nullptr;   // device: mode[0] = 0 per-layer launches, 16 / 8 all-layers kernel with that many rows
     {                      // per block; mode[1] = its macro-tile height in rows
-        static int fused_on = -1, resident16 = 0, resident8 = 0, force = -1;
+        static int fused_on = -1, resident16 = 0, resident8 = 0, force = -1, pre_warps = 0;
         if (fused_on < 0) {
             const char *e = getenv("RMT_EXT_FUSED");
             fused_on = (e && atoi(e) == 0) ? 0 : 1;
             if ((e = getenv("RMT_EXT_FORCE"))) force = atoi(e);
+            if ((e = getenv("RMT_EXT_PREWARPS"))) pre_warps = atoi(e);    // tuning hook: warps preparing ahead
         }
         const int Lyr = max_layers;
         if (fused_on && Lyr >= 1 && Lyr <= 8) {
@@ -1246,7 +1307,7 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
             const int macro = 1024, band = 512;            // candidate macro-tile heights (rows)
             const int nmrb = rmt_cdiv(Ny - 2, macro);
             const int nmac = nmrb * nxtf, nbnd = rmt_cdiv(Ny - 2, band) * nxtf, nbusy = nmac + nbnd;
-            if (XTf <= LMAX && prog_ints + 3L * nsegf + nbusy + 8 <= (long)ncell) {
+            if (XTf <= LMAX && prog_ints + 4L * nsegf + nbusy + 8 <= (long)ncell) {
                 int *progF = trow;                         // [L][nsegf] ints, then chain lengths, then cnt0 (trow
                 int *busy = trow + prog_ints;              //  holds ncell ints; the per-layer path rewrites it
                 int *cnt0 = busy + nbusy;                  //  afterwards if it is the one that runs)
@@ -1254,7 +1315,7 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
                 int blocks16 = resident16, blocks8 = resident8;
                 if ((long)blocks16 > ntasks) blocks16 = (int)ntasks;
                 if ((long)blocks8 > ntasks) blocks8 = (int)ntasks;
-                const long need_recs = (long)(blocks16 * 16 > blocks8 * 8 ? blocks16 * 16 : blocks8 * 8) * CAPW;
+                const long need_recs = 2L * (blocks16 * 16 > blocks8 * 8 ? blocks16 * 16 : blocks8 * 8) * CAPW;
                 if (need_recs <= (long)cap) {
                     mode = tile_counter + 2;
                     RMT_CUDA(cudaMemsetAsync(progF, 0, (size_t)(prog_ints + nbusy) * sizeof(int), s));
@@ -1262,10 +1323,10 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
                     int rwb = rmt_cdiv((long)Ny * 32, 256);
                     if (rwb > 148 * 8) rwb = 148 * 8;
                     k_ext_count0<<<rwb, 256, 0, s>>>(st, cnt0, busy, macro, busy + nmac, band, cnt0 + nsegf,
-                                                     cnt0 + 2 * nsegf, Ny, Nx, nxtf, XTf);
+                                                     cnt0 + 2 * nsegf, cnt0 + 3 * nsegf, Ny, Nx, nxtf, XTf);
                     RMT_LAUNCH_CHECK();
                     k_ext_decide<<<1, 64, 0, s>>>(cnt0, busy, nmrb, macro, busy + nmac, nbnd / nxtf, band, nxtf, Ny,
-                                                  Lyr, resident16 * 9 / 10, resident8 * 9 / 10, force, mode);
+                                                  Lyr, resident16 * 9 / 10, resident8 * 9 / 10, force, pre_warps, mode);
                     RMT_LAUNCH_CHECK();
                     int Lv = Lyr, nxv = nxtf, xtv = XTf;
                     void *args[] = {&X1e, &X2e, &st, &cnt0, &progF, &tile_counter, &recs, &mode, &Lv, &Ny, &Nx,

@@ -56,6 +56,25 @@ __device__ __forceinline__ double div_rc(const GField &A, const GField &B, const
     return (uf_e - uf_w) * invdx + (vf_n - vf_s) * invdy;
 }
 
+// Rhie-Chow divergence where every stencil point (i-2..i+2, j-2..j+2) is an interior node: the same
+// expressions with the central-difference branch of ddx2 / ddy2 taken unconditionally
+__device__ __forceinline__ double div_rc_interior(const GField &A, const GField &B, const GField &P, int j,
+                                                  int i, double invdx, double invdy, double d_f)
+{
+    const double i2dx = 0.5 * invdx, i2dy = 0.5 * invdy;
+    const double pm2 = P(j, i - 2), pm = P(j, i - 1), p0 = P(j, i), pp = P(j, i + 1), pp2 = P(j, i + 2);
+    const double gxm = (p0 - pm2) * i2dx, gx0 = (pp - pm) * i2dx, gxp = (pp2 - p0) * i2dx;
+    const double am = A(j, i - 1), a0 = A(j, i), ap = A(j, i + 1);
+    const double uf_e = 0.5 * (a0 + ap) - d_f * ((pp - p0) * invdx - 0.5 * (gx0 + gxp));
+    const double uf_w = 0.5 * (am + a0) - d_f * ((p0 - pm) * invdx - 0.5 * (gxm + gx0));
+    const double qm2 = P(j - 2, i), qm = P(j - 1, i), qp = P(j + 1, i), qp2 = P(j + 2, i);
+    const double gym = (p0 - qm2) * i2dy, gy0 = (qp - qm) * i2dy, gyp = (qp2 - p0) * i2dy;
+    const double bm = B(j - 1, i), b0 = B(j, i), bp = B(j + 1, i);
+    const double vf_n = 0.5 * (b0 + bp) - d_f * ((qp - p0) * invdy - 0.5 * (gy0 + gyp));
+    const double vf_s = 0.5 * (bm + b0) - d_f * ((p0 - qm) * invdy - 0.5 * (gym + gy0));
+    return (uf_e - uf_w) * invdx + (vf_n - vf_s) * invdy;
+}
+
 // periodic wide-central divergence at a reduced-grid node (functions.py:1236-1243)
 __device__ __forceinline__ double div_periodic(const GField &A, const GField &B, int j, int i, int my,
                                                int mx, double i2dx, double i2dy)
@@ -94,7 +113,8 @@ k_divergence(const double *__restrict__ a, const double *__restrict__ b,
         if (mode == 1) {
             const GField P{p_prev, Nx};
             double d_f = dt / (rho_sum[0] / ((double)Ny * (double)Nx));
-            d = div_rc(A, B, P, j, i, Ny, Nx, 1.0 / dx, 1.0 / dy, d_f);
+            if (i >= 2 && i < Nx - 2 && j >= 2 && j < Ny - 2) d = div_rc_interior(A, B, P, j, i, 1.0 / dx, 1.0 / dy, d_f);
+            else d = div_rc(A, B, P, j, i, Ny, Nx, 1.0 / dx, 1.0 / dy, d_f);
         } else {
             d = div_plain(A, B, j, i, 0.5 / dx, 0.5 / dy);
         }
