@@ -695,7 +695,7 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
 // (2L-1) groups of nxt tasks after it (layer l-1 of the next macro-row, for its last four rows);
 // the launcher keeps (2L-1)*nxt below the number of resident CTAs, so every awaited task is
 // resident or done: no deadlock.
-constexpr int CAPW = 8;                // phase-A records prepared per row warp (beyond: inline)
+constexpr int CAPW = 16;               // phase-A records prepared per row warp (beyond: inline)
 constexpr int LMAX = 512;              // targets listed per (row, x-tile)
 
 template <int RBT>
