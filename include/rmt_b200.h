@@ -168,6 +168,18 @@ int rmt_momentum_stage_2solids(const double *us, const double *vs, const double 
  * either solid, phi12 = (phi1 - phi2)/2, delta_s(x) = (1 + cos(pi x / w_c)) / (2 w_c) for |x| < w_c. */
 int rmt_contact_force(const double *phi1, const double *phi2, double *fx, double *fy, int Ny, int Nx, double dx,
                       double dy, double k_rep, double w_c, void *stream);
+/* Energy diagnostics and solid centroid in one pass (pyRMT/output.py:6-39 compute_kinetic_energy,
+ * :41-134 compute_strain_energy, :136-193 compute_viscous_dissipation; benchmarks/common.py:110-115
+ * disc_centroid).  out6 = {sum 0.5 rho |u|^2, sum strain-energy density over solid cells,
+ * sum 2 mu D:D, #cells with phi <= 0, sum x over them, sum y over them} -- the caller multiplies the
+ * first three by dx*dy and divides the coordinate sums by the count.  (a, b) and (X1, X2) may be NULL
+ * (their sums are then 0); Xc/Yc = node coordinates or NULL for i*dx, j*dy.
+ * work: rmt_diagnostics_workspace_doubles() doubles. */
+int rmt_diagnostics_workspace_doubles(void);
+int rmt_diagnostics(const double *a, const double *b, const double *X1, const double *X2, const double *phi,
+                    const double *Xc, const double *Yc, int Ny, int Nx, double dx, double dy, double rho_f,
+                    double rho_s, double mu_f, double mu_s, double kappa, double eta_s, double w_t, double *work,
+                    double *out6, void *stream);
 /* out = min(a, b) elementwise (functions.py:835, np.minimum(Ja, Jb)). */
 int rmt_min2(const double *a, const double *b, double *out, long n, void *stream);
 

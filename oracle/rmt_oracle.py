@@ -646,6 +646,49 @@ def reinitialize_phi_PDE(phi_in, dx, dy, num_iters, apply_phi_BCs_func, dt_reini
 
 
 # --------------------------------------------------------------------------
+# output.py -- energy diagnostics; common.py:110-115 -- centroid
+# --------------------------------------------------------------------------
+def compute_kinetic_energy(a, b, rho_f, rho_s, phi, w_t, dx, dy):           # output.py:6-39
+    H = smoothed_heaviside(phi, w_t)
+    rho = (1 - H) * rho_s + H * rho_f
+    return float(np.sum(0.5 * rho * (a ** 2 + b ** 2)) * dx * dy)
+
+
+def compute_strain_energy(X1, X2, phi, mu_s, dx, dy, kappa=0.0):             # output.py:41-134
+    """Central differences of the reference map with the edge value repeated outside the grid
+    (np.pad mode='edge', width 4, cropped again), F = G^-1 on solid cells with |det G| > 1e-10."""
+    def cdiff(f, axis, h):
+        up = np.concatenate([np.take(f, range(1, f.shape[axis]), axis), np.take(f, [-1], axis)], axis)
+        dn = np.concatenate([np.take(f, [0], axis), np.take(f, range(0, f.shape[axis] - 1), axis)], axis)
+        return (up - dn) / (2.0 * h)
+    G11, G12 = cdiff(X1, 1, dx), cdiff(X1, 0, dy)
+    G21, G22 = cdiff(X2, 1, dx), cdiff(X2, 0, dy)
+    det = G11 * G22 - G12 * G21
+    good = (np.abs(det) > 1e-10) & (phi <= 0.0)
+    d = np.where(good, det, 1.0)
+    F11, F12, F21, F22 = G22 / d, -G12 / d, -G21 / d, G11 / d
+    I1 = (F11 ** 2 + F21 ** 2) + (F12 ** 2 + F22 ** 2)
+    dens = 0.5 * mu_s * (I1 - 2.0) + 0.5 * kappa * (1.0 / d - 1.0) ** 2
+    return float(np.sum(np.where(good, dens, 0.0)) * dx * dy)
+
+
+def compute_viscous_dissipation(a, b, mu_f, phi, w_t, dx, dy, eta_s=0.0):    # output.py:136-193
+    Dxx = grad_central_x_2nd(a, dx)
+    Dyy = grad_central_y_2nd(b, dy)
+    Dxy = 0.5 * (grad_central_y_2nd(a, dy) + grad_central_x_2nd(b, dx))
+    H = smoothed_heaviside(phi, w_t)
+    mu = H * mu_f + (1 - H) * eta_s
+    return float(np.sum(2.0 * mu * (Dxx ** 2 + Dyy ** 2 + 2.0 * Dxy ** 2)) * dx * dy)
+
+
+def disc_centroid(phi, X, Y):                                               # benchmarks/common.py:110-115
+    m = phi <= 0.0
+    if not np.any(m):
+        return float("nan"), float("nan")
+    return float(X[m].mean()), float(Y[m].mean())
+
+
+# --------------------------------------------------------------------------
 # caller-side contract (benchmarks/common.py) used by drivers and tests
 # --------------------------------------------------------------------------
 def no_slip_lid_bc(u, v, lid_speed=1.0):               # benchmarks/common.py:27-37

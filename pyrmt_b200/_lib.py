@@ -50,6 +50,8 @@ _SIG = {
     "rmt_momentum_stage_2solids": [vp] * 19 + [i32, i32] + [dbl] * 7 + [i32, vp],
     "rmt_contact_force": [vp, vp, vp, vp, i32, i32, dbl, dbl, dbl, dbl, vp],
     "rmt_min2": [vp, vp, vp, i64, vp],
+    "rmt_diagnostics_workspace_doubles": [],
+    "rmt_diagnostics": [vp] * 7 + [i32, i32] + [dbl] * 9 + [vp, vp, vp],
     "rmt_divergence": [vp, vp, vp, i32, i32, dbl, dbl, vp],
     "rmt_divergence_rc": [vp, vp, vp, vp, vp, i32, i32, dbl, dbl, dbl, vp],
     "rmt_pressure_gradient": [vp, vp, vp, i32, i32, dbl, dbl, vp],

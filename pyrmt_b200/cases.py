@@ -73,8 +73,8 @@ def _disc_case(N, x0, y0, R):
 
 
 def _centroid(phi, Xd, Yd):
-    m = phi <= 0.0
-    return float(Xd[m].mean().item()), float(Yd[m].mean().item())
+    from .output import disc_centroid
+    return disc_centroid(phi, Xd, Yd)
 
 
 def soft_disc_in_lid(N=128, scheme="semilagrangian", t_end=8.0, sample_times=(1, 2, 3, 4, 5, 6, 7, 8),

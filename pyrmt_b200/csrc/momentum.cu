@@ -205,6 +205,72 @@ __global__ void k_min2(const double *__restrict__ a, const double *__restrict__ 
         out[k] = fmin(a[k], b[k]);
 }
 
+// ------------------------------------------------------- diagnostics (output.py:6-193, common.py:110-115)
+// One pass over the grid for the quantities the drivers log beside the step: kinetic energy density
+// 0.5 rho (a^2 + b^2), neo-Hookean strain energy density on solid cells (central differences of the
+// edge-padded reference map, output.py:70-83), viscous dissipation density 2 mu (Dxx^2 + Dyy^2 + 2 Dxy^2),
+// and the solid cell count / coordinate sums of disc_centroid.  Any input group may be absent (NULL).
+constexpr int kDiagBlocks = 148 * 8, kDiagVals = 6;
+
+__global__ void __launch_bounds__(256)
+k_diagnostics(const double *__restrict__ a, const double *__restrict__ b, const double *__restrict__ X1,
+              const double *__restrict__ X2, const double *__restrict__ phi, const double *__restrict__ Xc,
+              const double *__restrict__ Yc, int Ny, int Nx, double dx, double dy, double rho_f, double rho_s,
+              double mu_f, double mu_s, double kappa, double eta_s, double w_t, double *__restrict__ partial)
+{
+    __shared__ double red[32];
+    const double inv_w = 1.0 / w_t, i2dx = 1.0 / (2.0 * dx), i2dy = 1.0 / (2.0 * dy);
+    double acc[kDiagVals] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const long n = (long)Ny * Nx;
+    for (long c = blockIdx.x * (long)blockDim.x + threadIdx.x; c < n; c += (long)gridDim.x * blockDim.x) {
+        const int j = (int)(c / Nx), i = (int)(c - (long)j * Nx);
+        const double ph = phi[c];
+        const double H = heaviside_sin(ph, w_t, inv_w);
+        if (a && b) {
+            const double u = a[c], v = b[c];
+            acc[0] += 0.5 * ((1.0 - H) * rho_s + H * rho_f) * (u * u + v * v);
+            const GField A{a, Nx}, B{b, Nx};
+            const double dxx = ddx2(A, j, i, Nx, i2dx), dyy = ddy2(B, j, i, Ny, i2dy);
+            const double dxy = 0.5 * (ddy2(A, j, i, Ny, i2dy) + ddx2(B, j, i, Nx, i2dx));
+            acc[2] += 2.0 * (H * mu_f + (1.0 - H) * eta_s) * (dxx * dxx + dyy * dyy + 2.0 * dxy * dxy);
+        }
+        if (ph <= 0.0) {
+            if (X1 && X2) {
+                const int ip = min(i + 1, Nx - 1), im = max(i - 1, 0), jp = min(j + 1, Ny - 1), jm = max(j - 1, 0);
+                const size_t r = (size_t)j * Nx, rp = (size_t)jp * Nx, rm = (size_t)jm * Nx;
+                const double G11 = (X1[r + ip] - X1[r + im]) * i2dx, G12 = (X1[rp + i] - X1[rm + i]) * i2dy;
+                const double G21 = (X2[r + ip] - X2[r + im]) * i2dx, G22 = (X2[rp + i] - X2[rm + i]) * i2dy;
+                const double det = G11 * G22 - G12 * G21;
+                if (fabs(det) > 1e-10) {
+                    const double F11 = G22 / det, F12 = -G12 / det, F21 = -G21 / det, F22 = G11 / det;
+                    const double I1 = (F11 * F11 + F21 * F21) + (F12 * F12 + F22 * F22), Jm1 = 1.0 / det - 1.0;
+                    acc[1] += 0.5 * mu_s * (I1 - 2.0) + 0.5 * kappa * Jm1 * Jm1;
+                }
+            }
+            acc[3] += 1.0;
+            acc[4] += Xc ? Xc[c] : dx * i;
+            acc[5] += Yc ? Yc[c] : dy * j;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kDiagVals; ++k) {
+        const double t = block_sum(acc[k], red);
+        if (threadIdx.x == 0) partial[blockIdx.x * kDiagVals + k] = t;
+    }
+}
+
+__global__ void k_diagnostics_final(const double *__restrict__ partial, int nblocks, double *__restrict__ out)
+{
+    __shared__ double red[32];
+    for (int k = 0; k < kDiagVals; ++k) {
+        double t = 0.0;
+        for (int q = threadIdx.x; q < nblocks; q += blockDim.x) t += partial[q * kDiagVals + k];
+        t = block_sum(t, red);
+        if (threadIdx.x == 0) out[k] = t;
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------- momentum RHS / stage
 constexpr int MTX = 32, MTY = 16;            // output tile
 constexpr int UHALO = 3, THALO = 2;          // shared-memory halos (rim tiles use all of it)
@@ -580,6 +646,26 @@ int rmt_contact_force(const double *phi1, const double *phi2, double *fx, double
     if (!phi1 || !phi2 || !fx || !fy || Ny < 3 || Nx < 3 || !(w_c > 0.0)) return RMT_EINVAL;
     dim3 blk(TX, TY), grd(rmt_cdiv(Nx, TX), rmt_cdiv(Ny, TY));
     k_contact_force<<<grd, blk, 0, (cudaStream_t)stream>>>(phi1, phi2, fx, fy, Ny, Nx, dx, dy, k_rep, w_c);
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
+
+int rmt_diagnostics_workspace_doubles(void) { return kDiagBlocks * kDiagVals; }
+
+int rmt_diagnostics(const double *a, const double *b, const double *X1, const double *X2, const double *phi,
+                    const double *Xc, const double *Yc, int Ny, int Nx, double dx, double dy, double rho_f,
+                    double rho_s, double mu_f, double mu_s, double kappa, double eta_s, double w_t, double *work,
+                    double *out6, void *stream)
+{
+    if (!phi || !work || !out6 || Ny < 3 || Nx < 3 || !(w_t > 0.0) || (a == nullptr) != (b == nullptr) ||
+        (X1 == nullptr) != (X2 == nullptr))
+        return RMT_EINVAL;
+    long n = (long)Ny * Nx, blocks = (n + 255) / 256;
+    if (blocks > kDiagBlocks) blocks = kDiagBlocks;
+    k_diagnostics<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a, b, X1, X2, phi, Xc, Yc, Ny, Nx, dx, dy, rho_f,
+                                                                  rho_s, mu_f, mu_s, kappa, eta_s, w_t, work);
+    RMT_LAUNCH_CHECK();
+    k_diagnostics_final<<<1, 256, 0, (cudaStream_t)stream>>>(work, (int)blocks, out6);
     RMT_LAUNCH_CHECK();
     return RMT_OK;
 }

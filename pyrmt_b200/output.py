@@ -1,61 +1,76 @@
 """Energy diagnostics of upstream ``pyRMT/output.py`` (compute_kinetic_energy
-:6-39, compute_strain_energy :41-134, compute_viscous_dissipation :136-193).
+:6-39, compute_strain_energy :41-134, compute_viscous_dissipation :136-193) and the
+solid centroid of ``benchmarks/common.py:110-115``.
 
-They sit beside the timestep in every driver but are OFF the timed path (SURVEY
-2 #14, 8f rank 2): gradients and the Heaviside come from the device operators,
-the final elementwise products and sums are evaluated with torch/NumPy on
-whatever array type the caller uses.  HDF5/CSV writers are out of scope.
+They sit beside the timestep in every driver.  One device
+kernel (rmt_diagnostics) forms every density and reduces it in a single pass over
+the grid; only six doubles come back to the host.  ``diagnostics`` returns all of them
+from one launch; the upstream-named functions are thin views of it.  HDF5/CSV writers
+are out of scope.
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
 
-from .functions import smoothed_heaviside
-from .utils import grad_central_x_2nd, grad_central_y_2nd
+from . import _lib
+from ._runtime import F64, ctx, ptr, stream, to_dev
+
+_work = {}
 
 
-def _sum(x):
-    return float(x.sum().item()) if isinstance(x, torch.Tensor) else float(np.sum(x))
+def _run(a, b, X1, X2, phi, X, Y, dx, dy, rho_f=1.0, rho_s=1.0, mu_f=0.0, mu_s=0.0, kappa=0.0, eta_s=0.0,
+         w_t=None):
+    ph = to_dev(phi)
+    Ny, Nx = ph.shape
+    dev = [None if t is None else to_dev(t) for t in (a, b, X1, X2, X, Y)]
+    lib = ctx().lib
+    key = ph.device.index
+    if key not in _work:
+        _work[key] = torch.empty(lib.rmt_diagnostics_workspace_doubles(), dtype=F64, device=ph.device)
+    out = torch.empty(6, dtype=F64, device=ph.device)
+    w = float(w_t) if w_t is not None else 2.0 * float(dx)
+    _lib.check(lib.rmt_diagnostics(ptr(dev[0]), ptr(dev[1]), ptr(dev[2]), ptr(dev[3]), ptr(ph), ptr(dev[4]),
+                                   ptr(dev[5]), Ny, Nx, float(dx), float(dy), float(rho_f), float(rho_s),
+                                   float(mu_f), float(mu_s), float(kappa), float(eta_s), w, ptr(_work[key]),
+                                   ptr(out), stream()), "rmt_diagnostics")
+    return out.cpu().numpy()
+
+
+def diagnostics(a, b, X1, X2, phi, dx, dy, rho_f, rho_s, mu_f, mu_s, w_t, kappa=0.0, eta_s=0.0, X=None, Y=None):
+    """All diagnostics of one state from ONE kernel launch: dict with kinetic_energy, strain_energy,
+    viscous_dissipation, solid_cells, centroid (x, y) (NaN without solid cells)."""
+    s = _run(a, b, X1, X2, phi, X, Y, dx, dy, rho_f, rho_s, mu_f, mu_s, kappa, eta_s, w_t)
+    cell = float(dx) * float(dy)
+    n = s[3]
+    cen = (s[4] / n, s[5] / n) if n > 0 else (float("nan"), float("nan"))
+    return dict(kinetic_energy=float(s[0] * cell), strain_energy=float(s[1] * cell),
+                viscous_dissipation=float(s[2] * cell), solid_cells=int(n), centroid=cen)
 
 
 def compute_kinetic_energy(a, b, rho_f, rho_s, phi, w_t, dx, dy):
     """KE = sum(0.5 * rho_local * (a^2 + b^2)) dx dy  (output.py:6-39)."""
-    H = smoothed_heaviside(phi, w_t)
-    rho_local = (1 - H) * rho_s + H * rho_f
-    return _sum(0.5 * rho_local * (a**2 + b**2)) * dx * dy
-
-
-def _edge_pad(x, w):
-    if isinstance(x, torch.Tensor):
-        return torch.nn.functional.pad(x[None, None], (w, w, w, w), mode="replicate")[0, 0].contiguous()
-    return np.pad(x, w, mode="edge")
+    return float(_run(a, b, None, None, phi, None, None, dx, dy, rho_f=rho_f, rho_s=rho_s, w_t=w_t)[0] * dx * dy)
 
 
 def compute_strain_energy(X1, X2, phi, mu_s, dx, dy, kappa=0.0):
     """SE = sum over solid cells of 0.5 mu_s (I1 - 2) + 0.5 kappa (J - 1)^2  (output.py:41-134):
     central gradients of the edge-padded reference map, F = G^-1, I1 = tr(F^T F)."""
-    w = 4
-    g = lambda f, fn, h: fn(_edge_pad(f, w), h)[w:-w, w:-w]
-    G11, G12 = g(X1, grad_central_x_2nd, dx), g(X1, grad_central_y_2nd, dy)
-    G21, G22 = g(X2, grad_central_x_2nd, dx), g(X2, grad_central_y_2nd, dy)
-    detG = G11 * G22 - G12 * G21
-    xp = torch if isinstance(phi, torch.Tensor) else np
-    good = (xp.abs(detG) > 1e-10) & (phi <= 0.0)
-    safe = xp.where(good, detG, xp.ones_like(detG))
-    F11, F12, F21, F22 = G22 / safe, -G12 / safe, -G21 / safe, G11 / safe
-    I1 = (F11**2 + F21**2) + (F12**2 + F22**2)
-    dens = 0.5 * mu_s * (I1 - 2.0) + 0.5 * kappa * (1.0 / safe - 1.0) ** 2
-    return _sum(xp.where(good, dens, xp.zeros_like(dens))) * dx * dy
+    return float(_run(None, None, X1, X2, phi, None, None, dx, dy, mu_s=mu_s, kappa=kappa)[1] * dx * dy)
 
 
 def compute_viscous_dissipation(a, b, mu_f, phi, w_t, dx, dy, eta_s=0.0):
     """eps = sum(2 mu_local (Dxx^2 + Dyy^2 + 2 Dxy^2)) dx dy  (output.py:136-193)."""
-    Dxx, Dyy = grad_central_x_2nd(a, dx), grad_central_y_2nd(b, dy)
-    Dxy = 0.5 * (grad_central_y_2nd(a, dy) + grad_central_x_2nd(b, dx))
-    H = smoothed_heaviside(phi, w_t)
-    mu_local = H * mu_f + (1 - H) * eta_s
-    return _sum(2.0 * mu_local * (Dxx**2 + Dyy**2 + 2.0 * Dxy**2)) * dx * dy
+    return float(_run(a, b, None, None, phi, None, None, dx, dy, mu_f=mu_f, eta_s=eta_s, w_t=w_t)[2] * dx * dy)
+
+
+def disc_centroid(phi, X, Y):
+    """benchmarks/common.py:110-115 -- mean node coordinates of the cells with phi <= 0."""
+    dx = 1.0
+    s = _run(None, None, None, None, phi, X, Y, dx, dx)
+    if s[3] <= 0:
+        return float("nan"), float("nan")
+    return float(s[4] / s[3]), float(s[5] / s[3])
 
 
 def output_simulation_data(*args, **kwargs):

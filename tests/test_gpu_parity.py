@@ -339,6 +339,27 @@ def test_reinitialize_phi_pde_golden(P, golden):
     assert same(t.cpu().numpy(), g["phi"])                            # input not mutated
 
 
+def test_energy_diagnostics_golden(P, golden):
+    """The fused diagnostics kernel against values recorded from the reference."""
+    import pyrmt_b200.output as OUT
+    g = golden("diag")
+    dx, dy, w_t = float(g["dx"]), float(g["dy"]), float(g["w_t"])
+    rho_f, rho_s, mu_f, mu_s, kappa, eta_s = (float(x) for x in g["prm"])
+    rel = lambda x, r: abs(x - float(r)) / abs(float(r))
+    assert rel(OUT.compute_kinetic_energy(g["a"], g["b"], rho_f, rho_s, g["phi"], w_t, dx, dy), g["ke"]) < 1e-12
+    assert rel(OUT.compute_strain_energy(g["X1"], g["X2"], g["phi"], mu_s, dx, dy, kappa=kappa), g["se"]) < 1e-11
+    assert rel(OUT.compute_strain_energy(g["X1"], g["X2"], g["phi"], mu_s, dx, dy), g["se0"]) < 1e-11
+    assert rel(OUT.compute_viscous_dissipation(g["a"], g["b"], mu_f, g["phi"], w_t, dx, dy, eta_s=eta_s), g["diss"]) < 1e-12
+    assert rel(OUT.compute_viscous_dissipation(g["a"], g["b"], mu_f, g["phi"], w_t, dx, dy), g["diss0"]) < 1e-12
+    assert np.allclose(OUT.disc_centroid(g["phi"], g["X"], g["Y"]), g["centroid"], rtol=1e-13, atol=0)
+    d = OUT.diagnostics(g["a"], g["b"], g["X1"], g["X2"], g["phi"], dx, dy, rho_f, rho_s, mu_f, mu_s, w_t,
+                        kappa=kappa, eta_s=eta_s, X=g["X"], Y=g["Y"])
+    assert rel(d["kinetic_energy"], g["ke"]) < 1e-12 and rel(d["strain_energy"], g["se"]) < 1e-11
+    assert rel(d["viscous_dissipation"], g["diss"]) < 1e-12 and d["solid_cells"] == int((g["phi"] <= 0).sum())
+    assert np.allclose(d["centroid"], g["centroid"], rtol=1e-13, atol=0)
+    assert np.all(np.isnan(OUT.disc_centroid(np.ones((8, 8)), g["X"][:8, :8], g["Y"][:8, :8])))
+
+
 def test_curvature_golden(P, golden):
     g = golden("momentum")
     assert rel_linf(P.compute_curvature(g["phi"], float(g["dx"]), float(g["dy"])), g["curv"]) < 1e-10

@@ -179,6 +179,20 @@ def test_reinitialize_phi_pde(golden):
     assert same(O.reinitialize_phi_PDE(g["phi"], dx, dy, 5, None, 0.3), g["r_level_set"])
 
 
+def test_energy_diagnostics(golden):
+    """output.py:6-193 + common.py:110-115 against tests/golden/make_golden_diag.py."""
+    g = golden("diag")
+    dx, dy, w_t = float(g["dx"]), float(g["dy"]), float(g["w_t"])
+    rho_f, rho_s, mu_f, mu_s, kappa, eta_s = (float(x) for x in g["prm"])
+    rel = lambda x, r: abs(x - float(r)) / abs(float(r))
+    assert rel(O.compute_kinetic_energy(g["a"], g["b"], rho_f, rho_s, g["phi"], w_t, dx, dy), g["ke"]) < 1e-13
+    assert rel(O.compute_strain_energy(g["X1"], g["X2"], g["phi"], mu_s, dx, dy, kappa=kappa), g["se"]) < 1e-12
+    assert rel(O.compute_strain_energy(g["X1"], g["X2"], g["phi"], mu_s, dx, dy), g["se0"]) < 1e-12
+    assert rel(O.compute_viscous_dissipation(g["a"], g["b"], mu_f, g["phi"], w_t, dx, dy, eta_s=eta_s), g["diss"]) < 1e-13
+    assert rel(O.compute_viscous_dissipation(g["a"], g["b"], mu_f, g["phi"], w_t, dx, dy), g["diss0"]) < 1e-13
+    assert np.allclose(O.disc_centroid(g["phi"], g["X"], g["Y"]), g["centroid"], rtol=1e-14, atol=0)
+
+
 def test_projection_neumann(golden):
     g = golden("projection")
     dx, dy, dt = float(g["dx"]), float(g["dy"]), float(g["dt"])
