@@ -90,6 +90,13 @@ int rmt_sample(const double *u, const double *xq, const double *yq, double *out,
 int rmt_advect_sl_rk4(const double *q0, const double *q1, const double *a, const double *b,
                       const double *X, const double *Y, double *out0, double *out1, int Ny, int Nx,
                       double dt, double dx, double dy, int cubic, void *stream);
+/* The same on a row slab: the arrays hold rows [row_offset, row_offset + Ny_local) of a grid of Ny rows
+ * (coordinates, clamping and cell indices stay global, so the result equals the full-grid call as long
+ * as every departure point's stencil lies inside the stored rows -- the caller's halo must cover
+ * max|b| dt / dy + 2 rows).  Used by pyrmt_b200/slab.py. */
+int rmt_advect_sl_rk4_rows(const double *q0, const double *q1, const double *a, const double *b,
+                           const double *X, const double *Y, double *out0, double *out1, int Ny_local, int Nx,
+                           int Ny, int row_offset, double dt, double dx, double dy, int cubic, void *stream);
 /* pyRMT/functions.py:396-415 (scheme 1 weno5), :443-459 (0 central2), :489-496
  * (2 conservative): SSP-RK3, RHS fused into each stage.  work1/work2: (Ny,Nx). */
 int rmt_advect_euler_rk3(const double *q, const double *a, const double *b, const double *phi,

@@ -35,6 +35,7 @@ _SIG = {
     "rmt_disc_sdf": [vp, vp, vp, i64, vp, vp, vp, i32, vp, vp, i32, dbl, dbl, vp],
     "rmt_sample": [vp, vp, vp, vp, i64, dbl, dbl, i32, i32, i32, vp],
     "rmt_advect_sl_rk4": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, dbl, dbl, dbl, i32, vp],
+    "rmt_advect_sl_rk4_rows": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, dbl, dbl, dbl, i32, vp],
     "rmt_advect_euler_rk3": [vp, vp, vp, vp, vp, vp, vp, i32, i32, dbl, dbl, dbl, dbl, i32, vp],
     "rmt_advect_euler_rk3_pair": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, dbl, dbl, dbl, dbl, i32, i32, vp],
     "rmt_euler_rhs": [vp, vp, vp, vp, vp, i32, i32, dbl, dbl, dbl, i32, vp],

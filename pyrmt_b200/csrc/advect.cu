@@ -126,12 +126,17 @@ __global__ void k_advect_sl(const double *__restrict__ q0, const double *__restr
                             const double *__restrict__ a, const double *__restrict__ b,
                             const double *__restrict__ X, const double *__restrict__ Y,
                             double *__restrict__ o0, double *__restrict__ o1, int Ny, int Nx,
-                            double dt, double dx, double dy)
+                            double dt, double dx, double dy, int Nyl, int joff)
 {
+    // Row slab (rmt_advect_sl_rk4_rows): the arrays hold rows [joff, joff + Nyl) of a grid of Ny rows.
+    // Sampling works in global indices, so the sampled fields are addressed from the virtual row 0.
     int i = blockIdx.x * TX + threadIdx.x;
     int j = blockIdx.y * TY + threadIdx.y;
-    if (i >= Nx || j >= Ny) return;
+    if (i >= Nx || j >= Nyl) return;
     size_t c = (size_t)j * Nx + i;
+    const size_t voff = (size_t)joff * Nx;
+    a -= voff; b -= voff; q0 -= voff;
+    if (NQ == 2) q1 -= voff;
     double x = X[c], y = Y[c];
     const double half_dt = 0.5 * dt, sixth_dt = dt / 6.0;
     double k1x, k1y, k2x, k2y, k3x, k3y, k4x, k4y;
@@ -369,16 +374,26 @@ int rmt_advect_sl_rk4(const double *q0, const double *q1, const double *a, const
                       const double *X, const double *Y, double *out0, double *out1, int Ny, int Nx,
                       double dt, double dx, double dy, int cubic, void *stream)
 {
-    if (!q0 || !a || !b || !X || !Y || !out0 || Nx < 2 || Ny < 2) return RMT_EINVAL;
+    return rmt_advect_sl_rk4_rows(q0, q1, a, b, X, Y, out0, out1, Ny, Nx, Ny, 0, dt, dx, dy, cubic, stream);
+}
+
+int rmt_advect_sl_rk4_rows(const double *q0, const double *q1, const double *a, const double *b,
+                           const double *X, const double *Y, double *out0, double *out1, int Ny_local, int Nx,
+                           int Ny, int row_offset, double dt, double dx, double dy, int cubic, void *stream)
+{
+    if (!q0 || !a || !b || !X || !Y || !out0 || Nx < 2 || Ny < 2 || Ny_local < 1 || row_offset < 0 ||
+        row_offset + Ny_local > Ny)
+        return RMT_EINVAL;
     if ((q1 == nullptr) != (out1 == nullptr)) return RMT_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
-    dim3 blk(TX, TY), grd(rmt_cdiv(Nx, TX), rmt_cdiv(Ny, TY));
+    const int Nyl = Ny_local, jo = row_offset;
+    dim3 blk(TX, TY), grd(rmt_cdiv(Nx, TX), rmt_cdiv(Nyl, TY));
     if (q1) {
-        if (cubic) k_advect_sl<true, 2><<<grd, blk, 0, s>>>(q0, q1, a, b, X, Y, out0, out1, Ny, Nx, dt, dx, dy);
-        else k_advect_sl<false, 2><<<grd, blk, 0, s>>>(q0, q1, a, b, X, Y, out0, out1, Ny, Nx, dt, dx, dy);
+        if (cubic) k_advect_sl<true, 2><<<grd, blk, 0, s>>>(q0, q1, a, b, X, Y, out0, out1, Ny, Nx, dt, dx, dy, Nyl, jo);
+        else k_advect_sl<false, 2><<<grd, blk, 0, s>>>(q0, q1, a, b, X, Y, out0, out1, Ny, Nx, dt, dx, dy, Nyl, jo);
     } else {
-        if (cubic) k_advect_sl<true, 1><<<grd, blk, 0, s>>>(q0, q1, a, b, X, Y, out0, out1, Ny, Nx, dt, dx, dy);
-        else k_advect_sl<false, 1><<<grd, blk, 0, s>>>(q0, q1, a, b, X, Y, out0, out1, Ny, Nx, dt, dx, dy);
+        if (cubic) k_advect_sl<true, 1><<<grd, blk, 0, s>>>(q0, q1, a, b, X, Y, out0, out1, Ny, Nx, dt, dx, dy, Nyl, jo);
+        else k_advect_sl<false, 1><<<grd, blk, 0, s>>>(q0, q1, a, b, X, Y, out0, out1, Ny, Nx, dt, dx, dy, Nyl, jo);
     }
     RMT_LAUNCH_CHECK();
     return RMT_OK;

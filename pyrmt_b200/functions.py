@@ -114,17 +114,19 @@ def advect_semilagrangian_cubic_rk4(q, a, b, X, Y, dt, dx, dy):
     return _sl(q, a, b, X, Y, dt, dx, dy, 1)
 
 
-def advect_semilagrangian_pair(q0, q1, a, b, X, Y, dt, dx, dy, cubic=False):
+def advect_semilagrangian_pair(q0, q1, a, b, X, Y, dt, dx, dy, cubic=False, slab=None):
     """Both reference-map components with ONE shared backtrace (the reference
     recomputes it per component, soft_disc_in_lid_driven.py:88-91).  Results are
-    identical to two advect_semilagrangian_rk4 calls."""
+    identical to two advect_semilagrangian_rk4 calls.  ``slab=(Ny_global, row_offset)``: the
+    arrays are a row slab of a larger grid (pyrmt_b200/slab.py)."""
     as_np = is_np(q0)
     q0d, q1d, ad, bd, Xd, Yd = (to_dev(t) for t in (q0, q1, a, b, X, Y))
     Ny, Nx = shape2(q0d)
+    Nyg, joff = (Ny, 0) if slab is None else (int(slab[0]), int(slab[1]))
     o0, o1 = torch.empty_like(q0d), torch.empty_like(q1d)
-    _chk(ctx().lib.rmt_advect_sl_rk4(ptr(q0d), ptr(q1d), ptr(ad), ptr(bd), ptr(Xd), ptr(Yd), ptr(o0),
-                                     ptr(o1), Ny, Nx, float(dt), float(dx), float(dy), int(bool(cubic)),
-                                     stream()), "rmt_advect_sl_rk4")
+    _chk(ctx().lib.rmt_advect_sl_rk4_rows(ptr(q0d), ptr(q1d), ptr(ad), ptr(bd), ptr(Xd), ptr(Yd), ptr(o0),
+                                          ptr(o1), Ny, Nx, Nyg, joff, float(dt), float(dx), float(dy),
+                                          int(bool(cubic)), stream()), "rmt_advect_sl_rk4_rows")
     return to_user(o0, as_np), to_user(o1, as_np)
 
 
@@ -155,7 +157,7 @@ def advect_conservative_rk3(q, a, b, dx, dy, dt, phi, w_cut=0.0):
 
 
 def advect_reference_map_pair(q0, q1, a, b, X, Y, dt, dx, dy, phi, scheme='semilagrangian', w_cut=0.0,
-                              mask_solid=False):
+                              mask_solid=False, slab=None):
     """Both reference-map components in one call -- bitwise identical to two
     ``advect_reference_map`` calls (the drivers advect xi1 and xi2 with the same a, b, phi, dt:
     benchmarks/soft_disc_in_lid_driven.py:88-91) but a, b, phi are read once per stage and the
@@ -165,7 +167,8 @@ def advect_reference_map_pair(q0, q1, a, b, X, Y, dt, dx, dy, phi, scheme='semil
         raise FloatingPointError(
             "advect_reference_map: non-finite velocity (the simulation diverged)")
     if scheme in ('semilagrangian', 'semilagrangian_cubic'):
-        r0, r1 = advect_semilagrangian_pair(q0, q1, a, b, X, Y, dt, dx, dy, cubic=scheme.endswith('cubic'))
+        r0, r1 = advect_semilagrangian_pair(q0, q1, a, b, X, Y, dt, dx, dy, cubic=scheme.endswith('cubic'),
+                                            slab=slab)
         return (mask_solid_(r0, phi), mask_solid_(r1, phi)) if mask_solid else (r0, r1)
     if scheme not in _SCHEMES:
         raise ValueError("Unknown advection scheme %r (expected 'semilagrangian', "

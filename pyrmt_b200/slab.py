@@ -5,14 +5,15 @@ all-to-all back).  One process per GPU, torch.distributed (NCCL over NVLink) for
 exchanges, the same C-ABI kernels as the single-GPU path on every rank.
 
 What is sharded: the whole FSI step of benchmarks/soft_disc_in_lid_driven.py:78-106 for
-the Eulerian advection schemes (WENO5 / central2 / conservative) with wall-type BCs and the
-Neumann/DCT projection (`SlabFSISolver`), and its fluid half alone (`SlabFluidSolver`).
+every advection scheme, rim-gather BCs (walls, lid, free slip, the periodic wrap) and the
+Neumann/DCT or periodic/FFT projection (`SlabFSISolver`), and its fluid half alone
+(`SlabFluidSolver`).
 The narrow-band extrapolation is a serial raster sweep whose dependencies run down the
 flank of a body, so it is not cut at slab boundaries: every rank sweeps its own rows plus
 an overlap of `overlap` rows above them (the bodies that reach into its slab, from their
 first row on), which reproduces the serial result bit for bit as long as each such body
 starts inside the overlap -- checked every step by `guard`.  Semi-Lagrangian advection
-(needs a row offset in the sampling kernel) and periodic BCs across ranks are next.
+samples in global indices (`rmt_advect_sl_rk4_rows`).
 
 Layout: rank k owns rows [r0, r1) of the (Ny, Nx) grid and stores rows
 [e0, e1) = [r0 - H, r1 + H) clipped to the grid ("extended slab").  Kernels run on the
@@ -629,10 +630,21 @@ class SlabFSISolver(SlabFluidSolver):
         self._dbg("state", a, b, p, X1, X2)
         dx, dy = prm["dx"], prm["dy"]
         phi = F.rebuild_phi_from_reference_map(X1, X2, self.phi_init)
-        # Eulerian SSP-RK3 advection of both components + solid mask on the extended slab (halo 9 consumed)
+        # advection of both components + solid mask on the extended slab: Eulerian SSP-RK3 consumes 9 halo
+        # rows; semi-Lagrangian samples in global indices (rmt_advect_sl_rk4_rows) and needs the departure
+        # stencils inside the stored rows
         Y0 = prm.get("X"), prm.get("Y")
+        slab = None
+        if prm["scheme"].startswith("semilagrangian"):
+            if Y0[0] is None or tuple(Y0[0].shape) != tuple(a.shape):
+                raise ValueError("semi-Lagrangian advection on slabs needs prm['X'], prm['Y'] as extended slabs")
+            if check_guard:
+                reach = float(self.max_speed(a, b).item()) * dt / min(dx, dy) + 3.0
+                if reach > lay.H:
+                    raise RuntimeError("slab advection: departure points reach %.1f rows, halo is %d" % (reach, lay.H))
+            slab = (lay.Ny, lay.e0)
         X1, X2 = F.advect_reference_map_pair(X1, X2, a, b, Y0[0], Y0[1], dt, dx, dy, phi, prm["scheme"],
-                                             prm.get("w_cut", 0.0), mask_solid=True)
+                                             prm.get("w_cut", 0.0), mask_solid=True, slab=slab)
         self._dbg("advected", X1, X2, phi)
         # extrapolation on [r0 - top, r1 + bot): the bodies reaching into this slab, from their first row
         B1, B2, Bphi = self._gather_big((X1, X2, phi))
@@ -688,6 +700,7 @@ def slab_initial_state(solver, L, sdf, velocity=None):
         a0, b0 = velocity(Xh, Yh)
         a, b = up(a0), up(b0)
     solver._bc_and_halo(a, b)
+    solver.coords = (Xs, Ys)                     # extended-slab node coordinates (semi-Lagrangian advection)
     return (a, b, torch.zeros_like(Xs), X1, X2), dx, dy
 
 

@@ -22,6 +22,7 @@ ap.add_argument("--pfsi-time", type=int, default=0, help="time the periodic Tayl
 ap.add_argument("--pfluid-time", type=int, default=0, help="time the periodic pure-fluid slab step (momentum + FFT projection) at N x N")
 ap.add_argument("--pfsi-k", type=int, default=3, help="lattice side of the --pfsi check (discs of radius 0.24/k of the box)")
 ap.add_argument("--L", type=float, default=0.0, help="domain side for --pfsi-time (default (N-1)/128, i.e. dx = 1/128)")
+ap.add_argument("--scheme", default="weno5", help="advection scheme of the --fsi / --pfsi checks")
 ap.add_argument("--overlap", type=int, default=256)
 ap.add_argument("--steps", type=int, default=10)
 args = ap.parse_args()
@@ -101,12 +102,12 @@ if args.fsi:
     a0, b0 = bc(np.zeros((N, N)), np.zeros((N, N)))
     state = (up(a0), up(b0), up(np.zeros((N, N))), X1, X2)
     prm = dict(dx=dx, dy=dy, CFL=0.2, dt_cap=1e-3, mu_s=0.1, kappa=0.0, rho_s=1.0, rho_f=1.0, eta_s=0.01,
-               mu_f=0.01, w_t=2 * dx, layers=3, scheme="weno5", w_cut=0.0, phi_init=sdf, bc=bc, eig=eig,
+               mu_f=0.01, w_t=2 * dx, layers=3, scheme=args.scheme, w_cut=0.0, phi_init=sdf, bc=bc, eig=eig,
                X=Xd, Y=Yd)
     lay = SlabLayout(N, N, world, rank, halo=12)
     solver = SlabFSISolver(lay, bc, eig, sdf, overlap=args.overlap, layers=3)
     sstate = tuple(lay.take(t).contiguous() for t in state)
-    sprm = dict(prm, X=None, Y=None)
+    sprm = dict(prm, X=lay.take(Xd).contiguous(), Y=lay.take(Yd).contiguous())
     worst = {}
     for n in range(4):
         state, dt, _ = fsi_step(state, prm)
@@ -117,7 +118,7 @@ if args.fsi:
     t = torch.tensor([worst[k] for k in ("a", "b", "p", "X1", "X2")], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    out["fsi_check"] = {"N": N, "steps": 4, "rel_linf_vs_single_gpu": dict(zip(("a", "b", "p", "X1", "X2"), t.tolist()))}
+    out["fsi_check"] = {"N": N, "steps": 4, "scheme": args.scheme, "rel_linf_vs_single_gpu": dict(zip(("a", "b", "p", "X1", "X2"), t.tolist()))}
     del state, sstate, solver, X1, X2, Xd, Yd, phi0
     torch.cuda.empty_cache()
 
@@ -188,7 +189,7 @@ if args.pfsi:
     a0, b0 = bc(*tg_velocity(L)(X, Y))
     state = (up(a0), up(b0), up(np.zeros((N, N))), X1, X2)
     prm = dict(dx=dx, dy=dy, CFL=0.2, dt_cap=1e-3, mu_s=0.1, kappa=0.0, rho_s=1.0, rho_f=1.0, eta_s=0.01,
-               mu_f=0.01, w_t=2 * dx, layers=3, scheme="weno5", w_cut=0.0, phi_init=sdf, bc=bc, eig=eig,
+               mu_f=0.01, w_t=2 * dx, layers=3, scheme=args.scheme, w_cut=0.0, phi_init=sdf, bc=bc, eig=eig,
                bc_type="periodic", X=Xd, Y=Yd)
     lay = SlabLayout(N, N, world, rank, halo=12, periodic=True)
     solver = SlabFSISolver(lay, bc, None, sdf, overlap=args.overlap, layers=3, spacing=(dx, dy))
@@ -196,7 +197,7 @@ if args.pfsi:
     worst = {}
     for nm, ref, got in zip(("a", "b", "p", "X1", "X2"), state, sstate):
         worst[nm] = float(((got - ref[lay.e0:lay.e1]).abs().max() / max(float(ref.abs().max()), 1e-300)).item())
-    sprm = dict(prm, X=None, Y=None)
+    sprm = dict(prm, X=solver.coords[0], Y=solver.coords[1])
     for n in range(4):
         state, dt, _ = fsi_step(state, prm)
         sstate = solver.fsi_step(sstate, sprm, dt)
@@ -206,7 +207,7 @@ if args.pfsi:
     t = torch.tensor([worst[k] for k in ("a", "b", "p", "X1", "X2")], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    out["periodic_fsi_check"] = {"N": N, "steps": 4,
+    out["periodic_fsi_check"] = {"N": N, "steps": 4, "scheme": args.scheme,
                                  "rel_linf_vs_single_gpu": dict(zip(("a", "b", "p", "X1", "X2"), t.tolist()))}
     del state, sstate, solver, X1, X2, Xd, Yd, phi0, eig, X, Y
     torch.cuda.empty_cache()

@@ -592,6 +592,23 @@ def test_host_state_step_equals_device_step(P):
 
 
 # ----------------------------------------------------------------- slab decomposition (1 rank)
+def test_sl_rows_equals_full_grid(P, golden):
+    """rmt_advect_sl_rk4_rows on a row window with halo == the same rows of the full-grid call."""
+    import torch
+    g = golden("advect")
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    q, a, b, X, Y = (up(g[k]) for k in ("q", "a", "b", "X", "Y"))
+    dx, dy, dt = float(g["dx"]), float(g["dy"]), float(g["dt"])
+    Ny = q.shape[0]
+    for cubic in (False, True):
+        f0, f1 = P.advect_semilagrangian_pair(q, 2.0 * q, a, b, X, Y, dt, dx, dy, cubic=cubic)
+        e0, e1 = 5, Ny - 4
+        s0, s1 = P.advect_semilagrangian_pair(*(t[e0:e1].contiguous() for t in (q, 2.0 * q, a, b, X, Y)), dt, dx, dy,
+                                              cubic=cubic, slab=(Ny, e0))
+        inner = slice(4, e1 - e0 - 4)                     # rows whose departure stencils lie inside the window
+        assert torch.equal(s0[inner], f0[e0:e1][inner]) and torch.equal(s1[inner], f1[e0:e1][inner])
+
+
 def test_slab_solver_world1_equals_single_gpu(P):
     """The slab-decomposed FSI step with one rank (no halos, the same kernels and the
     transpose-based DCT building blocks) reproduces the single-GPU step; the 2-GPU
@@ -616,14 +633,17 @@ def test_slab_solver_world1_equals_single_gpu(P):
                X=Xd, Y=Yd)
     lay = SlabLayout(N, N, 1, 0, halo=12)
     solver = SlabFSISolver(lay, bc, eig, sdf, overlap=64, layers=3)
-    sstate = tuple(t.clone() for t in state)
-    for _ in range(3):
-        state, dt, _ = fsi_step(state, prm)
-        sstate = solver.fsi_step(sstate, dict(prm, X=None, Y=None), dt)
-        for nm, ref, got in zip("abp12", state, sstate):
-            if nm in "12":
-                assert torch.equal(ref, got), nm
-            assert float(((ref - got).abs().max() / ref.abs().max()).item()) < 1e-12, nm
+    for scheme in ("weno5", "semilagrangian"):
+        state1 = tuple(t.clone() for t in state)
+        sstate = tuple(t.clone() for t in state)
+        prm1 = dict(prm, scheme=scheme)
+        for _ in range(3):
+            state1, dt, _ = fsi_step(state1, prm1)
+            sstate = solver.fsi_step(sstate, prm1, dt)
+            for nm, ref, got in zip("abp12", state1, sstate):
+                if nm in "12":
+                    assert torch.equal(ref, got), (scheme, nm)
+                assert float(((ref - got).abs().max() / ref.abs().max()).item()) < 1e-12, (scheme, nm)
 
 
 def test_slab_solver_periodic_world1_equals_single_gpu(P):
