@@ -297,12 +297,7 @@ def main():
         sprm = dict(prm, X=None, Y=None)
 
         def step(st):
-            dt = Fn.compute_timestep(lay.owned(st[0]), lay.owned(st[1]), prm["dx"], prm["dy"], prm["CFL"],
-                                     prm["dt_cap"], prm["mu_s"], prm["rho_s"], 0.0, prm["rho_f"], mu_f=prm["mu_f"],
-                                     eta_s=prm["eta_s"], kappa=prm["kappa"])
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            return solver.fsi_step(st, sprm, float(t.item()), check_guard=False)
+            return solver.fsi_step(st, sprm, solver.compute_timestep(st[0], st[1], prm), check_guard=False)
         solver.fsi_step(state, sprm, 1e-7, check_guard=True)      # validates the overlap once (raises if too small)
     for _ in range(args.warmup):
         state = step(state)
@@ -316,7 +311,11 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    profiler.reset(timing=True)
+    # Per-entry-point CUDA events (two per call) are recorded inside the timed region when N = 1 (GPU-bound:
+    # they cost nothing there and the roofline is then measured live over the timed steps).  With N > 1 the
+    # step is short enough to be host-bound, so the timed region runs clean and the breakdown comes from
+    # a few extra profiled steps right after it.
+    profiler.reset(timing=(world == 1))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     from pyrmt_b200 import _lib as _rmt_lib
     barrier()
@@ -328,6 +327,13 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = int(_rmt_lib.load().rmt_launch_count() - launches0)   # counted inside librmt_b200.so
+    prof_steps = args.steps
+    if world > 1:
+        prof_steps = min(5, args.steps)
+        profiler.reset(timing=True)
+        for _ in range(prof_steps):
+            state = step(state)
+        torch.cuda.synchronize()
     per_kernel = profiler.summary()
     profiler.reset(timing=False)
     clocks = sampler.stop() if sampler else None
@@ -350,7 +356,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
                 "launches_timed": kcalls, "avg_launch_ms": kavg_ms,
-                "share_of_step": ktotal / ms,
+                "share_of_step": (ktotal / prof_steps) / (ms / args.steps),
                 "alg_bytes_per_launch": alg_launch}
     ncell_rank = state[0].numel() if world > 1 else cells
     if world == 1 and N == 4097:
@@ -361,13 +367,14 @@ def main():
     kernels_roofline = []
     for k, (c, t) in sorted(per_kernel.items(), key=lambda kv: -kv[1][1]):
         ab = ALG_BYTES_PER_CELL_LAUNCH.get(k, 0.0) * ncell_rank
-        kernels_roofline.append({"kernel": k, "share_of_step": t / ms, "avg_launch_ms": t / c,
+        kernels_roofline.append({"kernel": k, "share_of_step": (t / prof_steps) / (ms / args.steps),
+                                 "avg_launch_ms": t / c,
                                  "achieved_GBps": ab / (t / c * 1e-3) / 1e9 if t > 0 else None,
                                  "frac": ab / (t / c * 1e-3) / 1e9 / peak if t > 0 else None,
                                  "alg_bytes_per_launch": ab,
                                  "traffic": NCU_TRAFFIC_BYTES_4097.get(k) if (world == 1 and N == 4097) else None})
     step_gbs = cells * ALG_BYTES_PER_CELL_STEP.get(args.scheme, 512.0) * args.steps / (ms * 1e-3) / 1e9
-    breakdown = {k: {"calls": c, "ms_per_step": t / args.steps} for k, (c, t) in
+    breakdown = {k: {"calls": c, "ms_per_step": t / prof_steps} for k, (c, t) in
                  sorted(per_kernel.items(), key=lambda kv: -kv[1][1])}
 
     # ---- end to end: host state in, host state out, every step --------------

@@ -75,6 +75,12 @@ def compute_timestep(a, b, dx, dy, CFL, dt_min_cap, mu_s, rho_s, gamma, rho_f, m
         finite_cache.put(a, b, bad == 0.0)
     if bad:
         speed = float("nan")
+    return timestep_from_speed(speed, dx, dy, CFL, dt_min_cap, mu_s, rho_s, gamma, rho_f, mu_f, eta_s, kappa)
+
+
+def timestep_from_speed(speed, dx, dy, CFL, dt_min_cap, mu_s, rho_s, gamma, rho_f, mu_f=0.0, eta_s=0.0, kappa=0.0):
+    """The host formula of compute_timestep (functions.py:177-192) for a given max sqrt(a^2 + b^2)
+    (a slab-decomposed run reduces the speed over the ranks first)."""
     wave = np.sqrt((kappa + mu_s * 4.0 / 3.0) / (rho_s + 1e-12))
     dt_solid = CFL * dx / (wave + 1e-14)
     dt_fluid = CFL * dx / (speed + 1e-6)

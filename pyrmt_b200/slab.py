@@ -431,6 +431,15 @@ class SlabFluidSolver:
         out = ctx().max_speed(lay.owned(a), lay.owned(b))
         return self.comm.allreduce(out[:1].clone(), "max")
 
+    def compute_timestep(self, a, b, prm):
+        """compute_timestep (functions.py:165-192) of the whole grid: max speed over the owned rows,
+        all-reduced on the device, ONE host read, then the reference's formula."""
+        from . import functions as F
+        speed = float(self.max_speed(a, b).item())
+        return F.timestep_from_speed(speed, prm["dx"], prm["dy"], prm["CFL"], prm["dt_cap"], prm["mu_s"],
+                                     prm["rho_s"], prm.get("gamma", 0.0), prm["rho_f"], prm["mu_f"],
+                                     prm["eta_s"], prm["kappa"])
+
     # -- functions.py:673-762 ----------------------------------------------------------
     def momentum_step(self, u, v, p, X1, X2, phi, mu_s, kappa, eta_s, dx, dy, dt, rho_s, rho_f, mu_f, w_t):
         lay, lib, st = self.lay, self.lib, stream()
