@@ -11,11 +11,16 @@ of the loop of benchmarks/soft_disc_in_lid_driven.py:78-106 through the drop-in
 operator API (pyrmt_b200.driver.fsi_step).
 
   value         device-resident loop, state already in HBM, CUDA-event timed
-  e2e           the same step called with HOST state: the five state fields are
-                copied from pinned host memory to the device and the five results
-                back, every step, inside the timed region
-  roofline      the dominant kernel (by summed CUDA-event time in the timed
-                region): algorithmic bytes per launch / mean launch duration
+  e2e           the same step called with HOST state (pyrmt_b200.driver.fsi_step_host):
+                the five state fields are copied from pinned host memory to the
+                device and the five results back, every step, inside the timed
+                region (uploads ordered by first use, xi downloads overlapped with
+                the predictor / projection on copy streams)
+  roofline      the dominant entry point (by summed CUDA-event time in the timed
+                region): algorithmic bytes per launch / mean launch duration;
+                kernels_roofline lists every entry point with its ncu DRAM traffic
+  gpu_launches  kernels launched in the timed region, counted inside
+                librmt_b200.so (rmt_launch_count), per rank
   cpu_baseline  the CPU oracle (oracle/, a port of the reference's Numba/NumPy
                 path) on a bounded sample of the same workload, on this box's cores
 
@@ -23,8 +28,12 @@ operator API (pyrmt_b200.driver.fsi_step).
 Python + Numba and cannot travel to the GPU box).
 N > 1: the SAME 4097^2 problem is slab-decomposed over the N GPUs (pyrmt_b200/slab.py: y-slabs,
 NCCL halo exchange, all-to-all transposes in the DCT solve, overlap-swept extrapolation) --
-strong scaling; the results equal the single-GPU step (xi bit for bit).  The fluid half of
-the step on one 8193^2 grid is reported beside it as `slab_fluid_step`.
+strong scaling; the results equal the single-GPU step (xi bit for bit).  Beside it: the fluid
+half of the step on one 8193^2 grid (`slab_fluid_step`, Neumann/DCT) and BASELINE configs[4]
+(`config5_periodic`: periodic Taylor-Green FSI at 8193^2 and the periodic fluid step at 16385^2,
+distributed Hartley/FFT solve).  With N > 1 the step is short enough to be host-bound, so the
+timed region runs without per-call CUDA events and the kernel breakdown comes from a few extra
+profiled steps.
 """
 import argparse
 import json
@@ -65,7 +74,7 @@ ALG_BYTES_PER_CELL_LAUNCH = {
 
 
 # DRAM bytes per call (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full` capture of
-# this workload at 4097^2 on one B200 (profiles/r01e_ncu_full_summary.txt); per-call = sum over the
+# this workload at 4097^2 on one B200 (profiles/r01e_/r01h_ncu_full_summary.txt); per-call = sum over the
 # kernels the entry point launches.  Only reported for N = 1 at the default size.
 NCU_TRAFFIC_BYTES_4097 = {
     "rmt_momentum_stage": 1.603e9,         # mean of the four stages (1.46 / 1.74 / 1.74 / 1.48 GB)
