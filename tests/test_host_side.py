@@ -114,6 +114,20 @@ def test_host_tables_match_oracle(golden):
     assert np.array_equal(X, X2) and np.array_equal(Y, Y2) and dx == dx2 and dy == dy2
 
 
+def test_timestep_formula_matches_oracle(golden):
+    """functions.timestep_from_speed is compute_timestep's host formula (functions.py:177-192)."""
+    import pyrmt_b200.functions as F
+    from oracle import rmt_oracle as O
+    g = golden("timestep")
+    u, v, dx, dy = g["u"], g["v"], float(g["dx"]), float(g["dy"])
+    speed = float(np.max(np.sqrt(u ** 2 + v ** 2)))
+    for args in ((0.2, 1e-3, 0.1, 1.0, 0.0, 1.0, 0.01, 0.01, 0.0), (0.5, 1.0, 2.0, 1.3, 0.07, 0.9, 0.0, 0.0, 0.4)):
+        CFL, cap, mu_s, rho_s, gamma, rho_f, mu_f, eta_s, kappa = args
+        ref = O.compute_timestep(u, v, dx, dy, CFL, cap, mu_s, rho_s, gamma, rho_f, mu_f=mu_f, eta_s=eta_s, kappa=kappa)
+        got = F.timestep_from_speed(speed, dx, dy, CFL, cap, mu_s, rho_s, gamma, rho_f, mu_f, eta_s, kappa)
+        assert got == ref
+
+
 def test_reinit_and_unbuilt_rows():
     import pyrmt_b200.functions as F
     phi = np.ones((8, 8))
