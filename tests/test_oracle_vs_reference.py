@@ -92,3 +92,41 @@ def test_fsi_steps_n128(ref):
         assert dto == dt
         for x, y in zip(so, (a, b, p, X1, X2)):
             assert np.array_equal(x, y)
+
+
+def test_next_rows_against_live_reference(ref):
+    """SURVEY 8f rows on seeded inputs larger than the golden fixtures: two-solid step + contact force
+    (functions.py:765-895), PDE reinitialisation (:1369-1411), energy diagnostics (output.py:6-193)."""
+    import pyRMT.output as OUT
+    from oracle import rmt_oracle as O
+    N = 96
+    X, Y, dx, dy = ref.create_grid(N, N, 1.0, 1.0)
+    disc = lambda x0, y0, R: np.sqrt((X - x0) ** 2 + (Y - y0) ** 2) - R
+    pa, pb = disc(0.36, 0.5, 0.15), disc(0.655, 0.52, 0.15)
+    ma, mb = (pa <= 0).astype(float), (pb <= 0).astype(float)
+    X1a, X2a = ref.extrapolate_reference_map((X + 0.01 * np.sin(4 * Y)) * ma, Y * 0.98 * ma, pa, dx, dy, 3)
+    X1b, X2b = ref.extrapolate_reference_map(X * 1.02 * mb, (Y - 0.01 * X) * mb, pb, dx, dy, 3)
+    rng = np.random.default_rng(3)
+    u = 0.3 * np.sin(2 * np.pi * X) * np.cos(np.pi * Y) + 0.01 * rng.standard_normal((N, N))
+    v = -0.2 * np.cos(np.pi * X) * np.sin(2 * np.pi * Y)
+    p = 0.1 * np.cos(np.pi * X * Y)
+    bc = lambda a, b: O.no_slip_lid_bc(a, b, 1.0)
+    fr, fo = ref.compute_contact_force(pa, pb, 2.0, 3 * dx, dx, dy), O.compute_contact_force(pa, pb, 2.0, 3 * dx, dx, dy)
+    assert np.abs(fr[0]).max() > 0 and np.allclose(fr[0], fo[0], rtol=0, atol=1e-13 * np.abs(fr[0]).max())
+    assert np.allclose(fr[1], fo[1], rtol=0, atol=1e-13 * np.abs(fr[1]).max())
+    args = (u, v, p, X1a, X2a, X1b, X2b, bc, 0.9, 0.4, 0.0, dx, dy, 1e-3, 1.2, 1.0, pa, pb, 0.02, 2 * dx)
+    rr = ref.momentum_step_rk4_2solids(*args, k_rep=2.0, w_c=3 * dx)
+    ro = O.momentum_step_rk4_2solids(*args, k_rep=2.0, w_c=3 * dx)
+    for x, y in zip(rr, ro):
+        assert np.max(np.abs(x - y)) <= 1e-13 * np.max(np.abs(x))
+    phi = pa * (1.0 + 0.5 * np.sin(6 * X) * np.cos(5 * Y))
+    assert np.array_equal(ref.reinitialize_phi_PDE(phi, dx, dy, 15, ref.apply_phi_BCs, 0.3),
+                          O.reinitialize_phi_PDE(phi, dx, dy, 15, O.apply_phi_BCs, 0.3))
+    w_t = 2 * dx
+    rel = lambda a, b: abs(a - b) / abs(a)
+    assert rel(OUT.compute_kinetic_energy(u, v, 1.0, 1.3, pa, w_t, dx, dy),
+               O.compute_kinetic_energy(u, v, 1.0, 1.3, pa, w_t, dx, dy)) < 1e-13
+    assert rel(OUT.compute_strain_energy(X1a, X2a, pa, 0.7, dx, dy, kappa=0.2),
+               O.compute_strain_energy(X1a, X2a, pa, 0.7, dx, dy, kappa=0.2)) < 1e-12
+    assert rel(OUT.compute_viscous_dissipation(u, v, 0.02, pa, w_t, dx, dy, eta_s=0.03),
+               O.compute_viscous_dissipation(u, v, 0.02, pa, w_t, dx, dy, eta_s=0.03)) < 1e-13
