@@ -160,7 +160,7 @@ class Comm:
 
 # ------------------------------------------------------------------- device line ops
 class CudaOps:
-    """The three device primitives of the distributed transform (C ABI)."""
+    """The device primitives of the distributed transforms and reductions (C ABI)."""
 
     def dct_lines(self, x, eig=None, scale=1.0):
         nrows, N = x.shape
@@ -173,6 +173,10 @@ class CudaOps:
         _lib.check(ctx().lib.rmt_dht_lines(x.data_ptr(), out.data_ptr(), ptr(mul), x.shape[0], m, x.stride(0),
                                            out.stride(0), float(scale), stream()), "rmt_dht_lines")
         return out
+
+    def sum(self, x):
+        """Sum of a contiguous device tensor as a 1-element tensor (rmt_field_stats: two-pass tree)."""
+        return ctx().stats(x)[:1].clone()
 
     def transpose(self, x):
         R, C = x.shape
@@ -232,7 +236,7 @@ class DistPoissonDCT:
         At2 = torch.empty(Nx * nr_me, dtype=At.dtype, device=At.device)
         comm.all_to_all(sbuf, recv_counts, At2, send_counts)          # blocks (nc_q, nr_me) = rows of At
         sol = ops.dct_lines(ops.transpose(At2.view(Nx, nr_me)))        # (nr_me, Nx), rows again
-        total = comm.allreduce(sol.sum().reshape(1))
+        total = comm.allreduce(ops.sum(sol))
         return sol, total
 
 
@@ -301,9 +305,9 @@ class DistPoissonFFT:
         comm.all_to_all(sbuf, recv_counts, At2, send_counts)
         ops.dht_lines(ops.transpose(At2.view(mx, nr_me)), sol_rows, mx)
         ops.copy2d(sol_rows[:, 0:1], sol_rows[:, mx:mx + 1])           # _tile_overlap, x direction
-        part = sol_rows.sum().reshape(1)
+        part = ops.sum(sol_rows)
         if me == 0:
-            part = part + sol_rows[0].sum()                            # the overlap row Ny-1 repeats row 0
+            part = part + ops.sum(sol_rows[0])                         # the overlap row Ny-1 repeats row 0
         return comm.allreduce(part)
 
 
@@ -473,7 +477,7 @@ class SlabFluidSolver:
         lay, lib, st, comm = self.lay, self.lib, stream(), self.comm
         nl, Nx, ncell = lay.nl, lay.Nx, lay.Ny * lay.Nx
         if isinstance(rho, torch.Tensor):
-            rsum = comm.allreduce(lay.owned(rho).sum().reshape(1))
+            rsum = comm.allreduce(self.ops.sum(lay.owned(rho)))
             rd, rscalar = rho, 0.0
         else:
             rd, rscalar = None, float(rho)
@@ -494,7 +498,7 @@ class SlabFluidSolver:
                                               rscalar, ptr(p_prev), ptr(a), ptr(b), ptr(p), nl, Nx, dx, dy, dt,
                                               0, st), "rmt_projection_correct")
         self._apply_bc(a, b)
-        psum = comm.allreduce(lay.owned(p).sum().reshape(1)) * (float(nl * Nx) / float(ncell))
+        psum = comm.allreduce(self.ops.sum(lay.owned(p))) * (float(nl * Nx) / float(ncell))
         _lib.check(lib.rmt_subtract_mean(ptr(p), ptr(psum), p.numel(), st), "rmt_subtract_mean")
         comm.halo_exchange(lay, (a, b, p))
         return a, b, p
@@ -520,7 +524,7 @@ class SlabFluidSolver:
         # overlap row's slot, restored afterwards)
         comm.ring_exchange([(E[n_red:n_red + 1], E[1:2], E[0:1], E[1 + n_red:2 + n_red]) for E in (Ea, Eb)])
         if isinstance(rho, torch.Tensor):
-            rsum = comm.allreduce(lay.owned(rho).sum().reshape(1))
+            rsum = comm.allreduce(self.ops.sum(lay.owned(rho)))
             Er, rscalar = ext(rho), 0.0
         else:
             Er, rscalar = None, float(rho)
@@ -549,7 +553,7 @@ class SlabFluidSolver:
         for o, f in ((oa, a), (ob, b), (op, p)):
             ops.copy2d(o[1:1 + n_cmp], lay.owned(f))
         self._apply_bc(a, b)
-        psum = comm.allreduce(lay.owned(p).sum().reshape(1)) * (float(lay.nl * Nx) / float(ncell))
+        psum = comm.allreduce(self.ops.sum(lay.owned(p))) * (float(lay.nl * Nx) / float(ncell))
         _lib.check(lib.rmt_subtract_mean(ptr(p), ptr(psum), p.numel(), st), "rmt_subtract_mean")
         comm.halo_exchange(lay, (a, b, p))
         return a, b, p

@@ -91,6 +91,9 @@ class SciPyOps:
         out[:, :m].copy_(torch.from_numpy(np.ascontiguousarray(h)))
         return out
 
+    def sum(self, x):
+        return x.sum().reshape(1)
+
     def transpose(self, x):
         return x.t().contiguous()
 
