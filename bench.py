@@ -74,9 +74,11 @@ ALG_BYTES_PER_CELL_LAUNCH = {
 
 
 # DRAM bytes per call (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full` capture of
-# this workload at 4097^2 on one B200 (profiles/r01e_/r01h_ncu_full_summary.txt); per-call = sum over the
+# this workload at 4097^2 on one B200 (profiles/r01e_/r01h_/r01j_ncu_full_summary.txt); per-call = sum over the
 # kernels the entry point launches.  Only reported for N = 1 at the default size.
 NCU_TRAFFIC_BYTES_4097 = {
+    "rmt_extrapolate_rows": 0.61e9,        # k_ext_fused<8> alone: 0.27 GB read + 0.34 GB written (r01j capture); the
+                                           # seed copy kernel of the same call moves its 5 fields (0.69 GB) on top
     "rmt_momentum_stage": 1.603e9,         # mean of the four stages (1.46 / 1.74 / 1.74 / 1.48 GB)
     "rmt_advect_euler_rk3_pair": 2.82e9,   # three stage kernels: 0.75 + 1.04 + 1.03 GB
     "rmt_poisson_solve_dct": 1.31e9,       # 2 x lines<0> (0.22) + lines<1> (0.36) + 2 x transpose (0.22) + sum
