@@ -360,6 +360,40 @@ def test_energy_diagnostics_golden(P, golden):
     assert np.all(np.isnan(OUT.disc_centroid(np.ones((8, 8)), g["X"][:8, :8], g["Y"][:8, :8])))
 
 
+def test_snapshot_writer(P, O, golden, tmp_path, monkeypatch, capsys):
+    """output_simulation_data (output.py:213-321): CSV row, log line and snapshot from device tensors."""
+    import csv
+    import torch
+    import pyrmt_b200.output as OUT
+    g = golden("diag")
+    dx, dy, w_t = float(g["dx"]), float(g["dy"]), float(g["w_t"])
+    rho_f, rho_s, mu_f, mu_s, kappa, eta_s = (float(x) for x in g["prm"])
+    up = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    sxx, sxy, syy, J = O.solid_cauchy_stress(g["X1"], g["X2"], dx, dy, mu_s, kappa, g["phi"])
+    monkeypatch.chdir(tmp_path)
+    args = [up(g[k]) for k in ("phi",)] + [up((g["phi"] <= 0).astype(float))] + [up(g[k]) for k in ("X1", "X2", "a", "b")]
+    p = up(0.1 * g["a"])
+    for step in (1, 2, 10):
+        r = OUT.output_simulation_data(dx, dy, *args, p, 10, "case", step, 1e-3, up(sxx), up(sxy), up(syy), up(J),
+                                       mu_s=mu_s, mu_f=mu_f, rho_s=rho_s, rho_f=rho_f, w_t=w_t, eta_s=eta_s, kappa=kappa,
+                                       time=0.5, integrated_dissipation=0.25)
+        assert r == 0.25
+    rows = list(csv.DictReader(open(tmp_path / "outputs" / "case" / "energy_history.csv")))
+    assert [int(r["step"]) for r in rows] == [1, 10]                   # step 2 is skipped (frequency 10)
+    rel = lambda x, ref: abs(float(x) - float(ref)) / abs(float(ref))
+    assert rel(rows[0]["kinetic_energy"], g["ke"]) < 1e-12 and rel(rows[0]["strain_energy"], g["se"]) < 1e-11
+    assert rel(rows[0]["dissipation_rate"], g["diss"]) < 1e-12
+    assert rel(rows[0]["total_energy"], float(g["ke"]) + float(g["se"]) + 0.25) < 1e-12
+    snap = np.load(tmp_path / "outputs" / "case" / "data_000010.npz")
+    for k, ref in (("phi", g["phi"]), ("X1", g["X1"]), ("a", g["a"]), ("sigma_xy", sxy), ("J", J)):
+        assert same(snap[k], ref), k
+    div = O._compute_divergence(g["a"], g["b"], dx, dy)
+    ref_div = np.zeros_like(div)
+    ref_div[4:-4, 4:-4] = div[4:-4, 4:-4]
+    assert rel_linf(snap["div_vel"], ref_div) < TIGHT and float(snap["time"]) == 0.5
+    assert "[Step 00010]" in capsys.readouterr().out
+
+
 def test_curvature_golden(P, golden):
     g = golden("momentum")
     assert rel_linf(P.compute_curvature(g["phi"], float(g["dx"]), float(g["dy"])), g["curv"]) < 1e-10
