@@ -204,6 +204,18 @@ __device__ void fft_dif(double *re, double *im, int L, const double2 *__restrict
     if (n == 2) stage_radix2(re, im, L, g);
 }
 
+// the same with the length known at compile time: inlined, passes unrolled, strides folded
+template <int L>
+__device__ __forceinline__ void fft_dif_ct(double *re, double *im, const double2 *__restrict__ tw, const Grp &g)
+{
+    int n = L;
+#pragma unroll
+    for (; n >= 16; n >>= 4) stage_radix16(re, im, L, n, tw, g);
+#pragma unroll
+    for (; n >= 4; n >>= 2) stage_radix4(re, im, L, n, tw, g);
+    if (n == 2) stage_radix2(re, im, L, g);
+}
+
 // pack the even extension of the real line x[0..M] (shared memory) into M complex points
 __device__ __forceinline__ void pack_even(const double *x, double *re, double *im, int M, const Grp &g)
 {
@@ -244,14 +256,19 @@ __device__ __forceinline__ void cp_async_wait_all()
 // lines grp, grp + ngroups, ...  MODE 0: out = scale * DCT-I(in).  MODE 1 (Poisson
 // solve along this axis): out = DCT-I( DCT-I(in) * scale / eig ), eig laid out like in.
 // in == out is allowed (a group holds its whole line on chip before it writes).
-template <int MODE>
+// LGT > 0: the line length is 2^LGT + 1 at compile time -- pass strides, twiddle strides, the padded
+// index maps and the digit reversal then fold to constants and the passes unroll (the index arithmetic
+// is a third of this kernel's instructions otherwise); LGT = 0: any power of two at run time.
+template <int MODE, int LGT = 0>
 __global__ void __launch_bounds__(512, 1)
-k_dct_lines(const double *in, double *out, const double *__restrict__ eig, int nrows, int N,
-            const double2 *__restrict__ tw, const double2 *__restrict__ tw2, double scale, int tpg,
+k_dct_lines(const double *in, double *out, const double *__restrict__ eig, int nrows, int N_rt,
+            const double2 *__restrict__ tw, const double2 *__restrict__ tw2, double scale, int tpg_rt,
             double *__restrict__ partial)
 {
     extern __shared__ double sm[];
-    const int M = N - 1, lg = 31 - __clz(M);
+    const int N = LGT ? (1 << LGT) + 1 : N_rt;
+    const int M = N - 1, lg = LGT ? LGT : 31 - __clz(M);
+    const int tpg = LGT ? ((1 << LGT) / 16 > 512 ? 512 : ((1 << LGT) / 16 < 32 ? 32 : (1 << LGT) / 16)) : tpg_rt;
     const int G = blockDim.x / tpg, gi = threadIdx.x / tpg;
     const Grp g{(int)threadIdx.x % tpg, tpg, 1 + gi};
     const int plane = padi(M) + 1, per_group = 2 * plane + (N + 1);
@@ -270,7 +287,7 @@ k_dct_lines(const double *in, double *out, const double *__restrict__ eig, int n
         const int rn = r + ngroups;                 // prefetch the next line behind the (last) FFT
         if (MODE == 0 && rn < nrows)
             for (int k = g.tid; k < N; k += g.nthr) cp_async8(stage + k, in + (size_t)rn * N + k);
-        fft_dif(re, im, M, tw, g);
+        if (LGT) fft_dif_ct<(LGT ? (1 << LGT) : 2)>(re, im, tw, g); else fft_dif(re, im, M, tw, g);
         if (MODE == 1) {
             // spectrum x scale/eig -> staging buffer (natural order) -> packed again -> second FFT
             const double *er = eig + (size_t)r * N;
@@ -281,7 +298,7 @@ k_dct_lines(const double *in, double *out, const double *__restrict__ eig, int n
             g.sync();
             if (rn < nrows)
                 for (int k = g.tid; k < N; k += g.nthr) cp_async8(stage + k, in + (size_t)rn * N + k);
-            fft_dif(re, im, M, tw, g);
+            if (LGT) fft_dif_ct<(LGT ? (1 << LGT) : 2)>(re, im, tw, g); else fft_dif(re, im, M, tw, g);
         }
         double *o = out + (size_t)r * N;
         const double sc = (MODE == 1) ? 1.0 : scale;
@@ -613,6 +630,29 @@ LineLaunch line_launch(int M, int nrows)
     return L;
 }
 
+// launch k_dct_lines<MODE>, with the compile-time specialisation for the common line lengths
+template <int MODE>
+void launch_dct_lines(const LineLaunch &L, cudaStream_t s, const double *in, double *out, const double *eig,
+                      int nrows, int N, const double2 *tw, const double2 *tw2, double scale, double *partial)
+{
+    static bool attr_done = false;
+    if (!attr_done) {       // every instantiation that can be launched needs the shared-memory opt-in
+        cudaFuncSetAttribute(k_dct_lines<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+        cudaFuncSetAttribute(k_dct_lines<MODE, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+        cudaFuncSetAttribute(k_dct_lines<MODE, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+        cudaFuncSetAttribute(k_dct_lines<MODE, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+        cudaFuncSetAttribute(k_dct_lines<MODE, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+        attr_done = true;
+    }
+    switch (N - 1) {
+    case 1024: k_dct_lines<MODE, 10><<<L.ctas, L.threads, L.smem, s>>>(in, out, eig, nrows, N, tw, tw2, scale, L.tpg, partial); break;
+    case 2048: k_dct_lines<MODE, 11><<<L.ctas, L.threads, L.smem, s>>>(in, out, eig, nrows, N, tw, tw2, scale, L.tpg, partial); break;
+    case 4096: k_dct_lines<MODE, 12><<<L.ctas, L.threads, L.smem, s>>>(in, out, eig, nrows, N, tw, tw2, scale, L.tpg, partial); break;
+    case 8192: k_dct_lines<MODE, 13><<<L.ctas, L.threads, L.smem, s>>>(in, out, eig, nrows, N, tw, tw2, scale, L.tpg, partial); break;
+    default:   k_dct_lines<MODE, 0><<<L.ctas, L.threads, L.smem, s>>>(in, out, eig, nrows, N, tw, tw2, scale, L.tpg, partial);
+    }
+}
+
 // k_dht_lines for line length m = 2M: no staging copy, so more groups fit
 LineLaunch dht_launch(int M, int nrows)
 {
@@ -741,10 +781,9 @@ int rmt_dct_lines(const double *in, double *out, const double *eig, int nrows, i
     const LineLaunch L = line_launch(M, nrows);
     cudaStream_t s = (cudaStream_t)stream;
     if (eig)
-        k_dct_lines<1><<<L.ctas, L.threads, L.smem, s>>>(in, out, eig, nrows, N, T->tw, T->tw2, scale, L.tpg, nullptr);
+        launch_dct_lines<1>(L, s, in, out, eig, nrows, N, T->tw, T->tw2, scale, nullptr);
     else
-        k_dct_lines<0><<<L.ctas, L.threads, L.smem, s>>>(in, out, nullptr, nrows, N, T->tw, T->tw2, scale, L.tpg,
-                                                        nullptr);
+        launch_dct_lines<0>(L, s, in, out, nullptr, nrows, N, T->tw, T->tw2, scale, nullptr);
     RMT_LAUNCH_CHECK();
     return RMT_OK;
 }
@@ -809,18 +848,15 @@ int rmt_poisson_solve_dct(rmt_poisson_plan *P, const double *rhs, const double *
         const LineLaunch lx = line_launch(P->Lx, Ny), ly = line_launch(P->Ly, Nx);
         double *partial = P->red;                        // one partial sum per CTA
         const int nrow_cta = lx.ctas;
-        k_dct_lines<0><<<lx.ctas, lx.threads, lx.smem, s>>>(rhs, sol, nullptr, Ny, Nx, P->tw_x, P->tw2_x, 1.0,
-                                                           lx.tpg, nullptr);
+        launch_dct_lines<0>(lx, s, rhs, sol, nullptr, Ny, Nx, P->tw_x, P->tw2_x, 1.0, nullptr);
         RMT_LAUNCH_CHECK();
         k_transpose<<<tg_f, 256, 0, s>>>(sol, T2, Ny, Nx);
         RMT_LAUNCH_CHECK();
-        k_dct_lines<1><<<ly.ctas, ly.threads, ly.smem, s>>>(T2, T2, eigT, Nx, Ny, P->tw_y, P->tw2_y, scale,
-                                                           ly.tpg, nullptr);
+        launch_dct_lines<1>(ly, s, T2, T2, eigT, Nx, Ny, P->tw_y, P->tw2_y, scale, nullptr);
         RMT_LAUNCH_CHECK();
         k_transpose<<<tg_b, 256, 0, s>>>(T2, sol, Nx, Ny);
         RMT_LAUNCH_CHECK();
-        k_dct_lines<0><<<lx.ctas, lx.threads, lx.smem, s>>>(sol, sol, nullptr, Ny, Nx, P->tw_x, P->tw2_x, 1.0,
-                                                           lx.tpg, partial);
+        launch_dct_lines<0>(lx, s, sol, sol, nullptr, Ny, Nx, P->tw_x, P->tw2_x, 1.0, partial);
         RMT_LAUNCH_CHECK();
         k_sum_final<<<1, 256, 0, s>>>(partial, nrow_cta, sum_dst);
         RMT_LAUNCH_CHECK();
