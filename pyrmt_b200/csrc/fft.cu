@@ -323,12 +323,16 @@ k_dct_lines(const double *in, double *out, const double *__restrict__ eig, int n
 // The packing z[n] = x[2n] + i x[2n+1] is the load itself (straight into the planes), so a
 // group needs no staging copy: more groups per CTA hide each other's load latency instead.
 // in == out is allowed (a group holds its whole line on chip before it writes).
+// LGT > 0: m = 2^(LGT+1) at compile time (see k_dct_lines).
+template <int LGT = 0>
 __global__ void __launch_bounds__(512, 1)
-k_dht_lines(const double *in, double *out, const double *__restrict__ mul, int nrows, int m, long ldi,
-            long ldo, const double2 *__restrict__ tw, const double2 *__restrict__ tw2, double scale, int tpg)
+k_dht_lines(const double *in, double *out, const double *__restrict__ mul, int nrows, int m_rt, long ldi,
+            long ldo, const double2 *__restrict__ tw, const double2 *__restrict__ tw2, double scale, int tpg_rt)
 {
     extern __shared__ double sm[];
-    const int M = m >> 1, lg = 31 - __clz(M);
+    const int m = LGT ? (2 << LGT) : m_rt;
+    const int M = m >> 1, lg = LGT ? LGT : 31 - __clz(M);
+    const int tpg = LGT ? ((1 << LGT) / 16 > 512 ? 512 : ((1 << LGT) / 16 < 32 ? 32 : (1 << LGT) / 16)) : tpg_rt;
     const int G = blockDim.x / tpg, gi = threadIdx.x / tpg;
     const Grp g{(int)threadIdx.x % tpg, tpg, 1 + gi};
     const int plane = padi(M) + 1;
@@ -342,7 +346,7 @@ k_dht_lines(const double *in, double *out, const double *__restrict__ mul, int n
             ((k & 1) ? im : re)[padi(k >> 1)] = v;
         }
         g.sync();
-        fft_dif(re, im, M, tw, g);
+        if (LGT) fft_dif_ct<(LGT ? (1 << LGT) : 2)>(re, im, tw, g); else fft_dif(re, im, M, tw, g);
         double *o = out + (size_t)r * ldo;
         const double *f = mul ? mul + (size_t)r * m : nullptr;
         for (int k = g.tid; k <= M; k += g.nthr) {
@@ -684,7 +688,10 @@ int line_tables(int M, const LineTab **out)
     if (!e) e = make_half_twiddles(&t.tw2, M);
     if (!e) e = (int)cudaFuncSetAttribute(k_dct_lines<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
     if (!e) e = (int)cudaFuncSetAttribute(k_dct_lines<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
-    if (!e) e = (int)cudaFuncSetAttribute(k_dht_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+    if (!e) e = (int)cudaFuncSetAttribute(k_dht_lines<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+    if (!e) e = (int)cudaFuncSetAttribute(k_dht_lines<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+    if (!e) e = (int)cudaFuncSetAttribute(k_dht_lines<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+    if (!e) e = (int)cudaFuncSetAttribute(k_dht_lines<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
     if (e) return e;
     cache.reserve(64);
     cache.push_back(t);
@@ -799,8 +806,13 @@ int rmt_dht_lines(const double *in, double *out, const double *mul, int nrows, i
     const LineTab *T = nullptr;
     if (int e = line_tables(M, &T)) return e;
     const LineLaunch L = dht_launch(M, nrows);
-    k_dht_lines<<<L.ctas, L.threads, L.smem, (cudaStream_t)stream>>>(in, out, mul, nrows, m, ldi, ldo, T->tw,
-                                                                       T->tw2, scale, L.tpg);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (M) {
+    case 2048: k_dht_lines<11><<<L.ctas, L.threads, L.smem, s>>>(in, out, mul, nrows, m, ldi, ldo, T->tw, T->tw2, scale, L.tpg); break;
+    case 4096: k_dht_lines<12><<<L.ctas, L.threads, L.smem, s>>>(in, out, mul, nrows, m, ldi, ldo, T->tw, T->tw2, scale, L.tpg); break;
+    case 8192: k_dht_lines<13><<<L.ctas, L.threads, L.smem, s>>>(in, out, mul, nrows, m, ldi, ldo, T->tw, T->tw2, scale, L.tpg); break;
+    default:   k_dht_lines<0><<<L.ctas, L.threads, L.smem, s>>>(in, out, mul, nrows, m, ldi, ldo, T->tw, T->tw2, scale, L.tpg);
+    }
     RMT_LAUNCH_CHECK();
     return RMT_OK;
 }

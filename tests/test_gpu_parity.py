@@ -526,7 +526,7 @@ def test_dht_lines_building_block(P):
     from pyrmt_b200.slab import CudaOps
     ops = CudaOps()
     rng = np.random.default_rng(4)
-    for m in (16, 64, 4096, 16384):
+    for m in (16, 64, 4096, 8192, 16384):
         x = rng.standard_normal((5, m + 3))
         F = np.fft.fft(x[:, :m], axis=1)
         ref = F.real - F.imag
