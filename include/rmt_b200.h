@@ -126,6 +126,17 @@ int rmt_extrapolate(const double *X1, const double *X2, const double *phi, doubl
 int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, double *X1e, double *X2e,
                          int Ny, int Nx, int row_offset, double dx, double dy, int max_layers,
                          void *workspace, void *stream);
+/* Which sweep variant runs (all are bit-identical to the reference's serial raster sweep, functions.py:95-161):
+ *   variant -1 = chosen on the device from the layer-0 band geometry (default), 0 = per-layer launches,
+ *   16 / 8 = all-layers row-pipelined kernel with that many rows per block, 1 = all-layers kernel with one
+ *   CTA per isolated tile (falls back to the device's choice when the bands are not isolated);
+ *   rows = macro-tile height for 16 / 8 (0 = chosen on the device);
+ *   cap  = prepared-record capacity of the per-layer sweep (0 = default; small values exercise the
+ *          inline phase-A path).  Process-wide; a test / tuning hook. */
+int rmt_extrapolate_set_mode(int variant, int rows, long cap);
+/* out3 = {variant, rows or tile-size exponent, 0} the last rmt_extrapolate[_rows] call on this workspace ran
+ * with (synchronises the stream). */
+int rmt_extrapolate_last_mode(const void *workspace, int Ny, int Nx, int *out3, void *stream);
 /* device exp() used for the weights, exposed so tests can prove bit-equality
  * with the host libm (functions.py:120). */
 int rmt_exp_probe(const double *x, double *y, long n, void *stream);

@@ -227,8 +227,15 @@ __global__ void k_ext_fill(const unsigned char *__restrict__ st, const int *__re
 #ifdef RMT_EXT_TIMING
 __device__ unsigned long long g_ext_dbg[8];
 #define EXT_T(k) do { if (lane == 0) { long long now__ = clock64(); atomicAdd(&g_ext_dbg[k], (unsigned long long)(now__ - tmark)); tmark = now__; } } while (0)
+__device__ unsigned long long g_body_dbg[16];
+#define BODY_T(k) do { if (lane == 0) { long long now__ = clock64(); atomicAdd(&g_body_dbg[k], (unsigned long long)(now__ - bmark)); bmark = now__; } } while (0)
+#define BODY_T0() long long bmark = clock64()
+#define BODY_CNT(k) do { if (lane == 0) atomicAdd(&g_body_dbg[k], 1ull); } while (0)
 #else
 #define EXT_T(k) do { } while (0)
+#define BODY_T(k) do { } while (0)
+#define BODY_T0() do { } while (0)
+#define BODY_CNT(k) do { } while (0)
 #endif
 
 constexpr int RB = 16;                 // rows per CTA block = warps per CTA in the sweep
@@ -244,6 +251,7 @@ struct alignas(16) ExtRec {
     double prod[WIN][NACC];            // per contributing cell (in gather order): the 12 products
     double pw[MAXPEND], px[MAXPEND], py[MAXPEND];   // weight / coordinates of the undecided cells
     unsigned char pn[MAXPEND], pslot[MAXPEND];      // window index and prod[] slot of the undecided cells
+    int ptag[MAXPEND];                              // body variant: jj << 15 | ii of the undecided cells
 };
 static_assert(sizeof(ExtRec) % 16 == 0, "ExtRec must be copyable in 16-byte chunks");
 constexpr int REC_PEND_OFF = WIN * NACC * 8;                   // byte offset of pw
@@ -276,6 +284,19 @@ __device__ __forceinline__ int ld_relaxed_gpu(const int *p)
     return v;
 }
 #define SMEM_ORDER() asm volatile("" ::: "memory")   // compiler barrier; shared memory itself is in-order per warp
+// 16-byte shared-memory accesses done as ONE instruction (header + ready flag travel together)
+__device__ __forceinline__ void sts_v4(void *p, int4 v)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("st.volatile.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ int4 lds_v4(const void *p)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    int4 v;
+    asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
 
 // the 12 products of one contributing cell, in the order of the running sums:
 //   B1[k] += (w*a_k)*v1, B2[k] += (w*a_k)*v2, A[r][c] += (w*a_r)*a_c   with a = (1, x, y)
@@ -296,7 +317,9 @@ __device__ __forceinline__ void store_products(double *q, double w, double x, do
 // FUSED = true : all layers in one launch -- state 2l+3 = fitted by layer l; "known" is any odd state
 // below this layer's code `fresh`; every raster-earlier cell that is not known is a candidate (there
 // are no target marks); all reads go to L2 (other SMs wrote the previous layers).
-template <bool FUSED>
+// MODE 0: per-layer launches (plain loads); 1: all-layers kernel across SMs (L2 loads); 2: all-layers
+// kernel with a whole tile on ONE SM (block-scope coherent loads, served by L1).
+template <int MODE>
 __device__ __forceinline__ int ext_phase_a(ExtRec *R, const double *__restrict__ X1e,
                                            const double *__restrict__ X2e,
                                            const unsigned char *__restrict__ st, int j, int i, int Ny, int Nx,
@@ -304,33 +327,50 @@ __device__ __forceinline__ int ext_phase_a(ExtRec *R, const double *__restrict__
 {
     const unsigned lt = (1u << lane) - 1u;
     const double x0 = dx * i, y0 = dy * (j + joff);     // absolute coordinates of the GLOBAL grid (functions.py:105)
+    constexpr bool FUSED = MODE != 0;
     int cls[3];                                 // 0 no contribution, 1 known, 2 undecided
     double cw[3], cx_[3], cy_[3], c1[3], c2[3];
     unsigned mk[3], mp[3];
+    // all loads of the window first (three cells per lane), then the arithmetic
+    unsigned sv[3];
+    bool in[3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        const int n = lane + 32 * s;
+        const int jj = j + n / 9 - 4, ii = i + n % 9 - 4;
+        in[s] = n < WIN && jj >= 0 && jj < Ny && ii >= 0 && ii < Nx;
+        sv[s] = 0;
+        c1[s] = c2[s] = 0.0;
+        if (in[s]) {
+            const size_t cc = (size_t)jj * Nx + ii;
+            sv[s] = MODE == 1 ? __ldcg(st + cc) : MODE == 2 ? ld_cta_u8(st + cc) : st[cc];   // known cells are final
+            c1[s] = MODE == 1 ? __ldcg(X1e + cc) : MODE == 2 ? ld_cta_f64(X1e + cc) : X1e[cc];   // only meaningful
+            c2[s] = MODE == 1 ? __ldcg(X2e + cc) : MODE == 2 ? ld_cta_f64(X2e + cc) : X2e[cc];   // if known
+        }
+    }
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
         const int n = lane + 32 * s;
         cls[s] = 0;
-        cw[s] = cx_[s] = cy_[s] = c1[s] = c2[s] = 0.0;
-        if (n < WIN) {
+        cw[s] = cx_[s] = cy_[s] = 0.0;
+        if (in[s]) {
             const int dj = n / 9 - 4, di = n % 9 - 4;
             const int jj = j + dj, ii = i + di;
-            if (jj >= 0 && jj < Ny && ii >= 0 && ii < Nx) {
-                const size_t cc = (size_t)jj * Nx + ii;
-                const unsigned char sv = FUSED ? __ldcg(st + cc) : st[cc];   // known cells are final
-                const double v1 = FUSED ? __ldcg(X1e + cc) : X1e[cc];         // only meaningful if known
-                const double v2 = FUSED ? __ldcg(X2e + cc) : X2e[cc];
-                const double xi = dx * ii, yi = dy * (jj + joff);
-                const double ex = xi - x0, ey = yi - y0;
-                const double dist_sq = ex * ex + ey * ey;
-                const bool earlier = (dj < 0) || (dj == 0 && di < 0);
-                const bool known = FUSED ? ((sv & 1) && sv < fresh) : (sv == ST_KNOWN);
-                const bool cand = FUSED ? (!known && earlier) : (sv != ST_UNKNOWN && sv != ST_KNOWN && earlier);
-                if (dist_sq <= r2 && (known || cand)) {
-                    cls[s] = known ? 1 : 2;
-                    cw[s] = exp_glibc(-dist_sq / r2);
-                    cx_[s] = xi; cy_[s] = yi; c1[s] = v1; c2[s] = v2;
-                }
+            const double xi = dx * ii, yi = dy * (jj + joff);
+            const double ex = xi - x0, ey = yi - y0;
+            const double dist_sq = ex * ex + ey * ey;
+            const bool earlier = (dj < 0) || (dj == 0 && di < 0);
+            const bool known = FUSED ? ((sv[s] & 1) && (int)sv[s] < fresh) : (sv[s] == ST_KNOWN);
+            // undecided = a raster-earlier target of this layer.  MODE 0: marked 2 / 3 by the flag pass and the
+            // sweep; MODE 1: no marks, every raster-earlier cell that is not known is a candidate; MODE 2: the
+            // discovery warp marked this layer's targets with fresh - 1 (fresh once fitted).
+            const bool cand = MODE == 1 ? (!known && earlier)
+                            : MODE == 2 ? (earlier && ((int)sv[s] == fresh || (int)sv[s] == fresh - 1))
+                                        : (sv[s] != ST_UNKNOWN && sv[s] != ST_KNOWN && earlier);
+            if (dist_sq <= r2 && (known || cand)) {
+                cls[s] = known ? 1 : 2;
+                cw[s] = exp_glibc(-dist_sq / r2);
+                cx_[s] = xi; cy_[s] = yi;
             }
         }
         mk[s] = __ballot_sync(0xffffffffu, cls[s] == 1);
@@ -348,6 +388,10 @@ __device__ __forceinline__ int ext_phase_a(ExtRec *R, const double *__restrict__
             R->pw[r] = cw[s]; R->px[r] = cx_[s]; R->py[r] = cy_[s];
             R->pn[r] = (unsigned char)(lane + 32 * s);
             R->pslot[r] = (unsigned char)slot;
+            if (MODE == 2) {
+                const int n = lane + 32 * s;
+                R->ptag[r] = ((j + n / 9 - 4) << 15) | (i + n % 9 - 4);
+            }
         }
         slot_base += __popc(mv);
         pend_base += __popc(mp[s]);
@@ -373,7 +417,7 @@ k_ext_prepare(const double *__restrict__ X1e, const double *__restrict__ X2e,
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
     const int ntot = min(seg_off[nseg], cap);
     for (int t = warp; t < ntot; t += nwarp) {
-        const int info = ext_phase_a<false>(recs + t, X1e, X2e, st, trow[t], tcol[t], Ny, Nx, joff, dx, dy, r2, lane);
+        const int info = ext_phase_a<0>(recs + t, X1e, X2e, st, trow[t], tcol[t], Ny, Nx, joff, dx, dy, r2, lane);
         if (lane == 0) tinfo[t] = info;
     }
 }
@@ -492,7 +536,7 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                 info = info_next;
                 cp_async_wait_all();
             } else {
-                info = ext_phase_a<false>(&W.rec, X1e, X2e, st, j, i, Ny, Nx, joff, dx, dy, r2, lane);
+                info = ext_phase_a<0>(&W.rec, X1e, X2e, st, j, i, Ny, Nx, joff, dx, dy, r2, lane);
             }
             info_next = (t + 1 < t1 && t + 1 < cap) ? tinfo[t + 1] : 0;
             const int next = (t + 1 < t1) ? tcol[t + 1] : INT_MAX;   // loaded early: it gates the publish
@@ -847,7 +891,7 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
             // (4) phase A of the first CAPW targets into this warp's scratch records
             const int nprep = min(cnt, CAPW);
             for (int k = 0; k < nprep; ++k) {
-                const int info = ext_phase_a<true>(myrecs2 + bf * CAPW + k, X1e, X2e, st, jrow, xc0 + tl[k], Ny, Nx,
+                const int info = ext_phase_a<1>(myrecs2 + bf * CAPW + k, X1e, X2e, st, jrow, xc0 + tl[k], Ny, Nx,
                                                    joff, dx, dy, r2, lane, fresh);
                 if (lane == 0) S.tinf[bf][wib][k] = info;
             }
@@ -886,7 +930,7 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                 info = info_next;
                 cp_async_wait_all();
             } else {
-                info = ext_phase_a<true>(&W.rec, X1e, X2e, st, j, i, Ny, Nx, joff, dx, dy, r2, lane, fresh);
+                info = ext_phase_a<1>(&W.rec, X1e, X2e, st, j, i, Ny, Nx, joff, dx, dy, r2, lane, fresh);
             }
             info_next = (t + 1 < nt && t + 1 < CAPW) ? tinfw[t + 1] : 0;
             const int next = (t + 1 < nt) ? xc0 + tlw[t + 1] : INT_MAX;
@@ -1064,6 +1108,335 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
     }
 }
 
+// ===========================================================================================
+// All layers in one launch, ONE CTA PER ISOLATED TILE ("body" variant).
+//
+// When every band of targets keeps a margin of (layers + 5) cells to the borders of its tile, no fit
+// of any layer reads a cell that another tile writes: tiles are independent, and a tile's whole
+// dependency chain can stay inside one CTA.  The chain is then run by ONE warp per layer, which fits
+// the layer's targets strictly in raster order -- exactly the reference's serial sweep restricted to
+// the tile -- so nothing on the chain waits for another warp: no progress polling, no seqlocks, no
+// cross-SM traffic.  Everything that does not depend on the layer's own fits is done ahead of the
+// chain warp by helper warps of the same CTA:
+//   discovery warp (one per layer): scans the rows top to bottom (only the 32-column chunks the
+//       layer-0 chunk masks mark) once the previous layer has finished rows <= j+4, and appends the
+//       targets to a queue in raster order;
+//   prepare warps (P per layer): take queue entries in turn and run phase A (81 window
+//       classifications, weights, the 12 products of every cell known before the layer, the to-do list
+//       of raster-earlier undecided cells) straight into a ring of records in shared memory;
+//   chain warp: for each record in order: one lane per undecided cell reads its state and value
+//       (written by this very warp a few fits ago: L1-coherent block-scope loads), fills its slot,
+//       twelve lanes run the ordered sums, lanes 0/1 solve and publish.
+// Layer l+1 trails layer l by five rows inside the same CTA (row_done hand-off through shared
+// memory).  Cost: ~0.5 us per target of the fullest tile and layer, against ~1.8 us per DEPENDENT fit
+// plus per-row-block overheads in the row-pipelined variants -- it wins whenever the bodies are
+// isolated and a tile holds at most a few thousand targets (k_ext_decide compares the models).
+constexpr int BQ = 256;                // target queue entries per layer (ring)
+constexpr int BSLOT_MAX = 6;           // records per layer in shared memory (ring)
+constexpr int BODY_KMAX = 6;           // candidate tile sizes: (512 << k) rows x (XT << k) columns
+constexpr int BODY_LMAX = 5;           // layers the 640-thread CTA has warps for
+
+constexpr int BC_ROWS = 8, BC_COLS = 64;   // chain-private cache of the layer's latest fits: [row & 7][column & 63]
+struct BodyCtl {
+    int q_count;                       // targets discovered so far
+    int q_final;                       // discovery complete
+    int disc_row;                      // discovery has scanned every row <= disc_row
+    int row_done;                      // the chain warp has fitted every target of rows <= row_done
+    int prep_next;                     // next queue entry a prepare warp takes
+    int consumed;                      // the chain warp has consumed entries < consumed
+    int pad_[2];
+    int4 rhdr[BSLOT_MAX];              // {info, j, i, t + 1} once the record of queue entry t sits in the slot
+    int qrow[BQ], qcol[BQ];
+    double sums[NACC];
+    // what the chain warp itself fitted lately (single writer, single reader: no synchronisation):
+    // tag = j << 15 | i, bit 30 set for a rejected target; values (xi1, xi2)
+    int ctag[BC_ROWS][BC_COLS];
+    double cval[BC_ROWS][BC_COLS][2];
+};
+static_assert(sizeof(BodyCtl) % 16 == 0, "BodyCtl must keep 16-byte alignment in an array");
+
+__device__ __forceinline__ int body_tile_offset(int k, int Ny, int nxt)
+{
+    int off = 0;
+    for (int q = 0; q < k; ++q) off += ((Ny + (512 << q) - 1) / (512 << q)) * ((nxt + (1 << q) - 1) >> q);
+    return off;
+}
+
+__global__ void __launch_bounds__(640, 1)
+k_ext_body(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__restrict__ st,
+           const int *__restrict__ cnt0 /* + cmin0, cmax0, chunk0, [Ny*nxt] each */,
+           const int *__restrict__ tilecnt /* layer-0 targets per tile, all candidate sizes */,
+           const int *__restrict__ mode, int L, int P, int nslot, int Ny, int Nx, int joff, int nxt, int XT,
+           double dx, double dy, double r2)
+{
+    if (mode[0] != 1) return;                           // k_ext_decide picked another variant
+    const int k = mode[1];
+    const int Tr = 512 << k, nsegt = 1 << k;
+    const int ntx = (nxt + nsegt - 1) >> k, nty = (Ny + Tr - 1) / Tr;
+    if ((int)blockIdx.x >= ntx * nty) return;
+    if (tilecnt[body_tile_offset(k, Ny, nxt) + blockIdx.x] == 0) return;   // no band in this tile
+    const int ty = blockIdx.x / ntx, tx = blockIdx.x - ty * ntx;
+    const int seg0 = tx * nsegt, seg1 = min(seg0 + nsegt, nxt);
+    const int R0 = max(ty * Tr, 1), R1 = min((ty + 1) * Tr, Ny - 1);       // target rows [R0, R1)
+    const int nseg = Ny * nxt;
+    const int *cmin0 = cnt0 + nseg, *cmax0 = cnt0 + 2 * nseg, *chunk0 = cnt0 + 3 * nseg;
+
+    extern __shared__ unsigned char s_raw[];
+    BodyCtl *ctl = reinterpret_cast<BodyCtl *>(s_raw);
+    ExtRec *recs = reinterpret_cast<ExtRec *>(s_raw + (((size_t)L * sizeof(BodyCtl) + 15) & ~(size_t)15));
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int per = 2 + P;                              // warps per layer
+    const int layer = wib / per, role = wib - layer * per;
+    for (int e = threadIdx.x; e < L * (int)(sizeof(BodyCtl) / 4); e += blockDim.x) ((int *)ctl)[e] = 0;
+    __syncthreads();
+    if (threadIdx.x < L) { ctl[threadIdx.x].disc_row = R0 - 1; ctl[threadIdx.x].row_done = R0 - 1; }
+    for (int e = threadIdx.x; e < L * BC_ROWS * BC_COLS; e += blockDim.x)
+        (&ctl[e / (BC_ROWS * BC_COLS)].ctag[0][0])[e % (BC_ROWS * BC_COLS)] = -1;
+    __syncthreads();
+    if (layer >= L) return;
+    const int fresh = 2 * layer + 3;
+    volatile BodyCtl &C = ctl[layer];
+    ExtRec *myrecs = recs + (size_t)layer * nslot;
+
+    if (role == 1) {
+        // ---------------- discovery: the layer's targets, in raster order, into the queue ----------
+        volatile BodyCtl *CP = layer > 0 ? &ctl[layer - 1] : nullptr;
+        int qn = 0;
+        for (int j = R0; j < R1; ++j) {
+            // layer-l targets lie within l cells of layer-0 targets: rows j-l .. j+l of this tile
+            int any = 0;
+            if (lane <= 2 * layer) {
+                const int r = j - layer + lane;
+                if (r >= 0 && r < Ny)
+                    for (int sg = seg0; sg < seg1; ++sg) any |= cnt0[r * nxt + sg];
+            }
+            if (__any_sync(0xffffffffu, any != 0)) {
+                if (CP) {                               // previous layer complete on rows <= j+4 (window)
+                    const int need = min(j + 4, R1 - 1);
+                    while (CP->row_done < need) __nanosleep(40);
+                    __threadfence_block();
+                }
+                const unsigned char *rowc = st + (size_t)j * Nx, *rowa = rowc - Nx, *rowb = rowc + Nx;
+                for (int sg = seg0; sg < seg1; ++sg) {
+                    const int xc0 = sg * XT, xc1 = min(xc0 + XT, Nx);
+                    unsigned m = 0;
+                    const int r = j - layer + lane;
+                    if (lane <= 2 * layer && r >= 0 && r < Ny) {
+                        m = (unsigned)chunk0[r * nxt + sg];
+                        if (sg > seg0 && cmax0[r * nxt + sg - 1] + layer + 1 >= xc0) m |= 1u;
+                        if (sg + 1 < seg1 && cmin0[r * nxt + sg + 1] - layer - 1 < xc1)
+                            m |= 1u << ((xc1 - 1 - xc0) >> 5);
+                    }
+                    m = __reduce_or_sync(0xffffffffu, m);
+                    const unsigned chunks = m | (m << 1) | (m >> 1);
+                    for (int base = xc0; base < xc1; base += 32) {
+                        if (!((chunks >> ((base - xc0) >> 5)) & 1u)) continue;
+                        const int i = base + lane;
+                        bool tgt = false;
+                        if (i < xc1 && i >= 1 && i < Nx - 1) {
+                            const unsigned me = ld_cta_u8(rowc + i);
+                            if (!((me & 1) && me < fresh)) {
+                                unsigned kb = 0;
+#pragma unroll
+                                for (int d = -1; d <= 1; ++d) {
+                                    const unsigned a = ld_cta_u8(rowa + i + d), c = ld_cta_u8(rowb + i + d);
+                                    kb |= ((a & 1) && a < fresh) | ((c & 1) && c < fresh);
+                                    if (d) { const unsigned b = ld_cta_u8(rowc + i + d); kb |= ((b & 1) && b < fresh); }
+                                }
+                                tgt = kb != 0;
+                            }
+                        }
+                        const unsigned tm = __ballot_sync(0xffffffffu, tgt);
+                        if (tm) {
+                            while (qn + 32 - C.consumed > BQ) __nanosleep(40);     // room in the ring
+                            if (tgt) {
+                                const int o = (qn + __popc(tm & ((1u << lane) - 1u))) & (BQ - 1);
+                                ((int *)C.qrow)[o] = j;
+                                ((int *)C.qcol)[o] = i;
+                                // mark: "target of this layer, undecided" (even = still unknown to every
+                                // known-test); phase A of later targets lists exactly the marked cells
+                                ((unsigned char *)rowc)[i] = (unsigned char)(fresh - 1);
+                            }
+                            qn += __popc(tm);
+                            __threadfence_block();
+                            __syncwarp();
+                            if (lane == 0) C.q_count = qn;
+                        }
+                    }
+                }
+            }
+            if (lane == 0) C.disc_row = j;
+        }
+        __syncwarp();
+        if (lane == 0) C.q_final = 1;
+        return;
+    }
+
+    if (role >= 2) {
+        // ---------------- prepare: phase A of queue entry t into record slot t % nslot --------------
+        for (;;) {
+            BODY_T0();
+            int t = 0;
+            if (lane == 0) t = atomicAdd((int *)&C.prep_next, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            for (;;) {
+                const int fin = C.q_final;
+                const int cnt = C.q_count;
+                if (t < cnt) break;
+                if (fin) return;
+                __nanosleep(40);
+            }
+            BODY_T(8);
+            while (t - C.consumed >= nslot) __nanosleep(20);
+            __threadfence_block();
+            BODY_T(9);
+            const int j = C.qrow[t & (BQ - 1)], i = C.qcol[t & (BQ - 1)];
+            const int slot = t % nslot;
+            const int info = ext_phase_a<2>(myrecs + slot, X1e, X2e, st, j, i, Ny, Nx, joff, dx, dy, r2, lane, fresh);
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) sts_v4((void *)&C.rhdr[slot], make_int4(info, j, i, t + 1));   // one 16-byte store
+            BODY_T(10);
+            BODY_CNT(11);
+        }
+    }
+
+    // ---------------- the chain: fit the layer's targets in raster order ---------------------------
+    // Nothing this warp reads on the chain is written by another warp except the prepared record (shared
+    // memory, in order per warp: a compiler barrier after the ready flag is enough), so the loop carries no
+    // hardware fence; a release fence precedes each row_done update (once per row) for the next layer.
+    const int la = (lane < NACC) ? lane : 0;
+    int rdone = R0 - 1, cur_row = -1;
+    int *ctag = (int *)&C.ctag[0][0];
+    double *cval = (double *)&C.cval[0][0][0];
+    int slot = 0;
+    for (int t = 0;; ++t, slot = (slot + 1 == nslot) ? 0 : slot + 1) {
+        BODY_T0();
+        int4 hdr = lds_v4((const void *)&C.rhdr[slot]);
+        if (hdr.w != t + 1) {
+            bool finished = false;
+            for (;;) {
+                hdr = lds_v4((const void *)&C.rhdr[slot]);
+                if (hdr.w == t + 1) break;
+                const int dr = C.disc_row;              // read BEFORE the count: rows <= dr are all queued
+                const int fin = C.q_final;
+                const int cnt = C.q_count;
+                if (cnt == t) {                         // everything discovered so far is fitted
+                    if (fin) { finished = true; break; }
+                    if (dr > rdone) {
+                        rdone = dr;
+                        __threadfence_block();
+                        __syncwarp();
+                        if (lane == 0) C.row_done = dr;
+                    }
+                }
+                __nanosleep(20);
+            }
+            if (finished) break;
+        }
+        SMEM_ORDER();
+        BODY_T(0);
+        ExtRec &Rc = myrecs[slot];
+        const int info = hdr.x, j = hdr.y, i = hdr.z;
+        if (j != cur_row) {                             // rows above j are complete
+            cur_row = j;
+            if (j - 1 > rdone) {
+                rdone = j - 1;
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) C.row_done = j - 1;
+            }
+        }
+        const double x0 = dx * i, y0 = dy * (j + joff);
+        const int nslots = info & 255, npend = info >> 8;
+        const int nknown = nslots - npend;
+        BODY_T(1);
+        // ---- one lane per undecided cell (a raster-earlier target of this layer, fitted or rejected by
+        //      this warp): its value from the warp's own cache, else (entry recycled) from global memory
+        int nfail = 0;
+        for (int q0 = 0; q0 < npend; q0 += 32) {
+            const int r = q0 + lane;
+            bool fail = false;
+            if (r < npend) {
+                const int want = Rc.ptag[r];              // jj << 15 | ii
+                const int ce = ((want >> 15) & (BC_ROWS - 1)) * BC_COLS + (want & (BC_COLS - 1));
+                const int tag = ctag[ce];
+                double v1 = cval[2 * ce], v2 = cval[2 * ce + 1];
+                bool got;
+                if ((tag & ~(1 << 30)) == want) {
+                    got = !(tag & (1 << 30));
+                } else {
+                    const size_t cc = (size_t)(want >> 15) * Nx + (want & 32767);
+                    got = (ld_cta_u8(st + cc) == (unsigned)fresh);
+                    v1 = ld_cta_f64(X1e + cc); v2 = ld_cta_f64(X2e + cc);
+                }
+                // a rejected target contributes exact zeros (weight 0)
+                store_products(Rc.prod[Rc.pslot[r]], got ? Rc.pw[r] : 0.0, got ? Rc.px[r] : 0.0,
+                               got ? Rc.py[r] : 0.0, got ? v1 : 0.0, got ? v2 : 0.0);
+                fail = !got;
+            }
+            nfail += __popc(__ballot_sync(0xffffffffu, fail));
+        }
+        const int count = nknown + npend - nfail;        // known cells in the window (functions.py:147)
+        __syncwarp();
+        BODY_T(2);
+        // ---- ordered accumulation: lane a owns running sum a; the next chunk of 8 is loaded while the
+        //      current one is added (the list is zero-padded to a multiple of 8: exact no-ops)
+        double acc = 0.0;
+        {
+            const double *q = &Rc.prod[0][la];
+            const int nch = (nslots + 7) >> 3;            // nslots <= 80: the target itself is never a slot
+            double c0 = q[0 * NACC], c1 = q[1 * NACC], c2 = q[2 * NACC], c3 = q[3 * NACC], c4 = q[4 * NACC],
+                   c5 = q[5 * NACC], c6 = q[6 * NACC], c7 = q[7 * NACC];
+            for (int ch = 0; ch < nch; ++ch) {
+                const double *qn = q + (ch + 1 < nch ? ch + 1 : ch) * 8 * NACC;
+                const double n0 = qn[0 * NACC], n1 = qn[1 * NACC], n2 = qn[2 * NACC], n3 = qn[3 * NACC],
+                             n4 = qn[4 * NACC], n5 = qn[5 * NACC], n6 = qn[6 * NACC], n7 = qn[7 * NACC];
+                acc += c0; acc += c1; acc += c2; acc += c3; acc += c4; acc += c5; acc += c6; acc += c7;
+                c0 = n0; c1 = n1; c2 = n2; c3 = n3; c4 = n4; c5 = n5; c6 = n6; c7 = n7;
+            }
+        }
+        if (lane < NACC) ((double *)C.sums)[lane] = acc;
+        __syncwarp();
+        BODY_T(3);
+        const volatile double *sm = C.sums;
+        const int h = (lane & 1) * 3;                     // lane 0 solves for xi1, lane 1 for xi2
+        const double b0 = sm[h], b1 = sm[h + 1], b2 = sm[h + 2];
+        const double A00 = sm[6], A01 = sm[7], A02 = sm[8], A11 = sm[9], A12 = sm[10], A22 = sm[11];
+        const double A10 = A01, A20 = A02, A21 = A12;
+        const double m00 = A11 * A22 - A12 * A21, m01 = A10 * A22 - A12 * A20, m02 = A10 * A21 - A11 * A20;
+        const double det = (A00 * m00 - A01 * m01 + A02 * m02);
+        const bool fitted = (count >= 3) && (fabs(det) > 1e-10);
+        // Cramer's rule (fast_solve_3x3; its own |det| >= 1e-15 gate holds whenever fitted)
+        const double inv_det = 1.0 / det;
+        const double cx = (b0 * m00 - A01 * (b1 * A22 - A12 * b2) + A02 * (b1 * A21 - A11 * b2)) * inv_det;
+        const double cy = (A00 * (b1 * A22 - A12 * b2) - b0 * m01 + A02 * (A10 * b2 - b1 * A20)) * inv_det;
+        const double cz = (A00 * (A11 * b2 - b1 * A21) - A01 * (A10 * b2 - b1 * A20) + b0 * m02) * inv_det;
+        const double val = cx + cy * x0 + cz * y0;
+        BODY_T(4);
+        // ---- publish: the warp's cache first (the next fit reads it), then global memory.  Every lane
+        //      stores (even lanes hold xi1, odd lanes xi2; same address, same value: one transaction) so
+        //      the tail of the chain has no divergent branch
+        {
+            const int ce = (j & (BC_ROWS - 1)) * BC_COLS + (i & (BC_COLS - 1));
+            cval[2 * ce + (lane & 1)] = val;
+            ctag[ce] = ((j << 15) | i) | (fitted ? 0 : (1 << 30));
+            if (fitted) {
+                const size_t c = (size_t)j * Nx + i;
+                ((lane & 1) ? X2e : X1e)[c] = val;
+                st[c] = (unsigned char)fresh;             // readers in other warps order through row_done
+            }
+            C.consumed = t + 1;                           // frees the record slot and the queue entry
+        }
+        __syncwarp();
+        BODY_T(5);
+        BODY_CNT(6);
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) C.row_done = INT_MAX;
+}
+
 // Which variant sweeps this call?  The all-layers kernel keeps one CTA (SM) per (layer, macro-tile) for
 // the whole length of a chain, so it wins while there are fewer such tasks than SMs and loses when bodies
 // outnumber the SMs (then the per-layer launches pack the SMs better).  Decided on the device from the
@@ -1090,8 +1463,12 @@ __device__ inline int ext_longest_chain(const int *__restrict__ cnt0, const int 
 
 __global__ void k_ext_decide(const int *__restrict__ cnt0, const int *__restrict__ rows_macro, int nmrb,
                              int macro, const int *__restrict__ rows_band, int nbands, int band, int nxt,
-                             int Ny, int L, int limit16, int limit8, int force, int pre_warps, int *__restrict__ mode)
+                             int Ny, int L, int limit16, int limit8, int force_variant, int force_rows,
+                             int pre_warps, const int *__restrict__ tilecnt, const int *__restrict__ bviol,
+                             int body_ok, int fused_ok, int *__restrict__ mode)
 {
+    __shared__ int body_max[BODY_KMAX];
+    if (threadIdx.x < BODY_KMAX) body_max[threadIdx.x] = 0;
     __shared__ int busy, busy_band, longest_macro, longest_band, links_macro, links_band;
     if (threadIdx.x == 0) busy = busy_band = longest_macro = longest_band = links_macro = links_band = 0;
     __syncthreads();
@@ -1106,6 +1483,18 @@ __global__ void k_ext_decide(const int *__restrict__ cnt0, const int *__restrict
         atomicMax(&longest_macro, lm);
         atomicMax(&longest_band, lb);
     }
+    {   // fullest tile of every candidate body-tile size
+        int off = 0;
+        for (int k = 0; k < BODY_KMAX; ++k) {
+            const int Tr = 512 << k, ns = 1 << k;
+            const int nt = ((nxt + ns - 1) >> k) * ((Ny + Tr - 1) / Tr);
+            int m = 0;
+            for (int e = threadIdx.x; e < nt; e += blockDim.x) m = max(m, tilecnt[off + e]);
+            if (m) atomicMax(&body_max[k], m);
+            off += nt;
+            if (nt == 1) break;
+        }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         // all-layers kernel (16 or 8 rows per block; macro-tiles of `macro` or of `band` rows: shorter
@@ -1115,18 +1504,40 @@ __global__ void k_ext_decide(const int *__restrict__ cnt0, const int *__restrict
         // discs on a 6 x 6 lattice, 6.3 ms against 4.9 ms per-layer), so it only runs when nothing is cut.
         const float kRow16 = 6.6f, kRow8 = 7.4f, big = 3.0e38f;
         const int cut[2] = {links_macro, links_band};
-        float best = L * (360.f + 3.4f * longest_band);
-        int variant = 0, rows = macro;
+        const float cost_layers = L * (360.f + 3.4f * longest_band);
         const int nb[2] = {busy, busy_band}, ln[2] = {longest_macro, longest_band}, ht[2] = {macro, band};
-        for (int g = 0; g < 2; ++g) {
+        float cost_f[2] = {big, big};                       // [0]: 16-row blocks, [1]: 8-row blocks
+        int rows_f[2] = {macro, macro};
+        for (int g = 0; g < 2 && fused_ok; ++g) {
             const float c16 = (nb[g] * L <= limit16) ? kRow16 * ln[g] : big;
             const float c8 = (nb[g] * L <= limit8 && cut[g] == 0) ? kRow8 * ln[g] : big;
-            if (c16 < best) { best = c16; variant = 16; rows = ht[g]; }
-            if (c8 < best) { best = c8; variant = 8; rows = ht[g]; }
+            if (c16 < cost_f[0]) { cost_f[0] = c16; rows_f[0] = ht[g]; }
+            if (c8 < cost_f[1]) { cost_f[1] = c8; rows_f[1] = ht[g]; }
         }
-        if (force >= 0) {                        // RMT_EXT_FORCE: tuning hook (variant * 10000 + rows)
-            variant = force / 10000;
-            rows = force % 10000 ? force % 10000 : rows;
+        // body variant: the smallest tile size whose tiles are all isolated; one warp fits a tile's layer
+        // serially (kBody us per target), the layers run side by side a few rows apart
+        int body_k = -1;
+        for (int k = 0; k < BODY_KMAX && body_ok; ++k) {
+            const int Tr = 512 << k, ns = 1 << k;
+            const int nt = ((nxt + ns - 1) >> k) * ((Ny + Tr - 1) / Tr);
+            if (!bviol[k]) { body_k = k; break; }
+            if (nt == 1) break;
+        }
+        const float kBody = 0.55f;
+        const float cost_b = body_k >= 0 ? 20.f + kBody * body_max[body_k] * (1.f + 0.05f * (L - 1)) : big;
+        int variant = 0, rows = macro;
+        float best = cost_layers;
+        if (cost_f[0] < best) { best = cost_f[0]; variant = 16; rows = rows_f[0]; }
+        if (cost_f[1] < best) { best = cost_f[1]; variant = 8; rows = rows_f[1]; }
+        if (cost_b < best) { best = cost_b; variant = 1; rows = body_k; }
+        // rmt_extrapolate_set_mode / RMT_EXT_FORCE: a forced variant that cannot run here (bands too close
+        // to the tile borders for the body variant, workspace too small for the all-layers kernels) falls
+        // back to the model's choice
+        if (force_variant == 0) { variant = 0; rows = macro; }
+        if (force_variant == 1 && body_k >= 0) { variant = 1; rows = body_k; }
+        if ((force_variant == 16 || force_variant == 8) && fused_ok) {
+            variant = force_variant;
+            rows = force_rows >= 16 ? force_rows : rows_f[force_variant == 8];
         }
         mode[0] = variant;
         mode[1] = rows;
@@ -1140,15 +1551,21 @@ __global__ void k_ext_count0(const unsigned char *__restrict__ st, int *__restri
                              int *__restrict__ rows_band /* [row band][x-tile], zeroed */, int band,
                              int *__restrict__ cmin0, int *__restrict__ cmax0 /* first / last target column */,
                              int *__restrict__ chunk0 /* bit k: targets in columns [32k, 32k+32) of the tile */,
-                             int Ny, int Nx, int nxt, int XT)
+                             int *__restrict__ tilecnt /* zeroed: layer-0 targets per body tile, sizes k = 0.. */,
+                             int *__restrict__ bviol /* zeroed [BODY_KMAX]: a band comes within `margin` of a tile border */,
+                             int margin, int Ny, int Nx, int nxt, int XT)
 {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int nwarp = (gridDim.x * blockDim.x) >> 5;
-    for (int j = warp; j < Ny; j += nwarp) {
+    // one warp per (row, x-tile): the rows are short dependent chains of byte loads, so the more warps
+    // in flight the better
+    for (int task = warp; task < Ny * nxt; task += nwarp) {
+        const int j = task / nxt;
         const unsigned char *r1 = st + (size_t)j * Nx;
         const bool inner = (j >= 1 && j < Ny - 1);
         const unsigned char *r0 = inner ? r1 - Nx : r1, *r2 = inner ? r1 + Nx : r1;
-        for (int xt = 0; xt < nxt; ++xt) {
+        {
+            const int xt = task - j * nxt;
             int cnt = 0, cmin = INT_MAX, cmax = -1, chunks = 0;
             const int cend = min((xt + 1) * XT, Nx);
             for (int base = xt * XT; base < cend; base += 32) {
@@ -1173,6 +1590,21 @@ __global__ void k_ext_count0(const unsigned char *__restrict__ st, int *__restri
                 if (cnt) {       // rows with targets per tile: the length of the dependency chain through it
                     atomicAdd(&rows_macro[((j - 1) / macro) * nxt + xt], 1);
                     atomicAdd(&rows_band[((j - 1) / band) * nxt + xt], 1);
+                    // body variant: tiles of (512 << k) rows x (XT << k) columns; a border only counts where
+                    // targets can exist on its far side (rows < Ny-1, columns < Nx-1)
+                    int off = 0;
+                    for (int k = 0; k < BODY_KMAX; ++k) {
+                        const int Tr = 512 << k, ns = 1 << k;
+                        const int ntx = (nxt + ns - 1) >> k, nty = (Ny + Tr - 1) / Tr;
+                        const int ty = j / Tr, tx = xt >> k, rj = j - ty * Tr;
+                        atomicAdd(&tilecnt[off + ty * ntx + tx], cnt);
+                        off += ntx * nty;
+                        bool v = (ty > 0 && rj < margin) || ((ty + 1) * Tr < Ny - 1 && rj >= Tr - margin);
+                        if ((xt & (ns - 1)) == 0 && xt > 0 && cmin < xt * XT + margin) v = true;
+                        if (((xt + 1) & (ns - 1)) == 0 && (xt + 1) * XT < Nx - 1 && cmax >= (xt + 1) * XT - margin) v = true;
+                        if (v) atomicOr(&bviol[k], 1);
+                        if (ntx * nty == 1) break;        // larger tiles are the same single tile
+                    }
                 }
             }
         }
@@ -1187,12 +1619,32 @@ extern "C" {
 
 static inline int ext_nxt(int Nx) { int XT = ext_tune().XT; return (Nx + XT - 1) / XT; }
 
-// prepared-record capacity (targets per layer); beyond it the sweep computes phase A inline
-static inline long ext_cap(long ncell)
+// Variant selection override (rmt_extrapolate_set_mode; the RMT_EXT_* environment variables only seed it):
+//   variant -1 = chosen on the device by k_ext_decide, 0 = per-layer launches, 16 / 8 = all-layers kernel
+//   rows    macro-tile height of the all-layers kernel (0 = chosen on the device)
+//   cap     prepared-record capacity of the per-layer sweep (0 = default; a small value exercises inline phase A)
+struct ExtForce { int init, variant, rows, pre_warps; long cap; };
+static ExtForce g_force = {0, -1, 0, 0, 0};
+static ExtForce &ext_force()
 {
-    static long forced = -1;                     // RMT_EXT_CAP: test hook (exercises the inline path)
-    if (forced < 0) { const char *e = getenv("RMT_EXT_CAP"); forced = e ? atol(e) : 0; }
-    if (forced > 0) return forced;
+    if (!g_force.init) {
+        const char *e;
+        g_force.init = 1;
+        if ((e = getenv("RMT_EXT_FUSED")) && atoi(e) == 0) g_force.variant = 0;
+        if ((e = getenv("RMT_EXT_FORCE"))) { g_force.variant = atoi(e) / 10000; g_force.rows = atoi(e) % 10000; }
+        if ((e = getenv("RMT_EXT_PREWARPS"))) g_force.pre_warps = atoi(e);
+        if ((e = getenv("RMT_EXT_CAP"))) g_force.cap = atol(e);
+    }
+    return g_force;
+}
+// occupancy-derived grid sizes and the shared-memory opt-ins are per DEVICE (CUDA keeps function
+// attributes per device): one slot per device ordinal
+struct ExtDev { int init, resident16, resident8, sweep_blocks; };
+static ExtDev g_ext_dev[64];
+
+// prepared-record capacity (targets per layer); beyond it the sweep computes phase A inline
+static inline long ext_cap_default(long ncell)
+{
     long c = ncell / 48;
     if (c < 4096) c = 4096;
     if (c > 300000) c = 300000;
@@ -1209,7 +1661,7 @@ static ExtLayout ext_layout(int Ny, int Nx)
     ExtLayout L;
     size_t ncell = (size_t)Ny * (size_t)Nx;
     size_t nseg = (size_t)Ny * ext_nxt(Nx) + 2;
-    L.cap = ext_cap((long)ncell);
+    L.cap = ext_cap_default((long)ncell);
     {   // the all-layers kernel keeps CAPW records per row warp of every resident CTA
         long nmrb = ((Ny - 2 + RB - 1) / RB + 31) / 32, tasks = nmrb * 8 * ext_nxt(Nx);
         long fused = 2 * (tasks < 148 ? tasks : 148) * 16 * CAPW;   // two buffers; = 296 CTAs x 8 warps of the 8-row variant
@@ -1235,6 +1687,35 @@ int rmt_extrapolate(const double *X1, const double *X2, const double *phi, doubl
     return rmt_extrapolate_rows(X1, X2, phi, X1e, X2e, Ny, Nx, 0, dx, dy, max_layers, workspace, stream);
 }
 
+// where the device-side decision lives inside the workspace (mode[0] variant, mode[1] rows / tile size, mode[2])
+static int *ext_mode_ptr(void *workspace, int Ny, int Nx)
+{
+    const ExtLayout L = ext_layout(Ny, Nx);
+    const int nseg = Ny * ext_nxt(Nx);
+    int *seg_cnt = (int *)((char *)workspace + L.segs);
+    return seg_cnt + 3 * (nseg + 2) + 2;
+}
+
+int rmt_extrapolate_set_mode(int variant, int rows, long cap)
+{
+    if (!(variant == -1 || variant == 0 || variant == 1 || variant == 8 || variant == 16) || rows < 0 || cap < 0)
+        return RMT_EINVAL;
+    ExtForce &f = ext_force();
+    f.variant = variant;
+    f.rows = rows;
+    f.cap = cap;
+    return RMT_OK;
+}
+
+int rmt_extrapolate_last_mode(const void *workspace, int Ny, int Nx, int *out3, void *stream)
+{
+    if (!workspace || !out3 || Ny < 3 || Nx < 3) return RMT_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    RMT_CUDA(cudaMemcpyAsync(out3, ext_mode_ptr((void *)workspace, Ny, Nx), 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    RMT_CUDA(cudaStreamSynchronize(s));
+    return RMT_OK;
+}
+
 int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, double *X1e, double *X2e,
                          int Ny, int Nx, int row_offset, double dx, double dy, int max_layers,
                          void *workspace, void *stream)
@@ -1248,15 +1729,48 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
     ExtTune tune = ext_tune();
     int XT = tune.XT, MRB = tune.MRB, sleep_ns = tune.sleep_ns;
     const ExtLayout L = ext_layout(Ny, Nx);
+    const ExtForce force = ext_force();
     char *ws = (char *)workspace;
     unsigned char *st = (unsigned char *)(ws + L.st);
     int *seg_cnt = (int *)(ws + L.segs);
     int *seg_off = seg_cnt + (nseg + 2);
     int *prog = seg_off + (nseg + 2);
     int *tile_counter = prog + (nseg + 2);
+    int *mode = tile_counter + 2;       // device: mode[0] = 0 per-layer launches, 16 / 8 all-layers kernel with that
+                                        // many rows per block, 1 body variant; mode[1] = macro-tile rows / body tile size
     int *tcol = (int *)(ws + L.tcol), *trow = (int *)(ws + L.trow), *tinfo = (int *)(ws + L.tinfo);
     ExtRec *recs = (ExtRec *)(ws + L.recs);
     int cap = (int)L.cap;
+    if (force.cap > 0 && force.cap < cap) cap = (int)force.cap;     // test hook: inline phase A beyond `cap` targets
+
+    // per-device launch geometry (occupancy, shared-memory opt-ins)
+    int dev = 0;
+    RMT_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return RMT_EINVAL;
+    ExtDev &D = g_ext_dev[dev];
+    if (!D.init) {
+        int sms = 0, per_sm = 0;
+        RMT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        RMT_CUDA(cudaFuncSetAttribute(k_ext_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(FusedSmemT<16>)));
+        RMT_CUDA(cudaFuncSetAttribute(k_ext_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(FusedSmemT<8>)));
+        RMT_CUDA(cudaFuncSetAttribute(k_ext_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(SweepSmem)));
+        RMT_CUDA(cudaFuncSetAttribute(k_ext_body, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        RMT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_fused<16>, 16 * 32,
+                                                               sizeof(FusedSmemT<16>)));
+        if (per_sm < 1) return RMT_EINVAL;
+        D.resident16 = sms * per_sm;
+        RMT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_fused<8>, 8 * 32,
+                                                               sizeof(FusedSmemT<8>)));
+        if (per_sm < 1) return RMT_EINVAL;
+        D.resident8 = sms * per_sm;
+        RMT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_sweep, RB * 32, sizeof(SweepSmem)));
+        if (per_sm < 1) return RMT_EINVAL;
+        D.sweep_blocks = sms * per_sm;
+        D.init = 1;
+    }
 
     // stencil_radius_sq = (4*sqrt(dx**2+dy**2))**2, functions.py:76 (no contraction)
     volatile double dx2 = dx * dx, dy2 = dy * dy;
@@ -1266,68 +1780,71 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
 
     k_ext_seed<<<flat_blocks((long)ncell), 256, 0, s>>>(X1, X2, phi, X1e, X2e, st, (long)ncell);
     RMT_LAUNCH_CHECK();
+    RMT_CUDA(cudaMemsetAsync(tile_counter, 0, 6 * sizeof(int), s));      // tile counter, mode[0..3] = per-layer
 
-    // ---- all layers in one launch when that is faster (RMT_EXT_FUSED=0: never) ----
-    int *mode = nullptr;   // device: mode[0] = 0 per-layer launches, 16 / 8 all-layers kernel with that many rows
-    {                      // per block; mode[1] = its macro-tile height in rows
-        static int fused_on = -1, resident16 = 0, resident8 = 0, force = -1, pre_warps = 0;
-        if (fused_on < 0) {
-            const char *e = getenv("RMT_EXT_FUSED");
-            fused_on = (e && atoi(e) == 0) ? 0 : 1;
-            if ((e = getenv("RMT_EXT_FORCE"))) force = atoi(e);
-            if ((e = getenv("RMT_EXT_PREWARPS"))) pre_warps = atoi(e);    // tuning hook: warps preparing ahead
+    // ---- all layers in one launch when that is faster; which variant is decided on the device ----
+    const int Lyr = max_layers;
+    if (force.variant != 0 && Lyr >= 1 && Lyr <= 8) {
+        // x-tiles wide enough that a task never waits on a task more than ~3/4 of the resident CTAs ahead
+        int max_tiles = (D.resident16 * 3 / 4) / (2 * Lyr - 1);
+        if (max_tiles < 1) max_tiles = 1;
+        int XTf = (Nx > 1024) ? 512 : XT;             // both flanks of a body in one tile: fewer tasks
+        const int need_xt = ((Nx + max_tiles - 1) / max_tiles + 31) / 32 * 32;
+        if (need_xt > XTf) XTf = need_xt;
+        const int nxtf = (Nx + XTf - 1) / XTf, nsegf = Ny * nxtf;
+        const long prog_ints = (long)Lyr * nsegf;
+        const int macro = 1024, band = 512;            // candidate macro-tile heights (rows)
+        const int nmrb = rmt_cdiv(Ny - 2, macro);
+        const int nmac = nmrb * nxtf, nbnd = rmt_cdiv(Ny - 2, band) * nxtf, nbusy = nmac + nbnd;
+        long ntile_total = 0;                          // body tiles over all candidate sizes
+        for (int k = 0; k < BODY_KMAX; ++k) {
+            const long nt = (long)((nxtf + (1 << k) - 1) >> k) * rmt_cdiv(Ny, 512 << k);
+            ntile_total += nt;
+            if (nt == 1) break;
         }
-        const int Lyr = max_layers;
-        if (fused_on && Lyr >= 1 && Lyr <= 8) {
-            if (!resident16) {
-                int dev = 0, sms = 0, per_sm = 0;
-                RMT_CUDA(cudaGetDevice(&dev));
-                RMT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-                RMT_CUDA(cudaFuncSetAttribute(k_ext_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)sizeof(FusedSmemT<16>)));
-                RMT_CUDA(cudaFuncSetAttribute(k_ext_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)sizeof(FusedSmemT<8>)));
-                RMT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_fused<16>, 16 * 32,
-                                                                       sizeof(FusedSmemT<16>)));
-                if (per_sm < 1) return RMT_EINVAL;
-                resident16 = sms * per_sm;
-                RMT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_fused<8>, 8 * 32,
-                                                                       sizeof(FusedSmemT<8>)));
-                if (per_sm < 1) return RMT_EINVAL;
-                resident8 = sms * per_sm;
+        const int ntile0 = nxtf * rmt_cdiv(Ny, 512);
+        if (XTf <= 1024 && prog_ints + 4L * nsegf + nbusy + ntile_total + BODY_KMAX + 8 <= (long)ncell) {
+            int *progF = trow;                         // [L][nsegf] ints, then chain lengths, body tile counts and
+            int *busy = trow + prog_ints;              //  flags, then cnt0 (trow holds ncell ints; the per-layer path
+            int *tilecnt = busy + nbusy;               //  rewrites it afterwards if it is the one that runs)
+            int *bviol = tilecnt + ntile_total;
+            int *cnt0 = bviol + BODY_KMAX;
+            const long ntasks = (long)rmt_cdiv(Ny - 2, band) * Lyr * nxtf;   // with the smaller macro-tile
+            int blocks16 = D.resident16, blocks8 = D.resident8;
+            if ((long)blocks16 > ntasks) blocks16 = (int)ntasks;
+            if ((long)blocks8 > ntasks) blocks8 = (int)ntasks;
+            const long need_recs = 2L * (blocks16 * 16 > blocks8 * 8 ? blocks16 * 16 : blocks8 * 8) * CAPW;
+            const int fused_ok = (XTf <= LMAX && need_recs <= L.cap) ? 1 : 0;
+            // body variant: warps per layer = chain + discovery + P prepare warps in a CTA of <= 640 threads
+            int P = 0, nslot = 0;
+            size_t body_smem = 0;
+            if (Lyr <= BODY_LMAX) {
+                P = 20 / Lyr - 2;
+                if (P > 4) P = 4;
+                const size_t ctl_bytes = ((size_t)Lyr * sizeof(BodyCtl) + 15) & ~(size_t)15;
+                nslot = (int)((220 * 1024 - ctl_bytes) / ((size_t)Lyr * sizeof(ExtRec)));
+                if (nslot > BSLOT_MAX) nslot = BSLOT_MAX;
+                body_smem = ctl_bytes + (size_t)Lyr * nslot * sizeof(ExtRec);
             }
-            // x-tiles wide enough that a task never waits on a task more than ~3/4 of the resident CTAs ahead
-            int max_tiles = (resident16 * 3 / 4) / (2 * Lyr - 1);
-            if (max_tiles < 1) max_tiles = 1;
-            int XTf = (Nx > 1024) ? 512 : XT;             // both flanks of a body in one tile: fewer tasks
-            const int need_xt = ((Nx + max_tiles - 1) / max_tiles + 31) / 32 * 32;
-            if (need_xt > XTf) XTf = need_xt;
-            const int nxtf = (Nx + XTf - 1) / XTf, nsegf = Ny * nxtf;
-            const long prog_ints = (long)Lyr * nsegf;
-            const int macro = 1024, band = 512;            // candidate macro-tile heights (rows)
-            const int nmrb = rmt_cdiv(Ny - 2, macro);
-            const int nmac = nmrb * nxtf, nbnd = rmt_cdiv(Ny - 2, band) * nxtf, nbusy = nmac + nbnd;
-            if (XTf <= LMAX && prog_ints + 4L * nsegf + nbusy + 8 <= (long)ncell) {
-                int *progF = trow;                         // [L][nsegf] ints, then chain lengths, then cnt0 (trow
-                int *busy = trow + prog_ints;              //  holds ncell ints; the per-layer path rewrites it
-                int *cnt0 = busy + nbusy;                  //  afterwards if it is the one that runs)
-                const long ntasks = (long)rmt_cdiv(Ny - 2, band) * Lyr * nxtf;   // with the smaller macro-tile
-                int blocks16 = resident16, blocks8 = resident8;
-                if ((long)blocks16 > ntasks) blocks16 = (int)ntasks;
-                if ((long)blocks8 > ntasks) blocks8 = (int)ntasks;
-                const long need_recs = 2L * (blocks16 * 16 > blocks8 * 8 ? blocks16 * 16 : blocks8 * 8) * CAPW;
-                if (need_recs <= (long)cap) {
-                    mode = tile_counter + 2;
-                    RMT_CUDA(cudaMemsetAsync(progF, 0, (size_t)(prog_ints + nbusy) * sizeof(int), s));
-                    RMT_CUDA(cudaMemsetAsync(tile_counter, 0, sizeof(int), s));
-                    int rwb = rmt_cdiv((long)Ny * 32, 256);
-                    if (rwb > 148 * 8) rwb = 148 * 8;
-                    k_ext_count0<<<rwb, 256, 0, s>>>(st, cnt0, busy, macro, busy + nmac, band, cnt0 + nsegf,
-                                                     cnt0 + 2 * nsegf, cnt0 + 3 * nsegf, Ny, Nx, nxtf, XTf);
+            const int body_ok = (P >= 1 && nslot >= 2) ? 1 : 0;
+            if (fused_ok || body_ok) {
+                RMT_CUDA(cudaMemsetAsync(progF, 0, (size_t)(prog_ints + nbusy + ntile_total + BODY_KMAX) * sizeof(int), s));
+                int rwb = rmt_cdiv((long)Ny * nxtf * 32, 256);
+                if (rwb > 148 * 8) rwb = 148 * 8;
+                k_ext_count0<<<rwb, 256, 0, s>>>(st, cnt0, busy, macro, busy + nmac, band, cnt0 + nsegf,
+                                                 cnt0 + 2 * nsegf, cnt0 + 3 * nsegf, tilecnt, bviol, Lyr + 5, Ny, Nx,
+                                                 nxtf, XTf);
+                RMT_LAUNCH_CHECK();
+                k_ext_decide<<<1, 64, 0, s>>>(cnt0, busy, nmrb, macro, busy + nmac, nbnd / nxtf, band, nxtf, Ny,
+                                              Lyr, D.resident16 * 9 / 10, D.resident8 * 9 / 10, force.variant,
+                                              force.rows, force.pre_warps, tilecnt, bviol, body_ok, fused_ok, mode);
+                RMT_LAUNCH_CHECK();
+                if (body_ok) {
+                    k_ext_body<<<ntile0, Lyr * (2 + P) * 32, body_smem, s>>>(X1e, X2e, st, cnt0, tilecnt, mode, Lyr, P,
+                                                                             nslot, Ny, Nx, joff, nxtf, XTf, dx, dy, r2);
                     RMT_LAUNCH_CHECK();
-                    k_ext_decide<<<1, 64, 0, s>>>(cnt0, busy, nmrb, macro, busy + nmac, nbnd / nxtf, band, nxtf, Ny,
-                                                  Lyr, resident16 * 9 / 10, resident8 * 9 / 10, force, pre_warps, mode);
-                    RMT_LAUNCH_CHECK();
+                }
+                if (fused_ok) {
                     int Lv = Lyr, nxv = nxtf, xtv = XTf;
                     void *args[] = {&X1e, &X2e, &st, &cnt0, &progF, &tile_counter, &recs, &mode, &Lv, &Ny, &Nx,
                                     &joff, &nxv, &xtv, &dx, &dy, &r2};
@@ -1343,20 +1860,10 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
     }
 
     const size_t sweep_smem = sizeof(SweepSmem);
-    static int sweep_blocks = 0;
-    if (!sweep_blocks) {
-        int dev = 0, sms = 0, per_sm = 0;
-        RMT_CUDA(cudaGetDevice(&dev));
-        RMT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        RMT_CUDA(cudaFuncSetAttribute(k_ext_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sweep_smem));
-        RMT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_sweep, RB * 32, sweep_smem));
-        if (per_sm < 1) return RMT_EINVAL;
-        sweep_blocks = sms * per_sm;
-    }
     int row_warps_blocks = rmt_cdiv((long)Ny * 32, 256);
     if (row_warps_blocks > 148 * 8) row_warps_blocks = 148 * 8;
 
+    // the per-layer launches: they return at once when the device picked an all-layers variant
     for (int layer = 0; layer < max_layers; ++layer) {
         k_ext_flag<<<row_warps_blocks, 256, 0, s>>>(st, seg_cnt, Ny, Nx, nxt, XT, mode);
         RMT_LAUNCH_CHECK();
@@ -1368,7 +1875,7 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
                                                joff, dx, dy, r2, mode);
         RMT_LAUNCH_CHECK();
         // all CTAs must be co-resident (warps wait on each other): cooperative launch
-        int blocks = sweep_blocks;
+        int blocks = D.sweep_blocks;
         int need = rmt_cdiv(rmt_cdiv(Ny - 2, RB), MRB) * nxt;
         if (blocks > need) blocks = need;
         void *args[] = {&X1e, &X2e, &st, &seg_off, &tcol, &prog, &tile_counter, &recs, &tinfo, &cap,
@@ -1381,6 +1888,15 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
 }
 
 #ifdef RMT_EXT_TIMING
+int rmt_body_debug_read(unsigned long long *out16, int reset)
+{
+    RMT_CUDA(cudaMemcpyFromSymbol(out16, g_body_dbg, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        RMT_CUDA(cudaMemcpyToSymbol(g_body_dbg, z, sizeof(z)));
+    }
+    return RMT_OK;
+}
 int rmt_ext_debug_read(unsigned long long *out8, int reset)
 {
     RMT_CUDA(cudaMemcpyFromSymbol(out8, g_ext_dbg, sizeof(unsigned long long) * 8));

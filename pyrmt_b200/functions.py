@@ -267,6 +267,29 @@ def extrapolate_reference_map(X1, X2, phi, dx, dy, max_layers, row_offset=0):
     return to_user(o1, as_np), to_user(o2, as_np)
 
 
+_EXT_VARIANTS = {"auto": -1, "per_layer": 0, "body": 1, "fused8": 8, "fused16": 16}
+
+
+def _extrapolate_set_mode(variant="auto", rows=0, cap=0):
+    """Not upstream: pick the sweep variant of extrapolate_reference_map (all are bit-identical to the
+    reference's serial sweep).  'auto' = chosen on the device per call; 'per_layer', 'fused16', 'fused8',
+    'body' force one (a variant that cannot run on the given bands falls back to the device's choice).
+    ``cap`` > 0 limits the prepared-record capacity of the per-layer sweep (exercises inline phase A)."""
+    v = _EXT_VARIANTS[variant] if isinstance(variant, str) else int(variant)
+    _chk(ctx().lib.rmt_extrapolate_set_mode(v, int(rows), int(cap)), "rmt_extrapolate_set_mode")
+
+
+def _extrapolate_last_mode(Ny, Nx):
+    """(variant, rows) the last extrapolate_reference_map call on an (Ny, Nx) grid ran with."""
+    import ctypes as C
+    c = ctx()
+    out = (C.c_int * 3)()
+    _chk(c.lib.rmt_extrapolate_last_mode(ptr(c.extrap_workspace(Ny, Nx)), Ny, Nx, out, stream()),
+         "rmt_extrapolate_last_mode")
+    names = {v: k for k, v in _EXT_VARIANTS.items()}
+    return names.get(out[0], out[0]), int(out[1])
+
+
 # --------------------------------------------------------------------------
 # stress, Heaviside, momentum predictor
 # --------------------------------------------------------------------------

@@ -104,8 +104,25 @@ def test_extrapolation_bit_exact_golden(P, golden):
         assert same(r1, g[ea]) and same(r2, g[eb]), (a, ph)
 
 
+EXT_VARIANTS = [("auto", 0), ("per_layer", 0), ("per_layer", 48), ("fused16", 0), ("fused8", 0), ("body", 0)]
+
+
+@pytest.fixture
+def ext_mode(P):
+    """Force one sweep variant of the extrapolation for the duration of a test (C ABI
+    rmt_extrapolate_set_mode), restoring the device-side choice afterwards."""
+    def set_(variant, cap=0):
+        P._extrapolate_set_mode(variant, 0, cap)
+    yield set_
+    P._extrapolate_set_mode("auto", 0, 0)
+
+
+@pytest.mark.parametrize("variant,cap", EXT_VARIANTS)
 @pytest.mark.parametrize("N,L,layers", [(128, 1.0, 3), (257, 1.0, 3), (513, 4.0, 5)])
-def test_extrapolation_bit_exact_oracle(P, O, N, L, layers):
+def test_extrapolation_bit_exact_oracle(P, O, ext_mode, N, L, layers, variant, cap):
+    """Every sweep variant (device-chosen, per-layer launches with prepared and with inline phase A,
+    the two row-pipelined all-layers kernels, the one-CTA-per-tile body kernel) against the oracle."""
+    ext_mode(variant, cap)
     X, Y, dx, dy = O.create_grid(N, N, L, L)
     cx = np.array([0.3, 0.68, 0.5]) * L
     cy = np.array([0.3, 0.35, 0.75]) * L
@@ -115,8 +132,11 @@ def test_extrapolation_bit_exact_oracle(P, O, N, L, layers):
     X1 = (X + 0.03 * L * np.sin(2.2 * X / L) * np.cos(1.7 * Y / L)) * m
     X2 = (Y + 0.02 * L * np.cos(1.3 * X / L) * np.sin(2.9 * Y / L)) * m
     r1, r2 = P.extrapolate_reference_map(X1, X2, phi, dx, dy, layers)
+    ran = P._extrapolate_last_mode(N, N)[0]
+    if variant != "auto":
+        assert ran == variant, "forced %s but %s ran" % (variant, ran)
     o1, o2 = O.extrapolate_reference_map(X1, X2, phi, dx, dy, layers)
-    assert same(r1, o1) and same(r2, o2)
+    assert same(r1, o1) and same(r2, o2), (variant, ran)
 
 
 def test_extrapolation_linear_exact(P):
@@ -623,6 +643,96 @@ def test_host_state_step_equals_device_step(P):
         assert all(h.is_pinned() for h in hstate)
         for nm, d, h in zip("abp12", state, hstate):
             assert torch.equal(d.cpu(), h), nm
+
+
+# ----------------------------------------------------------------- config 4 at 1025^2 and 4097^2
+def _config4(O, N, scheme="weno5"):
+    """BASELINE configs[3] / SURVEY 8d config 4 (what bench.py times): 64 discs on the jittered 8 x 8
+    lattice, R = 0.04 L, lid-driven, WENO5.  Returns (oracle params, GPU params, initial ndarray state)."""
+    from pyrmt_b200.bc import no_slip_lid_bc
+    from pyrmt_b200.driver import LidBC, disc_lattice
+    from pyrmt_b200.levelset import DiscSDF
+    X, Y, dx, dy = O.create_grid(N, N, 1.0, 1.0)
+    cx, cy, R = disc_lattice(8, 1.0, 0.04)
+    eig = O._precompute_poisson_eigenvalues(N, N, dx, dy)
+    base = dict(dx=dx, dy=dy, CFL=0.2, dt_cap=1e-3, mu_s=0.1, kappa=0.0, rho_s=1.0, rho_f=1.0, eta_s=0.01,
+                mu_f=0.01, w_t=2 * dx, layers=3, scheme=scheme, w_cut=0.0, eig=eig, X=X, Y=Y)
+    po = dict(base, phi_init=lambda A, B: O.disc_sdf(A, B, cx, cy, R), bc=lambda u, v: no_slip_lid_bc(u, v, 1.0))
+    pg = dict(base, phi_init=DiscSDF(cx, cy, R, domain=(1.0, 1.0)), bc=LidBC(1.0))
+    ph = po["phi_init"](X, Y)
+    m = (ph <= 0).astype(float)
+    X1, X2 = O.extrapolate_reference_map(X * m, Y * m, ph, dx, dy, 3)
+    z = np.zeros_like(X)
+    a, b = po["bc"](z, z)
+    return po, pg, (a, b, z.copy(), X1, X2)
+
+
+@pytest.mark.parametrize("N", [1025, 4097])
+def test_config4_operators_bit_exact_at_bench_size(P, O, ext_mode, N):
+    """The xi path of the benchmarked workload at the benchmarked size, operator by operator and
+    bit for bit against the oracle: DiscSDF, the WENO5 pair advection, and the extrapolation under
+    EVERY sweep variant (so whichever the device picks in bench.py has oracle-backed evidence here)."""
+    import torch
+    po, pg, state = _config4(O, N)
+    dx, dy = po["dx"], po["dy"]
+    a, b, p, X1, X2 = state
+    up = lambda t: torch.from_numpy(np.ascontiguousarray(t)).cuda()
+    # a non-trivial, smooth, divergence-free-ish velocity so that the advection really moves xi
+    Xg, Yg = po["X"], po["Y"]
+    a = a + 0.3 * np.sin(2 * np.pi * Xg) * np.cos(2 * np.pi * Yg)
+    b = b - 0.3 * np.cos(2 * np.pi * Xg) * np.sin(2 * np.pi * Yg)
+    dt = 0.2 * dx / 1.3
+    phi_o = po["phi_init"](X1, X2)
+    phi_g = pg["phi_init"](up(X1), up(X2))
+    assert same(phi_g.cpu().numpy(), phi_o), "DiscSDF differs from the oracle at N=%d" % N
+    m = (phi_o <= 0).astype(float)
+    q1o = O.advect_reference_map(X1, a, b, Xg, Yg, dt, dx, dy, phi_o, "weno5", 0.0) * m
+    q2o = O.advect_reference_map(X2, a, b, Xg, Yg, dt, dx, dy, phi_o, "weno5", 0.0) * m
+    q1g, q2g = P.advect_reference_map_pair(up(X1), up(X2), up(a), up(b), None, None, dt, dx, dy, phi_g, "weno5",
+                                           0.0, mask_solid=True)
+    assert same(q1g.cpu().numpy(), q1o) and same(q2g.cpu().numpy(), q2o), "WENO5 pair differs at N=%d" % N
+    e1o, e2o = O.extrapolate_reference_map(q1o, q2o, phi_o, dx, dy, 3)
+    ran = {}
+    for variant, cap in EXT_VARIANTS:
+        ext_mode(variant, cap)
+        e1g, e2g = P.extrapolate_reference_map(q1g, q2g, phi_g, dx, dy, 3)
+        ran[(variant, cap)] = P._extrapolate_last_mode(N, N)
+        assert same(e1g.cpu().numpy(), e1o) and same(e2g.cpu().numpy(), e2o), (N, variant, cap, ran)
+        if variant != "auto":
+            assert ran[(variant, cap)][0] == variant, (N, variant, ran)
+    print("extrapolation variants at N=%d:" % N, ran)
+    # the 64 bodies of config 4 sit alone in their 512 x 512 tiles: the device must pick the body variant
+    if N == 4097:
+        assert ran[("auto", 0)] == ("body", 0), ran
+
+
+@pytest.mark.parametrize("N,nsteps", [(1025, 2), (4097, 1)])
+def test_config4_fsi_steps_vs_oracle_at_bench_size(P, O, N, nsteps):
+    """Full FSI steps of the benchmarked workload, each fed the oracle's state (SURVEY 8d parity
+    protocol at 1025 and 4097): u, v, p within 1e-10, xi bit for bit -- through driver.fsi_step, the
+    call bench.py times, with the device-chosen extrapolation variant."""
+    import torch
+    from pyrmt_b200.driver import fsi_step
+    po, pg, state = _config4(O, N)
+    up = lambda t: torch.from_numpy(np.ascontiguousarray(t)).cuda()
+    pgd = dict(pg, X=None, Y=None)
+    # a few device steps first so that the velocity and the reference map are non-trivial
+    dev = tuple(up(t) for t in state)
+    for _ in range(3):
+        dev, _, _ = fsi_step(dev, pgd)
+    state = tuple(t.cpu().numpy() for t in dev)
+    for n in range(nsteps):
+        so, dto, _ = O.fsi_step(state, po)
+        sg, dtg, _ = fsi_step(tuple(up(t) for t in state), pgd)
+        assert abs(dtg - dto) <= 1e-15 * max(abs(dto), 1e-300) * 4
+        for nm, x, r in zip(("a", "b", "p", "X1", "X2"), sg, so):
+            x = x.cpu().numpy()
+            if nm in ("X1", "X2"):
+                assert same(x, r), (N, n, nm, rel_linf(x, r))
+            err = rel_linf(x, r)
+            assert err < TOL, (N, n, nm, err)
+        state = so
+    assert P._extrapolate_last_mode(N, N)[0] in ("body", "fused8", "fused16", "per_layer")
 
 
 # ----------------------------------------------------------------- slab decomposition (1 rank)
