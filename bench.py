@@ -159,33 +159,87 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def oracle_rate(n_nodes, steps, warmup, scheme):
-    """Mcell-steps/s of the CPU oracle on a bounded sample (same physics, fewer cells)."""
+def _host_threads():
+    """Use every host core for the CPU arm, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1).
+    Must run before numpy / numba / the oracle's OpenMP library are loaded."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ["NUMBA_NUM_THREADS"] = str(n)
+    return n
+
+
+def _omp_threads():
+    import ctypes
+    try:
+        return int(ctypes.CDLL("libgomp.so.1").omp_get_max_threads())
+    except Exception:
+        return None
+
+
+def cpu_fsi_step(M, state, prm):
+    """One step of benchmarks/soft_disc_in_lid_driven.py:78-106 with the functions of module M -- the
+    staged reference (pyRMT.functions) or the oracle port (same names, same signatures)."""
+    a, b, p, X1, X2 = state
+    dx, dy = prm["dx"], prm["dy"]
+    dt = M.compute_timestep(a, b, dx, dy, prm["CFL"], prm["dt_cap"], prm["mu_s"], prm["rho_s"], 0.0, prm["rho_f"],
+                            mu_f=prm["mu_f"], eta_s=prm["eta_s"], kappa=prm["kappa"])
+    phi = M.rebuild_phi_from_reference_map(X1, X2, prm["phi_init"])
+    solid_mask = (phi <= 0).astype(float)
+    X1 = M.advect_reference_map(X1, a, b, prm["X"], prm["Y"], dt, dx, dy, phi, prm["scheme"], 0.0) * solid_mask
+    X2 = M.advect_reference_map(X2, a, b, prm["X"], prm["Y"], dt, dx, dy, phi, prm["scheme"], 0.0) * solid_mask
+    X1, X2 = M.extrapolate_reference_map(X1, X2, phi, dx, dy, prm["layers"])
+    phi = M.rebuild_phi_from_reference_map(X1, X2, prm["phi_init"])
+    a_s, b_s, *_ = M.momentum_step_rk4(a, b, p, X1, X2, prm["bc"], prm["mu_s"], prm["kappa"], prm["eta_s"], dx, dy,
+                                       dt, prm["rho_s"], prm["rho_f"], phi, prm["mu_f"], prm["w_t"], 0.0)
+    H = M.smoothed_heaviside(phi, prm["w_t"])
+    rho_local = (1 - H) * prm["rho_s"] + H * prm["rho_f"]
+    a, b, p, _, _ = M.pressure_projection_amg(a_s, b_s, dx, dy, dt, rho_local, velocity_bc=prm["bc"], A=None,
+                                              ml=None, p_prev=p, eigenvalues=prm["eig"], bc_type="neumann")
+    return (a, b, p, X1, X2)
+
+
+def cpu_case(N, scheme):
+    """The bench workload (64 discs, lid-driven) on an N x N node grid as host arrays: (params, state)."""
     import numpy as np
     from oracle import rmt_oracle as O
-    from pyrmt_b200.bc import no_slip_lid_bc
     from pyrmt_b200.driver import disc_lattice
-    N = n_nodes
     X, Y, dx, dy = O.create_grid(N, N, 1.0, 1.0)
     cx, cy, R = disc_lattice(8, 1.0, 0.04)
-    phi0 = lambda A, B: O.disc_sdf(A, B, cx, cy, R)
-    lid = lambda u, v: no_slip_lid_bc(u, v, 1.0)
+    phi0 = lambda A, B: O.disc_sdf(A, B, cx, cy, R)          # the user-side phi0 callable (C helper: fast)
+    lid = lambda u, v: O.no_slip_lid_bc(u, v, 1.0)           # benchmarks/common.py:27-37
     prm = dict(dx=dx, dy=dy, CFL=0.2, dt_cap=1e-3, mu_s=0.1, kappa=0.0, rho_s=1.0, rho_f=1.0, eta_s=0.01,
                mu_f=0.01, w_t=2 * dx, layers=3, scheme=scheme, w_cut=0.0, bc=lid, X=X, Y=Y, phi_init=phi0,
-               eig=O._precompute_poisson_eigenvalues(N, N, dx, dy))
+               eig=O._precompute_poisson_eigenvalues(N, N, dx, dy), discs=(cx, cy, R))
     ph = phi0(X, Y)
     m = (ph <= 0).astype(float)
     X1, X2 = O.extrapolate_reference_map(X * m, Y * m, ph, dx, dy, 3)
     z = np.zeros_like(X)
     a, b = lid(z, z)
-    state = (a, b, z.copy(), X1, X2)
+    return prm, (a, b, z.copy(), X1, X2)
+
+
+def cpu_rate(n_nodes, steps, warmup, scheme, want_reference=True):
+    """Mcell-steps/s of the CPU arm on a bounded sample (same physics, fewer cells): the UNMODIFIED reference
+    (oracle/_ref, staged by oracle/make_ref.py; Numba on all host cores) when it is there and numba imports,
+    else the oracle port (C/OpenMP + NumPy/pocketfft).  Returns (rate, ms/step, kind, threads, final state)."""
+    M, kind, threads = None, "port", None
+    if want_reference:
+        from oracle import make_ref
+        M = make_ref.load()
+        if M is not None:
+            import numba
+            kind, threads = "reference", int(numba.get_num_threads())
+    from oracle import rmt_oracle as O
+    if M is None:
+        M, threads = O, _omp_threads()
+    prm, state = cpu_case(n_nodes, scheme)
     for _ in range(warmup):
-        state, _, _ = O.fsi_step(state, prm)
+        state = cpu_fsi_step(M, state, prm)
     t0 = time.perf_counter()
     for _ in range(steps):
-        state, _, _ = O.fsi_step(state, prm)
+        state = cpu_fsi_step(M, state, prm)
     el = time.perf_counter() - t0
-    return N * N * steps / el / 1e6, el / steps * 1e3
+    return n_nodes * n_nodes * steps / el / 1e6, el / steps * 1e3, kind, threads, (prm, state)
 
 
 def slab_fluid_rate(N, steps, rank, world):
@@ -228,23 +282,72 @@ def slab_fluid_rate(N, steps, rank, world):
             "finite": bool(torch.isfinite(a).all().item())}
 
 
+CPU_KIND_TEXT = {
+    "reference": "the UNMODIFIED reference (pyRMT.functions staged under oracle/_ref): Numba kernels on %d threads "
+                 "(only the 4 parallel=True kernels are multithreaded upstream), NumPy / pocketfft single-threaded",
+    "port": "CPU oracle = C/OpenMP port of the reference's Numba kernels + NumPy/pocketfft, OpenMP kernels on %d "
+            "threads, NumPy parts single-threaded as upstream",
+}
+
+
+def slab_parity_vs_1gpu(N, scheme, rank, world, nsteps=3):
+    """N > 1: the slab-decomposed FSI step against the single-GPU step on the same N x N problem (config-4
+    geometry: bodies straddle the cuts).  Every rank runs the single-GPU step redundantly and compares its
+    own rows; the verdict is all-reduced.  Untimed."""
+    import torch
+    import torch.distributed as dist
+    from pyrmt_b200.driver import fsi_step, make_case
+    from pyrmt_b200.slab import SlabFSISolver, SlabLayout
+    state, prm = make_case(N, L=1.0, k_side=8, R_frac=0.04, scheme=scheme, bc_kind="lid")
+    lay = SlabLayout(N, N, world, rank, halo=12)
+    solver = SlabFSISolver(lay, prm["bc"], prm["eig"], prm["phi_init"], overlap=min(512, N // 2), layers=prm["layers"])
+    sstate = tuple(lay.take(t).contiguous() for t in state)
+    sprm = dict(prm, X=None, Y=None)
+    worst = torch.zeros(5, dtype=torch.float64, device="cuda")
+    xi_equal = True
+    for _ in range(nsteps):
+        state, dt, _ = fsi_step(state, prm)
+        sstate = solver.fsi_step(sstate, sprm, dt, check_guard=True)
+        for k, (ref, got) in enumerate(zip(state, sstate)):
+            r, g = ref[lay.r0:lay.r1], lay.owned(got)
+            worst[k] = torch.maximum(worst[k], (r - g).abs().max() / ref.abs().max().clamp_min(1e-300))
+            if k >= 3:
+                xi_equal = xi_equal and bool(torch.equal(r, g))
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    flag = torch.tensor([1.0 if xi_equal else 0.0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    rel = dict(zip(("u", "v", "p", "xi1", "xi2"), (float(x) for x in worst.tolist())))
+    return {"against": "the single-GPU step of the same %dx%d problem, %d steps, own rows of every rank" % (N, N, nsteps),
+            "grid": [N, N], "rel_linf": rel, "max_rel_linf": max(rel.values()), "xi_bit_exact": bool(flag.item() > 0.5),
+            "tolerance": 1e-12, "ok": bool(max(rel.values()) <= 1e-12)}
+
+
 def run_reference(args, rank):
+    """The reference arm: the reference's own CPU implementation of the step on this box's host cores.  The
+    timed workload is a BOUNDED SAMPLE of the b200 arm's config -- the same 64-disc lid-driven case on a
+    --ref-size grid -- and the line says so: `config.grid` / `config.workload` are what actually ran."""
     if rank != 0:
         return
+    cores = _host_threads()
     n = args.ref_size
-    rate, ms = oracle_rate(n, args.steps, min(args.warmup, 2), args.scheme)
-    cores = os.cpu_count() or 1
-    sample = ("%d steps of the same 64-disc lid-driven %s step on a %dx%d node grid (1/%d of the cells); "
-              "CPU oracle = C/OpenMP port of the reference's Numba kernels + NumPy/pocketfft, "
-              "OpenMP kernels on %d threads, NumPy parts single-threaded as upstream"
-              % (args.steps, args.scheme, n, n, round((args.size / n) ** 2), cores))
+    warm = max(1, min(args.warmup, 2))             # the first step carries the Numba JIT
+    rate, ms, kind, threads, _ = cpu_rate(n, args.steps, warm, args.scheme)
+    threads = threads or cores
+    cfg = workload_config(n, args.scheme, 1)
+    cfg["workload"] = ("bounded sample of the b200 arm's workload (4097x4097): " + cfg["workload"]
+                       + "; per-cell cost of the CPU path is size-independent (SURVEY 6.2), so Mcell-steps/s compares")
+    cfg["sample_of"] = [args.size, args.size]
+    cfg.pop("cache", None)
+    cfg["parallelism"] = "host CPU, %d threads" % threads
+    sample = ("%d steps of the same 64-disc lid-driven %s step on a %dx%d node grid (1/%d of the cells of %dx%d); "
+              % (args.steps, args.scheme, n, n, round((args.size / n) ** 2), args.size, args.size)
+              + CPU_KIND_TEXT[kind] % threads)
     line = {"impl": "reference", "metric": "Mcell-steps/s full FSI step", "value": rate,
-            "unit": "Mcell-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 2),
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.size, args.scheme, args.gpus),
-            "cpu_baseline": {"value": rate, "unit": "Mcell-steps/s", "cores": cores, "kind": "port",
-                             "sample": sample},
+            "unit": "Mcell-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": rate, "unit": "Mcell-steps/s", "cores": threads, "host_cores": cores,
+                             "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": "Mcell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -425,39 +528,71 @@ def main():
                        "the five state fields (per rank: its slab) pinned host -> device -> slab fsi step -> pinned host"}
 
     # ---- N > 1: the part of the step that IS slab-decomposed (momentum + projection) ----
+    # ---- the sharded sides of the path: the Neumann fluid half at 8193^2 (N > 1) and BASELINE configs[4]
+    #      (periodic Taylor-Green: FSI at 8193^2, fluid half at 16385^2) -- at EVERY N including 1, so that
+    #      the driver's scaling run carries its own 1 -> 8 curve for them
     slab = cfg5 = None
-    if world > 1 and not args.no_slab:
-        slab = slab_fluid_rate(args.slab_size, 10, rank, world)
+    del state
+    torch.cuda.empty_cache()
+    if not args.no_slab:
+        if world > 1:
+            slab = slab_fluid_rate(args.slab_size, 10, rank, world)
         # SURVEY 8d config 5 (periodic Taylor-Green, distributed FFT solve): the full FSI step at the largest
         # size where the reference's absolute-coordinate LSQ is still meaningful, the fluid half at 16385^2
         from pyrmt_b200.slab import time_periodic_fluid, time_periodic_fsi
         torch.cuda.empty_cache()
         cfg5 = {"fsi_step": time_periodic_fsi(args.cfg5_fsi_size, world, rank, steps=5, warmup=3)}
         torch.cuda.empty_cache()
+        cfg5["fsi_step_semilagrangian"] = time_periodic_fsi(args.cfg5_fsi_size, world, rank, steps=5, warmup=3,
+                                                            scheme="semilagrangian")
+        torch.cuda.empty_cache()
         cfg5["fluid_step"] = time_periodic_fluid(args.cfg5_fluid_size, world, rank, steps=5, warmup=3)
+        torch.cuda.empty_cache()
         cfg5["note"] = ("full FSI at 16385^2 is not runnable with the reference's own algorithm (absolute-coordinate "
-                        "normal equations lose all significance at index ~16384, see DESIGN.md 6): 8193^2 is the "
-                        "FSI size, 16385^2 the fluid-half size")
+                        "normal equations lose all significance at index ~16384: pinned by "
+                        "tests/test_gpu_parity.py::test_extrapolation_large_row_offset_matches_oracle, DESIGN.md 6): "
+                        "8193^2 is the FSI size, 16385^2 the fluid-half size")
 
-    cpu = None
+    # ---- parity, untimed: N = 1 -> one GPU step from the CPU arm's state against the CPU arm's own next step
+    #      (rel L-inf on u, v, p, xi; xi bit for bit);  N > 1 -> the slab-decomposed step against the
+    #      single-GPU step of the same 1025^2 problem (every rank runs the single-GPU step redundantly)
+    cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
         n = args.ref_size
-        rate, cms = oracle_rate(n, args.cpu_steps, 1, args.scheme)
-        cpu = {"value": rate, "unit": "Mcell-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+        rate, cms, kind, threads, (cprm, cstate) = cpu_rate(n, args.cpu_steps, 1, args.scheme)
+        threads = threads or (os.cpu_count() or 1)
+        cpu = {"value": rate, "unit": "Mcell-steps/s", "cores": threads, "host_cores": os.cpu_count() or 1,
+               "kind": kind,
                "sample": "%d steps of the same workload on a %dx%d node grid (1/%d of the cells), %.0f ms/step; "
-                         "C/OpenMP + NumPy/pocketfft port of the reference's Numba path"
-                         % (args.cpu_steps, n, n, round((N / n) ** 2), cms)}
+                         % (args.cpu_steps, n, n, round((N / n) ** 2), cms) + CPU_KIND_TEXT[kind] % threads}
+        from oracle import make_ref, rmt_oracle as O
+        M = make_ref.load() if kind == "reference" else O
+        ref_next = cpu_fsi_step(M, cstate, cprm)
+        _, gprm = make_case(n, L=1.0, k_side=8, R_frac=0.04, scheme=args.scheme, bc_kind="lid")
+        up = lambda t: torch.from_numpy(np.ascontiguousarray(t)).cuda()
+        got = fsi_step(tuple(up(t) for t in cstate), dict(gprm, X=None if args.scheme == "weno5" else gprm["X"]))[0]
+        rel, exact = {}, True
+        for nm, g, r in zip(("u", "v", "p", "xi1", "xi2"), got, ref_next):
+            g = g.cpu().numpy()
+            rel[nm] = float(np.max(np.abs(g - r)) / max(np.max(np.abs(r)), 1e-300))
+            if nm.startswith("xi"):
+                exact = exact and bool(np.array_equal(g, r))
+        parity = {"against": "the CPU arm (%s) on the same input state" % kind, "grid": [n, n], "rel_linf": rel,
+                  "max_rel_linf": max(rel.values()), "xi_bit_exact": exact, "tolerance": 1e-10,
+                  "ok": bool(max(rel.values()) <= 1e-10)}
+    elif world > 1 and not args.no_slab:
+        parity = slab_parity_vs_1gpu(1025, args.scheme, rank, world)
 
     if rank == 0:
         line = {"metric": "Mcell-steps/s full FSI step", "value": value, "unit": "Mcell-steps/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": workload_config(N, args.scheme, world),
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "step_roofline": {"alg_bytes_per_cell_step": ALG_BYTES_PER_CELL_STEP.get(args.scheme, 512.0),
                                   "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak},
-                "cpu_baseline": cpu, "kernels": breakdown, "kernels_roofline": kernels_roofline[:8],
+                "cpu_baseline": cpu, "parity": parity, "kernels": breakdown, "kernels_roofline": kernels_roofline[:8],
                 "finite": finite, "slab_fluid_step": slab, "config5_periodic": cfg5}
         print(json.dumps(line))
     if world > 1:

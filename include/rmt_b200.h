@@ -252,6 +252,11 @@ int rmt_poisson_plan_create(int Ny, int Nx, int kind, rmt_poisson_plan **plan);
 void rmt_poisson_plan_destroy(rmt_poisson_plan *plan);
 /* 1 if the plan uses the shared-memory FFT path in both directions, else 0. */
 int rmt_poisson_plan_is_fast(const rmt_poisson_plan *plan);
+/* The fast paths cache tables derived from `eig` (its transpose; the periodic inverse symbol) inside the
+ * plan and rebuild them only when the eig POINTER changes.  A caller that passes a different table at a
+ * recycled address (or edits the table in place) must call this first (pyrmt_b200/_runtime.py keys the
+ * table by content and does). */
+int rmt_poisson_plan_invalidate(rmt_poisson_plan *plan);
 /* sol = idctn(dctn(rhs)/eig), then sol -= mean(sol).  eig: (Ny, Nx).
  * sum_out (device, 1 double): if non-NULL the mean is NOT removed; sum(sol) is
  * written there instead so the consumer (rmt_projection_correct) can fold the

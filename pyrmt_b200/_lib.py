@@ -66,6 +66,7 @@ _SIG = {
     "rmt_poisson_plan_create": [i32, i32, i32, C.POINTER(vp)],
     "rmt_poisson_plan_destroy": [vp],
     "rmt_poisson_plan_is_fast": [vp],
+    "rmt_poisson_plan_invalidate": [vp],
     "rmt_poisson_solve_dct": [vp, vp, vp, vp, vp, vp],
     "rmt_poisson_solve_fft": [vp, vp, vp, vp, vp, vp, vp],
     "rmt_dct_lines": [vp, vp, vp, i32, i32, dbl, vp],

@@ -64,7 +64,7 @@ def shape2(t):
 _LAUNCHES = {"rmt_max_speed": 2, "rmt_field_stats": 2, "rmt_advect_euler_rk3": 3, "rmt_advect_euler_rk3_pair": 3, "rmt_extrapolate": 1, "rmt_extrapolate_rows": 1,
              "rmt_poisson_solve_dct": 4, "rmt_poisson_solve_fft": 16, "rmt_abi_version": 0, "rmt_launch_count": 0, "rmt_diagnostics_workspace_doubles": 0, "rmt_diagnostics": 2,
              "rmt_reduce_workspace_doubles": 0, "rmt_extrapolate_workspace_bytes": 0, "rmt_extrapolate_set_mode": 0, "rmt_extrapolate_last_mode": 0,
-             "rmt_poisson_plan_create": 0, "rmt_poisson_plan_destroy": 0, "rmt_poisson_plan_is_fast": 0}
+             "rmt_poisson_plan_create": 0, "rmt_poisson_plan_destroy": 0, "rmt_poisson_plan_is_fast": 0, "rmt_poisson_plan_invalidate": 0}
 
 
 class Profiler:
@@ -126,6 +126,7 @@ class _Ctx:
         n = self.lib.rmt_reduce_workspace_doubles()
         self.red = torch.empty(n, dtype=F64, device=dev)
         self.plans = {}
+        self.plan_tables = {}  # plan key -> (identity, device tensors, the caller's objects kept alive)
         self.extrap_ws = {}
         self.tables = {}      # id(ndarray) -> (weakref/obj, device tensor)
         self.finite_cache = None
@@ -140,6 +141,42 @@ class _Ctx:
             p = h
             self.plans[key] = p
         return p
+
+    @staticmethod
+    def _table_identity(t):
+        """What makes two eigenvalue tables "the same table" for the plan's derived data: a raw pointer is
+        not enough (allocators recycle addresses, ndarrays can be edited in place)."""
+        if isinstance(t, torch.Tensor):
+            return ("t", t.data_ptr(), t._version, tuple(t.shape), str(t.device), str(t.dtype))
+        a = np.asarray(t)
+        flat = a.reshape(-1)
+        step = max(1, flat.size // 2048)
+        sample = flat[::step]
+        return ("a", id(t), a.shape, a.strides, str(a.dtype), float(np.sum(sample, dtype=np.float64)),
+                float(flat[0]) if flat.size else 0.0, float(flat[-1]) if flat.size else 0.0)
+
+    def plan_with_tables(self, Ny, Nx, kind, tables, dtypes):
+        """The Poisson plan of (Ny, Nx, kind) bound to the caller's eigenvalue table(s): device copies are
+        made once per table identity and kept alive with the plan (their addresses cannot be recycled while
+        the plan's derived tables refer to them); a new identity invalidates the derived tables."""
+        plan = self.plan(Ny, Nx, kind)
+        key = (Ny, Nx, kind)
+        ident = tuple(self._table_identity(t) for t in tables)
+        ent = self.plan_tables.get(key)
+        if ent is None or ent[0] != ident:
+            devs = []
+            for t, dt in zip(tables, dtypes):
+                if isinstance(t, torch.Tensor):
+                    d = t.to(self.dev)
+                    d = (d if d.dtype == dt else d.to(dt)).contiguous()
+                else:
+                    npdt = np.float64 if dt == F64 else np.uint8
+                    d = torch.from_numpy(np.ascontiguousarray(t, dtype=npdt)).to(self.dev)
+                devs.append(d)
+            _lib.check(self.lib.rmt_poisson_plan_invalidate(plan), "rmt_poisson_plan_invalidate")
+            ent = (ident, tuple(devs), tuple(tables))
+            self.plan_tables[key] = ent
+        return plan, ent[1]
 
     def extrap_workspace(self, Ny, Nx):
         key = (Ny, Nx)
@@ -202,15 +239,23 @@ class FiniteCache:
         self.ref = None
 
     def put(self, a, b, ok):
-        self.ref = (weakref.ref(a), a._version, weakref.ref(b), b._version, ok)
+        # identity = the tensor objects, their torch versions AND their storage addresses; kernels that write
+        # through raw pointers (the BC table) do not bump _version, so those call invalidate(), and a verdict
+        # is only served for the guards of ONE step (two advect calls, or one pair call)
+        self.ref = [weakref.ref(a), a._version, weakref.ref(b), b._version, ok, a.data_ptr(), b.data_ptr(), 2]
 
     def get(self, a, b):
         r = self.ref
         if r is None:
             return None
-        if r[0]() is a and r[2]() is b and r[1] == a._version and r[3] == b._version:
+        if (r[0]() is a and r[2]() is b and r[1] == a._version and r[3] == b._version
+                and r[5] == a.data_ptr() and r[6] == b.data_ptr() and r[7] > 0):
+            r[7] -= 1
             return r[4]
         return None
+
+    def invalidate(self):
+        self.ref = None
 
 
 finite_cache = FiniteCache()

@@ -151,6 +151,8 @@ def apply_bc_(bc, u, v):
     Ny, Nx = u.shape
     table = table_for(bc, Ny, Nx)
     if table is not None:
+        from ._runtime import finite_cache
+        finite_cache.invalidate()        # in-place write through raw pointers: torch's _version does not see it
         table.apply_(u, v)
         return u, v
     # slow path: honour the arbitrary callable on the host

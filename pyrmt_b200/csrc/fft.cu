@@ -773,6 +773,16 @@ void rmt_poisson_plan_destroy(rmt_poisson_plan *P)
 
 int rmt_poisson_plan_is_fast(const rmt_poisson_plan *P) { return (P && P->fast) ? 1 : 0; }
 
+// The plan keeps tables DERIVED from the caller's eigenvalue table (its transpose / inverse symbol).  A raw
+// device pointer is not an identity (allocators recycle addresses), so the owner of the table says when it
+// changed: the derived tables are rebuilt on the next solve.
+int rmt_poisson_plan_invalidate(rmt_poisson_plan *P)
+{
+    if (!P) return RMT_EINVAL;
+    P->eig_src = nullptr;
+    return RMT_OK;
+}
+
 // ---- building blocks of the slab-decomposed (multi-GPU) DCT solve ------------------------
 // DCT-I along the rows of a (nrows, N) array, N - 1 a power of two in [8, 8192].
 //   eig == NULL: out = scale * DCT-I(in);   eig != NULL: out = DCT-I(DCT-I(in) * scale / eig).

@@ -580,11 +580,11 @@ def _solve_poisson_dct(rhs_2d, eigenvalues):
     rd = to_dev(rhs_2d)
     Ny, Nx = shape2(rd)
     c = ctx()
-    eig = c.table(eigenvalues)
-    if tuple(eig.shape) != (Ny, Nx):
-        raise ValueError("eigenvalues shape %s does not match the grid %s" % (tuple(eig.shape), (Ny, Nx)))
+    if tuple(np.shape(eigenvalues)) != (Ny, Nx):
+        raise ValueError("eigenvalues shape %s does not match the grid %s" % (tuple(np.shape(eigenvalues)), (Ny, Nx)))
+    plan, (eig,) = c.plan_with_tables(Ny, Nx, 0, (eigenvalues,), (F64,))
     sol = torch.empty_like(rd)
-    _chk(c.lib.rmt_poisson_solve_dct(c.plan(Ny, Nx, 0), ptr(rd), ptr(eig), ptr(sol), None, stream()),
+    _chk(c.lib.rmt_poisson_solve_dct(plan, ptr(rd), ptr(eig), ptr(sol), None, stream()),
          "rmt_poisson_solve_dct")
     return to_user(sol, as_np)
 
@@ -623,13 +623,12 @@ def _solve_poisson_fft(rhs_full, eigenvalues_periodic):
     Ny, Nx = shape2(rd)
     c = ctx()
     eig_h, null_h = eigenvalues_periodic
-    eig = c.table(eig_h)
-    null = c.table(null_h, torch.uint8)
-    if tuple(eig.shape) != (Ny - 1, Nx - 1):
+    if tuple(np.shape(eig_h)) != (Ny - 1, Nx - 1):
         raise ValueError("periodic eigenvalues shape %s does not match the reduced grid %s"
-                         % (tuple(eig.shape), (Ny - 1, Nx - 1)))
+                         % (tuple(np.shape(eig_h)), (Ny - 1, Nx - 1)))
+    plan, (eig, null) = c.plan_with_tables(Ny, Nx, 1, (eig_h, null_h), (F64, torch.uint8))
     sol = torch.empty_like(rd)
-    _chk(c.lib.rmt_poisson_solve_fft(c.plan(Ny, Nx, 1), ptr(rd), ptr(eig), ptr(null), ptr(sol), None,
+    _chk(c.lib.rmt_poisson_solve_fft(plan, ptr(rd), ptr(eig), ptr(null), ptr(sol), None,
                                      stream()), "rmt_poisson_solve_fft")
     return to_user(sol, as_np)
 
@@ -692,17 +691,17 @@ def pressure_projection_amg(a_star, b_star, dx, dy, dt, rho, velocity_bc, A=None
     ssum = torch.empty(4, dtype=F64, device=ad.device)
     if periodic:
         eig_h, null_h = eigenvalues
-        eig, null = c.table(eig_h), c.table(null_h, torch.uint8)
-        if tuple(eig.shape) != (Ny - 1, Nx - 1):
+        if tuple(np.shape(eig_h)) != (Ny - 1, Nx - 1):
             raise ValueError("periodic eigenvalues do not match the reduced grid")
-        _chk(lib.rmt_poisson_solve_fft(c.plan(Ny, Nx, 1), ptr(rhs), ptr(eig), ptr(null), ptr(sol), ptr(ssum),
+        plan, (eig, null) = c.plan_with_tables(Ny, Nx, 1, (eig_h, null_h), (F64, torch.uint8))
+        _chk(lib.rmt_poisson_solve_fft(plan, ptr(rhs), ptr(eig), ptr(null), ptr(sol), ptr(ssum),
                                        st), "rmt_poisson_solve_fft")
     else:
-        eig = c.table(eigenvalues)
-        if tuple(eig.shape) != (Ny, Nx):
+        if tuple(np.shape(eigenvalues)) != (Ny, Nx):
             raise ValueError("eigenvalues shape %s does not match the grid %s"
-                             % (tuple(eig.shape), (Ny, Nx)))
-        _chk(lib.rmt_poisson_solve_dct(c.plan(Ny, Nx, 0), ptr(rhs), ptr(eig), ptr(sol), ptr(ssum), st),
+                             % (tuple(np.shape(eigenvalues)), (Ny, Nx)))
+        plan, (eig,) = c.plan_with_tables(Ny, Nx, 0, (eigenvalues,), (F64,))
+        _chk(lib.rmt_poisson_solve_dct(plan, ptr(rhs), ptr(eig), ptr(sol), ptr(ssum), st),
              "rmt_poisson_solve_dct")
     a, b, p = torch.empty_like(ad), torch.empty_like(ad), torch.empty_like(ad)
     _chk(lib.rmt_projection_correct(ptr(sol), ptr(ssum), ptr(ad), ptr(bd), ptr(rd), rscalar, ptr(pp), ptr(a),

@@ -154,8 +154,18 @@ class Comm:
 
     def allreduce(self, t, op="sum"):
         if self.world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX, group=self.group)
+            red = {"sum": dist.ReduceOp.SUM, "max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN}[op]
+            dist.all_reduce(t, op=red, group=self.group)
         return t
+
+    def all_agree(self, flags):
+        """Per-rank verdicts (sequence of bools, True = fine) -> the verdicts of the WHOLE job (logical and
+        over the ranks), so that every rank raises together instead of one rank raising while the others
+        walk into the next collective and hang."""
+        t = torch.tensor([1.0 if f else 0.0 for f in flags], dtype=F64,
+                         device="cuda" if (self.nccl or not self.on) and torch.cuda.is_available() else "cpu")
+        self.allreduce(t, "min")
+        return [bool(x > 0.5) for x in t.tolist()]
 
 
 # ------------------------------------------------------------------- device line ops
@@ -431,15 +441,32 @@ class SlabFluidSolver:
         self.comm.halo_exchange(self.lay, (u, v))
 
     def max_speed(self, a, b):
+        """[max sqrt(a^2 + b^2), #non-finite] over the whole grid (device tensor; all-reduced: both entries
+        are non-negative and only '== 0' matters for the second, so one MAX does for both)."""
         lay = self.lay
         out = ctx().max_speed(lay.owned(a), lay.owned(b))
-        return self.comm.allreduce(out[:1].clone(), "max")
+        return self.comm.allreduce(out.clone(), "max")
+
+    def velocity_is_finite(self, a, b):
+        """The guard of advect_reference_map (functions.py:524-526) for the whole grid: the same verdict on
+        every rank (cached for the step, as on one GPU)."""
+        from ._runtime import finite_cache
+        hit = finite_cache.get(a, b)
+        if hit is None:
+            hit = float(self.max_speed(a, b)[1].item()) == 0.0
+        finite_cache.put(a, b, hit)
+        return hit
 
     def compute_timestep(self, a, b, prm):
         """compute_timestep (functions.py:165-192) of the whole grid: max speed over the owned rows,
         all-reduced on the device, ONE host read, then the reference's formula."""
         from . import functions as F
-        speed = float(self.max_speed(a, b).item())
+        from ._runtime import finite_cache
+        out = self.max_speed(a, b).cpu()
+        speed, bad = float(out[0]), float(out[1])
+        finite_cache.put(a, b, bad == 0.0)           # the step's finite guard is answered by the same reduction
+        if bad:
+            speed = float("nan")
         return F.timestep_from_speed(speed, prm["dx"], prm["dy"], prm["CFL"], prm["dt_cap"], prm["mu_s"],
                                      prm["rho_s"], prm.get("gamma", 0.0), prm["rho_f"], prm["mu_f"],
                                      prm["eta_s"], prm["kappa"])
@@ -471,12 +498,28 @@ class SlabFluidSolver:
         return un, vn, sxx, sxy, syy, J
 
     # -- functions.py:1255-1364 (Neumann, constant density) ---------------------------------
-    def projection(self, a_star, b_star, p_prev, rho, dx, dy, dt):
+    def _require_constant_density(self, rho):
+        """np.ptp(rho) > 1e-10 selects the variable-density branch upstream (functions.py:1298), which is
+        out of scope: raise on EVERY rank (min / max all-reduced) instead of silently treating it as
+        constant."""
+        st4 = ctx().stats(self.lay.owned(rho).contiguous())
+        ext = torch.stack((-st4[1], st4[2]))
+        self.comm.allreduce(ext, "max")
+        lo, hi = (float(x) for x in ext.cpu())
+        if hi + lo > 1e-10:
+            raise NotImplementedError(
+                "variable-density projection (np.ptp(rho) > 1e-10) is out of scope for the B200 path")
+
+    def projection(self, a_star, b_star, p_prev, rho, dx, dy, dt, density_checked=False):
+        """``density_checked``: the caller knows rho is constant (rho_s == rho_f), so the ptp test -- one
+        all-reduce and one host read per call -- is skipped."""
         if self.lay.periodic:
             return self.projection_periodic(a_star, b_star, p_prev, rho, dx, dy, dt)
         lay, lib, st, comm = self.lay, self.lib, stream(), self.comm
         nl, Nx, ncell = lay.nl, lay.Nx, lay.Ny * lay.Nx
         if isinstance(rho, torch.Tensor):
+            if not density_checked:
+                self._require_constant_density(rho)
             rsum = comm.allreduce(self.ops.sum(lay.owned(rho)))
             rd, rscalar = rho, 0.0
         else:
@@ -648,11 +691,15 @@ class SlabFSISolver(SlabFluidSolver):
         # stencils inside the stored rows
         Y0 = prm.get("X"), prm.get("Y")
         slab = None
+        # Every verdict that can stop the step is formed for the WHOLE job (all-reduced) before anything is
+        # raised: a rank-local raise would leave the other ranks blocked in the next NCCL exchange.
+        if not self.velocity_is_finite(a, b):                      # functions.py:524-526
+            raise FloatingPointError("advect_reference_map: non-finite velocity (the simulation diverged)")
         if prm["scheme"].startswith("semilagrangian"):
             if Y0[0] is None or tuple(Y0[0].shape) != tuple(a.shape):
                 raise ValueError("semi-Lagrangian advection on slabs needs prm['X'], prm['Y'] as extended slabs")
             if check_guard:
-                reach = float(self.max_speed(a, b).item()) * dt / min(dx, dy) + 3.0
+                reach = float(self.max_speed(a, b)[0].item()) * dt / min(dx, dy) + 3.0   # all-reduced: same on all ranks
                 if reach > lay.H:
                     raise RuntimeError("slab advection: departure points reach %.1f rows, halo is %d" % (reach, lay.H))
             slab = (lay.Ny, lay.e0)
@@ -661,9 +708,11 @@ class SlabFSISolver(SlabFluidSolver):
         self._dbg("advected", X1, X2, phi)
         # extrapolation on [r0 - top, r1 + bot): the bodies reaching into this slab, from their first row
         B1, B2, Bphi = self._gather_big((X1, X2, phi))
-        if check_guard and not self.guard(Bphi, dx, dy):
-            raise RuntimeError("slab extrapolation: a body reaches above the %d-row overlap of rank %d; "
-                               "increase `overlap`" % (self.top, lay.rank))
+        if check_guard:
+            (ok,) = comm.all_agree([self.guard(Bphi, dx, dy)])
+            if not ok:
+                raise RuntimeError("slab extrapolation: a body reaches above the %d-row overlap of some rank "
+                                   "(this is rank %d); increase `overlap`" % (self.top, lay.rank))
         E1, E2 = F.extrapolate_reference_map(B1, B2, Bphi, dx, dy, self.layers, row_offset=lay.r0 - self.top)
         self._dbg("extrapolated", E1, E2)
         n_own = lay.r1 - lay.r0
@@ -678,7 +727,9 @@ class SlabFSISolver(SlabFluidSolver):
                                           dt, prm["rho_s"], prm["rho_f"], prm["mu_f"], prm["w_t"])
         self._dbg("predictor", a_s, b_s)
         _, rho_local = F.heaviside_and_density(phi, prm["w_t"], prm["rho_s"], prm["rho_f"])
-        a, b, p = self.projection(a_s, b_s, p, rho_local, dx, dy, dt)
+        # rho_local = (1 - H) rho_s + H rho_f is constant iff rho_s == rho_f (known on the host: no device test)
+        a, b, p = self.projection(a_s, b_s, p, rho_local, dx, dy, dt,
+                                  density_checked=(float(prm["rho_s"]) == float(prm["rho_f"])))
         self._dbg("projected", a, b, p)
         return (a, b, p, X1n, X2n)
 
@@ -757,8 +808,9 @@ def time_periodic_fsi(N, world, rank, steps=5, warmup=3, L=None, overlap=512, sc
     solver = SlabFSISolver(lay, PeriodicBC(), None, sdf, overlap=overlap, layers=3, spacing=(h, h))
     box = {"state": None}
     box["state"], dx, dy = slab_initial_state(solver, L, sdf, taylor_green(L))
+    Xs, Ys = solver.coords if scheme.startswith("semilagrangian") else (None, None)
     prm = dict(dx=dx, dy=dy, mu_s=1.0, kappa=0.0, rho_s=1.0, rho_f=1.0, eta_s=0.0, mu_f=1e-3, w_t=2 * dx,
-               scheme=scheme, w_cut=0.0, X=None, Y=None)
+               scheme=scheme, w_cut=0.0, X=Xs, Y=Ys)
     dt = min(0.2 * dx / np.sqrt(4.0 / 3.0), 0.2 * dx * dx / (4 * 1e-3), 1e-4)     # compute_timestep at rest
     guard = {"on": True}
 
@@ -769,13 +821,16 @@ def time_periodic_fsi(N, world, rank, steps=5, warmup=3, L=None, overlap=512, sc
     guard["on"] = False
     ms = _timed(step, steps, max(warmup - 1, 0), solver.comm)
     st = box["state"]
+    xi_max = torch.stack((lay.owned(st[3]).abs().max(), lay.owned(st[4]).abs().max())).max().reshape(1)
+    solver.comm.allreduce(xi_max, "max")                   # over the whole grid, not this rank's slab
+    fin = solver.comm.all_agree([all(torch.isfinite(t).all().item() for t in st)])[0]
     return {"what": "periodic Taylor-Green multi-disc FSI step (%s + SSP-RK3, 3-layer extrapolation, RK4 momentum, "
                     "periodic FFT projection), y-slabs over %d GPUs: NCCL halo / wrap exchange + two all-to-all "
                     "transposes per solve; strong scaling of one %dx%d grid" % (scheme, world, N, N),
             "grid": [N, N], "L": L, "discs": int(cx.size), "dt": dt, "ms_per_step": ms,
             "value": N * N / ms / 1e3, "unit": "Mcell-steps/s",
-            "finite": bool(all(torch.isfinite(t).all().item() for t in st)),
-            "max_abs_xi": float(max(st[3].abs().max(), st[4].abs().max()).item()),
+            "finite": bool(fin),
+            "max_abs_xi": float(xi_max.item()),
             "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}
 
 

@@ -139,6 +139,46 @@ def test_extrapolation_bit_exact_oracle(P, O, ext_mode, N, L, layers, variant, c
     assert same(r1, o1) and same(r2, o2), (variant, ran)
 
 
+@pytest.mark.parametrize("L,row_offset", [(128.0, 16000), (1.0, 0)])
+def test_extrapolation_large_row_offset_matches_oracle(P, O, L, row_offset):
+    """Pins DESIGN.md 6 ("the full FSI step is ill-posed at 16385^2 in the reference's own formulation"):
+    the least-squares fit forms its normal equations in ABSOLUTE coordinates (functions.py:105-150), so
+    (a) at grid index ~16000 with dx = 1/128 the 3x3 determinant is a difference of huge terms and the
+        fitted values are dominated by rounding noise -- the ORACLE produces that noise on a window of rows
+        [16000, 16000+257) of a 16385-row grid, and the CUDA kernel (rmt_extrapolate_rows with the same
+        row_offset) must reproduce it BIT FOR BIT, garbage included;
+    (b) on the unit box at dx = 1/16384 the absolute gate |det| > 1e-10 (functions.py:155) rejects every
+        target in both: xi stays unextrapolated.
+    Either way the kernel at large row_offset is pinned to the reference, so the substitution in bench.py's
+    config 5 (FSI at 8193^2, fluid half at 16385^2) is a property of the reference, not of the kernel."""
+    Ng, n = 16385, 257                                     # the global grid; the window of rows / columns
+    dx = dy = L / (Ng - 1)
+    j0 = row_offset
+    xg = np.linspace(0.0, L, Ng)                           # create_grid's node coordinates (functions.py:25-31)
+    Xw, Yw = np.meshgrid(xg[:n], xg[j0:j0 + n])            # rows [j0, j0 + n), columns [0, n)
+    cxw, cyw, R = Xw[0, n // 2], Yw[n // 2, 0], 70 * dx
+    phi = np.sqrt((Xw - cxw) ** 2 + (Yw - cyw) ** 2) - R
+    m = (phi <= 0).astype(float)
+    X1, X2 = Xw * m, Yw * m
+    # the oracle runs the reference's algorithm unmodified on a grid that holds the window at its true rows
+    # (rows 0..j0-1 are far outside every body: phi > 0, nothing known, nothing fitted there)
+    tall = lambda w, fill: np.concatenate([np.full((j0, n), fill), w], axis=0)
+    t1, t2 = O.extrapolate_reference_map(tall(X1, 0.0), tall(X2, 0.0), tall(phi, 1.0), dx, dy, 3)
+    o1, o2 = t1[j0:], t2[j0:]
+    assert not (t1[:j0] != 0).any() and not (t2[:j0] != 0).any()
+    g1, g2 = P.extrapolate_reference_map(X1, X2, phi, dx, dy, 3, row_offset=j0)
+    assert same(g1, o1) and same(g2, o2)
+    band = (phi > 0) & (phi < 2.5 * dx)
+    changed = (o1 != X1) | (o2 != X2)
+    if L == 1.0:
+        assert not changed.any(), "unit box at dx = 1/16384: the |det| > 1e-10 gate must reject every target"
+    else:
+        assert changed[band].any()
+        err = np.max(np.abs(o2[band] - Yw[band])) / dy    # exact for a linear field in exact arithmetic
+        print("LSQ error of a LINEAR field at row ~%d, dx = 1/128: %.3g cells" % (j0, err))
+        assert err > 1e-2, "the absolute-coordinate fit was expected to be visibly noisy at index ~16000"
+
+
 def test_extrapolation_linear_exact(P):
     # tests/test_interp_extrap_energy.py:39-56 of the reference
     N = 65
@@ -516,6 +556,32 @@ def test_dct_solve_vs_oracle(P, O, N):
     from pyrmt_b200._runtime import ctx
     assert ctx().lib.rmt_poisson_plan_is_fast(ctx().plan(N, N, 0)) == 1
     assert rel_linf(P._solve_poisson_dct(rhs, eig), O._solve_poisson_dct(rhs, eig)) < 1e-11
+
+
+def test_dct_solve_same_grid_new_table(P, O):
+    """the plan caches the TRANSPOSED eigenvalue table.  A second table for the same grid
+    (other dx; possibly at a recycled device address) and an in-place edit of a table must both be seen."""
+    import gc
+    import torch
+    N = 257
+    rng = np.random.default_rng(11)
+    rhs = rng.standard_normal((N, N))
+    rhs -= rhs.mean()
+    for dx in (1.0 / (N - 1), 3.0 / (N - 1), 0.25 / (N - 1)):
+        eig = O._precompute_poisson_eigenvalues(N, N, dx, 2 * dx)
+        assert rel_linf(P._solve_poisson_dct(rhs, eig), O._solve_poisson_dct(rhs, eig)) < 1e-11, dx
+        del eig
+        gc.collect()
+        torch.cuda.empty_cache()
+    eig = O._precompute_poisson_eigenvalues(N, N, 1.0 / (N - 1), 1.0 / (N - 1))
+    assert rel_linf(P._solve_poisson_dct(rhs, eig), O._solve_poisson_dct(rhs, eig)) < 1e-11
+    eig *= 1.7                                             # same ndarray object, new contents
+    assert rel_linf(P._solve_poisson_dct(rhs, eig), O._solve_poisson_dct(rhs, eig)) < 1e-11
+    et = torch.from_numpy(eig).cuda()                      # device tensor input, then edited in place
+    rt = torch.from_numpy(rhs).cuda()
+    assert rel_linf(P._solve_poisson_dct(rt, et).cpu().numpy(), O._solve_poisson_dct(rhs, eig)) < 1e-11
+    et.mul_(0.5)
+    assert rel_linf(P._solve_poisson_dct(rt, et).cpu().numpy(), O._solve_poisson_dct(rhs, 0.5 * eig)) < 1e-11
 
 
 def test_dct_nonsquare_vs_oracle(P, O):

@@ -130,7 +130,10 @@ def _worker(rank, world, port, Ny, Nx, out):
         sol = sol.numpy() - float(total) / (Ny * Nx)
         err = float(np.max(np.abs(sol - ref[lay.r0:lay.r1])) / np.max(np.abs(ref)))
         mx = comm.allreduce(torch.tensor([float(rank + 3)]), "max")
-        out[rank] = (ok_halo, err, float(mx))
+        # collective verdicts: one rank's failure must become every rank's verdict
+        agree = comm.all_agree([True, rank != world - 1, rank != 0])
+        mn = comm.allreduce(torch.tensor([float(rank + 3)]), "min")
+        out[rank] = (ok_halo, err, float(mx), agree, float(mn))
     finally:
         dist.destroy_process_group()
 
@@ -148,10 +151,11 @@ def test_halo_exchange_and_distributed_dct_gloo(world, Ny, Nx):
             p.join(120)
             assert p.exitcode == 0
         for r in range(world):
-            ok_halo, err, mx = out[r]
+            ok_halo, err, mx, agree, mn = out[r]
             assert ok_halo, "halo exchange wrong on rank %d" % r
             assert err < 1e-12, (r, err)
-            assert mx == world + 2
+            assert mx == world + 2 and mn == 3.0
+            assert agree == [True, False, False], "rank %d would not raise with the others" % r
 
 
 def test_periodic_layout():
