@@ -247,15 +247,13 @@ struct EulerFields {      // up to two transported fields that share (a, b, phi)
     double *out[2];
 };
 
+// One node of a stage, any scheme, any position (rim fallbacks included): the generic path.
 template <int SCHEME, int NQ>
-__global__ void __launch_bounds__(256, 4)
-k_euler_stage(const EulerFields F, const double *__restrict__ a, const double *__restrict__ b,
-              const double *__restrict__ phi, int Ny, int Nx, double dx, double dy, double dt,
-              double w_cut, double c0, double c1, int first, int mask_solid)
+__device__ __forceinline__ void euler_cell(const EulerFields &F, const double *__restrict__ a,
+                                           const double *__restrict__ b, const double *__restrict__ phi, int j,
+                                           int i, int Ny, int Nx, double dx, double dy, double dt, double w_cut,
+                                           double c0, double c1, int first, int mask_solid)
 {
-    int i = blockIdx.x * TX + threadIdx.x;
-    int j = blockIdx.y * TY + threadIdx.y;
-    if (i >= Nx || j >= Ny) return;
     size_t c = (size_t)j * Nx + i;
     const int halo = (SCHEME == 1) ? 2 : 1;
     const bool interior = (i >= halo && i < Nx - halo && j >= halo && j < Ny - halo);
@@ -292,6 +290,277 @@ k_euler_stage(const EulerFields F, const double *__restrict__ a, const double *_
         const double upd = qc + dt * rhs;
         const double r = first ? upd : (c0 * F.q0[f][c] + c1 * upd);
         F.out[f][c] = mask_solid ? r * m : r;
+    }
+}
+
+template <int SCHEME, int NQ>
+__global__ void __launch_bounds__(256, 4)
+k_euler_stage(const EulerFields F, const double *__restrict__ a, const double *__restrict__ b,
+              const double *__restrict__ phi, int Ny, int Nx, double dx, double dy, double dt,
+              double w_cut, double c0, double c1, int first, int mask_solid)
+{
+    int i = blockIdx.x * TX + threadIdx.x;
+    int j = blockIdx.y * TY + threadIdx.y;
+    if (i >= Nx || j >= Ny) return;
+    euler_cell<SCHEME, NQ>(F, a, b, phi, j, i, Ny, Nx, dx, dy, dt, w_cut, c0, c1, first, mask_solid);
+}
+
+// ------------------------------------------------------- WENO5, active chunks only
+// The reference's RHS is zero wherever phi > w_cut (functions.py:341 `continue`), which is ~2/3 of
+// the grid in the multi-body cases, so the WENO5 path works on CHUNKS of 31 columns x 16 rows:
+//   * k_weno_classify / k_weno_lists sort the chunks into NEAR (an active node within 3 nodes of
+//     the chunk: some active node's stencil can read it) and FAR, once per call;
+//   * stages 1 and 2 touch near chunks only; nothing ever reads their output in a far chunk;
+//   * stage 3 computes near chunks and writes far chunks from q directly (a far node's three
+//     stage values are pointwise functions of q: RHS == 0 in every stage) -- the same expression
+//     tree, so the result is what the node-by-node kernel writes, bit for bit.
+// A near chunk is walked by ONE WARP, top to bottom, lane l on column x0 - 1 + l (lane 0 is a
+// helper column).  Both left-biased face values of a node are the same function
+//     Fm(k) = weno_minus(q[k-2 .. k+2])          (functions.py:256-286)
+// at k and k-1 (functions.py:352-366), so each Fm is evaluated ONCE: along y it is carried
+// from the previous row in a register (the five-row window of q lives in registers, one new
+// row loaded per step), along x it comes from the left lane by a shuffle.  That halves the fp64
+// work (the IEEE divisions of the nonlinear weights dominate this kernel) without changing a
+// bit of the result.  Chunks that touch the rim of the grid take the generic node-by-node code.
+constexpr int CW = 31, CH = 16;
+struct WenoLists {
+    int *summary;        // per chunk: classification bits (k_weno_classify)
+    int *near_list;      // chunk ids, bit 30 set: no node with phi <= 0 in the chunk
+    int *far_list;
+    int *counters;       // [0] near, [1] far, [2..4] work tickets of the three stages
+};
+
+__global__ void __launch_bounds__(256)
+k_weno_classify(const double *__restrict__ phi, WenoLists W, int Ny, int Nx, int ncx, int ncy, double w_cut)
+{
+    if (blockIdx.x == 0 && threadIdx.x < 8) W.counters[threadIdx.x] = 0;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int ch = warp; ch < ncx * ncy; ch += nwarp) {
+        const int ty = ch / ncx, tx = ch - ty * ncx;
+        const int x0 = tx * CW, y0 = ty * CH;
+        const int i = x0 + lane;
+        const bool colok = lane < CW && i < Nx;
+        const int h = min(CH, Ny - y0), wdt = min(CW, Nx - x0);
+        unsigned any = 0, top = 0, bot = 0, neg = 0;
+        if (colok) {
+            const bool ci = i >= 2 && i < Nx - 2;
+            for (int r = 0; r < h; ++r) {
+                const int j = y0 + r;
+                const double ph = __ldg(phi + (size_t)j * Nx + i);
+                const bool act = ci && j >= 2 && j < Ny - 2 && !(ph > w_cut);
+                any |= act;
+                top |= act && r < 3;
+                bot |= act && r >= h - 3;
+                neg |= (ph <= 0.0);
+            }
+        }
+        const unsigned many = __ballot_sync(0xffffffffu, any), mtop = __ballot_sync(0xffffffffu, top),
+                       mbot = __ballot_sync(0xffffffffu, bot), mneg = __ballot_sync(0xffffffffu, neg);
+        const unsigned L3 = 7u, R3 = 7u << (wdt >= 3 ? wdt - 3 : 0);
+        int bits = 0;
+        bits |= (many != 0) << 0;
+        bits |= (mtop != 0) << 1;
+        bits |= (mbot != 0) << 2;
+        bits |= ((many & L3) != 0) << 3;
+        bits |= ((many & R3) != 0) << 4;
+        bits |= ((mtop & L3) != 0) << 5;
+        bits |= ((mtop & R3) != 0) << 6;
+        bits |= ((mbot & L3) != 0) << 7;
+        bits |= ((mbot & R3) != 0) << 8;
+        bits |= (mneg != 0) << 9;
+        if (lane == 0) W.summary[ch] = bits;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_weno_lists(WenoLists W, int ncx, int ncy)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool valid = ch < ncx * ncy, near = false;
+    int own = 0;
+    if (valid) {
+        const int ty = ch / ncx, tx = ch - ty * ncx;
+        own = W.summary[ch];
+        auto S = [&](int yy, int xx) { return (yy >= 0 && yy < ncy && xx >= 0 && xx < ncx) ? W.summary[yy * ncx + xx] : 0; };
+        near = (own & 1) | ((S(ty - 1, tx) >> 2) & 1) | ((S(ty + 1, tx) >> 1) & 1) | ((S(ty, tx - 1) >> 4) & 1) |
+               ((S(ty, tx + 1) >> 3) & 1) | ((S(ty - 1, tx - 1) >> 8) & 1) | ((S(ty - 1, tx + 1) >> 7) & 1) |
+               ((S(ty + 1, tx - 1) >> 6) & 1) | ((S(ty + 1, tx + 1) >> 5) & 1);
+    }
+    const int entry = ch | (((own >> 9) & 1) ? 0 : (1 << 30));
+    const unsigned mn = __ballot_sync(0xffffffffu, valid && near), mf = __ballot_sync(0xffffffffu, valid && !near);
+    int bn = 0, bf = 0;
+    if (lane == 0) {
+        if (mn) bn = atomicAdd(&W.counters[0], __popc(mn));
+        if (mf) bf = atomicAdd(&W.counters[1], __popc(mf));
+    }
+    bn = __shfl_sync(0xffffffffu, bn, 0);
+    bf = __shfl_sync(0xffffffffu, bf, 0);
+    const unsigned lt = (1u << lane) - 1u;
+    if (valid && near) W.near_list[bn + __popc(mn & lt)] = entry;
+    if (valid && !near) W.far_list[bf + __popc(mf & lt)] = entry;
+}
+
+__device__ __forceinline__ bool weno_tame(double v) { return fabs(v) < 1e60; }
+
+template <int NQ>
+__device__ __forceinline__ void weno_chunk_fast(const EulerFields &F, const double *__restrict__ a,
+                                                const double *__restrict__ b, const double *__restrict__ phi,
+                                                int x0, int y0, int Nx, double dx, double dy, double dt,
+                                                double w_cut, double c0, double c1, int first, int mask_solid,
+                                                int lane)
+{
+    const int i = x0 - 1 + lane;
+    const bool outl = lane >= 1;                          // lane 0: helper column x0 - 1
+    double w[NQ][5];                                      // q on rows j-2 .. j+2 of this column
+    double fprev[NQ];                                     // Fm_y(j-1)
+    int j = y0 - 1;
+#pragma unroll
+    for (int f = 0; f < NQ; ++f) {
+        fprev[f] = 0.0;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) w[f][r] = __ldg(F.qs[f] + (size_t)(j - 2 + r) * Nx + i);
+    }
+    // scalars of the row below the current one are fetched one step ahead
+    size_t cn = (size_t)y0 * Nx + i;
+    double ph_n = __ldg(phi + cn), u_n = __ldg(a + cn), v_n = __ldg(b + cn);
+    double ph_c = 0.0, u_c = 0.0, v_c = 0.0;
+    bool act_c = false;
+    for (; j < y0 + CH; ++j) {
+        const bool more = j + 1 < y0 + CH;
+        const bool act_n = more && outl && !(ph_n > w_cut);
+        const bool needy_c = act_c && v_c >= 0.0, needy_n = act_n && v_n >= 0.0;
+        double wn[NQ];
+#pragma unroll
+        for (int f = 0; f < NQ; ++f) wn[f] = __ldg(F.qs[f] + (size_t)(j + 3) * Nx + i);
+        const double ph_k = ph_n, u_k = u_n, v_k = v_n;   // row j+1, becomes current next step
+        if (j + 2 < y0 + CH) {
+            cn += Nx;
+            ph_n = __ldg(phi + cn); u_n = __ldg(a + cn); v_n = __ldg(b + cn);
+        }
+        double fy[NQ];
+        if (needy_c || needy_n) {
+#pragma unroll
+            for (int f = 0; f < NQ; ++f) fy[f] = weno_minus(w[f][0], w[f][1], w[f][2], w[f][3], w[f][4]);
+        } else {
+#pragma unroll
+            for (int f = 0; f < NQ; ++f) fy[f] = 0.0;
+        }
+        if (j >= y0) {                                    // warp-uniform
+            const size_t c = (size_t)j * Nx + i;
+            const bool needx = act_c && u_c >= 0.0;
+            const bool needx_r = __shfl_down_sync(0xffffffffu, (int)needx, 1) && lane < 31;
+            double xl[NQ][5];                             // q[j][i-2], [i-1], [i+1], [i+2], [i+3]
+            if (act_c || needx_r) {
+#pragma unroll
+                for (int f = 0; f < NQ; ++f) {
+                    const double *r = F.qs[f] + c;
+                    xl[f][0] = __ldg(r - 2); xl[f][1] = __ldg(r - 1); xl[f][2] = __ldg(r + 1);
+                    xl[f][3] = __ldg(r + 2); xl[f][4] = __ldg(r + 3);
+                }
+            }
+            double fx[NQ];
+            if (needx || needx_r) {
+#pragma unroll
+                for (int f = 0; f < NQ; ++f) fx[f] = weno_minus(xl[f][0], xl[f][1], w[f][2], xl[f][2], xl[f][3]);
+            } else {
+#pragma unroll
+                for (int f = 0; f < NQ; ++f) fx[f] = 0.0;
+            }
+            const double m = (mask_solid && !(ph_c <= 0.0)) ? 0.0 : 1.0;
+#pragma unroll
+            for (int f = 0; f < NQ; ++f) {
+                const double fxm = __shfl_up_sync(0xffffffffu, fx[f], 1);
+                double rhs = 0.0;
+                if (act_c) {
+                    double dqdx, dqdy;
+                    if (u_c >= 0.0) {
+                        dqdx = (fx[f] - fxm) / dx;
+                    } else if (weno_tame(xl[f][1]) && weno_tame(w[f][2]) && weno_tame(xl[f][2]) &&
+                               weno_tame(xl[f][3]) && weno_tame(xl[f][4])) {
+                        dqdx = 0.0;                      // both faces see the same five points (functions.py:367-376)
+                    } else {
+                        const double qp = weno_plus(xl[f][1], w[f][2], xl[f][2], xl[f][3], xl[f][4]);
+                        dqdx = (qp - qp) / dx;
+                    }
+                    if (v_c >= 0.0) {
+                        dqdy = (fy[f] - fprev[f]) / dy;
+                    } else if (weno_tame(w[f][1]) && weno_tame(w[f][2]) && weno_tame(w[f][3]) &&
+                               weno_tame(w[f][4]) && weno_tame(wn[f])) {
+                        dqdy = 0.0;
+                    } else {
+                        const double qp = weno_plus(w[f][1], w[f][2], w[f][3], w[f][4], wn[f]);
+                        dqdy = (qp - qp) / dy;
+                    }
+                    rhs = -(u_c * dqdx + v_c * dqdy);
+                }
+                if (outl) {
+                    const double upd = w[f][2] + dt * rhs;
+                    const double r = first ? upd : (c0 * __ldg(F.q0[f] + c) + c1 * upd);
+                    F.out[f][c] = mask_solid ? r * m : r;
+                }
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < NQ; ++f) {
+            w[f][0] = w[f][1]; w[f][1] = w[f][2]; w[f][2] = w[f][3]; w[f][3] = w[f][4]; w[f][4] = wn[f];
+            fprev[f] = fy[f];
+        }
+        ph_c = ph_k; u_c = u_k; v_c = v_k; act_c = act_n;
+    }
+}
+
+// stage: 0, 1, 2.  Near chunks are computed; far chunks are written by the last stage only.
+template <int NQ>
+__global__ void __launch_bounds__(256, 2)
+k_weno_stage(const EulerFields F, const double *__restrict__ a, const double *__restrict__ b,
+             const double *__restrict__ phi, WenoLists W, int stage, int Ny, int Nx, int ncx, double dx,
+             double dy, double dt, double w_cut, double c0, double c1, int mask_solid)
+{
+    const int lane = threadIdx.x & 31;
+    const int nnear = W.counters[0], nfar = (stage == 2) ? W.counters[1] : 0;
+    const int first = stage == 0;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&W.counters[2 + stage], 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= nnear + nfar) break;
+        const bool far = t >= nnear;
+        const int e = far ? W.far_list[t - nnear] : W.near_list[t];
+        const int ch = e & ((1 << 30) - 1);
+        const int ty = ch / ncx, tx = ch - ty * ncx;
+        const int x0 = tx * CW, y0 = ty * CH;
+        const int i = x0 - 1 + lane;
+        if (far) {
+            // RHS == 0 in all three stages: q1 = q + dt*0, q2 = 3/4 q + 1/4 (q1 + dt*0), q' = 1/3 q + 2/3 (q2 + dt*0)
+            const bool anyneg = !(e >> 30);
+            if (lane >= 1 && i < Nx) {
+                const int j1 = min(y0 + CH, Ny);
+                for (int j = y0; j < j1; ++j) {
+                    const size_t c = (size_t)j * Nx + i;
+                    double m = 1.0;
+                    if (mask_solid) m = (anyneg && __ldg(phi + c) <= 0.0) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int f = 0; f < NQ; ++f) {
+                        const double q = __ldg(F.q0[f] + c);
+                        const double q1 = q + dt * 0.0;
+                        const double q2 = 0.75 * q + 0.25 * (q1 + dt * 0.0);
+                        const double r = c0 * q + c1 * (q2 + dt * 0.0);
+                        F.out[f][c] = mask_solid ? r * m : r;
+                    }
+                }
+            }
+            continue;
+        }
+        const bool fast = x0 >= 3 && x0 + CW - 1 + 3 < Nx && y0 >= 3 && y0 + CH - 1 + 3 < Ny;
+        if (fast) {
+            weno_chunk_fast<NQ>(F, a, b, phi, x0, y0, Nx, dx, dy, dt, w_cut, c0, c1, first, mask_solid, lane);
+        } else if (lane >= 1 && i < Nx) {
+            const int j1 = min(y0 + CH, Ny);
+            for (int j = y0; j < j1; ++j)
+                euler_cell<1, NQ>(F, a, b, phi, j, i, Ny, Nx, dx, dy, dt, w_cut, c0, c1, first, mask_solid);
+        }
     }
 }
 
@@ -333,11 +602,72 @@ __global__ void k_euler_rhs(const double *__restrict__ qs, const double *__restr
 
 inline int flat_blocks(long n) { long b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
 
+// per-device chunk lists of the WENO5 path (grown on demand; one stream per device at a time, like
+// the other workspaces of this library)
+struct WenoWs { int *buf; size_t cap; };
+static WenoWs g_weno_ws[64];
+
+static int weno_lists(int Ny, int Nx, WenoLists *W, int *ncx_out, int *ncy_out)
+{
+    int dev = 0;
+    RMT_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return RMT_EINVAL;
+    const int ncx = rmt_cdiv(Nx, CW), ncy = rmt_cdiv(Ny, CH);
+    const size_t nch = (size_t)ncx * ncy, need = 3 * nch + 64;
+    WenoWs &ws = g_weno_ws[dev];
+    if (ws.cap < need) {
+        if (ws.buf) cudaFree(ws.buf);
+        ws.buf = nullptr; ws.cap = 0;
+        RMT_CUDA(cudaMalloc((void **)&ws.buf, need * sizeof(int)));
+        ws.cap = need;
+    }
+    W->counters = ws.buf;
+    W->summary = ws.buf + 64;
+    W->near_list = W->summary + nch;
+    W->far_list = W->near_list + nch;
+    *ncx_out = ncx; *ncy_out = ncy;
+    return RMT_OK;
+}
+
+template <int NQ>
+static int weno_rk3(const double *const *q, const double *a, const double *b, const double *phi,
+                    double *const *out, double *const *w1, double *const *w2, int Ny, int Nx, double dx,
+                    double dy, double dt, double w_cut, int mask_solid, cudaStream_t s)
+{
+    WenoLists W;
+    int ncx, ncy;
+    int rc = weno_lists(Ny, Nx, &W, &ncx, &ncy);
+    if (rc != RMT_OK) return rc;
+    const int nch = ncx * ncy;
+    EulerFields F1{}, F2{}, F3{};
+    for (int f = 0; f < NQ; ++f) {
+        F1.q0[f] = q[f]; F1.qs[f] = q[f];  F1.out[f] = w1[f];
+        F2.q0[f] = q[f]; F2.qs[f] = w1[f]; F2.out[f] = w2[f];
+        F3.q0[f] = q[f]; F3.qs[f] = w2[f]; F3.out[f] = out[f];
+    }
+    const int cblocks = min(rmt_cdiv(nch, 8), 148 * 8);
+    k_weno_classify<<<cblocks, 256, 0, s>>>(phi, W, Ny, Nx, ncx, ncy, w_cut);
+    RMT_LAUNCH_CHECK();
+    k_weno_lists<<<rmt_cdiv(nch, 256), 256, 0, s>>>(W, ncx, ncy);
+    RMT_LAUNCH_CHECK();
+    const int sblocks = min(rmt_cdiv(nch, 8), 148 * 2);
+    k_weno_stage<NQ><<<sblocks, 256, 0, s>>>(F1, a, b, phi, W, 0, Ny, Nx, ncx, dx, dy, dt, w_cut, 0.0, 1.0, 0);
+    RMT_LAUNCH_CHECK();
+    k_weno_stage<NQ><<<sblocks, 256, 0, s>>>(F2, a, b, phi, W, 1, Ny, Nx, ncx, dx, dy, dt, w_cut, 0.75, 0.25, 0);
+    RMT_LAUNCH_CHECK();
+    k_weno_stage<NQ><<<sblocks, 256, 0, s>>>(F3, a, b, phi, W, 2, Ny, Nx, ncx, dx, dy, dt, w_cut, 1.0 / 3.0,
+                                             2.0 / 3.0, mask_solid);
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
+
 template <int SCHEME, int NQ>
 static int euler_rk3(const double *const *q, const double *a, const double *b, const double *phi,
                      double *const *out, double *const *w1, double *const *w2, int Ny, int Nx, double dx,
                      double dy, double dt, double w_cut, int mask_solid, cudaStream_t s)
 {
+    if (SCHEME == 1 && Nx >= 2 * CW && Ny >= 2 * CH)
+        return weno_rk3<NQ>(q, a, b, phi, out, w1, w2, Ny, Nx, dx, dy, dt, w_cut, mask_solid, s);
     dim3 blk(TX, TY), grd(rmt_cdiv(Nx, TX), rmt_cdiv(Ny, TY));
     EulerFields F1{}, F2{}, F3{};
     for (int f = 0; f < NQ; ++f) {
