@@ -323,6 +323,16 @@ k_euler_stage(const EulerFields F, const double *__restrict__ a, const double *_
 // work (the IEEE divisions of the nonlinear weights dominate this kernel) without changing a
 // bit of the result.  Chunks that touch the rim of the grid take the generic node-by-node code.
 constexpr int CW = 31, CH = 16;
+constexpr int WSR = CH + 6, WSC = CW + 6;                 // staged rows / columns of a chunk (halo 3)
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 struct WenoLists {
     int *summary;        // per chunk: classification bits (k_weno_classify)
     int *near_list;      // chunk ids, bit 30 set: no node with phi <= 0 in the chunk
@@ -409,10 +419,28 @@ __device__ __forceinline__ void weno_chunk_fast(const EulerFields &F, const doub
                                                 const double *__restrict__ b, const double *__restrict__ phi,
                                                 int x0, int y0, int Nx, double dx, double dy, double dt,
                                                 double w_cut, double c0, double c1, int first, int mask_solid,
-                                                int lane)
+                                                int lane, double *__restrict__ sm)
 {
     const int i = x0 - 1 + lane;
     const bool outl = lane >= 1;                          // lane 0: helper column x0 - 1
+    // stage the chunk's q (rows y0-3 .. y0+CH+2, columns x0-3 .. x0+CW+2) in this warp's shared memory
+    // with asynchronous copies: every load of the chunk is in flight at once, and the walk below
+    // then runs at shared-memory latency
+    __syncwarp();
+#pragma unroll
+    for (int f = 0; f < NQ; ++f) {
+        const double *src = F.qs[f] + (size_t)(y0 - 3) * Nx + (x0 - 3) + lane;
+        double *dst = sm + f * (WSR * WSC) + lane;
+        for (int r = 0; r < WSR; ++r, src += Nx, dst += WSC) {
+            cp_async8(dst, src);
+            if (lane < WSC - 32) cp_async8(dst + 32, src + 32);
+        }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    const double *sq[NQ];
+#pragma unroll
+    for (int f = 0; f < NQ; ++f) sq[f] = sm + f * (WSR * WSC) + lane + 2;   // column i of staged row 0 (= y0-3)
     double w[NQ][5];                                      // q on rows j-2 .. j+2 of this column
     double fprev[NQ];                                     // Fm_y(j-1)
     int j = y0 - 1;
@@ -420,7 +448,7 @@ __device__ __forceinline__ void weno_chunk_fast(const EulerFields &F, const doub
     for (int f = 0; f < NQ; ++f) {
         fprev[f] = 0.0;
 #pragma unroll
-        for (int r = 0; r < 5; ++r) w[f][r] = __ldg(F.qs[f] + (size_t)(j - 2 + r) * Nx + i);
+        for (int r = 0; r < 5; ++r) w[f][r] = sq[f][r * WSC];
     }
     // scalars of the row below the current one are fetched one step ahead
     size_t cn = (size_t)y0 * Nx + i;
@@ -433,7 +461,7 @@ __device__ __forceinline__ void weno_chunk_fast(const EulerFields &F, const doub
         const bool needy_c = act_c && v_c >= 0.0, needy_n = act_n && v_n >= 0.0;
         double wn[NQ];
 #pragma unroll
-        for (int f = 0; f < NQ; ++f) wn[f] = __ldg(F.qs[f] + (size_t)(j + 3) * Nx + i);
+        for (int f = 0; f < NQ; ++f) wn[f] = sq[f][(j + 3 - (y0 - 3)) * WSC];
         const double ph_k = ph_n, u_k = u_n, v_k = v_n;   // row j+1, becomes current next step
         if (j + 2 < y0 + CH) {
             cn += Nx;
@@ -449,15 +477,19 @@ __device__ __forceinline__ void weno_chunk_fast(const EulerFields &F, const doub
         }
         if (j >= y0) {                                    // warp-uniform
             const size_t c = (size_t)j * Nx + i;
+            double q0c[NQ];
+            if (!first && outl) {
+#pragma unroll
+                for (int f = 0; f < NQ; ++f) q0c[f] = __ldg(F.q0[f] + c);
+            }
             const bool needx = act_c && u_c >= 0.0;
             const bool needx_r = __shfl_down_sync(0xffffffffu, (int)needx, 1) && lane < 31;
             double xl[NQ][5];                             // q[j][i-2], [i-1], [i+1], [i+2], [i+3]
             if (act_c || needx_r) {
 #pragma unroll
                 for (int f = 0; f < NQ; ++f) {
-                    const double *r = F.qs[f] + c;
-                    xl[f][0] = __ldg(r - 2); xl[f][1] = __ldg(r - 1); xl[f][2] = __ldg(r + 1);
-                    xl[f][3] = __ldg(r + 2); xl[f][4] = __ldg(r + 3);
+                    const double *r = sq[f] + (j - (y0 - 3)) * WSC;
+                    xl[f][0] = r[-2]; xl[f][1] = r[-1]; xl[f][2] = r[1]; xl[f][3] = r[2]; xl[f][4] = r[3];
                 }
             }
             double fx[NQ];
@@ -497,7 +529,7 @@ __device__ __forceinline__ void weno_chunk_fast(const EulerFields &F, const doub
                 }
                 if (outl) {
                     const double upd = w[f][2] + dt * rhs;
-                    const double r = first ? upd : (c0 * __ldg(F.q0[f] + c) + c1 * upd);
+                    const double r = first ? upd : (c0 * q0c[f] + c1 * upd);
                     F.out[f][c] = mask_solid ? r * m : r;
                 }
             }
@@ -518,7 +550,9 @@ k_weno_stage(const EulerFields F, const double *__restrict__ a, const double *__
              const double *__restrict__ phi, WenoLists W, int stage, int Ny, int Nx, int ncx, double dx,
              double dy, double dt, double w_cut, double c0, double c1, int mask_solid)
 {
+    extern __shared__ double s_weno[];
     const int lane = threadIdx.x & 31;
+    double *sm = s_weno + (threadIdx.x >> 5) * (NQ * WSR * WSC);
     const int nnear = W.counters[0], nfar = (stage == 2) ? W.counters[1] : 0;
     const int first = stage == 0;
     for (;;) {
@@ -555,7 +589,7 @@ k_weno_stage(const EulerFields F, const double *__restrict__ a, const double *__
         }
         const bool fast = x0 >= 3 && x0 + CW - 1 + 3 < Nx && y0 >= 3 && y0 + CH - 1 + 3 < Ny;
         if (fast) {
-            weno_chunk_fast<NQ>(F, a, b, phi, x0, y0, Nx, dx, dy, dt, w_cut, c0, c1, first, mask_solid, lane);
+            weno_chunk_fast<NQ>(F, a, b, phi, x0, y0, Nx, dx, dy, dt, w_cut, c0, c1, first, mask_solid, lane, sm);
         } else if (lane >= 1 && i < Nx) {
             const int j1 = min(y0 + CH, Ny);
             for (int j = y0; j < j1; ++j)
@@ -651,11 +685,13 @@ static int weno_rk3(const double *const *q, const double *a, const double *b, co
     k_weno_lists<<<rmt_cdiv(nch, 256), 256, 0, s>>>(W, ncx, ncy);
     RMT_LAUNCH_CHECK();
     const int sblocks = min(rmt_cdiv(nch, 8), 148 * 2);
-    k_weno_stage<NQ><<<sblocks, 256, 0, s>>>(F1, a, b, phi, W, 0, Ny, Nx, ncx, dx, dy, dt, w_cut, 0.0, 1.0, 0);
+    const size_t shm = (size_t)8 * NQ * WSR * WSC * sizeof(double);
+    RMT_CUDA(cudaFuncSetAttribute(k_weno_stage<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    k_weno_stage<NQ><<<sblocks, 256, shm, s>>>(F1, a, b, phi, W, 0, Ny, Nx, ncx, dx, dy, dt, w_cut, 0.0, 1.0, 0);
     RMT_LAUNCH_CHECK();
-    k_weno_stage<NQ><<<sblocks, 256, 0, s>>>(F2, a, b, phi, W, 1, Ny, Nx, ncx, dx, dy, dt, w_cut, 0.75, 0.25, 0);
+    k_weno_stage<NQ><<<sblocks, 256, shm, s>>>(F2, a, b, phi, W, 1, Ny, Nx, ncx, dx, dy, dt, w_cut, 0.75, 0.25, 0);
     RMT_LAUNCH_CHECK();
-    k_weno_stage<NQ><<<sblocks, 256, 0, s>>>(F3, a, b, phi, W, 2, Ny, Nx, ncx, dx, dy, dt, w_cut, 1.0 / 3.0,
+    k_weno_stage<NQ><<<sblocks, 256, shm, s>>>(F3, a, b, phi, W, 2, Ny, Nx, ncx, dx, dy, dt, w_cut, 1.0 / 3.0,
                                              2.0 / 3.0, mask_solid);
     RMT_LAUNCH_CHECK();
     return RMT_OK;
