@@ -72,6 +72,10 @@ __device__ __forceinline__ unsigned char ld_cta_u8(const unsigned char *p)
     asm volatile("ld.relaxed.cta.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return (unsigned char)v;
 }
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ double ld_cta_f64(const double *p)
 {
     double v;
@@ -227,14 +231,16 @@ __global__ void k_ext_fill(const unsigned char *__restrict__ st, const int *__re
 #ifdef RMT_EXT_TIMING
 __device__ unsigned long long g_ext_dbg[8];
 #define EXT_T(k) do { if (lane == 0) { long long now__ = clock64(); atomicAdd(&g_ext_dbg[k], (unsigned long long)(now__ - tmark)); tmark = now__; } } while (0)
-__device__ unsigned long long g_body_dbg[16];
-#define BODY_T(k) do { if (lane == 0) { long long now__ = clock64(); atomicAdd(&g_body_dbg[k], (unsigned long long)(now__ - bmark)); bmark = now__; } } while (0)
-#define BODY_T0() long long bmark = clock64()
-#define BODY_CNT(k) do { if (lane == 0) atomicAdd(&g_body_dbg[k], 1ull); } while (0)
+__device__ unsigned long long g_body_dbg[16 * 8];   // [layer][counter]
+#define BODY_T(k) do { if (lane == 0) { long long now__ = clock64(); atomicAdd(&g_body_dbg[(k) + 16 * layer], (unsigned long long)(now__ - bmark)); bmark = now__; } } while (0)
+#define BODY_T0() long long bmark = clock64(); long long dmark = bmark
+#define DISC_T(k) do { if (lane == 0) { long long now__ = clock64(); atomicAdd(&g_body_dbg[(k) + 16 * (layer + 3)], (unsigned long long)(now__ - dmark)); dmark = now__; } } while (0)
+#define BODY_CNT(k) do { if (lane == 0) atomicAdd(&g_body_dbg[(k) + 16 * layer], 1ull); } while (0)
 #else
 #define EXT_T(k) do { } while (0)
 #define BODY_T(k) do { } while (0)
 #define BODY_T0() do { } while (0)
+#define DISC_T(k) do { } while (0)
 #define BODY_CNT(k) do { } while (0)
 #endif
 
@@ -290,6 +296,10 @@ __device__ __forceinline__ void sts_v4(void *p, int4 v)
     const unsigned a = (unsigned)__cvta_generic_to_shared(p);
     asm volatile("st.volatile.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void st_generic_v4(void *p, int4 v)      // generic address (distributed shared memory)
+{
+    asm volatile("st.volatile.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ int4 lds_v4(const void *p)
 {
     const unsigned a = (unsigned)__cvta_generic_to_shared(p);
@@ -318,12 +328,18 @@ __device__ __forceinline__ void store_products(double *q, double w, double x, do
 // below this layer's code `fresh`; every raster-earlier cell that is not known is a candidate (there
 // are no target marks); all reads go to L2 (other SMs wrote the previous layers).
 // MODE 0: per-layer launches (plain loads); 1: all-layers kernel across SMs (L2 loads); 2: all-layers
-// kernel with a whole tile on ONE SM (block-scope coherent loads, served by L1).
-template <int MODE>
+// kernel with a whole tile on ONE SM (block-scope coherent loads, served by L1); 3: as 2 for the helper CTA
+// on the neighbouring SM (L2 loads: the tile's own SM wrote the data).
+struct ExtNoWait { __device__ __forceinline__ bool operator()() const { return true; } };
+// `before_store()` runs after the window has been loaded, classified and weighted (registers only) and
+// before the first store into R: a caller whose record slot may still be in use waits there, so the
+// expensive part of phase A overlaps the wait.  It returns false to abandon the record (result -1).
+template <int MODE, class Hook = ExtNoWait>
 __device__ __forceinline__ int ext_phase_a(ExtRec *R, const double *__restrict__ X1e,
                                            const double *__restrict__ X2e,
                                            const unsigned char *__restrict__ st, int j, int i, int Ny, int Nx,
-                                           int joff, double dx, double dy, double r2, int lane, int fresh = ST_FRESH)
+                                           int joff, double dx, double dy, double r2, int lane, int fresh = ST_FRESH,
+                                           Hook before_store = Hook())
 {
     const unsigned lt = (1u << lane) - 1u;
     const double x0 = dx * i, y0 = dy * (j + joff);     // absolute coordinates of the GLOBAL grid (functions.py:105)
@@ -343,9 +359,9 @@ __device__ __forceinline__ int ext_phase_a(ExtRec *R, const double *__restrict__
         c1[s] = c2[s] = 0.0;
         if (in[s]) {
             const size_t cc = (size_t)jj * Nx + ii;
-            sv[s] = MODE == 1 ? __ldcg(st + cc) : MODE == 2 ? ld_cta_u8(st + cc) : st[cc];   // known cells are final
-            c1[s] = MODE == 1 ? __ldcg(X1e + cc) : MODE == 2 ? ld_cta_f64(X1e + cc) : X1e[cc];   // only meaningful
-            c2[s] = MODE == 1 ? __ldcg(X2e + cc) : MODE == 2 ? ld_cta_f64(X2e + cc) : X2e[cc];   // if known
+            sv[s] = (MODE == 1 || MODE == 3) ? __ldcg(st + cc) : MODE == 2 ? ld_cta_u8(st + cc) : st[cc];   // known cells are final
+            c1[s] = (MODE == 1 || MODE == 3) ? __ldcg(X1e + cc) : MODE == 2 ? ld_cta_f64(X1e + cc) : X1e[cc];   // only meaningful
+            c2[s] = (MODE == 1 || MODE == 3) ? __ldcg(X2e + cc) : MODE == 2 ? ld_cta_f64(X2e + cc) : X2e[cc];   // if known
         }
     }
 #pragma unroll
@@ -365,7 +381,7 @@ __device__ __forceinline__ int ext_phase_a(ExtRec *R, const double *__restrict__
             // sweep; MODE 1: no marks, every raster-earlier cell that is not known is a candidate; MODE 2: the
             // discovery warp marked this layer's targets with fresh - 1 (fresh once fitted).
             const bool cand = MODE == 1 ? (!known && earlier)
-                            : MODE == 2 ? (earlier && ((int)sv[s] == fresh || (int)sv[s] == fresh - 1))
+                            : MODE >= 2 ? (earlier && ((int)sv[s] == fresh || (int)sv[s] == fresh - 1))
                                         : (sv[s] != ST_UNKNOWN && sv[s] != ST_KNOWN && earlier);
             if (dist_sq <= r2 && (known || cand)) {
                 cls[s] = known ? 1 : 2;
@@ -376,6 +392,7 @@ __device__ __forceinline__ int ext_phase_a(ExtRec *R, const double *__restrict__
         mk[s] = __ballot_sync(0xffffffffu, cls[s] == 1);
         mp[s] = __ballot_sync(0xffffffffu, cls[s] == 2);
     }
+    if (!before_store()) return -1;
     int slot_base = 0, pend_base = 0;
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
@@ -388,7 +405,7 @@ __device__ __forceinline__ int ext_phase_a(ExtRec *R, const double *__restrict__
             R->pw[r] = cw[s]; R->px[r] = cx_[s]; R->py[r] = cy_[s];
             R->pn[r] = (unsigned char)(lane + 32 * s);
             R->pslot[r] = (unsigned char)slot;
-            if (MODE == 2) {
+            if (MODE >= 2) {
                 const int n = lane + 32 * s;
                 R->ptag[r] = ((j + n / 9 - 4) << 15) | (i + n % 9 - 4);
             }
@@ -1131,12 +1148,43 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
 // memory).  Cost: ~0.5 us per target of the fullest tile and layer, against ~1.8 us per DEPENDENT fit
 // plus per-row-block overheads in the row-pipelined variants -- it wins whenever the bodies are
 // isolated and a tile holds at most a few thousand targets (k_ext_decide compares the models).
+// Spin-loop watchdog of the body kernel: a wait that lasts ~2^23 polls (seconds) is a protocol failure;
+// the warp records where it was and leaves, so the kernel ends (and the result is wrong) instead of
+// hanging the device.  [layer][role 0 chain / 1 discovery / 2 prepare][8]
+__device__ int g_body_watch[8 * 3 * 8];
+#define BODY_WATCH_NOW(code, tval)                                                                     \
+    do {                                                                                               \
+        if (lane == 0) {                                                                               \
+            int *w__ = g_body_watch + (layer * 3 + (role == 0 ? 0 : role <= W ? 1 : 2)) * 8;                         \
+            w__[0] = (code); w__[1] = (tval); w__[2] = C.q_count; w__[3] = C.consumed;                 \
+            w__[4] = C.row_done; w__[5] = C.disc_row; w__[6] = C.prep_next; w__[7] = C.q_final;        \
+        }                                                                                              \
+    } while (0)
+#define BODY_WATCH(code, tval)                                                                         \
+    do {                                                                                               \
+        if (++spins > (1 << 23)) {                                                                     \
+            if (lane == 0) {                                                                           \
+                int *w__ = g_body_watch + (layer * 3 + (role == 0 ? 0 : role <= W ? 1 : 2)) * 8;                     \
+                w__[0] = (code); w__[1] = (tval); w__[2] = C.q_count; w__[3] = C.consumed;             \
+                w__[4] = C.row_done; w__[5] = C.disc_row; w__[6] = C.prep_next; w__[7] = C.q_final;    \
+            }                                                                                          \
+            return;                                                                                    \
+        }                                                                                              \
+    } while (0)
+// discovery-side fence: block scope, or cluster scope when a helper CTA on another SM reads what this CTA wrote
+#define BODY_FENCE() do { if (clustered) asm volatile("fence.acq_rel.cluster;" ::: "memory"); else __threadfence_block(); } while (0)
 constexpr int BQ = 256;                // target queue entries per layer (ring)
 constexpr int BSLOT_MAX = 6;           // records per layer in shared memory (ring)
 constexpr int BODY_KMAX = 6;           // candidate tile sizes: (512 << k) rows x (XT << k) columns
 constexpr int BODY_LMAX = 5;           // layers the 640-thread CTA has warps for
 
-constexpr int BC_ROWS = 8, BC_COLS = 64;   // chain-private cache of the layer's latest fits: [row & 7][column & 63]
+constexpr int BC_ROWS = 8, BC_COLS = 128;  // chain-private cache of the layer's latest fits: [row & 7][column & 127]
+__device__ __forceinline__ int body_cache_slot(int jj, int ii)
+{
+    // bodies on a lattice sit a multiple of 128 columns apart: fold the high column bits in
+    return (jj & (BC_ROWS - 1)) * BC_COLS + ((ii + (ii >> 7) * 41) & (BC_COLS - 1));
+}
+constexpr int BODY_DEP = 1 << 16;          // record header: the target's window holds the PREVIOUS queue entry
 struct BodyCtl {
     int q_count;                       // targets discovered so far
     int q_final;                       // discovery complete
@@ -1144,10 +1192,11 @@ struct BodyCtl {
     int row_done;                      // the chain warp has fitted every target of rows <= row_done
     int prep_next;                     // next queue entry a prepare warp takes
     int consumed;                      // the chain warp has consumed entries < consumed
-    int pad_[2];
+    int disc_turn;                     // the row whose discovery warp may append now
+    int q_tail;                        // queue length including the rows appended so far
     int4 rhdr[BSLOT_MAX];              // {info, j, i, t + 1} once the record of queue entry t sits in the slot
     int qrow[BQ], qcol[BQ];
-    double sums[NACC];
+    double sums[2][NACC];              // one set per half warp (two independent targets are fitted at once)
     // what the chain warp itself fitted lately (single writer, single reader: no synchronisation):
     // tag = j << 15 | i, bit 30 set for a rejected target; values (xi1, xi2)
     int ctag[BC_ROWS][BC_COLS];
@@ -1162,62 +1211,53 @@ __device__ __forceinline__ int body_tile_offset(int k, int Ny, int nxt)
     return off;
 }
 
-__global__ void __launch_bounds__(640, 1)
-k_ext_body(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__restrict__ st,
-           const int *__restrict__ cnt0 /* + cmin0, cmax0, chunk0, [Ny*nxt] each */,
-           const int *__restrict__ tilecnt /* layer-0 targets per tile, all candidate sizes */,
-           const int *__restrict__ mode, int L, int P, int nslot, int Ny, int Nx, int joff, int nxt, int XT,
-           double dx, double dy, double r2)
+// The work of one warp of the body kernel.  `ctl` / `recs` are generic pointers to the shared memory of the
+// cluster's first CTA (the warp's own CTA, or -- for the prepare warps of the helper CTA -- the neighbouring
+// SM's, reached through distributed shared memory).
+template <bool REMOTE>
+__device__ __forceinline__ void
+body_work(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__restrict__ st,
+          const int *__restrict__ cnt0, const int *__restrict__ cmin0, const int *__restrict__ cmax0,
+          const int *__restrict__ chunk0, BodyCtl *ctl, ExtRec *recs, const int layer, const int role,
+          const bool clustered, const int W, const int nslot, const int Ny, const int Nx, const int joff, const int nxt,
+          const int XT, const int seg0, const int seg1, const int R0, const int R1, const double dx,
+          const double dy, const double r2, const int flags)
 {
-    if (mode[0] != 1) return;                           // k_ext_decide picked another variant
-    const int k = mode[1];
-    const int Tr = 512 << k, nsegt = 1 << k;
-    const int ntx = (nxt + nsegt - 1) >> k, nty = (Ny + Tr - 1) / Tr;
-    if ((int)blockIdx.x >= ntx * nty) return;
-    if (tilecnt[body_tile_offset(k, Ny, nxt) + blockIdx.x] == 0) return;   // no band in this tile
-    const int ty = blockIdx.x / ntx, tx = blockIdx.x - ty * ntx;
-    const int seg0 = tx * nsegt, seg1 = min(seg0 + nsegt, nxt);
-    const int R0 = max(ty * Tr, 1), R1 = min((ty + 1) * Tr, Ny - 1);       // target rows [R0, R1)
-    const int nseg = Ny * nxt;
-    const int *cmin0 = cnt0 + nseg, *cmax0 = cnt0 + 2 * nseg, *chunk0 = cnt0 + 3 * nseg;
-
-    extern __shared__ unsigned char s_raw[];
-    BodyCtl *ctl = reinterpret_cast<BodyCtl *>(s_raw);
-    ExtRec *recs = reinterpret_cast<ExtRec *>(s_raw + (((size_t)L * sizeof(BodyCtl) + 15) & ~(size_t)15));
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int per = 2 + P;                              // warps per layer
-    const int layer = wib / per, role = wib - layer * per;
-    for (int e = threadIdx.x; e < L * (int)(sizeof(BodyCtl) / 4); e += blockDim.x) ((int *)ctl)[e] = 0;
-    __syncthreads();
-    if (threadIdx.x < L) { ctl[threadIdx.x].disc_row = R0 - 1; ctl[threadIdx.x].row_done = R0 - 1; }
-    for (int e = threadIdx.x; e < L * BC_ROWS * BC_COLS; e += blockDim.x)
-        (&ctl[e / (BC_ROWS * BC_COLS)].ctag[0][0])[e % (BC_ROWS * BC_COLS)] = -1;
-    __syncthreads();
-    if (layer >= L) return;
+    const int lane = threadIdx.x & 31;
     const int fresh = 2 * layer + 3;
     volatile BodyCtl &C = ctl[layer];
+    int spins = 0;
     ExtRec *myrecs = recs + (size_t)layer * nslot;
 
-    if (role == 1) {
+    if (role >= 1 && role <= W) {
         // ---------------- discovery: the layer's targets, in raster order, into the queue ----------
+        // W warps take the rows in turn (row r of the tile belongs to warp r % W).  SCANNING a row for
+        // targets reads only cells that are final for this layer (known / not known never depends on
+        // this layer's own marks or fits), so a warp scans its row while the other one is still busy
+        // with the row above; APPENDING to the queue is done strictly in row order (disc_turn).
         volatile BodyCtl *CP = layer > 0 ? &ctl[layer - 1] : nullptr;
-        int qn = 0;
-        for (int j = R0; j < R1; ++j) {
+        for (int j = R0 + (role - 1); j < R1; j += W) {
             // layer-l targets lie within l cells of layer-0 targets: rows j-l .. j+l of this tile
             int any = 0;
+            spins = 0;
             if (lane <= 2 * layer) {
                 const int r = j - layer + lane;
                 if (r >= 0 && r < Ny)
                     for (int sg = seg0; sg < seg1; ++sg) any |= cnt0[r * nxt + sg];
             }
-            if (__any_sync(0xffffffffu, any != 0)) {
+            const bool has = __any_sync(0xffffffffu, any != 0);
+            // ---- scan: lane c keeps (first column, target mask) of the c-th flagged 32-column chunk
+            int fbase = 0, nfc = 0;
+            unsigned fmask = 0;
+            bool overflow = false;                      // > 32 flagged chunks: the rest is scanned in turn
+            const unsigned char *rowc = st + (size_t)j * Nx, *rowa = rowc - Nx, *rowb = rowc + Nx;
+            if (has) {
                 if (CP) {                               // previous layer complete on rows <= j+4 (window)
                     const int need = min(j + 4, R1 - 1);
-                    while (CP->row_done < need) __nanosleep(40);
-                    __threadfence_block();
+                    while (CP->row_done < need) { __nanosleep(60); BODY_WATCH(1, j); }
+                    BODY_FENCE();                        // cumulative: the helper CTA reads the previous layer's fits
                 }
-                const unsigned char *rowc = st + (size_t)j * Nx, *rowa = rowc - Nx, *rowb = rowc + Nx;
-                for (int sg = seg0; sg < seg1; ++sg) {
+                for (int sg = seg0; sg < seg1 && !overflow; ++sg) {
                     const int xc0 = sg * XT, xc1 = min(xc0 + XT, Nx);
                     unsigned m = 0;
                     const int r = j - layer + lane;
@@ -1228,55 +1268,170 @@ k_ext_body(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__
                             m |= 1u << ((xc1 - 1 - xc0) >> 5);
                     }
                     m = __reduce_or_sync(0xffffffffu, m);
-                    const unsigned chunks = m | (m << 1) | (m >> 1);
-                    for (int base = xc0; base < xc1; base += 32) {
-                        if (!((chunks >> ((base - xc0) >> 5)) & 1u)) continue;
-                        const int i = base + lane;
-                        bool tgt = false;
-                        if (i < xc1 && i >= 1 && i < Nx - 1) {
-                            const unsigned me = ld_cta_u8(rowc + i);
-                            if (!((me & 1) && me < fresh)) {
-                                unsigned kb = 0;
+                    // layer 0: the chunk masks of row j are exact; deeper layers reach `layer` cells further
+                    const unsigned chunks = layer ? (m | (m << 1) | (m >> 1)) : m;
+                    // Block-scope coherent loads cost an L2 round trip each, and this scan has to stay ahead of
+                    // the chain warp: the nine bytes of THREE flagged chunks are requested at once, then judged.
+                    const int nchunk = (xc1 - xc0 + 31) >> 5;
+                    unsigned rem = chunks & (nchunk >= 32 ? 0xffffffffu : ((1u << nchunk) - 1u));
+                    while (rem) {
+                        if (nfc + 3 > 32) { overflow = true; break; }
+                        int bs[3];
+                        unsigned v[3][9];
 #pragma unroll
-                                for (int d = -1; d <= 1; ++d) {
-                                    const unsigned a = ld_cta_u8(rowa + i + d), c = ld_cta_u8(rowb + i + d);
-                                    kb |= ((a & 1) && a < fresh) | ((c & 1) && c < fresh);
-                                    if (d) { const unsigned b = ld_cta_u8(rowc + i + d); kb |= ((b & 1) && b < fresh); }
-                                }
-                                tgt = kb != 0;
+                        for (int u = 0; u < 3; ++u) {
+                            bs[u] = -1;
+                            if (rem) { bs[u] = xc0 + 32 * (__ffs(rem) - 1); rem &= rem - 1; }
+                            const int i = bs[u] + lane;
+                            const bool ok = bs[u] >= 0 && i < xc1 && i >= 1 && i < Nx - 1;
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) {
+                                v[u][d] = ok ? ld_cta_u8(rowa + i + d - 1) : 0u;
+                                v[u][3 + d] = ok ? ld_cta_u8(rowc + i + d - 1) : 0u;
+                                v[u][6 + d] = ok ? ld_cta_u8(rowb + i + d - 1) : 0u;
                             }
                         }
-                        const unsigned tm = __ballot_sync(0xffffffffu, tgt);
-                        if (tm) {
-                            while (qn + 32 - C.consumed > BQ) __nanosleep(40);     // room in the ring
-                            if (tgt) {
-                                const int o = (qn + __popc(tm & ((1u << lane) - 1u))) & (BQ - 1);
-                                ((int *)C.qrow)[o] = j;
-                                ((int *)C.qcol)[o] = i;
-                                // mark: "target of this layer, undecided" (even = still unknown to every
-                                // known-test); phase A of later targets lists exactly the marked cells
-                                ((unsigned char *)rowc)[i] = (unsigned char)(fresh - 1);
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) {
+                            if (bs[u] < 0) continue;     // warp-uniform
+                            const int i = bs[u] + lane;
+                            const unsigned me = v[u][4];
+                            bool tgt = false;
+                            if (i < xc1 && i >= 1 && i < Nx - 1 && !((me & 1) && me < fresh)) {
+                                unsigned kb = 0;
+#pragma unroll
+                                for (int e = 0; e < 9; ++e)
+                                    if (e != 4) kb |= ((v[u][e] & 1) && v[u][e] < fresh);
+                                tgt = kb != 0;
                             }
-                            qn += __popc(tm);
-                            __threadfence_block();
-                            __syncwarp();
-                            if (lane == 0) C.q_count = qn;
+                            const unsigned tm = __ballot_sync(0xffffffffu, tgt);
+                            if (tm) {
+                                if (lane == nfc) { fbase = bs[u]; fmask = tm; }
+                                ++nfc;
+                            }
                         }
                     }
                 }
             }
-            if (lane == 0) C.disc_row = j;
+            // ---- my turn: append the row's targets, mark them, publish
+            while (C.disc_turn != j) { __nanosleep(20); BODY_WATCH(6, j); }
+            if (nfc || overflow) {
+                int qn = C.q_tail;
+                const int row_start = qn;               // entries [row_start, qn) of this row are not published yet
+                bool streaming = overflow;              // a long row is published as it is found (no reordering)
+                auto append = [&](int base, unsigned tm) -> bool {
+                    if (!streaming && qn - row_start + __popc(tm) > 32) {   // too long to reorder: publish
+                        streaming = true;
+                        BODY_FENCE();
+                        __syncwarp();
+                        if (lane == 0) C.q_count = qn;
+                    }
+                    // room in the ring (one spare entry: the prepare warps look at entry t - 1)
+                    while (qn + 33 - C.consumed > BQ) {
+                        __nanosleep(200);
+                        if (++spins > (1 << 23)) return false;
+                    }
+                    if ((tm >> lane) & 1u) {
+                        const int o = (qn + __popc(tm & ((1u << lane) - 1u))) & (BQ - 1);
+                        ((int *)C.qrow)[o] = j;
+                        ((int *)C.qcol)[o] = base + lane;
+                        // mark: "target of this layer, undecided" (even = still unknown to every
+                        // known-test); phase A of later targets lists exactly the marked cells
+                        ((unsigned char *)rowc)[base + lane] = (unsigned char)(fresh - 1);
+                    }
+                    qn += __popc(tm);
+                    if (streaming) {
+                        BODY_FENCE();
+                        __syncwarp();
+                        if (lane == 0) C.q_count = qn;
+                    }
+                    return true;
+                };
+                for (int c = 0; c < nfc; ++c) {
+                    const int base = __shfl_sync(0xffffffffu, fbase, c);
+                    const unsigned tm = __shfl_sync(0xffffffffu, fmask, c);
+                    if (!append(base, tm)) { BODY_WATCH_NOW(2, qn); return; }
+                }
+                if (overflow) {
+                    // the rare wide row: every chunk the scan above did not reach, one at a time
+                    int seen = 0;
+                    for (int sg = seg0; sg < seg1; ++sg) {
+                        const int xc0 = sg * XT, xc1 = min(xc0 + XT, Nx);
+                        for (int base = xc0; base < xc1; base += 32) {
+                            const int i = base + lane;
+                            bool tgt = false;
+                            if (i < xc1 && i >= 1 && i < Nx - 1) {
+                                const unsigned me = ld_cta_u8(rowc + i);
+                                if (!((me & 1) && me < fresh)) {
+                                    unsigned kb = 0;
+#pragma unroll
+                                    for (int d = -1; d <= 1; ++d) {
+                                        const unsigned a = ld_cta_u8(rowa + i + d), c = ld_cta_u8(rowb + i + d);
+                                        kb |= ((a & 1) && a < fresh) | ((c & 1) && c < fresh);
+                                        if (d) { const unsigned b = ld_cta_u8(rowc + i + d); kb |= ((b & 1) && b < fresh); }
+                                    }
+                                    tgt = kb != 0;
+                                }
+                            }
+                            const unsigned tm = __ballot_sync(0xffffffffu, tgt);
+                            if (!tm) continue;
+                            if (seen++ < nfc) continue;  // already appended from the scan (same order)
+                            if (!append(base, tm)) { BODY_WATCH_NOW(2, qn); return; }
+                        }
+                    }
+                }
+                if (!streaming && qn > row_start) {
+                    // Queue order within the row.  Runs of targets separated by >= 5 columns are independent
+                    // inside the row (a fit reads its own row only 4 columns to the left), so the runs left
+                    // and right of a gap near the middle are INTERLEAVED: L0 R0 L1 R1 ...  Neighbouring
+                    // queue entries are then usually independent and the chain warp fits them two at a time.
+                    // Every entry still follows all the raster-earlier targets of its window.
+                    const int nrow = qn - row_start;
+                    __syncwarp();
+                    int col = 0;
+                    if (lane < nrow) col = ((int *)C.qcol)[(row_start + lane) & (BQ - 1)];
+                    const int prevc = __shfl_up_sync(0xffffffffu, col, 1);
+                    const unsigned bnd = (flags & 1) ? __ballot_sync(0xffffffffu, lane > 0 && lane < nrow && col - prevc >= 5) : 0u;
+                    if (bnd) {
+                        // the boundary nearest the middle of the list
+                        const int mid = nrow >> 1;
+                        const unsigned lo = bnd & ((2u << mid) - 1u), hi = bnd & ~((2u << mid) - 1u);
+                        int sp = -1;
+                        if (lo) sp = 31 - __clz(lo);
+                        if (hi) { const int h2 = __ffs(hi) - 1; if (sp < 0 || h2 - mid < mid - sp) sp = h2; }
+                        const int na = sp, nb = nrow - sp;
+                        __syncwarp();
+                        if (lane < nrow) {
+                            int pos;
+                            if (lane < sp) pos = (lane < nb) ? 2 * lane : lane + nb;
+                            else { const int k2 = lane - sp; pos = (k2 < na) ? 2 * k2 + 1 : k2 + na; }
+                            ((int *)C.qcol)[(row_start + pos) & (BQ - 1)] = col;
+                        }
+                    }
+                    BODY_FENCE();
+                    __syncwarp();
+                    if (lane == 0) C.q_count = qn;
+                }
+                if (lane == 0) C.q_tail = qn;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                C.disc_row = j;
+                if (j == R1 - 1) C.q_final = 1;
+                __threadfence_block();
+                C.disc_turn = j + 1;
+            }
+            __syncwarp();
         }
-        __syncwarp();
-        if (lane == 0) C.q_final = 1;
         return;
     }
 
-    if (role >= 2) {
+    if (role > W) {
         // ---------------- prepare: phase A of queue entry t into record slot t % nslot --------------
         for (;;) {
             BODY_T0();
             int t = 0;
+            spins = 0;
             if (lane == 0) t = atomicAdd((int *)&C.prep_next, 1);
             t = __shfl_sync(0xffffffffu, t, 0);
             for (;;) {
@@ -1284,18 +1439,38 @@ k_ext_body(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__
                 const int cnt = C.q_count;
                 if (t < cnt) break;
                 if (fin) return;
-                __nanosleep(40);
+                __nanosleep(250);                       // idle helpers must not take issue slots from the chain warps
+                BODY_WATCH(3, t);
             }
             BODY_T(8);
-            while (t - C.consumed >= nslot) __nanosleep(20);
-            __threadfence_block();
-            BODY_T(9);
+            if (REMOTE) asm volatile("fence.acq_rel.cluster;" ::: "memory"); else __threadfence_block();
             const int j = C.qrow[t & (BQ - 1)], i = C.qcol[t & (BQ - 1)];
             const int slot = t % nslot;
-            const int info = ext_phase_a<2>(myrecs + slot, X1e, X2e, st, j, i, Ny, Nx, joff, dx, dy, r2, lane, fresh);
-            __threadfence_block();
+            // the record slot may still hold entry t - nslot: wait for it only when phase A is ready to store
+            bool timed_out = false;
+            auto slot_free = [&]() -> bool {
+                BODY_T(10);
+                while (t - C.consumed >= nslot) {
+                    __nanosleep(150);
+                    if (++spins > (1 << 23)) { timed_out = true; return false; }
+                }
+                if (REMOTE) asm volatile("fence.acq_rel.cluster;" ::: "memory"); else __threadfence_block();
+                BODY_T(9);
+                return true;
+            };
+            int info = ext_phase_a<REMOTE ? 3 : 2>(myrecs + slot, X1e, X2e, st, j, i, Ny, Nx, joff, dx, dy, r2, lane, fresh,
+                                                   slot_free);
+            if (timed_out) { BODY_WATCH_NOW(4, t); return; }
+            if (t > 0) {                                // is the previous queue entry inside this target's window?
+                const int jp = C.qrow[(t - 1) & (BQ - 1)], ip = C.qcol[(t - 1) & (BQ - 1)];
+                if (j - jp >= 0 && j - jp <= 4 && abs(i - ip) <= 4 && (jp < j || ip < i)) info |= BODY_DEP;
+            }
+            if (REMOTE) asm volatile("fence.acq_rel.cluster;" ::: "memory"); else __threadfence_block();
             __syncwarp();
-            if (lane == 0) sts_v4((void *)&C.rhdr[slot], make_int4(info, j, i, t + 1));   // one 16-byte store
+            if (lane == 0) {                            // one 16-byte store: header and ready flag travel together
+                if (REMOTE) st_generic_v4((void *)&C.rhdr[slot], make_int4(info, j, i, t + 1));
+                else sts_v4((void *)&C.rhdr[slot], make_int4(info, j, i, t + 1));
+            }
             BODY_T(10);
             BODY_CNT(11);
         }
@@ -1305,12 +1480,17 @@ k_ext_body(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__
     // Nothing this warp reads on the chain is written by another warp except the prepared record (shared
     // memory, in order per warp: a compiler barrier after the ready flag is enough), so the loop carries no
     // hardware fence; a release fence precedes each row_done update (once per row) for the next layer.
-    const int la = (lane < NACC) ? lane : 0;
+    // TWO targets per pass: lanes 0-15 fit the head of the queue, lanes 16-31 the entry behind it whenever
+    // that one does not read the head's result (its record says so) -- on the flanks of a body the
+    // interleaved queue order makes that the common case, and a pass costs the same for one target or two.
+    const int half = lane >> 4, hl = lane & 15;
+    const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
+    const int la = (hl < NACC) ? hl : 0;
     int rdone = R0 - 1, cur_row = -1;
     int *ctag = (int *)&C.ctag[0][0];
     double *cval = (double *)&C.cval[0][0][0];
     int slot = 0;
-    for (int t = 0;; ++t, slot = (slot + 1 == nslot) ? 0 : slot + 1) {
+    for (int t = 0;;) {
         BODY_T0();
         int4 hdr = lds_v4((const void *)&C.rhdr[slot]);
         if (hdr.w != t + 1) {
@@ -1331,35 +1511,47 @@ k_ext_body(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__
                     }
                 }
                 __nanosleep(20);
+                BODY_WATCH(5, t);
             }
             if (finished) break;
         }
+        spins = 0;
+        const int slot2 = (slot + 1 == nslot) ? 0 : slot + 1;
+        // the decision is a snapshot of a flag another warp sets: take lane 0's view for the whole warp
+        // (lanes that left the wait loop at different times could otherwise disagree)
+        int4 hdr2 = lds_v4((const void *)&C.rhdr[slot2]);
+        hdr2.x = __shfl_sync(0xffffffffu, hdr2.x, 0); hdr2.y = __shfl_sync(0xffffffffu, hdr2.y, 0);
+        hdr2.z = __shfl_sync(0xffffffffu, hdr2.z, 0); hdr2.w = __shfl_sync(0xffffffffu, hdr2.w, 0);
+        const bool paired = (flags & 2) && (hdr2.w == t + 2) && !(hdr2.x & BODY_DEP);
         SMEM_ORDER();
         BODY_T(0);
-        ExtRec &Rc = myrecs[slot];
-        const int info = hdr.x, j = hdr.y, i = hdr.z;
-        if (j != cur_row) {                             // rows above j are complete
-            cur_row = j;
-            if (j - 1 > rdone) {
-                rdone = j - 1;
+        if (hdr.y != cur_row) {                         // rows above the head's row are complete
+            cur_row = hdr.y;
+            if (cur_row - 1 > rdone) {
+                rdone = cur_row - 1;
                 __threadfence_block();
                 __syncwarp();
-                if (lane == 0) C.row_done = j - 1;
+                if (lane == 0) C.row_done = rdone;
             }
         }
+        const bool mine = half == 0 || paired;           // this half warp has a target
+        const int4 hm = half ? hdr2 : hdr;
+        ExtRec &Rc = myrecs[half ? slot2 : slot];
+        const int info = hm.x, j = hm.y, i = hm.z;
         const double x0 = dx * i, y0 = dy * (j + joff);
-        const int nslots = info & 255, npend = info >> 8;
+        const int nslots = mine ? (info & 255) : 0, npend = mine ? ((info >> 8) & 255) : 0;
         const int nknown = nslots - npend;
+        const int npend_max = max(__shfl_sync(0xffffffffu, npend, 0), __shfl_sync(0xffffffffu, npend, 16));
         BODY_T(1);
         // ---- one lane per undecided cell (a raster-earlier target of this layer, fitted or rejected by
         //      this warp): its value from the warp's own cache, else (entry recycled) from global memory
         int nfail = 0;
-        for (int q0 = 0; q0 < npend; q0 += 32) {
-            const int r = q0 + lane;
+        for (int q0 = 0; q0 < npend_max; q0 += 16) {
+            const int r = q0 + hl;
             bool fail = false;
             if (r < npend) {
                 const int want = Rc.ptag[r];              // jj << 15 | ii
-                const int ce = ((want >> 15) & (BC_ROWS - 1)) * BC_COLS + (want & (BC_COLS - 1));
+                const int ce = body_cache_slot(want >> 15, want & 32767);
                 const int tag = ctag[ce];
                 double v1 = cval[2 * ce], v2 = cval[2 * ce + 1];
                 bool got;
@@ -1367,40 +1559,49 @@ k_ext_body(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__
                     got = !(tag & (1 << 30));
                 } else {
                     const size_t cc = (size_t)(want >> 15) * Nx + (want & 32767);
-                    got = (ld_cta_u8(st + cc) == (unsigned)fresh);
-                    v1 = ld_cta_f64(X1e + cc); v2 = ld_cta_f64(X2e + cc);
+                    if (flags & 4) {
+                        got = (__ldcg(st + cc) == (unsigned)fresh);
+                        v1 = __ldcg(X1e + cc); v2 = __ldcg(X2e + cc);
+                    } else {
+                        got = (ld_cta_u8(st + cc) == (unsigned)fresh);
+                        v1 = ld_cta_f64(X1e + cc); v2 = ld_cta_f64(X2e + cc);
+                    }
+#ifdef RMT_EXT_TIMING
+                    atomicAdd(&g_body_dbg[12 + 16 * layer], 1ull);
+#endif
                 }
                 // a rejected target contributes exact zeros (weight 0)
                 store_products(Rc.prod[Rc.pslot[r]], got ? Rc.pw[r] : 0.0, got ? Rc.px[r] : 0.0,
                                got ? Rc.py[r] : 0.0, got ? v1 : 0.0, got ? v2 : 0.0);
                 fail = !got;
             }
-            nfail += __popc(__ballot_sync(0xffffffffu, fail));
+            nfail += __popc(__ballot_sync(0xffffffffu, fail) & hmask);
         }
         const int count = nknown + npend - nfail;        // known cells in the window (functions.py:147)
         __syncwarp();
         BODY_T(2);
-        // ---- ordered accumulation: lane a owns running sum a; the next chunk of 8 is loaded while the
-        //      current one is added (the list is zero-padded to a multiple of 8: exact no-ops)
+        // ---- ordered accumulation: lane a of each half owns running sum a; the next chunk of 8 is loaded
+        //      while the current one is added (the list is zero-padded to a multiple of 8: exact no-ops)
         double acc = 0.0;
         {
             const double *q = &Rc.prod[0][la];
             const int nch = (nslots + 7) >> 3;            // nslots <= 80: the target itself is never a slot
+            const int nch_max = max(__shfl_sync(0xffffffffu, nch, 0), __shfl_sync(0xffffffffu, nch, 16));
             double c0 = q[0 * NACC], c1 = q[1 * NACC], c2 = q[2 * NACC], c3 = q[3 * NACC], c4 = q[4 * NACC],
                    c5 = q[5 * NACC], c6 = q[6 * NACC], c7 = q[7 * NACC];
-            for (int ch = 0; ch < nch; ++ch) {
-                const double *qn = q + (ch + 1 < nch ? ch + 1 : ch) * 8 * NACC;
+            for (int ch = 0; ch < nch_max; ++ch) {
+                const double *qn = q + (ch + 1 < nch ? ch + 1 : (nch ? nch - 1 : 0)) * 8 * NACC;
                 const double n0 = qn[0 * NACC], n1 = qn[1 * NACC], n2 = qn[2 * NACC], n3 = qn[3 * NACC],
                              n4 = qn[4 * NACC], n5 = qn[5 * NACC], n6 = qn[6 * NACC], n7 = qn[7 * NACC];
-                acc += c0; acc += c1; acc += c2; acc += c3; acc += c4; acc += c5; acc += c6; acc += c7;
+                if (ch < nch) { acc += c0; acc += c1; acc += c2; acc += c3; acc += c4; acc += c5; acc += c6; acc += c7; }
                 c0 = n0; c1 = n1; c2 = n2; c3 = n3; c4 = n4; c5 = n5; c6 = n6; c7 = n7;
             }
         }
-        if (lane < NACC) ((double *)C.sums)[lane] = acc;
+        if (hl < NACC) ((double *)C.sums[half])[hl] = acc;
         __syncwarp();
         BODY_T(3);
-        const volatile double *sm = C.sums;
-        const int h = (lane & 1) * 3;                     // lane 0 solves for xi1, lane 1 for xi2
+        const volatile double *sm = C.sums[half];
+        const int h = (lane & 1) * 3;                     // even lanes solve for xi1, odd lanes for xi2
         const double b0 = sm[h], b1 = sm[h + 1], b2 = sm[h + 2];
         const double A00 = sm[6], A01 = sm[7], A02 = sm[8], A11 = sm[9], A12 = sm[10], A22 = sm[11];
         const double A10 = A01, A20 = A02, A21 = A12;
@@ -1415,26 +1616,96 @@ k_ext_body(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__
         const double val = cx + cy * x0 + cz * y0;
         BODY_T(4);
         // ---- publish: the warp's cache first (the next fit reads it), then global memory.  Every lane
-        //      stores (even lanes hold xi1, odd lanes xi2; same address, same value: one transaction) so
-        //      the tail of the chain has no divergent branch
-        {
-            const int ce = (j & (BC_ROWS - 1)) * BC_COLS + (i & (BC_COLS - 1));
+        //      of a half stores (even lanes hold xi1, odd lanes xi2; same address, same value)
+        const int ce = body_cache_slot(j, i);
+        // two targets that map to the same cache entry: only the second keeps it (no torn entry)
+        const bool clash = paired && __shfl_sync(0xffffffffu, ce, 0) == __shfl_sync(0xffffffffu, ce, 16);
+        if (mine && !(clash && half == 0)) {
             cval[2 * ce + (lane & 1)] = val;
             ctag[ce] = ((j << 15) | i) | (fitted ? 0 : (1 << 30));
-            if (fitted) {
-                const size_t c = (size_t)j * Nx + i;
-                ((lane & 1) ? X2e : X1e)[c] = val;
-                st[c] = (unsigned char)fresh;             // readers in other warps order through row_done
-            }
-            C.consumed = t + 1;                           // frees the record slot and the queue entry
         }
+        if (mine && fitted) {
+            const size_t c = (size_t)j * Nx + i;
+            ((lane & 1) ? X2e : X1e)[c] = val;
+            st[c] = (unsigned char)fresh;                 // readers in other warps order through row_done
+        }
+        const int adv = paired ? 2 : 1;
+        t += adv;
+        slot = paired ? ((slot2 + 1 == nslot) ? 0 : slot2 + 1) : slot2;
         __syncwarp();
+        C.consumed = t;                                   // frees the record slots and the queue entries
         BODY_T(5);
         BODY_CNT(6);
+        if (paired) BODY_CNT(7);
     }
     __threadfence_block();
     __syncwarp();
     if (lane == 0) C.row_done = INT_MAX;
+}
+
+// grid = tiles x cluster size.  With a cluster of two CTAs the second one is a helper on the neighbouring SM:
+// all of its warps are prepare warps that write their records straight into the first CTA's shared memory
+// (the chain consumes records faster than the 4 prepare warps per layer of one CTA produce them).
+__global__ void __launch_bounds__(768, 1)
+k_ext_body(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *__restrict__ st,
+           const int *__restrict__ cnt0 /* + cmin0, cmax0, chunk0, [Ny*nxt] each */,
+           const int *__restrict__ tilecnt /* layer-0 targets per tile, all candidate sizes */,
+           const int *__restrict__ mode, int L, int P, int W, int nslot, int Ny, int Nx, int joff, int nxt, int XT,
+           double dx, double dy, double r2, int flags /* 1: interleave the queue, 2: fit two targets per pass */)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csize = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+    const int tile = (int)blockIdx.x / csize;
+    // every exit below is taken by all CTAs of a cluster alike (no cluster barrier is left waiting)
+    if (mode[0] != 1) return;                           // k_ext_decide picked another variant
+    const int k = mode[1];
+    const int Tr = 512 << k, nsegt = 1 << k;
+    const int ntx = (nxt + nsegt - 1) >> k, nty = (Ny + Tr - 1) / Tr;
+    if (tile >= ntx * nty) return;
+    if (tilecnt[body_tile_offset(k, Ny, nxt) + tile] == 0) return;          // no band in this tile
+    const int ty = tile / ntx, tx = tile - ty * ntx;
+    const int seg0 = tx * nsegt, seg1 = min(seg0 + nsegt, nxt);
+    const int R0 = max(ty * Tr, 1), R1 = min((ty + 1) * Tr, Ny - 1);       // target rows [R0, R1)
+    const int nseg = Ny * nxt;
+    const int *cmin0 = cnt0 + nseg, *cmax0 = cnt0 + 2 * nseg, *chunk0 = cnt0 + 3 * nseg;
+
+    extern __shared__ unsigned char s_raw[];
+    // the tile's own CTA addresses its shared memory directly; the helper goes through the cluster window
+    BodyCtl *ctl = reinterpret_cast<BodyCtl *>(s_raw);
+    ExtRec *recs = reinterpret_cast<ExtRec *>(s_raw + (((size_t)L * sizeof(BodyCtl) + 15) & ~(size_t)15));
+    const int wib = threadIdx.x >> 5;
+    if (crank == 0) {
+        for (int e = threadIdx.x; e < L * (int)(sizeof(BodyCtl) / 4); e += blockDim.x) ((int *)ctl)[e] = 0;
+        __syncthreads();
+        if (threadIdx.x < L) { ctl[threadIdx.x].disc_row = R0 - 1; ctl[threadIdx.x].row_done = R0 - 1; ctl[threadIdx.x].disc_turn = R0; }
+        for (int e = threadIdx.x; e < L * BC_ROWS * BC_COLS; e += blockDim.x)
+            (&ctl[e / (BC_ROWS * BC_COLS)].ctag[0][0])[e % (BC_ROWS * BC_COLS)] = -1;
+        __syncthreads();
+    }
+    if (csize > 1) cluster.sync();                      // the helper CTA sees initialised control blocks
+    int layer, role;
+    if (crank == 0) {
+        const int per = 1 + W + P;                      // warps per layer: chain, W x discovery, P x prepare
+        layer = wib / per;
+        role = wib - layer * per;
+    } else {
+        layer = wib % L;                                // helper CTA: prepare warps only
+        role = W + 1;
+    }
+    if (layer < L) {
+        if (crank == 0) {
+            body_work<false>(X1e, X2e, st, cnt0, cmin0, cmax0, chunk0, ctl, recs, layer, role, csize > 1, W, nslot, Ny, Nx,
+                             joff, nxt, XT, seg0, seg1, R0, R1, dx, dy, r2, flags);
+        } else {
+            unsigned char *base = (unsigned char *)cluster.map_shared_rank((void *)s_raw, 0);
+            BodyCtl *rctl = reinterpret_cast<BodyCtl *>(base);
+            ExtRec *rrecs = reinterpret_cast<ExtRec *>(base + (((size_t)L * sizeof(BodyCtl) + 15) & ~(size_t)15));
+            body_work<true>(X1e, X2e, st, cnt0, cmin0, cmax0, chunk0, rctl, rrecs, layer, role, true, W, nslot, Ny, Nx,
+                            joff, nxt, XT, seg0, seg1, R0, R1, dx, dy, r2, flags);
+        }
+    }
+    if (csize > 1) cluster.sync();                      // the first CTA's shared memory outlives the helper's accesses
 }
 
 // Which variant sweeps this call?  The all-layers kernel keeps one CTA (SM) per (layer, macro-tile) for
@@ -1816,11 +2087,13 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
             const long need_recs = 2L * (blocks16 * 16 > blocks8 * 8 ? blocks16 * 16 : blocks8 * 8) * CAPW;
             const int fused_ok = (XTf <= LMAX && need_recs <= L.cap) ? 1 : 0;
             // body variant: warps per layer = chain + discovery + P prepare warps in a CTA of <= 640 threads
-            int P = 0, nslot = 0;
+            int P = 0, Wd = 1, nslot = 0;
             size_t body_smem = 0;
             if (Lyr <= BODY_LMAX) {
-                P = 20 / Lyr - 2;
-                if (P > 4) P = 4;
+                int per = 24 / Lyr;                // warps per layer in a CTA of 768 threads
+                if (per > 8) per = 8;
+                Wd = per >= 6 ? 2 : 1;             // discovery warps (rows in turn)
+                P = per - 1 - Wd;                  // prepare warps
                 const size_t ctl_bytes = ((size_t)Lyr * sizeof(BodyCtl) + 15) & ~(size_t)15;
                 nslot = (int)((220 * 1024 - ctl_bytes) / ((size_t)Lyr * sizeof(ExtRec)));
                 if (nslot > BSLOT_MAX) nslot = BSLOT_MAX;
@@ -1840,8 +2113,30 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
                                               force.rows, force.pre_warps, tilecnt, bviol, body_ok, fused_ok, mode);
                 RMT_LAUNCH_CHECK();
                 if (body_ok) {
-                    k_ext_body<<<ntile0, Lyr * (2 + P) * 32, body_smem, s>>>(X1e, X2e, st, cnt0, tilecnt, mode, Lyr, P,
-                                                                             nslot, Ny, Nx, joff, nxtf, XTf, dx, dy, r2);
+                    static int body_flags = -1;      // debugging hook: RMT_BODY_FLAGS (default 3 = everything on)
+                    if (body_flags < 0) { const char *e = getenv("RMT_BODY_FLAGS"); body_flags = e ? atoi(e) : 3; }
+                    // a cluster of two CTAs per tile when the tiles leave SMs free for the helpers
+                    static int body_cluster = -1;    // RMT_BODY_CLUSTER=2: a helper CTA per tile (measured slower: see DESIGN.md)
+                    if (body_cluster < 0) { const char *e = getenv("RMT_BODY_CLUSTER"); body_cluster = e ? atoi(e) : 1; }
+                    const int csz = body_cluster >= 2 ? 2 : 1;
+                    if (csz == 1) {
+                        k_ext_body<<<ntile0, 768, body_smem, s>>>(X1e, X2e, st, cnt0, tilecnt, mode, Lyr, P, Wd, nslot, Ny, Nx,
+                                                                  joff, nxtf, XTf, dx, dy, r2, body_flags);
+                    } else {
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(ntile0 * csz);
+                    cfg.blockDim = dim3(768);
+                    cfg.dynamicSmemBytes = body_smem;
+                    cfg.stream = s;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at;
+                    cfg.numAttrs = 1;
+                    RMT_CUDA(cudaLaunchKernelEx(&cfg, k_ext_body, X1e, X2e, st, (const int *)cnt0, (const int *)tilecnt,
+                                                (const int *)mode, Lyr, P, Wd, nslot, Ny, Nx, joff, nxtf, XTf, dx, dy, r2,
+                                                body_flags));
+                    }
                     RMT_LAUNCH_CHECK();
                 }
                 if (fused_ok) {
@@ -1888,11 +2183,20 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
 }
 
 #ifdef RMT_EXT_TIMING
-int rmt_body_debug_read(unsigned long long *out16, int reset)
+int rmt_body_watch_read(int *out192, int reset)
 {
-    RMT_CUDA(cudaMemcpyFromSymbol(out16, g_body_dbg, sizeof(unsigned long long) * 16));
+    RMT_CUDA(cudaMemcpyFromSymbol(out192, g_body_watch, sizeof(int) * 192));
     if (reset) {
-        unsigned long long z[16] = {0};
+        int z[192] = {0};
+        RMT_CUDA(cudaMemcpyToSymbol(g_body_watch, z, sizeof(z)));
+    }
+    return RMT_OK;
+}
+int rmt_body_debug_read(unsigned long long *out128, int reset)
+{
+    RMT_CUDA(cudaMemcpyFromSymbol(out128, g_body_dbg, sizeof(unsigned long long) * 128));
+    if (reset) {
+        unsigned long long z[128] = {0};
         RMT_CUDA(cudaMemcpyToSymbol(g_body_dbg, z, sizeof(z)));
     }
     return RMT_OK;
