@@ -140,6 +140,10 @@ int rmt_extrapolate_last_mode(const void *workspace, int Ny, int Nx, int *out3, 
 /* device exp() used for the weights, exposed so tests can prove bit-equality
  * with the host libm (functions.py:120). */
 int rmt_exp_probe(const double *x, double *y, long n, void *stream);
+/* the WENO5 kernels replace x / 6 and the three a_k / s of functions.py:256-318 by a correctly rounded
+ * reciprocal-and-residual sequence; exposed so tests can prove bit-equality with IEEE division.
+ * mode 0: out = a / 6 (b unused); mode 1: out = a / b. */
+int rmt_weno_div_probe(const double *a, const double *b, double *out, long n, int mode, void *stream);
 
 /* ------------------------------------------------- stress + momentum (a10-a13) */
 /* pyRMT/functions.py:545-658 solid_cauchy_stress. */

@@ -45,6 +45,7 @@ _SIG = {
     "rmt_extrapolate_set_mode": [i32, i32, i64],
     "rmt_extrapolate_last_mode": [vp, i32, i32, C.POINTER(i32), vp],
     "rmt_exp_probe": [vp, vp, i64, vp],
+    "rmt_weno_div_probe": [vp, vp, vp, i64, i32, vp],
     "rmt_solid_stress": [vp, vp, vp, vp, vp, vp, vp, i32, i32, dbl, dbl, dbl, dbl, dbl, dbl, i32, vp],
     "rmt_curvature": [vp, vp, i32, i32, dbl, dbl, vp],
     "rmt_surface_tension": [vp, vp, vp, i32, i32, dbl, dbl, dbl, dbl, vp],

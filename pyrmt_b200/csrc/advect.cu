@@ -170,37 +170,77 @@ __global__ void k_advect_sl(const double *__restrict__ q0, const double *__restr
 // ------------------------------------------------------------------- WENO5
 __device__ __forceinline__ double sq(double v) { return v * v; }
 
-__device__ __forceinline__ double weno_mix(double r0, double r1, double r2, double b0, double b1,
-                                           double b2)
+// a / b from y = RN(1 / b), correctly rounded (IEEE a / b bit for bit) in five fused operations:
+// q = RN(a y) is within two ulps, one residual step makes it faithful, and for a faithful q and a
+// correctly rounded reciprocal the second step q + (a - b q) y rounds to RN(a / b) (Markstein 1990,
+// the closing step of every Newton-Raphson divider; fma() is not subject to -fmad=false).  The
+// residuals must be exact, which needs operands, reciprocal and quotient well inside the normal
+// range: |a|, |b| in [1e-140, 1e140].  A reconstruction whose operands leave that range (zeros,
+// subnormals, huge, non-finite) takes the plain IEEE version below, as a whole.
+// rmt_weno_div_probe lets the tests compare this against `/` on tens of millions of operands.
+__device__ __forceinline__ bool div_range_ok(double a) { const double m = fabs(a); return m >= 1e-140 && m <= 1e140; }
+__device__ __forceinline__ double div_by_recip_raw(double a, double b, double y)
+{
+    const double q0 = a * y;
+    const double r0 = fma(-b, q0, a);
+    const double q1 = fma(r0, y, q0);
+    const double r1 = fma(-b, q1, a);
+    return fma(r1, y, q1);
+}
+__device__ __forceinline__ double div_by_recip(double a, double b, double y)    // guarded form (probe, tests)
+{
+    if (!(div_range_ok(a) && div_range_ok(b))) return a / b;
+    return div_by_recip_raw(a, b, y);
+}
+
+// the reference's expression tree with IEEE divisions throughout (functions.py:256-286 / :289-318 after
+// the stencil has been ordered): n0..n2 numerators of the three candidate values, b0..b2 smoothness
+__device__ __noinline__ double weno_mix_ieee(double n0, double n1, double n2, double b0, double b1, double b2)
 {
     const double eps = 1.0e-6;
+    double r0 = n0 / 6.0, r1 = n1 / 6.0, r2 = n2 / 6.0;
     double a0 = 0.1 / sq(eps + b0), a1 = 0.6 / sq(eps + b1), a2 = 0.3 / sq(eps + b2);
     double s = a0 + a1 + a2;
     return (a0 / s) * r0 + (a1 / s) * r1 + (a2 / s) * r2;
 }
 
+__device__ __forceinline__ double weno_mix(double n0, double n1, double n2, double b0, double b1, double b2)
+{
+    const double eps = 1.0e-6;
+    double a0 = 0.1 / sq(eps + b0), a1 = 0.6 / sq(eps + b1), a2 = 0.3 / sq(eps + b2);
+    double s = a0 + a1 + a2;
+    if (!(div_range_ok(n0) && div_range_ok(n1) && div_range_ok(n2) && div_range_ok(a0) && div_range_ok(a1) &&
+          div_range_ok(a2) && div_range_ok(s)))
+        return weno_mix_ieee(n0, n1, n2, b0, b1, b2);
+    const double sixth = 1.0 / 6.0;
+    const double r0 = div_by_recip_raw(n0, 6.0, sixth), r1 = div_by_recip_raw(n1, 6.0, sixth),
+                 r2 = div_by_recip_raw(n2, 6.0, sixth);
+    const double y = 1.0 / s;                  // one reciprocal serves the three quotients
+    return div_by_recip_raw(a0, s, y) * r0 + div_by_recip_raw(a1, s, y) * r1 + div_by_recip_raw(a2, s, y) * r2;
+}
+
 // left-biased value at k+1/2 from (k-2..k+2), functions.py:256-286
 __device__ __forceinline__ double weno_minus(double vm2, double vm1, double v0, double vp1, double vp2)
 {
-    double r0 = (2.0 * vm2 - 7.0 * vm1 + 11.0 * v0) / 6.0;
-    double r1 = (-vm1 + 5.0 * v0 + 2.0 * vp1) / 6.0;
-    double r2 = (2.0 * v0 + 5.0 * vp1 - vp2) / 6.0;
+    double n0 = 2.0 * vm2 - 7.0 * vm1 + 11.0 * v0;
+    double n1 = -vm1 + 5.0 * v0 + 2.0 * vp1;
+    double n2 = 2.0 * v0 + 5.0 * vp1 - vp2;
     double b0 = (13.0 / 12.0) * sq(vm2 - 2.0 * vm1 + v0) + 0.25 * sq(vm2 - 4.0 * vm1 + 3.0 * v0);
     double b1 = (13.0 / 12.0) * sq(vm1 - 2.0 * v0 + vp1) + 0.25 * sq(vm1 - vp1);
     double b2 = (13.0 / 12.0) * sq(v0 - 2.0 * vp1 + vp2) + 0.25 * sq(3.0 * v0 - 4.0 * vp1 + vp2);
-    return weno_mix(r0, r1, r2, b0, b1, b2);
+    return weno_mix(n0, n1, n2, b0, b1, b2);
 }
 
 // right-biased value at k+1/2 from (k-1..k+3), functions.py:289-318
 __device__ __forceinline__ double weno_plus(double vm1, double v0, double vp1, double vp2, double vp3)
 {
-    double r0 = (2.0 * vp3 - 7.0 * vp2 + 11.0 * vp1) / 6.0;
-    double r1 = (-vp2 + 5.0 * vp1 + 2.0 * v0) / 6.0;
-    double r2 = (2.0 * vp1 + 5.0 * v0 - vm1) / 6.0;
+    double n0 = 2.0 * vp3 - 7.0 * vp2 + 11.0 * vp1;
+    double n1 = -vp2 + 5.0 * vp1 + 2.0 * v0;
+    double n2 = 2.0 * vp1 + 5.0 * v0 - vm1;
     double b0 = (13.0 / 12.0) * sq(vp3 - 2.0 * vp2 + vp1) + 0.25 * sq(3.0 * vp1 - 4.0 * vp2 + vp3);
     double b1 = (13.0 / 12.0) * sq(vp2 - 2.0 * vp1 + v0) + 0.25 * sq(vp2 - v0);
     double b2 = (13.0 / 12.0) * sq(vp1 - 2.0 * v0 + vm1) + 0.25 * sq(vp1 - 4.0 * v0 + 3.0 * vm1);
-    return weno_mix(r0, r1, r2, b0, b1, b2);
+    return weno_mix(n0, n1, n2, b0, b1, b2);
 }
 
 // d q / d(line) at index k of n with the reference's face selection and rim
@@ -598,6 +638,14 @@ k_weno_stage(const EulerFields F, const double *__restrict__ a, const double *__
     }
 }
 
+// test probe: mode 0: a / 6 through div6; mode 1: a / b through div_by_recip with y = 1 / b
+__global__ void k_weno_div_probe(const double *__restrict__ a, const double *__restrict__ b,
+                                 double *__restrict__ out, long n, int mode)
+{
+    for (long k = blockIdx.x * (long)blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x)
+        out[k] = mode == 0 ? div_by_recip(a[k], 6.0, 1.0 / 6.0) : div_by_recip(a[k], b[k], 1.0 / b[k]);
+}
+
 // standalone RHS (API parity for _weno5_rhs/_central2_rhs/_conservative_rhs)
 template <int SCHEME>
 __global__ void k_euler_rhs(const double *__restrict__ qs, const double *__restrict__ a,
@@ -797,6 +845,14 @@ int rmt_advect_euler_rk3_pair(const double *q0, const double *q1, const double *
     case 2: return euler_rk3<2, 2>(qq, a, b, phi, oo, w1, w2, Ny, Nx, dx, dy, dt, w_cut, mask_solid, s);
     }
     return RMT_EINVAL;
+}
+
+int rmt_weno_div_probe(const double *a, const double *b, double *out, long n, int mode, void *stream)
+{
+    if (!a || !out || n <= 0 || (mode != 0 && mode != 1) || (mode == 1 && !b)) return RMT_EINVAL;
+    k_weno_div_probe<<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, mode);
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
 }
 
 int rmt_euler_rhs(const double *q, const double *a, const double *b, const double *phi, double *out,

@@ -94,6 +94,36 @@ def test_device_exp_is_libm_exp(O):
     assert same(yd.cpu().numpy(), O.libm_exp(x)), "device exp differs from host libm exp"
 
 
+def test_weno_division_is_ieee_division():
+    """The WENO5 kernels divide through a reciprocal + two exact-residual steps (advect.cu div_by_recip);
+    it must equal IEEE division bit for bit: 6.0 as the divisor and random divisors, operands over the
+    whole exponent range the kernels can see plus the guarded extremes."""
+    import torch
+    from pyrmt_b200 import _lib
+    from pyrmt_b200._runtime import ctx, ptr, stream
+    rng = np.random.default_rng(11)
+    n = 20_000_000
+    mant = rng.random(n) + 1.0
+    a = mant * 2.0 ** rng.integers(-900, 900, n) * rng.choice([-1.0, 1.0], n)
+    edge = np.array([0.0, -0.0, 6.0, -6.0, 1e-320, 1e-300, 1e300, np.inf, -np.inf, np.nan, 3.0, 1.0 / 3.0,
+                     np.nextafter(6.0, 7.0), np.nextafter(6.0, 5.0), 2.0 ** -1022, 1.7976931348623157e308])
+    a = np.concatenate([a, edge, rng.random(4_000_000) * 12.0 - 6.0])
+    ad = torch.from_numpy(a).cuda()
+    out = torch.empty_like(ad)
+    _lib.check(ctx().lib.rmt_weno_div_probe(ptr(ad), None, ptr(out), ad.numel(), 0, stream()), "div6")
+    with np.errstate(all="ignore"):
+        assert same(out.cpu().numpy(), a / 6.0), "div6 differs from IEEE a / 6.0"
+    # random divisors, including significands of all ones and powers of two
+    mb = rng.random(a.size) + 1.0
+    mb[:1000] = np.nextafter(2.0, 1.0)
+    mb[1000:2000] = 1.0
+    b = mb * 2.0 ** rng.integers(-300, 300, a.size)
+    bd = torch.from_numpy(b).cuda()
+    _lib.check(ctx().lib.rmt_weno_div_probe(ptr(ad), ptr(bd), ptr(out), ad.numel(), 1, stream()), "div")
+    with np.errstate(all="ignore"):
+        assert same(out.cpu().numpy(), a / b), "div_by_recip differs from IEEE a / b"
+
+
 def test_extrapolation_bit_exact_golden(P, golden):
     g = golden("extrap")
     dx, dy = float(g["dx"]), float(g["dy"])
