@@ -78,6 +78,14 @@ int rmt_apply_bc(double *u, double *v, const long long *dst, const long long *sr
 int rmt_disc_sdf(const double *X1, const double *X2, double *phi, long n, const double *cx,
                  const double *cy, const double *R, int ndisc, const int *bin_start, const int *cand,
                  int gb, double Lx, double Ly, void *stream);
+/* rmt_disc_sdf followed by rmt_solid_stress (functions.py:1366-1367 then :545-658) in one pass: the
+ * drivers rebuild phi from the extrapolated map and hand both to momentum_step_rk4
+ * (soft_disc_in_lid_driven.py:93-97).  phi is bitwise the rmt_disc_sdf result. */
+int rmt_disc_sdf_stress(const double *X1, const double *X2, double *phi, double *sxx, double *sxy,
+                        double *syy, double *J, int Ny, int Nx, double dx, double dy, double mu_s,
+                        double kappa, double w_cut, double detg_clamp, int isochoric, const double *cx,
+                        const double *cy, const double *R, int ndisc, const int *bin_start, const int *cand,
+                        int gb, double Lx, double Ly, void *stream);
 
 /* ------------------------------------------------------------ interpolators */
 /* pyRMT/interpolators.py:4-62 (cubic=0) and :64-141 (cubic=1); nq query points. */
@@ -241,6 +249,16 @@ int rmt_projection_correct(const double *sol, const double *sol_sum, const doubl
                            const double *b_star, const double *rho, double rho_scalar,
                            const double *p_prev, double *a, double *b, double *p, int Ny, int Nx,
                            double dx, double dy, double dt, int periodic, void *stream);
+/* The same back end with `p -= mean(p)` (:1361) folded in: p = p_prev + pc - p_prev_sum[0]/(Ny*Nx)
+ * (mean(pc) is zero to rounding, so mean(p_prev) is mean(p_prev + pc) to rounding; p_prev_sum == NULL: 0),
+ * and sum(p) of the field written here goes to p_sum_out (device scalar) for the next step -- p is
+ * neither re-read for its mean nor rewritten.  partial: rmt_projection_partials(Ny, Nx) doubles. */
+long rmt_projection_partials(int Ny, int Nx);
+int rmt_projection_correct_centered(const double *sol, const double *sol_sum, const double *a_star,
+                                    const double *b_star, const double *rho, double rho_scalar,
+                                    const double *p_prev, const double *p_prev_sum, double *a, double *b,
+                                    double *p, double *partial, double *p_sum_out, int Ny, int Nx, double dx,
+                                    double dy, double dt, int periodic, void *stream);
 /* x[k] = x[k] - s[0]/n  in place (the np.mean removals :1118,:1232,:1362). */
 int rmt_subtract_mean(double *x, const double *sum, long n, void *stream);
 

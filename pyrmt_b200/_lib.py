@@ -33,6 +33,8 @@ _SIG = {
     "rmt_field_stats": [vp, i64, vp, vp, vp],
     "rmt_apply_bc": [vp, vp, vp, vp, vp, vp, i32, vp],
     "rmt_disc_sdf": [vp, vp, vp, i64, vp, vp, vp, i32, vp, vp, i32, dbl, dbl, vp],
+    "rmt_disc_sdf_stress": [vp, vp, vp, vp, vp, vp, vp, i32, i32, dbl, dbl, dbl, dbl, dbl, dbl, i32, vp, vp, vp, i32, vp, vp,
+                            i32, dbl, dbl, vp],
     "rmt_sample": [vp, vp, vp, vp, i64, dbl, dbl, i32, i32, i32, vp],
     "rmt_advect_sl_rk4": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, dbl, dbl, dbl, i32, vp],
     "rmt_advect_sl_rk4_rows": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, dbl, dbl, dbl, i32, vp],
@@ -64,6 +66,8 @@ _SIG = {
     "rmt_projection_rhs": [vp, vp, vp, vp, dbl, vp, vp, i32, i32, dbl, dbl, dbl, i32, vp],
     "rmt_projection_correct": [vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, i32, i32, dbl, dbl, dbl, i32, vp],
     "rmt_subtract_mean": [vp, vp, i64, vp],
+    "rmt_projection_partials": [i32, i32],
+    "rmt_projection_correct_centered": [vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp, vp, i32, i32, dbl, dbl, dbl, i32, vp],
     "rmt_poisson_plan_create": [i32, i32, i32, C.POINTER(vp)],
     "rmt_poisson_plan_destroy": [vp],
     "rmt_poisson_plan_is_fast": [vp],
@@ -75,7 +79,7 @@ _SIG = {
     "rmt_transpose": [vp, vp, i32, i32, vp],
     "rmt_copy2d": [vp, vp, i32, i32, i64, i64, vp],
 }
-_RESTYPE = {"rmt_launch_count": C.c_ulonglong, "rmt_extrapolate_workspace_bytes": i64, "rmt_poisson_plan_destroy": None}
+_RESTYPE = {"rmt_launch_count": C.c_ulonglong, "rmt_extrapolate_workspace_bytes": i64, "rmt_projection_partials": i64, "rmt_poisson_plan_destroy": None}
 
 EXPORTS = tuple(_SIG)
 

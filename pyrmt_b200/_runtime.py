@@ -63,7 +63,7 @@ def shape2(t):
 # rmt_extrapolate launches 1 + 4 per layer: its caller adds the 4 per layer).
 _LAUNCHES = {"rmt_max_speed": 2, "rmt_field_stats": 2, "rmt_advect_euler_rk3": 5, "rmt_advect_euler_rk3_pair": 5, "rmt_extrapolate": 1, "rmt_extrapolate_rows": 1,
              "rmt_poisson_solve_dct": 4, "rmt_poisson_solve_fft": 16, "rmt_abi_version": 0, "rmt_launch_count": 0, "rmt_diagnostics_workspace_doubles": 0, "rmt_diagnostics": 2,
-             "rmt_reduce_workspace_doubles": 0, "rmt_extrapolate_workspace_bytes": 0, "rmt_extrapolate_set_mode": 0, "rmt_extrapolate_last_mode": 0,
+             "rmt_reduce_workspace_doubles": 0, "rmt_projection_partials": 0, "rmt_projection_correct_centered": 2, "rmt_extrapolate_workspace_bytes": 0, "rmt_extrapolate_set_mode": 0, "rmt_extrapolate_last_mode": 0,
              "rmt_poisson_plan_create": 0, "rmt_poisson_plan_destroy": 0, "rmt_poisson_plan_is_fast": 0, "rmt_poisson_plan_invalidate": 0}
 
 
@@ -177,6 +177,15 @@ class _Ctx:
             ent = (ident, tuple(devs), tuple(tables))
             self.plan_tables[key] = ent
         return plan, ent[1]
+
+    def scratch(self, name, ndoubles):
+        """A named fp64 scratch buffer that is reused across calls (grown on demand)."""
+        d = self.__dict__.setdefault("_scratch", {})
+        t = d.get(name)
+        if t is None or t.numel() < ndoubles:
+            t = torch.empty(int(ndoubles), dtype=F64, device=self.dev)
+            d[name] = t
+        return t
 
     def extrap_workspace(self, Ny, Nx):
         key = (Ny, Nx)

@@ -88,6 +88,80 @@ __device__ __forceinline__ double heaviside_sin(double x, double w_t, double inv
     return 0.5 * (1.0 + x * inv_w + inv_pi * sin(pi * x * inv_w));
 }
 
+// ---- neo-Hookean Cauchy stress of one node, pyRMT/functions.py:545-658 ------
+// X1, X2, PHI: functors (j, i) -> value.  w_cut > 0: band mode (central differences where
+// phi < w_cut); w_cut == 0: legacy mode (phi <= 0, one-sided differences next to the interface).
+template <class FX, class FP>
+__device__ __forceinline__ void solid_stress_cell(const FX &X1, const FX &X2, const FP &PHI, int j, int i, int Ny,
+                                                  int Nx, double dx, double dy, double mu_s, double kappa,
+                                                  double w_cut, double detg_clamp, int isochoric, double &oxx,
+                                                  double &oxy, double &oyy, double &oJ)
+{
+    oxx = 0.0; oxy = 0.0; oyy = 0.0; oJ = 1.0;
+    if (!(i >= 1 && i < Nx - 1 && j >= 1 && j < Ny - 1)) return;
+    const double ph = PHI(j, i);
+    const bool band = (w_cut > 0.0) ? (ph < w_cut) : (ph <= 0.0);
+    if (!band) return;
+    const double inv_2dx = 1.0 / (2.0 * dx), inv_2dy = 1.0 / (2.0 * dy);
+    const double x1c = X1(j, i), x2c = X2(j, i);
+    const double x1l = X1(j, i - 1), x1r = X1(j, i + 1), x2l = X2(j, i - 1), x2r = X2(j, i + 1);
+    const double x1b = X1(j - 1, i), x1t = X1(j + 1, i), x2b = X2(j - 1, i), x2t = X2(j + 1, i);
+    double g11, g21, g12, g22;
+    if (w_cut > 0.0) {
+        g11 = (x1r - x1l) * inv_2dx;
+        g21 = (x2r - x2l) * inv_2dx;
+        g12 = (x1t - x1b) * inv_2dy;
+        g22 = (x2t - x2b) * inv_2dy;
+    } else {
+        const bool lf = PHI(j, i - 1) > 0.0, rf = PHI(j, i + 1) > 0.0;
+        if (lf && !rf) {
+            g11 = (x1r - x1c) / dx;
+            g21 = (x2r - x2c) / dx;
+        } else if (rf && !lf) {
+            g11 = (x1c - x1l) / dx;
+            g21 = (x2c - x2l) / dx;
+        } else {
+            g11 = (x1r - x1l) * inv_2dx;
+            g21 = (x2r - x2l) * inv_2dx;
+        }
+        const bool bf = PHI(j - 1, i) > 0.0, tf = PHI(j + 1, i) > 0.0;
+        if (bf && !tf) {
+            g12 = (x1t - x1c) / dy;
+            g22 = (x2t - x2c) / dy;
+        } else if (tf && !bf) {
+            g12 = (x1c - x1b) / dy;
+            g22 = (x2c - x2b) / dy;
+        } else {
+            g12 = (x1t - x1b) * inv_2dy;
+            g22 = (x2t - x2b) * inv_2dy;
+        }
+    }
+    double detG = g11 * g22 - g12 * g21;
+    if (fabs(detG) < 1e-10) return;
+    if (detg_clamp > 0.0) {
+        const double lo = 1.0 / detg_clamp;
+        if (detG < lo) detG = lo;
+        else if (detG > detg_clamp) detG = detg_clamp;
+    }
+    const double f11 = g22 / detG, f12 = -g12 / detG, f21 = -g21 / detG, f22 = g11 / detG;
+    const double b11 = f11 * f11 + f12 * f12;
+    const double b12 = f11 * f21 + f12 * f22;
+    const double b22 = f21 * f21 + f22 * f22;
+    const double jv = 1.0 / detG;
+    oJ = jv;
+    const double vol = kappa * (jv - 1.0);
+    if (isochoric) {
+        const double trh = 0.5 * (b11 + b22), jm2 = 1.0 / (jv * jv);
+        oxx = mu_s * jm2 * (b11 - trh) + vol;
+        oxy = mu_s * jm2 * b12;
+        oyy = mu_s * jm2 * (b22 - trh) + vol;
+    } else {
+        oxx = mu_s * b11 + vol;
+        oxy = mu_s * b12;
+        oyy = mu_s * b22 + vol;
+    }
+}
+
 // ---- block-wide reductions (deterministic tree) ----------------------------
 __device__ __forceinline__ double warp_sum(double v)
 {

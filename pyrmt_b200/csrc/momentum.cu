@@ -44,74 +44,9 @@ k_solid_stress(const double *__restrict__ X1, const double *__restrict__ X2,
     int j = blockIdx.y * TY + threadIdx.y;
     if (i >= Nx || j >= Ny) return;
     size_t c = (size_t)j * Nx + i;
-    double oxx = 0.0, oxy = 0.0, oyy = 0.0, oJ = 1.0;
-    if (i >= 1 && i < Nx - 1 && j >= 1 && j < Ny - 1) {
-        double ph = phi[c];
-        bool band = (w_cut > 0.0) ? (ph < w_cut) : (ph <= 0.0);
-        if (band) {
-            const double inv_2dx = 1.0 / (2.0 * dx), inv_2dy = 1.0 / (2.0 * dy);
-            double x1c = X1[c], x2c = X2[c];
-            double x1l = __ldg(X1 + c - 1), x1r = __ldg(X1 + c + 1);
-            double x2l = __ldg(X2 + c - 1), x2r = __ldg(X2 + c + 1);
-            double x1b = __ldg(X1 + c - Nx), x1t = __ldg(X1 + c + Nx);
-            double x2b = __ldg(X2 + c - Nx), x2t = __ldg(X2 + c + Nx);
-            double g11, g21, g12, g22;
-            if (w_cut > 0.0) {
-                g11 = (x1r - x1l) * inv_2dx;
-                g21 = (x2r - x2l) * inv_2dx;
-                g12 = (x1t - x1b) * inv_2dy;
-                g22 = (x2t - x2b) * inv_2dy;
-            } else {
-                bool lf = __ldg(phi + c - 1) > 0.0, rf = __ldg(phi + c + 1) > 0.0;
-                if (lf && !rf) {
-                    g11 = (x1r - x1c) / dx;
-                    g21 = (x2r - x2c) / dx;
-                } else if (rf && !lf) {
-                    g11 = (x1c - x1l) / dx;
-                    g21 = (x2c - x2l) / dx;
-                } else {
-                    g11 = (x1r - x1l) * inv_2dx;
-                    g21 = (x2r - x2l) * inv_2dx;
-                }
-                bool bf = __ldg(phi + c - Nx) > 0.0, tf = __ldg(phi + c + Nx) > 0.0;
-                if (bf && !tf) {
-                    g12 = (x1t - x1c) / dy;
-                    g22 = (x2t - x2c) / dy;
-                } else if (tf && !bf) {
-                    g12 = (x1c - x1b) / dy;
-                    g22 = (x2c - x2b) / dy;
-                } else {
-                    g12 = (x1t - x1b) * inv_2dy;
-                    g22 = (x2t - x2b) * inv_2dy;
-                }
-            }
-            double detG = g11 * g22 - g12 * g21;
-            if (!(fabs(detG) < 1e-10)) {
-                if (detg_clamp > 0.0) {
-                    double lo = 1.0 / detg_clamp;
-                    if (detG < lo) detG = lo;
-                    else if (detG > detg_clamp) detG = detg_clamp;
-                }
-                double f11 = g22 / detG, f12 = -g12 / detG, f21 = -g21 / detG, f22 = g11 / detG;
-                double b11 = f11 * f11 + f12 * f12;
-                double b12 = f11 * f21 + f12 * f22;
-                double b22 = f21 * f21 + f22 * f22;
-                double jv = 1.0 / detG;
-                oJ = jv;
-                double vol = kappa * (jv - 1.0);
-                if (isochoric) {
-                    double trh = 0.5 * (b11 + b22), jm2 = 1.0 / (jv * jv);
-                    oxx = mu_s * jm2 * (b11 - trh) + vol;
-                    oxy = mu_s * jm2 * b12;
-                    oyy = mu_s * jm2 * (b22 - trh) + vol;
-                } else {
-                    oxx = mu_s * b11 + vol;
-                    oxy = mu_s * b12;
-                    oyy = mu_s * b22 + vol;
-                }
-            }
-        }
-    }
+    double oxx, oxy, oyy, oJ;
+    const GField G1{X1, Nx}, G2{X2, Nx}, GP{phi, Nx};
+    solid_stress_cell(G1, G2, GP, j, i, Ny, Nx, dx, dy, mu_s, kappa, w_cut, detg_clamp, isochoric, oxx, oxy, oyy, oJ);
     sxx[c] = oxx;
     sxy[c] = oxy;
     syy[c] = oyy;

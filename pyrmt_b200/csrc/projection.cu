@@ -209,6 +209,59 @@ k_projection_correct(const double *__restrict__ sol, const double *__restrict__ 
     p[c] = p_prev ? (p_prev[c] + pc) : pc;
 }
 
+// The same back end with mean(p) removed in the same pass: p = p_prev + pc - p_prev_sum/N (mean(pc) is zero
+// to rounding, so mean(p_prev) IS mean(p_prev + pc) to rounding), and the block sums of the p written here
+// go to `partial` so that the next step gets its sum(p_prev) without reading p again.
+__global__ void __launch_bounds__(256)
+k_projection_correct_centered(const double *__restrict__ sol, const double *__restrict__ sol_sum,
+                              const double *__restrict__ a_star, const double *__restrict__ b_star,
+                              const double *__restrict__ rho, double rho_scalar,
+                              const double *__restrict__ p_prev, const double *__restrict__ p_prev_sum,
+                              double *__restrict__ a, double *__restrict__ b, double *__restrict__ p,
+                              double *__restrict__ partial, int Ny, int Nx, double dx, double dy, double dt,
+                              int periodic)
+{
+    __shared__ double red[TY];
+    const int i = blockIdx.x * TX + threadIdx.x;
+    const int j = blockIdx.y * TY + threadIdx.y;
+    double pv = 0.0;
+    if (i < Nx && j < Ny) {
+        const size_t c = (size_t)j * Nx + i;
+        const double n = (double)Ny * (double)Nx;
+        const Shifted PC{sol, Nx, sol_sum ? sol_sum[0] / n : 0.0};
+        double gx, gy;
+        if (periodic == 2) pgrad_slab(PC, j, i, Ny, Nx, 0.5 / dx, 0.5 / dy, gx, gy);
+        else if (periodic) pgrad_periodic(PC, j, i, Ny, Nx, 0.5 / dx, 0.5 / dy, gx, gy);
+        else pgrad_neumann(PC, j, i, Ny, Nx, 0.5 / dx, 0.5 / dy, gx, gy);
+        const double r = rho ? rho[c] : rho_scalar;
+        const double dtr = dt / r;
+        a[c] = a_star[c] - dtr * gx;
+        b[c] = b_star[c] - dtr * gy;
+        const double pc = PC(j, i);
+        const double m = p_prev_sum ? p_prev_sum[0] / n : 0.0;
+        pv = (p_prev ? (p_prev[c] + pc) : pc) - m;
+        p[c] = pv;
+    }
+    // deterministic block sum (warp tree, then the TY warp sums in order)
+    pv = warp_sum(pv);
+    if (threadIdx.x == 0) red[threadIdx.y] = pv;
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        double s = 0.0;
+        for (int w = 0; w < TY; ++w) s += red[w];
+        partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+__global__ void k_sum_partials(const double *__restrict__ part, long n, double *__restrict__ out)
+{
+    __shared__ double red[32];
+    double s = 0.0;
+    for (long k = threadIdx.x; k < n; k += blockDim.x) s += part[k];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
 __global__ void k_subtract_mean(double *__restrict__ x, const double *__restrict__ sum, long n)
 {
     const double m = sum[0] / (double)n;
@@ -299,6 +352,25 @@ int rmt_projection_correct(const double *sol, const double *sol_sum, const doubl
     k_projection_correct<<<grd, blk, 0, (cudaStream_t)stream>>>(sol, sol_sum, a_star, b_star, rho,
                                                                rho_scalar, p_prev, a, b, p, Ny, Nx, dx,
                                                                dy, dt, periodic);
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
+
+long rmt_projection_partials(int Ny, int Nx) { return (long)rmt_cdiv(Nx, TX) * rmt_cdiv(Ny, TY); }
+
+int rmt_projection_correct_centered(const double *sol, const double *sol_sum, const double *a_star,
+                                    const double *b_star, const double *rho, double rho_scalar,
+                                    const double *p_prev, const double *p_prev_sum, double *a, double *b,
+                                    double *p, double *partial, double *p_sum_out, int Ny, int Nx, double dx,
+                                    double dy, double dt, int periodic, void *stream)
+{
+    if (!sol || !a_star || !b_star || !a || !b || !p || !partial || !p_sum_out || Ny < 4 || Nx < 4) return RMT_EINVAL;
+    dim3 blk(TX, TY), grd(rmt_cdiv(Nx, TX), rmt_cdiv(Ny, TY));
+    cudaStream_t s = (cudaStream_t)stream;
+    k_projection_correct_centered<<<grd, blk, 0, s>>>(sol, sol_sum, a_star, b_star, rho, rho_scalar, p_prev,
+                                                     p_prev_sum, a, b, p, partial, Ny, Nx, dx, dy, dt, periodic);
+    RMT_LAUNCH_CHECK();
+    k_sum_partials<<<1, 1024, 0, s>>>(partial, (long)grd.x * grd.y, p_sum_out);
     RMT_LAUNCH_CHECK();
     return RMT_OK;
 }

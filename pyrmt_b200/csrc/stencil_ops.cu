@@ -289,36 +289,92 @@ __global__ void k_apply_bc(double *__restrict__ u, double *__restrict__ v,
 // candidates cand[start[bin] .. start[bin+1]) that can attain the minimum for
 // some point of that bin (a conservative superset built on the host), so the
 // result equals the full minimum bit for bit.
-__global__ void k_disc_sdf(const double *__restrict__ X1, const double *__restrict__ X2,
-                           double *__restrict__ phi, long n, const double *__restrict__ cx,
-                           const double *__restrict__ cy, const double *__restrict__ R, int ndisc,
-                           const int *__restrict__ bin_start, const int *__restrict__ cand, int gb,
-                           double Lx, double Ly, double inv_bw_x, double inv_bw_y)
+struct DiscSet {
+    const double *cx, *cy, *R;
+    int ndisc;
+    const int *bin_start, *cand;
+    int gb;
+    double Lx, Ly, inv_bw_x, inv_bw_y;
+};
+
+__device__ __forceinline__ double disc_sdf_point(double x, double y, const DiscSet &D)
 {
-    for (long c = blockIdx.x * (long)blockDim.x + threadIdx.x; c < n; c += (long)gridDim.x * blockDim.x) {
-        double x = X1[c], y = X2[c];
-        double best = 0.0;
-        bool have = false;
-        // points outside the binned box (or non-finite) take the exhaustive loop
-        if (gb > 0 && x >= 0.0 && x <= Lx && y >= 0.0 && y <= Ly) {
-            int bx = min((int)floor(x * inv_bw_x), gb - 1);
-            int by = min((int)floor(y * inv_bw_y), gb - 1);
-            int b = by * gb + bx;
-            for (int t = bin_start[b]; t < bin_start[b + 1]; ++t) {
-                int k = cand[t];
-                double ex = x - cx[k], ey = y - cy[k];
-                double d = sqrt(ex * ex + ey * ey) - R[k];
-                if (!have || d < best) { best = d; have = true; }
-            }
-        } else {
-            for (int k = 0; k < ndisc; ++k) {
-                double ex = x - cx[k], ey = y - cy[k];
-                double d = sqrt(ex * ex + ey * ey) - R[k];
-                if (!have || d < best) { best = d; have = true; }
-            }
+    double best = 0.0;
+    bool have = false;
+    // points outside the binned box (or non-finite) take the exhaustive loop
+    if (D.gb > 0 && x >= 0.0 && x <= D.Lx && y >= 0.0 && y <= D.Ly) {
+        int bx = min((int)floor(x * D.inv_bw_x), D.gb - 1);
+        int by = min((int)floor(y * D.inv_bw_y), D.gb - 1);
+        int b = by * D.gb + bx;
+        for (int t = D.bin_start[b]; t < D.bin_start[b + 1]; ++t) {
+            int k = D.cand[t];
+            double ex = x - D.cx[k], ey = y - D.cy[k];
+            double d = sqrt(ex * ex + ey * ey) - D.R[k];
+            if (!have || d < best) { best = d; have = true; }
         }
-        phi[c] = best;
+    } else {
+        for (int k = 0; k < D.ndisc; ++k) {
+            double ex = x - D.cx[k], ey = y - D.cy[k];
+            double d = sqrt(ex * ex + ey * ey) - D.R[k];
+            if (!have || d < best) { best = d; have = true; }
+        }
     }
+    return best;
+}
+
+__global__ void k_disc_sdf(const double *__restrict__ X1, const double *__restrict__ X2,
+                           double *__restrict__ phi, long n, const DiscSet D)
+{
+    for (long c = blockIdx.x * (long)blockDim.x + threadIdx.x; c < n; c += (long)gridDim.x * blockDim.x)
+        phi[c] = disc_sdf_point(X1[c], X2[c], D);
+}
+
+// phi = phi0(xi) AND the solid stress of that xi, phi in one pass (the drivers rebuild the level set
+// from the extrapolated map and hand both to the momentum predictor: soft_disc_in_lid_driven.py:93-97):
+// the level set of the tile and a one-node halo is formed in shared memory, so xi is read once and
+// phi never comes back from HBM for the stress.
+struct SmemPhi {
+    const double *s;
+    int j0, i0;
+    __device__ __forceinline__ double operator()(int j, int i) const { return s[(j - j0) * (TX + 2) + (i - i0)]; }
+};
+struct GlobalField {
+    const double *p;
+    int Nx;
+    __device__ __forceinline__ double operator()(int j, int i) const { return __ldg(p + (size_t)j * Nx + i); }
+};
+
+__global__ void __launch_bounds__(256)
+k_sdf_stress(const double *__restrict__ X1, const double *__restrict__ X2, double *__restrict__ phi,
+             double *__restrict__ sxx, double *__restrict__ sxy, double *__restrict__ syy,
+             double *__restrict__ J, int Ny, int Nx, double dx, double dy, double mu_s, double kappa,
+             double w_cut, double detg_clamp, int isochoric, const DiscSet D)
+{
+    __shared__ double sphi[(TY + 2) * (TX + 2)];
+    const int i0 = blockIdx.x * TX - 1, j0 = blockIdx.y * TY - 1;
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    for (int e = tid; e < (TY + 2) * (TX + 2); e += TX * TY) {
+        const int jj = j0 + e / (TX + 2), ii = i0 + e % (TX + 2);
+        double v = 0.0;
+        if (jj >= 0 && jj < Ny && ii >= 0 && ii < Nx) {
+            const size_t c = (size_t)jj * Nx + ii;
+            v = disc_sdf_point(__ldg(X1 + c), __ldg(X2 + c), D);
+        }
+        sphi[e] = v;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * TX + threadIdx.x, j = blockIdx.y * TY + threadIdx.y;
+    if (i >= Nx || j >= Ny) return;
+    const size_t c = (size_t)j * Nx + i;
+    const SmemPhi P{sphi, j0, i0};
+    const GlobalField G1{X1, Nx}, G2{X2, Nx};
+    double oxx, oxy, oyy, oJ;
+    solid_stress_cell(G1, G2, P, j, i, Ny, Nx, dx, dy, mu_s, kappa, w_cut, detg_clamp, isochoric, oxx, oxy, oyy, oJ);
+    phi[c] = P(j, i);
+    sxx[c] = oxx;
+    sxy[c] = oxy;
+    syy[c] = oyy;
+    J[c] = oJ;
 }
 
 inline int flat_blocks(long n) { long b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
@@ -430,8 +486,24 @@ int rmt_disc_sdf(const double *X1, const double *X2, double *phi, long n, const 
 {
     if (!X1 || !X2 || !phi || n <= 0 || ndisc <= 0) return RMT_EINVAL;
     double ibx = gb > 0 ? (double)gb / Lx : 0.0, iby = gb > 0 ? (double)gb / Ly : 0.0;
-    k_disc_sdf<<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(X1, X2, phi, n, cx, cy, R, ndisc,
-                                                               bin_start, cand, gb, Lx, Ly, ibx, iby);
+    const DiscSet D{cx, cy, R, ndisc, bin_start, cand, gb, Lx, Ly, ibx, iby};
+    k_disc_sdf<<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(X1, X2, phi, n, D);
+    RMT_LAUNCH_CHECK();
+    return RMT_OK;
+}
+
+int rmt_disc_sdf_stress(const double *X1, const double *X2, double *phi, double *sxx, double *sxy,
+                        double *syy, double *J, int Ny, int Nx, double dx, double dy, double mu_s,
+                        double kappa, double w_cut, double detg_clamp, int isochoric, const double *cx,
+                        const double *cy, const double *R, int ndisc, const int *bin_start, const int *cand,
+                        int gb, double Lx, double Ly, void *stream)
+{
+    if (!X1 || !X2 || !phi || !sxx || !sxy || !syy || !J || Ny < 3 || Nx < 3 || ndisc <= 0) return RMT_EINVAL;
+    double ibx = gb > 0 ? (double)gb / Lx : 0.0, iby = gb > 0 ? (double)gb / Ly : 0.0;
+    const DiscSet D{cx, cy, R, ndisc, bin_start, cand, gb, Lx, Ly, ibx, iby};
+    dim3 blk(TX, TY), grd(rmt_cdiv(Nx, TX), rmt_cdiv(Ny, TY));
+    k_sdf_stress<<<grd, blk, 0, (cudaStream_t)stream>>>(X1, X2, phi, sxx, sxy, syy, J, Ny, Nx, dx, dy, mu_s, kappa,
+                                                       w_cut, detg_clamp, isochoric, D);
     RMT_LAUNCH_CHECK();
     return RMT_OK;
 }

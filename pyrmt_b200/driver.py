@@ -33,14 +33,24 @@ def fsi_step(state, prm, dt=None):
         X1 = F.mask_solid(F.advect_reference_map(X1, a, b, prm["X"], prm["Y"], dt, dx, dy, phi, sch, wc), phi)
         X2 = F.mask_solid(F.advect_reference_map(X2, a, b, prm["X"], prm["Y"], dt, dx, dy, phi, sch, wc), phi)
     X1, X2 = F.extrapolate_reference_map(X1, X2, phi, dx, dy, prm["layers"])
-    phi = F.rebuild_phi_from_reference_map(X1, X2, prm["phi_init"])
-    a_s, b_s, sxx, sxy, syy, J = F.momentum_step_rk4(
+    # level set of the extrapolated map + the stress the predictor needs, in one pass (two operators upstream)
+    phi, stress = F.rebuild_phi_and_stress(X1, X2, prm["phi_init"], dx, dy, prm["mu_s"], prm["kappa"], prm["w_t"])
+    a_s, b_s, sxx, sxy, syy, J = F.momentum_step_rk4_with_stress(
         a, b, p, X1, X2, prm["bc"], prm["mu_s"], prm["kappa"], prm["eta_s"], dx, dy, dt, prm["rho_s"],
-        prm["rho_f"], phi, prm["mu_f"], prm["w_t"], prm.get("gamma", 0.0))
-    _, rho_local = F.heaviside_and_density(phi, prm["w_t"], prm["rho_s"], prm["rho_f"])
+        prm["rho_f"], phi, prm["mu_f"], prm["w_t"], prm.get("gamma", 0.0), stress=stress)
+    rho_local = _density(phi, prm)
     a, b, p, _, _ = F.pressure_projection_amg(a_s, b_s, dx, dy, dt, rho_local, prm["bc"], p_prev=p,
                                               eigenvalues=prm["eig"], bc_type=prm.get("bc_type", "neumann"))
     return (a, b, p, X1, X2), dt, dict(phi=phi, sxx=sxx, sxy=sxy, syy=syy, J=J)
+
+
+def _density(phi, prm):
+    """rho_local = (1 - H) rho_s + H rho_f (soft_disc_in_lid_driven.py:102-103).  With equal densities the
+    field is the constant rho_f to rounding and np.ptp(rho) <= 1e-10 sends the projection down its
+    constant-density branch (functions.py:1298) either way: the scalar is passed instead of a field."""
+    if float(prm["rho_s"]) == float(prm["rho_f"]):
+        return float(prm["rho_f"])
+    return F.heaviside_and_density(phi, prm["w_t"], prm["rho_s"], prm["rho_f"])[1]
 
 
 _copy_streams = {}
@@ -88,12 +98,12 @@ def fsi_step_host(host_state, prm, dt=None):
         out[4].copy_(X2, non_blocking=True)
     X1.record_stream(s_out)
     X2.record_stream(s_out)
-    phi = F.rebuild_phi_from_reference_map(X1, X2, prm["phi_init"])
+    phi, stress = F.rebuild_phi_and_stress(X1, X2, prm["phi_init"], dx, dy, prm["mu_s"], prm["kappa"], prm["w_t"])
     main.wait_event(ev_p)
-    a_s, b_s, *_ = F.momentum_step_rk4(a, b, p, X1, X2, prm["bc"], prm["mu_s"], prm["kappa"], prm["eta_s"], dx, dy,
+    a_s, b_s, *_ = F.momentum_step_rk4_with_stress(a, b, p, X1, X2, prm["bc"], prm["mu_s"], prm["kappa"], prm["eta_s"], dx, dy,
                                        dt, prm["rho_s"], prm["rho_f"], phi, prm["mu_f"], prm["w_t"],
-                                       prm.get("gamma", 0.0))
-    _, rho_local = F.heaviside_and_density(phi, prm["w_t"], prm["rho_s"], prm["rho_f"])
+                                       prm.get("gamma", 0.0), stress=stress)
+    rho_local = _density(phi, prm)
     a, b, p, _, _ = F.pressure_projection_amg(a_s, b_s, dx, dy, dt, rho_local, prm["bc"], p_prev=p,
                                               eigenvalues=prm["eig"], bc_type=prm.get("bc_type", "neumann"))
     ev_done = main.record_event()

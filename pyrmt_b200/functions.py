@@ -327,6 +327,21 @@ def heaviside_and_density(phi, w_t, rho_s, rho_f):
     return to_user(H, as_np), to_user(rho, as_np)
 
 
+def rebuild_phi_and_stress(X1, X2, phi_init, dx, dy, mu_s, kappa, w_t, stress_band=False, detg_clamp=3.0):
+    """``rebuild_phi_from_reference_map`` (functions.py:1366-1367) followed by the ``solid_cauchy_stress`` call
+    of ``momentum_step_rk4`` (:693-700) -- the drivers always run the two back to back on the extrapolated map.
+    With a ``DiscSDF`` level set and CUDA tensors this is ONE kernel (xi read once, phi not re-read);
+    anything else falls back to the two operators.  -> (phi, (sxx, sxy, syy, J))."""
+    from .levelset import DiscSDF
+    w_cut_stress = float(w_t) if stress_band else 0.0
+    clamp = float(detg_clamp) if stress_band else 0.0
+    if isinstance(phi_init, DiscSDF) and not is_np(X1):
+        phi, sxx, sxy, syy, J = phi_init.with_stress(X1, X2, dx, dy, mu_s, kappa, w_cut_stress, clamp)
+        return phi, (sxx, sxy, syy, J)
+    phi = rebuild_phi_from_reference_map(X1, X2, phi_init)
+    return phi, solid_cauchy_stress(X1, X2, dx, dy, mu_s, kappa, phi, w_cut=w_cut_stress, detg_clamp=clamp)
+
+
 def mask_solid_(q, phi):
     return mask_solid(q, phi)
 
@@ -386,11 +401,19 @@ def velocity_rhs_blended_optimized(u, v, p, sigma_sxx, sigma_sxy, sigma_syy, dx,
 
 def momentum_step_rk4(u, v, p, X1, X2, velocity_bc, mu_s, kappa, eta_s, dx, dy, dt, rho_s, rho_f, phi, mu_f,
                       w_t, gamma=0.0, stress_band=False, detg_clamp=3.0):
+    """pyRMT/functions.py:673-762 -- classical RK4 momentum predictor (see ``momentum_step_rk4_with_stress``)."""
+    return momentum_step_rk4_with_stress(u, v, p, X1, X2, velocity_bc, mu_s, kappa, eta_s, dx, dy, dt, rho_s, rho_f,
+                                         phi, mu_f, w_t, gamma, stress_band, detg_clamp, None)
+
+
+def momentum_step_rk4_with_stress(u, v, p, X1, X2, velocity_bc, mu_s, kappa, eta_s, dx, dy, dt, rho_s, rho_f, phi,
+                                  mu_f, w_t, gamma=0.0, stress_band=False, detg_clamp=3.0, stress=None):
     """pyRMT/functions.py:673-762 -- classical RK4 momentum predictor.
 
     One stress kernel, then four fused stage kernels (RHS + Kelvin-Voigt term +
     stage update) with the BC table applied between them; H and rho_local are
-    evaluated from phi inside the stage kernel."""
+    evaluated from phi inside the stage kernel.  ``stress`` (not upstream): the (sxx, sxy, syy, J) of
+    ``rebuild_phi_and_stress`` for the same (X1, X2, phi, stress_band, detg_clamp), to skip the stress kernel."""
     as_np = is_np(u)
     ud, vd, pd, x1, x2, ph = (to_dev(t) for t in (u, v, p, X1, X2, phi))
     Ny, Nx = shape2(ud)
@@ -400,9 +423,12 @@ def momentum_step_rk4(u, v, p, X1, X2, velocity_bc, mu_s, kappa, eta_s, dx, dy, 
 
     w_cut_stress = float(w_t) if stress_band else 0.0
     clamp = float(detg_clamp) if stress_band else 0.0
-    sxx, sxy, syy, J = (torch.empty_like(ud) for _ in range(4))
-    _chk(lib.rmt_solid_stress(ptr(x1), ptr(x2), ptr(ph), ptr(sxx), ptr(sxy), ptr(syy), ptr(J), Ny, Nx, dx, dy,
-                              float(mu_s), float(kappa), w_cut_stress, clamp, 0, st), "rmt_solid_stress")
+    if stress is not None:
+        sxx, sxy, syy, J = (to_dev(t) for t in stress)
+    else:
+        sxx, sxy, syy, J = (torch.empty_like(ud) for _ in range(4))
+        _chk(lib.rmt_solid_stress(ptr(x1), ptr(x2), ptr(ph), ptr(sxx), ptr(sxy), ptr(syy), ptr(J), Ny, Nx, dx, dy,
+                                  float(mu_s), float(kappa), w_cut_stress, clamp, 0, st), "rmt_solid_stress")
     fsx = fsy = None
     if gamma > 1e-12:
         fsx, fsy = torch.empty_like(ud), torch.empty_like(ud)
@@ -704,12 +730,19 @@ def pressure_projection_amg(a_star, b_star, dx, dy, dt, rho, velocity_bc, A=None
         _chk(lib.rmt_poisson_solve_dct(plan, ptr(rhs), ptr(eig), ptr(sol), ptr(ssum), st),
              "rmt_poisson_solve_dct")
     a, b, p = torch.empty_like(ad), torch.empty_like(ad), torch.empty_like(ad)
-    _chk(lib.rmt_projection_correct(ptr(sol), ptr(ssum), ptr(ad), ptr(bd), ptr(rd), rscalar, ptr(pp), ptr(a),
-                                    ptr(b), ptr(p), Ny, Nx, dx, dy, dt, periodic, st),
-         "rmt_projection_correct")
+    # p -= mean(p) (:1361) inside the back end: mean(p_prev + pc) is mean(p_prev) to rounding, and sum(p_prev)
+    # was produced by the call that made p_prev (carried on the tensor; anything else is summed here)
+    pp_sum = None
+    if pp is not None:
+        carried = getattr(pp, "_rmt_sum", None)
+        pp_sum = carried[0] if carried is not None and carried[1] == pp._version else c.stats(pp)
+    partial = c.scratch("proj_partial", int(lib.rmt_projection_partials(Ny, Nx)))
+    psum = torch.empty(1, dtype=F64, device=ad.device)
+    _chk(lib.rmt_projection_correct_centered(ptr(sol), ptr(ssum), ptr(ad), ptr(bd), ptr(rd), rscalar, ptr(pp),
+                                             ptr(pp_sum), ptr(a), ptr(b), ptr(p), ptr(partial), ptr(psum), Ny, Nx,
+                                             dx, dy, dt, periodic, st), "rmt_projection_correct_centered")
+    p._rmt_sum = (psum, p._version)
     a, b = apply_bc_(velocity_bc, a, b)
-    psum = c.stats(p)
-    _chk(lib.rmt_subtract_mean(ptr(p), ptr(psum), p.numel(), st), "rmt_subtract_mean")
     return to_user(a, as_np), to_user(b, as_np), to_user(p, as_np), A, ml
 
 

@@ -88,6 +88,28 @@ class DiscSDF:
         return to_user(phi, as_np)
 
 
+    def with_stress(self, X1, X2, dx, dy, mu_s, kappa, w_cut, detg_clamp, isochoric=0):
+        """phi0(X1, X2) and the solid Cauchy stress of (X1, X2, phi) in one pass (rmt_disc_sdf_stress):
+        -> (phi, sxx, sxy, syy, J), all CUDA tensors.  phi is bitwise what ``__call__`` returns."""
+        x1, x2 = to_dev(X1), to_dev(X2)
+        if x1.shape != x2.shape or x1.dim() != 2:
+            raise ValueError("X1 and X2 must be 2-D and of the same shape")
+        Ny, Nx = int(x1.shape[0]), int(x1.shape[1])
+        t = self._on(x1.device)
+        phi, sxx, sxy, syy, J = (torch.empty_like(x1) for _ in range(5))
+        if self._bins is not None:
+            gb, _, _, Lx, Ly = self._bins
+            st, cd = ptr(t["start"]), ptr(t["cand"])
+        else:
+            gb, Lx, Ly, st, cd = 0, 1.0, 1.0, None, None
+        _lib.check(ctx().lib.rmt_disc_sdf_stress(ptr(x1), ptr(x2), ptr(phi), ptr(sxx), ptr(sxy), ptr(syy), ptr(J),
+                                                 Ny, Nx, float(dx), float(dy), float(mu_s), float(kappa),
+                                                 float(w_cut), float(detg_clamp), int(isochoric), ptr(t["cx"]),
+                                                 ptr(t["cy"]), ptr(t["R"]), int(self.cx.size), st, cd, gb, Lx, Ly,
+                                                 stream()), "rmt_disc_sdf_stress")
+        return phi, sxx, sxy, syy, J
+
+
 def initialize_disc(X, Y, x0, y0, R):
     """benchmarks/common.py:55-57 on the device."""
     return DiscSDF([x0], [y0], [R])(X, Y)
