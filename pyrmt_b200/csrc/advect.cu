@@ -39,8 +39,12 @@ __device__ __forceinline__ bool clamp_coords(double xq, double yq, double inv_dx
     return true;
 }
 
+// jlo, jhi: the rows [jlo, jhi) that exist in memory (a row slab addressed from the virtual row 0; the whole
+// grid: 0, Ny).  Sample rows are clamped into them AFTER the weights are formed, so a node whose departure
+// point leaves the slab (only halo nodes, whose results are discarded: the caller checks that the owned
+// rows' stencils stay inside) reads valid memory, and every other result is unchanged bit for bit.
 __device__ __forceinline__ double bilinear(const double *__restrict__ u, double xq, double yq,
-                                           double dx, double dy, int Nx, int Ny)
+                                           double dx, double dy, int Nx, int Ny, int jlo, int jhi)
 {
     double x, y;
     if (!clamp_coords(xq, yq, 0.0, dx, dy, Nx, Ny, x, y)) return nan("");
@@ -48,6 +52,7 @@ __device__ __forceinline__ double bilinear(const double *__restrict__ u, double 
     if (ix >= Nx - 1) ix = Nx - 2;
     if (iy >= Ny - 1) iy = Ny - 2;
     double fx = x - ix, fy = y - iy;
+    iy = min(max(iy, jlo), jhi - 2);
     const double *r0 = u + (size_t)iy * Nx + ix;
     const double *r1 = r0 + Nx;
     double v00 = __ldg(r0), v10 = __ldg(r0 + 1), v01 = __ldg(r1), v11 = __ldg(r1 + 1);
@@ -57,7 +62,7 @@ __device__ __forceinline__ double bilinear(const double *__restrict__ u, double 
 // Two fields sampled at the same point share the index/weight computation.
 __device__ __forceinline__ void bilinear2(const double *__restrict__ a, const double *__restrict__ b,
                                           double xq, double yq, double dx, double dy, int Nx, int Ny,
-                                          double &va, double &vb)
+                                          int jlo, int jhi, double &va, double &vb)
 {
     double x, y;
     if (!clamp_coords(xq, yq, 0.0, dx, dy, Nx, Ny, x, y)) { va = vb = nan(""); return; }
@@ -65,6 +70,7 @@ __device__ __forceinline__ void bilinear2(const double *__restrict__ a, const do
     if (ix >= Nx - 1) ix = Nx - 2;
     if (iy >= Ny - 1) iy = Ny - 2;
     double fx = x - ix, fy = y - iy;
+    iy = min(max(iy, jlo), jhi - 2);
     double w00 = (1 - fx) * (1 - fy), w10 = fx * (1 - fy), w01 = (1 - fx) * fy, w11 = fx * fy;
     size_t o = (size_t)iy * Nx + ix;
     va = w00 * __ldg(a + o) + w10 * __ldg(a + o + 1) + w01 * __ldg(a + o + Nx) + w11 * __ldg(a + o + Nx + 1);
@@ -80,7 +86,7 @@ __device__ __forceinline__ double catmull_rom(double v0, double v1, double v2, d
 }
 
 __device__ __forceinline__ double bicubic(const double *__restrict__ u, double xq, double yq,
-                                          double dx, double dy, int Nx, int Ny)
+                                          double dx, double dy, int Nx, int Ny, int jlo, int jhi)
 {
     double x, y;
     if (!clamp_coords(xq, yq, 0.0, dx, dy, Nx, Ny, x, y)) return nan("");
@@ -89,7 +95,7 @@ __device__ __forceinline__ double bicubic(const double *__restrict__ u, double x
     double rows[4], lo = 1e18, hi = -1e18;
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-        int yg = min(max(iy - 1 + m, 0), Ny - 1);
+        int yg = min(max(min(max(iy - 1 + m, 0), Ny - 1), jlo), jhi - 1);
         double c[4];
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
@@ -113,8 +119,8 @@ __global__ void k_sample(const double *__restrict__ u, const double *__restrict_
                          double dy, int Nx, int Ny)
 {
     for (long k = blockIdx.x * (long)blockDim.x + threadIdx.x; k < nq; k += (long)gridDim.x * blockDim.x)
-        out[k] = CUBIC ? bicubic(u, xq[k], yq[k], dx, dy, Nx, Ny)
-                       : bilinear(u, xq[k], yq[k], dx, dy, Nx, Ny);
+        out[k] = CUBIC ? bicubic(u, xq[k], yq[k], dx, dy, Nx, Ny, 0, Ny)
+                       : bilinear(u, xq[k], yq[k], dx, dy, Nx, Ny, 0, Ny);
 }
 
 // ------------------------------------------------- semi-Lagrangian RK4 backtrace
@@ -135,6 +141,7 @@ __global__ void k_advect_sl(const double *__restrict__ q0, const double *__restr
     if (i >= Nx || j >= Nyl) return;
     size_t c = (size_t)j * Nx + i;
     const size_t voff = (size_t)joff * Nx;
+    const int jhi = joff + Nyl;
     a -= voff; b -= voff; q0 -= voff;
     if (NQ == 2) q1 -= voff;
     double x = X[c], y = Y[c];
@@ -142,10 +149,10 @@ __global__ void k_advect_sl(const double *__restrict__ q0, const double *__restr
     double k1x, k1y, k2x, k2y, k3x, k3y, k4x, k4y;
     auto vel = [&](double xx, double yy, double &vx, double &vy) {
         if (CUBIC) {
-            vx = bicubic(a, xx, yy, dx, dy, Nx, Ny);
-            vy = bicubic(b, xx, yy, dx, dy, Nx, Ny);
+            vx = bicubic(a, xx, yy, dx, dy, Nx, Ny, joff, jhi);
+            vy = bicubic(b, xx, yy, dx, dy, Nx, Ny, joff, jhi);
         } else {
-            bilinear2(a, b, xx, yy, dx, dy, Nx, Ny, vx, vy);
+            bilinear2(a, b, xx, yy, dx, dy, Nx, Ny, joff, jhi, vx, vy);
         }
     };
     vel(x, y, k1x, k1y);
@@ -155,15 +162,15 @@ __global__ void k_advect_sl(const double *__restrict__ q0, const double *__restr
     double xb = x - sixth_dt * (k1x + 2 * k2x + 2 * k3x + k4x);
     double yb = y - sixth_dt * (k1y + 2 * k2y + 2 * k3y + k4y);
     if (CUBIC) {
-        o0[c] = bicubic(q0, xb, yb, dx, dy, Nx, Ny);
-        if (NQ == 2) o1[c] = bicubic(q1, xb, yb, dx, dy, Nx, Ny);
+        o0[c] = bicubic(q0, xb, yb, dx, dy, Nx, Ny, joff, jhi);
+        if (NQ == 2) o1[c] = bicubic(q1, xb, yb, dx, dy, Nx, Ny, joff, jhi);
     } else if (NQ == 2) {
         double r0, r1;
-        bilinear2(q0, q1, xb, yb, dx, dy, Nx, Ny, r0, r1);
+        bilinear2(q0, q1, xb, yb, dx, dy, Nx, Ny, joff, jhi, r0, r1);
         o0[c] = r0;
         o1[c] = r1;
     } else {
-        o0[c] = bilinear(q0, xb, yb, dx, dy, Nx, Ny);
+        o0[c] = bilinear(q0, xb, yb, dx, dy, Nx, Ny, joff, jhi);
     }
 }
 

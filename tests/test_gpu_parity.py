@@ -917,6 +917,19 @@ def test_sl_rows_equals_full_grid(P, golden):
                                               cubic=cubic, slab=(Ny, e0))
         inner = slice(4, e1 - e0 - 4)                     # rows whose departure stencils lie inside the window
         assert torch.equal(s0[inner], f0[e0:e1][inner]) and torch.equal(s1[inner], f1[e0:e1][inner])
+        # a large time step: the halo nodes' departure points leave the window.  Their sample rows are clamped
+        # into the stored rows (no out-of-slab read; their values are discarded by the caller), and rows
+        # whose stencils stay inside are still identical
+        big_dt = 40.0 * dt
+        reach = int(np.ceil(float(b.abs().max()) * big_dt / dy)) + 3
+        f0, f1 = P.advect_semilagrangian_pair(q, 2.0 * q, a, b, X, Y, big_dt, dx, dy, cubic=cubic)
+        w0, w1 = Ny // 3, Ny // 3 + 4 * reach + 8
+        s0, s1 = P.advect_semilagrangian_pair(*(t[w0:w1].contiguous() for t in (q, 2.0 * q, a, b, X, Y)), big_dt, dx, dy,
+                                              cubic=cubic, slab=(Ny, w0))
+        torch.cuda.synchronize()
+        inner = slice(reach, w1 - w0 - reach)
+        assert torch.equal(s0[inner], f0[w0:w1][inner]) and torch.equal(s1[inner], f1[w0:w1][inner])
+        assert bool(torch.isfinite(s0).all())
 
 
 def test_slab_solver_world1_equals_single_gpu(P):
