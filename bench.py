@@ -52,15 +52,18 @@ ALG_BYTES_PER_CELL_STEP = {"semilagrangian": 496.0, "weno5": 512.0, "central2": 
 # Algorithmic (compulsory) bytes per cell and launch of each entry point: every input
 # field read once + every output written once, 8 B each ("Kernels").
 ALG_BYTES_PER_CELL_LAUNCH = {
-    "rmt_momentum_stage": 8.0 * 13.5,     # stages 1..4: 11, 15, 15, 13 fields
+    "rmt_momentum_stage": 8.0 * 12.0,     # stages 1..4: 11, 13, 13, 11 fields (sigma_s is read in the solid third only)
     "rmt_advect_euler_rk3": 8.0 * 17.0,   # 3 stage kernels per call: 5 + 6 + 6 fields
     "rmt_poisson_solve_dct": 8.0 * 7.0,   # rows 2, columns (+eig) 3, rows 2
     "rmt_solid_stress": 8.0 * 7.0,
-    "rmt_projection_rhs": 8.0 * 5.0,
+    "rmt_projection_rhs": 8.0 * 4.0,      # a*, b*, p in, rhs out (scalar density)
     "rmt_projection_correct": 8.0 * 8.0,
+    "rmt_projection_correct_centered": 8.0 * 7.0,   # sol, a*, b*, p in; a, b, p out
+    "rmt_disc_sdf_stress": 8.0 * 7.0,     # xi1, xi2 in; phi, sxx, sxy, syy, J out
     "rmt_extrapolate": 8.0 * 5.0,        # a dependency-chain (latency) kernel, not a bandwidth one
     "rmt_extrapolate_rows": 8.0 * 5.0,
-    "rmt_advect_euler_rk3_pair": 8.0 * 25.0,   # 3 stage kernels per call, two fields: 7 + 9 + 9
+    "rmt_advect_euler_rk3_pair": 8.0 * 7.0,    # operator boundary: xi1, xi2, a, b, phi in, xi1', xi2' out (the three
+                                               # SSP-RK3 stages move more: see `traffic`)
     "rmt_dct_lines": 8.0 * 2.0,
     "rmt_disc_sdf": 8.0 * 3.0,
     "rmt_mask_mul": 8.0 * 3.0,
@@ -76,16 +79,17 @@ ALG_BYTES_PER_CELL_LAUNCH = {
 # DRAM bytes per call (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full` capture of
 # this workload at 4097^2 on one B200 (profiles/r01e_/r01h_/r01j_ncu_full_summary.txt); per-call = sum over the
 # kernels the entry point launches.  Only reported for N = 1 at the default size.
-NCU_TRAFFIC_BYTES_4097 = {
-    "rmt_extrapolate_rows": 0.61e9,        # k_ext_fused<8> alone: 0.27 GB read + 0.34 GB written (r01j capture); the
-                                           # seed copy kernel of the same call moves its 5 fields (0.69 GB) on top
-    "rmt_momentum_stage": 1.603e9,         # mean of the four stages (1.46 / 1.74 / 1.74 / 1.48 GB)
-    "rmt_advect_euler_rk3_pair": 2.82e9,   # three stage kernels: 0.75 + 1.04 + 1.03 GB
-    "rmt_poisson_solve_dct": 1.31e9,       # 2 x lines<0> (0.22) + lines<1> (0.36) + 2 x transpose (0.22) + sum
-    "rmt_projection_correct": 1.04e9,
-    "rmt_projection_rhs": 0.66e9,
-    "rmt_solid_stress": 0.71e9,
-    "rmt_disc_sdf": 0.38e9,
+NCU_TRAFFIC_BYTES_4097 = {                 # profiles/r02_ncu_full_summary.txt (one steady step, round 2)
+    "rmt_extrapolate_rows": 0.70e9,        # k_ext_body 0.036 GB (it works out of L1/L2 and shared memory) + the seed
+                                           # kernel's 5 fields (0.65 GB) + the layer-0 count (0.02 GB)
+    "rmt_momentum_stage": 1.595e9,         # mean of the four stages (1.46 / 1.73 / 1.73 / 1.47 GB)
+    "rmt_advect_euler_rk3_pair": 1.83e9,   # classify 0.14 + three stage kernels 0.38 + 0.50 + 0.81 GB
+    "rmt_poisson_solve_dct": 1.235e9,      # 2 x lines<0> (0.22 + 0.21) + lines<1> (0.36) + 2 x transpose (0.22)
+    "rmt_projection_correct_centered": 0.904e9,
+    "rmt_projection_rhs": 0.519e9,
+    "rmt_disc_sdf_stress": 1.02e9,
+    "rmt_disc_sdf": 0.376e9,
+    "rmt_max_speed": 0.272e9,
 }
 
 
@@ -475,6 +479,8 @@ def main():
     ncell_rank = state[0].numel() if world > 1 else cells
     if world == 1 and N == 4097:
         roofline["traffic"] = NCU_TRAFFIC_BYTES_4097.get(kname)
+        if roofline["traffic"]:
+            roofline["frac_by_traffic"] = roofline["traffic"] / (kavg_ms * 1e-3) / 1e9 / peak
     roofline["note"] = ("dominant entry point by summed CUDA-event time; rmt_extrapolate* is bound by the serial "
                         "dependency chain of the reference's raster sweep (latency), not by HBM -- see DESIGN.md 5; "
                         "`kernels_roofline` lists every entry point")
@@ -486,7 +492,10 @@ def main():
                                  "achieved_GBps": ab / (t / c * 1e-3) / 1e9 if t > 0 else None,
                                  "frac": ab / (t / c * 1e-3) / 1e9 / peak if t > 0 else None,
                                  "alg_bytes_per_launch": ab,
-                                 "traffic": NCU_TRAFFIC_BYTES_4097.get(k) if (world == 1 and N == 4097) else None})
+                                 "traffic": NCU_TRAFFIC_BYTES_4097.get(k) if (world == 1 and N == 4097) else None,
+                                 # the same fraction from the DRAM bytes ncu measured for this entry point
+                                 "frac_by_traffic": (NCU_TRAFFIC_BYTES_4097[k] / (t / c * 1e-3) / 1e9 / peak)
+                                 if (world == 1 and N == 4097 and k in NCU_TRAFFIC_BYTES_4097 and t > 0) else None})
     step_gbs = cells * ALG_BYTES_PER_CELL_STEP.get(args.scheme, 512.0) * args.steps / (ms * 1e-3) / 1e9
     breakdown = {k: {"calls": c, "ms_per_step": t / prof_steps} for k, (c, t) in
                  sorted(per_kernel.items(), key=lambda kv: -kv[1][1])}

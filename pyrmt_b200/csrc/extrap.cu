@@ -1839,18 +1839,31 @@ __global__ void k_ext_count0(const unsigned char *__restrict__ st, int *__restri
             const int xt = task - j * nxt;
             int cnt = 0, cmin = INT_MAX, cmax = -1, chunks = 0;
             const int cend = min((xt + 1) * XT, Nx);
-            for (int base = xt * XT; base < cend; base += 32) {
-                int i = base + lane;
-                bool tgt = false;
-                if (inner && i >= 1 && i < Nx - 1 && i < cend && !(r1[i] & 1))
-                    tgt = ((r0[i - 1] | r0[i] | r0[i + 1] | r1[i - 1] | r1[i + 1] | r2[i - 1] | r2[i] |
-                            r2[i + 1]) & 1) != 0;
-                const unsigned m = __ballot_sync(0xffffffffu, tgt);
-                cnt += __popc(m);
-                if (m) {
-                    cmin = min(cmin, base + __ffs(m) - 1);
-                    cmax = base + 31 - __clz(m);
-                    chunks |= 1 << ((base - xt * XT) >> 5);
+            // four 32-column chunks per round, every byte requested before any is looked at: the scan is a chain
+            // of L2 round trips otherwise (96 us at 4097^2 when the eight neighbours waited for the cell itself)
+            for (int base0 = xt * XT; base0 < cend; base0 += 128) {
+                unsigned me[4], nb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base0 + 32 * u + lane;
+                    me[u] = 1u;
+                    nb[u] = 0u;
+                    if (inner && i >= 1 && i < Nx - 1 && i < cend) {
+                        me[u] = r1[i];
+                        nb[u] = r0[i - 1] | r0[i] | r0[i + 1] | r1[i - 1] | r1[i + 1] | r2[i - 1] | r2[i] | r2[i + 1];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int base = base0 + 32 * u;
+                    const bool tgt = !(me[u] & 1) && (nb[u] & 1);
+                    const unsigned m = __ballot_sync(0xffffffffu, tgt);
+                    cnt += __popc(m);
+                    if (m) {
+                        cmin = min(cmin, base + __ffs(m) - 1);
+                        cmax = base + 31 - __clz(m);
+                        chunks |= 1 << ((base - xt * XT) >> 5);
+                    }
                 }
             }
             if (lane == 0) {

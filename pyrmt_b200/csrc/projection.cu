@@ -221,26 +221,44 @@ k_projection_correct_centered(const double *__restrict__ sol, const double *__re
                               double *__restrict__ partial, int Ny, int Nx, double dx, double dy, double dt,
                               int periodic)
 {
+    // 32 x 16 nodes per CTA, two rows per thread: the loads of both nodes are in flight together
     __shared__ double red[TY];
     const int i = blockIdx.x * TX + threadIdx.x;
-    const int j = blockIdx.y * TY + threadIdx.y;
+    const double n = (double)Ny * (double)Nx;
+    const Shifted PC{sol, Nx, sol_sum ? sol_sum[0] / n : 0.0};
+    const double m = p_prev_sum ? p_prev_sum[0] / n : 0.0;
+    double gx[2], gy[2], as[2], bs[2], rr[2], pp[2], pc[2];
+    bool in[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int j = blockIdx.y * (2 * TY) + threadIdx.y + TY * r;
+        in[r] = i < Nx && j < Ny;
+        gx[r] = gy[r] = as[r] = bs[r] = pp[r] = pc[r] = 0.0;
+        rr[r] = 1.0;
+        if (in[r]) {
+            const size_t c = (size_t)j * Nx + i;
+            if (periodic == 2) pgrad_slab(PC, j, i, Ny, Nx, 0.5 / dx, 0.5 / dy, gx[r], gy[r]);
+            else if (periodic) pgrad_periodic(PC, j, i, Ny, Nx, 0.5 / dx, 0.5 / dy, gx[r], gy[r]);
+            else pgrad_neumann(PC, j, i, Ny, Nx, 0.5 / dx, 0.5 / dy, gx[r], gy[r]);
+            rr[r] = rho ? __ldg(rho + c) : rho_scalar;
+            as[r] = __ldg(a_star + c);
+            bs[r] = __ldg(b_star + c);
+            pc[r] = PC(j, i);
+            pp[r] = p_prev ? __ldg(p_prev + c) : 0.0;
+        }
+    }
     double pv = 0.0;
-    if (i < Nx && j < Ny) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        if (!in[r]) continue;
+        const int j = blockIdx.y * (2 * TY) + threadIdx.y + TY * r;
         const size_t c = (size_t)j * Nx + i;
-        const double n = (double)Ny * (double)Nx;
-        const Shifted PC{sol, Nx, sol_sum ? sol_sum[0] / n : 0.0};
-        double gx, gy;
-        if (periodic == 2) pgrad_slab(PC, j, i, Ny, Nx, 0.5 / dx, 0.5 / dy, gx, gy);
-        else if (periodic) pgrad_periodic(PC, j, i, Ny, Nx, 0.5 / dx, 0.5 / dy, gx, gy);
-        else pgrad_neumann(PC, j, i, Ny, Nx, 0.5 / dx, 0.5 / dy, gx, gy);
-        const double r = rho ? rho[c] : rho_scalar;
-        const double dtr = dt / r;
-        a[c] = a_star[c] - dtr * gx;
-        b[c] = b_star[c] - dtr * gy;
-        const double pc = PC(j, i);
-        const double m = p_prev_sum ? p_prev_sum[0] / n : 0.0;
-        pv = (p_prev ? (p_prev[c] + pc) : pc) - m;
-        p[c] = pv;
+        const double dtr = dt / rr[r];
+        a[c] = as[r] - dtr * gx[r];
+        b[c] = bs[r] - dtr * gy[r];
+        const double v = (p_prev ? (pp[r] + pc[r]) : pc[r]) - m;
+        p[c] = v;
+        pv += v;
     }
     // deterministic block sum (warp tree, then the TY warp sums in order)
     pv = warp_sum(pv);
@@ -356,7 +374,7 @@ int rmt_projection_correct(const double *sol, const double *sol_sum, const doubl
     return RMT_OK;
 }
 
-long rmt_projection_partials(int Ny, int Nx) { return (long)rmt_cdiv(Nx, TX) * rmt_cdiv(Ny, TY); }
+long rmt_projection_partials(int Ny, int Nx) { return (long)rmt_cdiv(Nx, TX) * rmt_cdiv(Ny, 2 * TY); }
 
 int rmt_projection_correct_centered(const double *sol, const double *sol_sum, const double *a_star,
                                     const double *b_star, const double *rho, double rho_scalar,
@@ -365,7 +383,7 @@ int rmt_projection_correct_centered(const double *sol, const double *sol_sum, co
                                     double dy, double dt, int periodic, void *stream)
 {
     if (!sol || !a_star || !b_star || !a || !b || !p || !partial || !p_sum_out || Ny < 4 || Nx < 4) return RMT_EINVAL;
-    dim3 blk(TX, TY), grd(rmt_cdiv(Nx, TX), rmt_cdiv(Ny, TY));
+    dim3 blk(TX, TY), grd(rmt_cdiv(Nx, TX), rmt_cdiv(Ny, 2 * TY));
     cudaStream_t s = (cudaStream_t)stream;
     k_projection_correct_centered<<<grd, blk, 0, s>>>(sol, sol_sum, a_star, b_star, rho, rho_scalar, p_prev,
                                                      p_prev_sum, a, b, p, partial, Ny, Nx, dx, dy, dt, periodic);

@@ -347,7 +347,7 @@ struct GlobalField {
 // 32 x 16 output tile per 256-thread CTA: phi of the tile and its one-node halo (34 x 18 nodes, 2.4
 // evaluations per thread for 2 outputs) goes to shared memory first
 constexpr int STY = 2 * TY;
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256, 4)
 k_sdf_stress(const double *__restrict__ X1, const double *__restrict__ X2, double *__restrict__ phi,
              double *__restrict__ sxx, double *__restrict__ sxy, double *__restrict__ syy,
              double *__restrict__ J, int Ny, int Nx, double dx, double dy, double mu_s, double kappa,
@@ -356,14 +356,28 @@ k_sdf_stress(const double *__restrict__ X1, const double *__restrict__ X2, doubl
     __shared__ double sphi[(STY + 2) * (TX + 2)];
     const int i0 = blockIdx.x * TX - 1, j0 = blockIdx.y * STY - 1;
     const int tid = threadIdx.y * TX + threadIdx.x;
-    for (int e = tid; e < (STY + 2) * (TX + 2); e += TX * TY) {
-        const int jj = j0 + e / (TX + 2), ii = i0 + e % (TX + 2);
-        double v = 0.0;
-        if (jj >= 0 && jj < Ny && ii >= 0 && ii < Nx) {
-            const size_t c = (size_t)jj * Nx + ii;
-            v = disc_sdf_point(__ldg(X1 + c), __ldg(X2 + c), D);
+    {   // 612 nodes for 256 threads: three per thread, their loads issued together (each evaluation is a
+        // chain of dependent look-ups -- xi, bin, candidate, centre -- so the three chains overlap)
+        constexpr int NE = (STY + 2) * (TX + 2);
+        double xs[3], ys[3];
+        bool ok[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int e = tid + TX * TY * k;
+            const int jj = j0 + e / (TX + 2), ii = i0 + e % (TX + 2);
+            ok[k] = e < NE && jj >= 0 && jj < Ny && ii >= 0 && ii < Nx;
+            xs[k] = ys[k] = 0.0;
+            if (ok[k]) {
+                const size_t c = (size_t)jj * Nx + ii;
+                xs[k] = __ldg(X1 + c);
+                ys[k] = __ldg(X2 + c);
+            }
         }
-        sphi[e] = v;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int e = tid + TX * TY * k;
+            if (e < NE) sphi[e] = ok[k] ? disc_sdf_point(xs[k], ys[k], D) : 0.0;
+        }
     }
     __syncthreads();
     const SmemPhi P{sphi, j0, i0};
