@@ -384,11 +384,13 @@ class RemoteCopies:
             fv[dv] = vals[pv]
 
 
-def local_bc_table(bc, lay):
+def local_bc_table(bc, lay, extended=False):
     """The global gather table of a BC callable restricted to the rows this rank owns, re-indexed
     into the extended slab -> (BCTable, RemoteCopies or None).  Sources stored in the same slab
     (wall / lid / free-slip BCs, the column wrap of a periodic BC) go into the table; sources on
-    another rank (the row wrap of a periodic BC) into the RemoteCopies."""
+    another rank (the row wrap of a periodic BC) into the RemoteCopies.
+    ``extended``: the entries of every STORED row (halo rows included) whose source is stored here too --
+    what a stage needs when its halo rows are computed locally instead of exchanged (-> BCTable only)."""
     from .bc import BCTable, _FIELD_BIT, table_for
     full = table_for(bc, lay.Ny, lay.Nx)
     if full is None:
@@ -406,6 +408,16 @@ def local_bc_table(bc, lay):
     rem = None
     if remote.any():
         rem = RemoteCopies(lay, dst[remote], src[remote], ca[remote], cb[remote], drank[remote], owner(srow[remote]))
+    if extended:
+        lo, hi = stored[lay.rank]
+        drow = cell(dst) // Nx
+        keep = (drow >= lo) & (drow < hi) & (~has | ((srow >= lo) & (srow < hi)))
+        dst, src, ca, cb, has = dst[keep], src[keep], ca[keep], cb[keep], has[keep]
+        shift = lay.e0 * Nx
+        rel = lambda k: (k & _FIELD_BIT) | (cell(k) - shift)
+        src2 = src.copy()
+        src2[has] = rel(src[has])
+        return BCTable(rel(dst).astype(np.int64), src2.astype(np.int64), ca, cb, (lay.nl, Nx)), None
     keep = (drank == lay.rank) & ~remote
     dst, src, ca, cb, has = dst[keep], src[keep], ca[keep], cb[keep], has[keep]
     shift = lay.e0 * Nx
@@ -422,6 +434,8 @@ class SlabFluidSolver:
     def __init__(self, lay, bc, eig, comm=None, spacing=None):
         self.lay, self.comm = lay, comm or Comm()
         self.table, self.remote = local_bc_table(bc, lay)
+        # wall-type layouts: the BC on every stored row, for stages whose halo rows are computed locally
+        self.table_ext = None if lay.periodic else local_bc_table(bc, lay, extended=True)[0]
         dev = torch.device("cuda", torch.cuda.current_device())
         if lay.periodic:      # bc_type='periodic' (functions.py:1277-1290): FFT solve on the reduced grid
             self.poisson = DistPoissonFFT(lay, eig, spacing, self.comm, device=dev)
@@ -484,12 +498,22 @@ class SlabFluidSolver:
         acc_u, acc_v = torch.empty_like(u), torch.empty_like(u)
         un, vn = torch.empty_like(u), torch.empty_like(u)
 
+        # A stage reads its input within two rows, so running it on the extended slab leaves two more of
+        # the outermost halo rows wrong each time (one-sided stencils at the artificial edge): after the
+        # stress and four stages <= 9 of the H >= 12 halo rows are spoilt and the owned rows are exact.
+        # Wall-type layouts therefore exchange the halo ONCE, after the last stage; the periodic layout
+        # keeps the per-stage exchange (its wrap rows travel with the remote BC copies).
+        lazy_halo = self.table_ext is not None and lay.H >= 10
+
         def stage(k, iu, iv, ou, ov):
             _lib.check(lib.rmt_momentum_stage(ptr(iu), ptr(iv), ptr(p), ptr(sxx), ptr(sxy), ptr(syy), ptr(phi),
                                               None, None, ptr(u), ptr(v), ptr(acc_u), ptr(acc_v), ptr(ou),
                                               ptr(ov), nl, Nx, dx, dy, dt, mu_f, eta_s, w_t, rho_s, rho_f, k, st),
                        "rmt_momentum_stage")
-            self._bc_and_halo(ou, ov)
+            if lazy_halo and k < 4:
+                self.table_ext.apply_(ou, ov)       # halo rows included: they are this rank's own values now
+            else:
+                self._bc_and_halo(ou, ov)
 
         stage(1, sa_u, sa_v, sb_u, sb_v)
         stage(2, sb_u, sb_v, sa_u, sa_v)
@@ -726,10 +750,13 @@ class SlabFSISolver(SlabFluidSolver):
         a_s, b_s, *_ = self.momentum_step(a, b, p, X1n, X2n, phi, prm["mu_s"], prm["kappa"], prm["eta_s"], dx, dy,
                                           dt, prm["rho_s"], prm["rho_f"], prm["mu_f"], prm["w_t"])
         self._dbg("predictor", a_s, b_s)
-        _, rho_local = F.heaviside_and_density(phi, prm["w_t"], prm["rho_s"], prm["rho_f"])
-        # rho_local = (1 - H) rho_s + H rho_f is constant iff rho_s == rho_f (known on the host: no device test)
-        a, b, p = self.projection(a_s, b_s, p, rho_local, dx, dy, dt,
-                                  density_checked=(float(prm["rho_s"]) == float(prm["rho_f"])))
+        # rho_local = (1 - H) rho_s + H rho_f is the constant rho_f to rounding iff rho_s == rho_f (known on the
+        # host): the projection then takes its scalar-density branch (no H / rho pass, no sum(rho) all-reduce)
+        if float(prm["rho_s"]) == float(prm["rho_f"]):
+            a, b, p = self.projection(a_s, b_s, p, float(prm["rho_f"]), dx, dy, dt, density_checked=True)
+        else:
+            _, rho_local = F.heaviside_and_density(phi, prm["w_t"], prm["rho_s"], prm["rho_f"])
+            a, b, p = self.projection(a_s, b_s, p, rho_local, dx, dy, dt)
         self._dbg("projected", a, b, p)
         return (a, b, p, X1n, X2n)
 

@@ -69,6 +69,11 @@ def test_local_bc_table_reproduces_global_bc():
             assert rem is None
             su, sv = t.apply_host(L.take(u).copy(), L.take(v).copy())
             assert np.array_equal(L.owned(su), ru[L.r0:L.r1]) and np.array_equal(L.owned(sv), rv[L.r0:L.r1])
+            # extended table (stages that compute their halo rows locally): the BC on EVERY stored row
+            te, rem = local_bc_table(bc, L, extended=True)
+            assert rem is None
+            eu, ev = te.apply_host(L.take(u).copy(), L.take(v).copy())
+            assert np.array_equal(eu, ru[L.e0:L.e1]) and np.array_equal(ev, rv[L.e0:L.e1])
 
 
 class SciPyOps:
