@@ -23,6 +23,8 @@
 #ifndef RMT_B200_H
 #define RMT_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -311,6 +313,48 @@ int rmt_dht_lines(const double *in, double *out, const double *mul, int nrows, i
 int rmt_transpose(const double *in, double *out, int R, int C, void *stream);
 /* dst[r*dst_ld + c] = src[r*src_ld + c], rows x cols block (all-to-all pack / unpack). */
 int rmt_copy2d(const double *src, double *dst, int rows, int cols, long src_ld, long dst_ld, void *stream);
+
+/* ------------------------------------------------ slab exchanges over NVLink peer memory */
+/* The reference is one process on one grid.  Cut into row slabs (one process per GPU on one node), its
+ * whole-grid stencils (pyRMT/utils.py:4-114), transforms (pyRMT/functions.py:1107-1119 dctn / idctn,
+ * :1216-1233 fft2 / ifft2) and means (:1119, :1231, :1361) need a halo exchange, an all-to-all transpose
+ * and an all-reduce.  These entry points do them with plain stores into the neighbour's memory (CUDA IPC
+ * mapping; NVLink / NVSwitch underneath) -- pyrmt_b200/slab.py PeerComm is the caller. */
+#define RMT_PEER_MAX 16           /* ranks of one node */
+#define RMT_PUT_MAX 32            /* 2-D block copies per rmt_peer_put2d launch */
+/* An arena other processes can map: cudaMalloc + zero fill (synchronous; set-up only). */
+int rmt_peer_alloc(size_t bytes, void **ptr);
+int rmt_peer_free(void *ptr);
+/* 64-byte CUDA IPC handle of an arena / mapping of another process's arena into this one. */
+int rmt_peer_export(void *ptr, unsigned char *handle64);
+int rmt_peer_import(const unsigned char *handle64, void **ptr);
+int rmt_peer_release(void *ptr);
+/* dst[r*dst_ld + c] = src[r*src_ld + c] for n <= RMT_PUT_MAX blocks in ONE launch; dst (or src) may be
+ * peer memory.  `desc` is a host array. */
+typedef struct rmt_put2d {
+    const double *src;
+    double *dst;
+    int rows, cols;
+    long src_ld, dst_ld;
+} rmt_put2d;
+int rmt_peer_put2d(const rmt_put2d *desc, int n, void *stream);
+/* The transpose AND the all-to-all of the distributed line transforms in one kernel:
+ * in (R, C; row stride ldi);  for column c in [start[q], start[q+1]):  dst[q][(c - start[q]) * dst_ld[q] + r]
+ * = in[r][c].  start (nparts + 1 entries, start[0] = 0, start[nparts] = C), dst and dst_ld are host arrays;
+ * dst[q] is a device pointer valid in this process (own memory or a mapped peer arena). */
+int rmt_transpose_scatter(const double *in, int R, int C, long ldi, int nparts, const int *start,
+                          double *const *dst, const long *dst_ld, void *stream);
+/* Barrier over the ranks of the node on `stream`: flags[q] = rank q's array of >= world uint64 counters as
+ * mapped in this process.  Rank r release-stores `epoch` into flags[q][r] of every peer (system scope, after a
+ * system fence: everything this stream did before is visible to the peer first), then waits until
+ * flags[r][q] >= epoch for every q.  `epoch` must grow by one per barrier, identically on all ranks.
+ * A peer that never arrives sets *err (device int) after timeout_s seconds instead of hanging the GPU. */
+int rmt_peer_barrier(void *const *flags, int rank, int world, unsigned long long epoch, double timeout_s,
+                     int *err, void *stream);
+/* out[k] = reduction over q = 0..world-1, in that order, of slots[q*stride + k]; op 0 sum, 1 max, 2 min
+ * (the local half of the peer all-reduce: bitwise identical on every rank). */
+int rmt_peer_reduce(const double *slots, int world, long stride, int n, int op, double *out, void *stream);
+
 
 #ifdef __cplusplus
 }

@@ -78,6 +78,15 @@ _SIG = {
     "rmt_dht_lines": [vp, vp, vp, i32, i32, i64, i64, dbl, vp],
     "rmt_transpose": [vp, vp, i32, i32, vp],
     "rmt_copy2d": [vp, vp, i32, i32, i64, i64, vp],
+    "rmt_peer_alloc": [C.c_size_t, C.POINTER(vp)],
+    "rmt_peer_free": [vp],
+    "rmt_peer_export": [vp, vp],
+    "rmt_peer_import": [vp, C.POINTER(vp)],
+    "rmt_peer_release": [vp],
+    "rmt_peer_put2d": [vp, i32, vp],
+    "rmt_transpose_scatter": [vp, i32, i32, i64, i32, vp, vp, vp, vp],
+    "rmt_peer_barrier": [vp, i32, i32, C.c_ulonglong, dbl, vp, vp],
+    "rmt_peer_reduce": [vp, i32, i64, i32, i32, vp, vp],
 }
 _RESTYPE = {"rmt_launch_count": C.c_ulonglong, "rmt_extrapolate_workspace_bytes": i64, "rmt_projection_partials": i64, "rmt_poisson_plan_destroy": None}
 

@@ -64,6 +64,7 @@ def shape2(t):
 _LAUNCHES = {"rmt_max_speed": 2, "rmt_field_stats": 2, "rmt_advect_euler_rk3": 5, "rmt_advect_euler_rk3_pair": 5, "rmt_extrapolate": 1, "rmt_extrapolate_rows": 1,
              "rmt_poisson_solve_dct": 4, "rmt_poisson_solve_fft": 16, "rmt_abi_version": 0, "rmt_launch_count": 0, "rmt_diagnostics_workspace_doubles": 0, "rmt_diagnostics": 2,
              "rmt_reduce_workspace_doubles": 0, "rmt_projection_partials": 0, "rmt_projection_correct_centered": 2, "rmt_extrapolate_workspace_bytes": 0, "rmt_extrapolate_set_mode": 0, "rmt_extrapolate_last_mode": 0,
+             "rmt_peer_alloc": 0, "rmt_peer_free": 0, "rmt_peer_export": 0, "rmt_peer_import": 0, "rmt_peer_release": 0,
              "rmt_poisson_plan_create": 0, "rmt_poisson_plan_destroy": 0, "rmt_poisson_plan_is_fast": 0, "rmt_poisson_plan_invalidate": 0}
 
 

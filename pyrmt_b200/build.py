@@ -32,6 +32,7 @@ UNITS = {
     "projection.cu": [],
     "fft.cu": [],
     "extrap.cu": ["-fmad=false"],
+    "peer.cu": [],
 }
 
 
@@ -80,7 +81,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return r
 
     if jobs:
-        with ThreadPoolExecutor(max_workers=min(6, len(jobs))) as ex:
+        with ThreadPoolExecutor(max_workers=min(7, len(jobs))) as ex:
             list(ex.map(run, jobs))
     if force or jobs or _stale(LIB, objs):
         run([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"])

@@ -90,8 +90,11 @@ class Comm:
         self.rank = dist.get_rank(group) if self.on else 0
         self.nccl = self.on and dist.get_backend(group) == "nccl"
 
-    def halo_exchange(self, lay, fields, width=None):
-        """Fill the halo rows of every extended slab in `fields` from the neighbours' owned rows."""
+    def halo_exchange(self, lay, fields, width=None, reduce=()):
+        """Fill the halo rows of every extended slab in `fields` from the neighbours' owned rows.
+        `reduce`: (tensor, op) pairs all-reduced in place along the way (PeerComm: same barrier)."""
+        for t, op in reduce:
+            self.allreduce(t, op)
         if self.world == 1:
             return
         H = lay.H if width is None else width
@@ -168,6 +171,315 @@ class Comm:
         return [bool(x > 0.5) for x in t.tolist()]
 
 
+    def exchange_flat(self, send, recv, slot_n=None):
+        """Sparse point-to-point exchange of flat fp64 buffers: send = {peer: tensor}, recv = {peer: tensor
+        to fill} (the remote BC copies).  slot_n: the largest message of the pattern over ALL ranks."""
+        ops = [dist.P2POp(dist.isend, send[q], q, self.group) for q in sorted(send)]
+        ops += [dist.P2POp(dist.irecv, recv[q], q, self.group) for q in sorted(recv)]
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+
+    def gather_overlap(self, lay, fields, top, bot, top_of, bot_of):
+        """Rows [r0 - top, r1 + bot) of every field, the extra rows taken from the neighbours' owned rows
+        (the extrapolation overlap).  top_of(rank) / bot_of(rank): the same extents for any rank."""
+        n_own = lay.r1 - lay.r0
+        big = [torch.empty((top + n_own + bot, lay.Nx), dtype=F64, device=f.device) for f in fields]
+        for B, f in zip(big, fields):
+            B[top:top + n_own].copy_(lay.owned(f))
+        if self.world > 1:
+            ops = []
+            for B, f in zip(big, fields):
+                own = lay.owned(f)
+                if lay.rank + 1 < lay.world:
+                    want = min(top_of(lay.rank + 1), n_own)
+                    ops.append(dist.P2POp(dist.isend, own[n_own - want:], self.rank + 1, self.group))
+                    if bot:
+                        ops.append(dist.P2POp(dist.irecv, B[top + n_own:], self.rank + 1, self.group))
+                if lay.rank > 0:
+                    if top:
+                        ops.append(dist.P2POp(dist.irecv, B[:top], self.rank - 1, self.group))
+                    wantb = bot_of(lay.rank - 1)
+                    if wantb:
+                        ops.append(dist.P2POp(dist.isend, own[:wantb], self.rank - 1, self.group))
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        return big
+
+
+class _DevMem:
+    """A raw device range as a __cuda_array_interface__ object (zero-copy torch view of arena memory)."""
+
+    def __init__(self, address, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": "<f8",
+                                         "data": (int(address), False), "version": 2, "strides": None}
+
+
+class _Region:
+    def __init__(self, nbytes, local, peers, meta=None):
+        self.nbytes, self.local, self.peers, self.meta = nbytes, local, peers, meta
+
+
+class PeerComm(Comm):
+    """The same exchange patterns as `Comm`, but over NVLink PEER MEMORY instead of NCCL calls: every rank
+    owns arenas (csrc/peer.cu: cudaMalloc + CUDA IPC) that all other ranks of the node map, and an exchange
+    is [kernels that store straight into the neighbour's arena] -> [rmt_peer_barrier on the stream] ->
+    [local kernels that consume the arena].  No host synchronisation, no proxy thread, ~3 launches per
+    exchange; the all-to-all of the distributed transforms is fused with the local transpose
+    (`scatter` = rmt_transpose_scatter) and the column lines are transformed in place in the arena.
+
+    Ordering: all ranks issue the same sequence of exchanges.  `self.epoch` counts barriers; a staging
+    region holds two copies and exchange e uses copy e & 1, so a copy written before barrier e is read after
+    it and written again before barrier e + 2 at the earliest -- by then its reader has signalled barrier
+    e + 1, which in stream order comes after its reads.  torch.distributed is used for set-up only (the IPC
+    handles travel by all_gather_object), so any backend does -- the 2-process single-GPU test runs on gloo."""
+
+    SLOT = 64                                   # doubles per rank and all-reduce
+    NRED = 4                                    # all-reduces that can share one barrier
+
+    def __init__(self, group=None, timeout_s=120.0):
+        super().__init__(group)
+        if not (self.on and self.world > 1):
+            raise RuntimeError("PeerComm needs an initialised process group with more than one rank")
+        if self.world > 16:
+            raise ValueError("PeerComm: at most 16 ranks (one node)")
+        import ctypes as C
+        self.C = C
+        self.lib = ctx().lib
+        self.timeout_s = float(timeout_s)
+        self.regions, self.epoch = {}, 0
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        # control arena: barrier counters (256 B) + two copies of the all-reduce slots
+        self.ctrl = self.region("ctrl", 256 + 2 * self.NRED * self.world * self.SLOT * 8)
+        self._flags = (C.c_void_p * self.world)(*self.ctrl.peers)
+
+        class Put(C.Structure):
+            _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int),
+                        ("src_ld", C.c_long), ("dst_ld", C.c_long)]
+        self._Put = Put
+
+    # -- arenas ---------------------------------------------------------------------------------
+    def region(self, key, nbytes, meta=None):
+        """Collective on first use of `key` (every rank must reach it in the same order): an arena of
+        max-over-ranks(nbytes) bytes on every rank, mapped everywhere.  `meta`: a number whose maximum over
+        the ranks is kept in region.meta (e.g. an agreed slot size)."""
+        r = self.regions.get(key)
+        if r is not None:
+            if nbytes > r.nbytes:
+                raise RuntimeError("PeerComm region %r is %d bytes, %d needed" % (key, r.nbytes, nbytes))
+            return r
+        C = self.C
+        sizes = [None] * self.world
+        dist.all_gather_object(sizes, (int(nbytes), meta), group=self.group)
+        total = (max(x[0] for x in sizes) + 255) // 256 * 256
+        meta = max(x[1] for x in sizes) if meta is not None else None
+        base = C.c_void_p()
+        _lib.check(self.lib.rmt_peer_alloc(total, C.byref(base)), "rmt_peer_alloc")
+        handle = (C.c_ubyte * 64)()
+        _lib.check(self.lib.rmt_peer_export(base, handle), "rmt_peer_export")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=self.group)
+        peers = []
+        for q in range(self.world):
+            if q == self.rank:
+                peers.append(base.value)
+                continue
+            h = (C.c_ubyte * 64).from_buffer_copy(handles[q])
+            mapped = C.c_void_p()
+            _lib.check(self.lib.rmt_peer_import(h, C.byref(mapped)), "rmt_peer_import (CUDA IPC between the ranks)")
+            peers.append(mapped.value)
+        dist.barrier(group=self.group)                 # nobody stores into an arena that is not mapped yet
+        r = self.regions[key] = _Region(total, base.value, peers, meta)
+        return r
+
+    def view(self, region, offset_bytes, shape):
+        """Zero-copy fp64 tensor over this rank's own arena."""
+        return torch.as_tensor(_DevMem(region.local + offset_bytes, shape), device=self.dev)
+
+    def close(self):
+        torch.cuda.synchronize()
+        if self.on:
+            dist.barrier(group=self.group)
+        for r in self.regions.values():
+            for q, p in enumerate(r.peers):
+                if q != self.rank:
+                    self.lib.rmt_peer_release(p)
+        if self.on:
+            dist.barrier(group=self.group)
+        for r in self.regions.values():
+            self.lib.rmt_peer_free(r.local)
+        self.regions = {}
+
+    def check(self):
+        """Raise if a barrier ever timed out (host sync)."""
+        if int(self.err.item()):
+            raise RuntimeError("PeerComm: a peer did not reach a barrier within %.0f s (rank %d)"
+                               % (self.timeout_s, self.rank))
+
+    # -- primitives -----------------------------------------------------------------------------
+    def put(self, blocks):
+        """blocks: (src address, dst address, rows, cols, src_ld, dst_ld) in doubles -- one launch per 32."""
+        for k in range(0, len(blocks), 32):
+            chunk = blocks[k:k + 32]
+            arr = (self._Put * len(chunk))(*[self._Put(*b) for b in chunk])
+            _lib.check(self.lib.rmt_peer_put2d(arr, len(chunk), stream()), "rmt_peer_put2d")
+
+    def barrier(self):
+        self.epoch += 1
+        _lib.check(self.lib.rmt_peer_barrier(self._flags, self.rank, self.world, self.epoch, self.timeout_s,
+                                             self.err.data_ptr(), stream()), "rmt_peer_barrier")
+
+    def scatter(self, A, starts, dst, dst_ld):
+        """rmt_transpose_scatter of the 2-D tensor A (unit column stride): column block q of A, transposed, to
+        address dst[q] with row stride dst_ld[q]."""
+        C = self.C
+        n = len(dst)
+        R, Cc = A.shape
+        _lib.check(self.lib.rmt_transpose_scatter(A.data_ptr(), R, Cc, A.stride(0), n, (C.c_int * (n + 1))(*starts),
+                                                  (C.c_void_p * n)(*dst), (C.c_long * n)(*dst_ld), stream()),
+                   "rmt_transpose_scatter")
+
+    # -- the exchange patterns ------------------------------------------------------------------------
+    def halo_exchange(self, lay, fields, width=None, reduce=()):
+        H = lay.H if width is None else width
+        Nx, nf, me = lay.Nx, len(fields), self.rank
+        reg = self.region(("halo", nf, H, Nx), 2 * nf * 2 * H * Nx * 8)
+        par = (self.epoch + 1) & 1
+        slot = lambda base, k, side: base + (((par * nf + k) * 2 + side) * H * Nx) * 8
+        up, down = me + 1 < self.world, me > 0
+        puts, gets = [], []
+        for k, f in enumerate(fields):
+            ld = f.stride(0)
+            if up:
+                puts.append((f[lay.o1 - H:lay.o1].data_ptr(), slot(reg.peers[me + 1], k, 0), H, Nx, ld, Nx))
+                gets.append((slot(reg.local, k, 1), f[lay.o1:lay.o1 + H].data_ptr(), H, Nx, Nx, ld))
+            if down:
+                puts.append((f[lay.o0:lay.o0 + H].data_ptr(), slot(reg.peers[me - 1], k, 1), H, Nx, ld, Nx))
+                gets.append((slot(reg.local, k, 0), f[lay.o0 - H:lay.o0].data_ptr(), H, Nx, Nx, ld))
+        red = [self._reduce_puts(t, k, par) for k, (t, _) in enumerate(reduce)]
+        self.put(puts + [b for blocks in red for b in blocks])
+        self.barrier()
+        self.put(gets)
+        for k, (t, op) in enumerate(reduce):
+            self._reduce_finish(t, op, k, par)
+
+    def ring_exchange(self, items):
+        me, P = self.rank, self.world
+        nxt, prv = (me + 1) % P, (me - 1) % P
+        blocks = [t for it in items for t in it if t is not None]
+        cols = max(t.shape[-1] for t in blocks)                       # every block is a few rows of one grid
+        slot_n = 4 * cols
+        if max(t.numel() for t in blocks) > slot_n:
+            raise RuntimeError("PeerComm.ring_exchange: blocks of at most 4 rows")
+        reg = self.region(("ring", len(items), cols), 2 * len(items) * 2 * slot_n * 8)
+        par = (self.epoch + 1) & 1
+        slot = lambda base, k, side: base + (((par * len(items) + k) * 2 + side) * slot_n) * 8
+        blk = lambda t: (t.shape[0], t.shape[1], t.stride(0)) if t.dim() == 2 else (1, t.numel(), t.numel())
+        puts, gets = [], []
+        for k, (to_next, to_prev, from_prev, from_next) in enumerate(items):
+            if to_next is not None:                                   # lands in next's "from prev" slot
+                r, c, ld = blk(to_next)
+                puts.append((to_next.data_ptr(), slot(reg.peers[nxt], k, 0), r, c, ld, c))
+            if to_prev is not None:
+                r, c, ld = blk(to_prev)
+                puts.append((to_prev.data_ptr(), slot(reg.peers[prv], k, 1), r, c, ld, c))
+            if from_prev is not None:
+                r, c, ld = blk(from_prev)
+                gets.append((slot(reg.local, k, 0), from_prev.data_ptr(), r, c, c, ld))
+            if from_next is not None:
+                r, c, ld = blk(from_next)
+                gets.append((slot(reg.local, k, 1), from_next.data_ptr(), r, c, c, ld))
+        self.put(puts)
+        self.barrier()
+        self.put(gets)
+
+    def exchange_flat(self, send, recv, slot_n):
+        """slot_n: an upper bound of every message of this exchange pattern, the same on all ranks."""
+        if max([t.numel() for t in list(send.values()) + list(recv.values())] or [0]) > slot_n:
+            raise RuntimeError("PeerComm.exchange_flat: a message exceeds the agreed %d doubles" % slot_n)
+        reg = self.region(("flat", slot_n), 2 * self.world * slot_n * 8)
+        par = (self.epoch + 1) & 1
+        slot = lambda base, src: base + ((par * self.world + src) * slot_n) * 8
+        self.put([(t.data_ptr(), slot(reg.peers[q], self.rank), 1, t.numel(), t.numel(), t.numel())
+                  for q, t in sorted(send.items())])
+        self.barrier()
+        self.put([(slot(reg.local, q), t.data_ptr(), 1, t.numel(), t.numel(), t.numel())
+                  for q, t in sorted(recv.items())])
+
+    # all-reduce = every rank stores its vector into slot [rank] of every rank, barrier, every rank reduces the
+    # slots in rank order (identical bits everywhere).  Up to NRED vectors can share one barrier (lane k).
+    def _reduce_off(self, lane, par):
+        return 256 + ((par * self.NRED + lane) * self.world) * self.SLOT * 8
+
+    def _reduce_puts(self, t, lane, par):
+        n = t.numel()
+        if n > self.SLOT or t.dtype != F64 or not t.is_cuda or not t.is_contiguous() or lane >= self.NRED:
+            raise ValueError("PeerComm.allreduce: contiguous fp64 CUDA vectors of <= %d entries" % self.SLOT)
+        off = self._reduce_off(lane, par) + self.rank * self.SLOT * 8
+        return [(t.data_ptr(), self.ctrl.peers[q] + off, 1, n, n, n) for q in range(self.world)]
+
+    def _reduce_finish(self, t, op, lane, par):
+        _lib.check(self.lib.rmt_peer_reduce(self.ctrl.local + self._reduce_off(lane, par), self.world, self.SLOT,
+                                            t.numel(), {"sum": 0, "max": 1, "min": 2}[op], t.data_ptr(), stream()),
+                   "rmt_peer_reduce")
+
+    def allreduce(self, t, op="sum"):
+        par = (self.epoch + 1) & 1
+        self.put(self._reduce_puts(t, 0, par))
+        self.barrier()
+        self._reduce_finish(t, op, 0, par)
+        return t
+
+    def all_agree(self, flags):
+        t = torch.tensor([1.0 if f else 0.0 for f in flags], dtype=F64, device=self.dev)
+        self.allreduce(t, "min")
+        return [bool(x > 0.5) for x in t.tolist()]
+
+    def gather_overlap(self, lay, fields, top, bot, top_of, bot_of):
+        """The neighbours store their rows straight into this rank's (top + own + bot)-row work fields, which
+        live in the arena (read by the extrapolation one barrier later, rewritten a step later)."""
+        me, Nx, nf = self.rank, lay.Nx, len(fields)
+        rows_of = lambda q: top_of(q) + (lay.rows[q][1] - lay.rows[q][0]) + bot_of(q)
+        geom = tuple(rows_of(q) for q in range(self.world))
+        reg = self.region(("overlap", nf, Nx, geom), nf * max(geom) * Nx * 8)
+        n_own = lay.r1 - lay.r0
+        field_at = lambda base, q, k: base + k * rows_of(q) * Nx * 8
+        puts = []
+        for k, f in enumerate(fields):
+            own = lay.owned(f)
+            ld = own.stride(0)
+            puts.append((own.data_ptr(), field_at(reg.local, me, k) + top * Nx * 8, n_own, Nx, ld, Nx))
+            if me + 1 < self.world and top_of(me + 1):
+                want = top_of(me + 1)                                   # my last rows -> the top of rank me+1
+                puts.append((own[n_own - want:].data_ptr(), field_at(reg.peers[me + 1], me + 1, k), want, Nx, ld, Nx))
+            if me > 0 and bot_of(me - 1):
+                wantb, q = bot_of(me - 1), me - 1                       # my first rows -> the bottom of rank me-1
+                n_q = lay.rows[q][1] - lay.rows[q][0]
+                puts.append((own.data_ptr(), field_at(reg.peers[q], q, k) + (top_of(q) + n_q) * Nx * 8,
+                             wantb, Nx, ld, Nx))
+        self.put(puts)
+        self.barrier()
+        return [self.view(reg, k * rows_of(me) * Nx * 8, (rows_of(me), Nx)) for k in range(nf)]
+
+
+def default_comm(group=None):
+    """PeerComm when several ranks drive CUDA devices (RMT_SLAB_COMM=nccl keeps the torch.distributed
+    collectives), the plain Comm otherwise (one rank; the CPU/gloo test doubles)."""
+    import os
+    on = dist.is_available() and dist.is_initialized()
+    if on and dist.get_world_size(group) > 1 and torch.cuda.is_available() \
+            and os.environ.get("RMT_SLAB_COMM", "peer").lower() != "nccl":
+        key = (id(group), torch.cuda.current_device())
+        if key not in _peer_comms:                     # one set of arenas per process group and device
+            _peer_comms[key] = PeerComm(group)
+        return _peer_comms[key]
+    return Comm(group)
+
+
+_peer_comms = {}
+
+
 # ------------------------------------------------------------------- device line ops
 class CudaOps:
     """The device primitives of the distributed transforms and reductions (C ABI)."""
@@ -221,11 +533,26 @@ class DistPoissonDCT:
         self.nr = [e - s for s, e in lay.rows]
         self.nc = [e - s for s, e in lay.cols]
 
-    def solve(self, rhs_owned):
-        """rhs_owned: (nr_me, Nx) contiguous.  Returns (sol_owned, global sum of sol as a 1-element tensor)."""
+    def solve(self, rhs_owned, out=None, reduce=True):
+        """rhs_owned: (nr_me, Nx) contiguous.  Returns (sol_owned, global sum of sol as a 1-element tensor);
+        with `out` (a contiguous (nr_me, Nx) view) the solution is written there and only the sum is
+        returned -- this rank's partial sum if reduce=False (the caller all-reduces it with its next exchange)."""
         lay, ops, comm = self.lay, self.ops, self.comm
         me, P = lay.rank, lay.world
         nr_me, nc_me, Ny, Nx = self.nr[me], self.nc[me], lay.Ny, lay.Nx
+        if out is not None:
+            if isinstance(comm, PeerComm):
+                sol = self._solve_peer(rhs_owned, out)
+            else:
+                sol, _ = self.solve(rhs_owned, reduce=False)
+                out.copy_(sol)
+                sol = out
+            part = ops.sum(sol)
+            return comm.allreduce(part) if reduce else part
+        if isinstance(comm, PeerComm):
+            sol = self._solve_peer(rhs_owned, torch.empty_like(rhs_owned))
+            part = ops.sum(sol)
+            return sol, (comm.allreduce(part) if reduce else part)
         A = ops.dct_lines(rhs_owned.clone())                          # rows, local
         At = ops.transpose(A)                                          # (Nx, nr_me): column blocks contiguous
         send_counts = [self.nc[q] * nr_me for q in range(P)]
@@ -246,8 +573,30 @@ class DistPoissonDCT:
         At2 = torch.empty(Nx * nr_me, dtype=At.dtype, device=At.device)
         comm.all_to_all(sbuf, recv_counts, At2, send_counts)          # blocks (nc_q, nr_me) = rows of At
         sol = ops.dct_lines(ops.transpose(At2.view(Nx, nr_me)))        # (nr_me, Nx), rows again
-        total = comm.allreduce(ops.sum(sol))
-        return sol, total
+        part = ops.sum(sol)
+        return sol, (comm.allreduce(part) if reduce else part)
+
+    def _solve_peer(self, rhs_owned, sol):
+        """The same solve with the transposes AND the all-to-alls done by two rmt_transpose_scatter launches
+        that store into the owners' arenas: B (my columns as lines, nc_me x Ny) and S (my rows, nr_me x Nx)
+        live in peer memory and are transformed in place -- no pack / unpack passes, no NCCL call."""
+        lay, ops, comm = self.lay, self.ops, self.comm
+        me, P = lay.rank, lay.world
+        nr_me, nc_me, Ny, Nx = self.nr[me], self.nc[me], lay.Ny, lay.Nx
+        Breg = comm.region(("dctB", Ny, Nx), max(self.nc) * Ny * 8)
+        Sreg = comm.region(("dctS", Ny, Nx), max(self.nr) * Nx * 8)
+        A = torch.empty_like(rhs_owned)
+        _lib.check(ctx().lib.rmt_dct_lines(ptr(rhs_owned), ptr(A), None, nr_me, Nx, 1.0, stream()), "rmt_dct_lines")
+        cs = [c[0] for c in lay.cols] + [Nx]
+        comm.scatter(A, cs, [Breg.peers[q] + lay.r0 * 8 for q in range(P)], [Ny] * P)   # -> B_q[c - c0_q, r0 + r]
+        comm.barrier()
+        B = comm.view(Breg, 0, (nc_me, Ny))
+        ops.dct_lines(B, eig=self.eigT, scale=self.scale)              # columns: fwd, 1/eig, inverse
+        rs = [r[0] for r in lay.rows] + [Ny]
+        comm.scatter(B, rs, [Sreg.peers[q] + lay.c0 * 8 for q in range(P)], [Nx] * P)   # -> S_q[r - r0_q, c0 + c]
+        comm.barrier()
+        _lib.check(ctx().lib.rmt_dct_lines(Sreg.local, ptr(sol), None, nr_me, Nx, 1.0, stream()), "rmt_dct_lines")
+        return sol
 
 
 class DistPoissonFFT:
@@ -294,6 +643,23 @@ class DistPoissonFFT:
         nr_me, nc_me = self.nr[me], self.nc[me]
         kw = dict(dtype=rhs_rows.dtype, device=rhs_rows.device)
         A = ops.dht_lines(rhs_rows, torch.empty((nr_me, mx), **kw), mx)
+        if isinstance(comm, PeerComm):      # transposes + all-to-alls fused: rmt_transpose_scatter into the arenas
+            Breg = comm.region(("dhtB", my, mx), max(self.nc) * my * 8)
+            Sreg = comm.region(("dhtS", my, mx), max(self.nr) * mx * 8)
+            r0 = lay.red_rows[me][0]
+            comm.scatter(A, [c[0] for c in lay.cols] + [mx], [Breg.peers[q] + r0 * 8 for q in range(P)], [my] * P)
+            comm.barrier()
+            B = comm.view(Breg, 0, (nc_me, my))
+            ops.dht_lines(B, B, my, mul=self.fT)
+            ops.dht_lines(B, B, my)
+            comm.scatter(B, [r[0] for r in lay.red_rows] + [my], [Sreg.peers[q] + lay.c0 * 8 for q in range(P)], [mx] * P)
+            comm.barrier()
+            ops.dht_lines(comm.view(Sreg, 0, (nr_me, mx)), sol_rows, mx)
+            ops.copy2d(sol_rows[:, 0:1], sol_rows[:, mx:mx + 1])
+            part = ops.sum(sol_rows)
+            if me == 0:
+                part = part + ops.sum(sol_rows[0])
+            return comm.allreduce(part)
         At = ops.transpose(A)                                          # (mx, nr_me)
         send_counts = [self.nc[q] * nr_me for q in range(P)]
         recv_counts = [nc_me * self.nr[q] for q in range(P)]
@@ -348,6 +714,9 @@ class RemoteCopies:
                 rel = cell(dst[n]) - lay.e0 * Nx
                 self.need[q] = (rel, isv(dst[n]), ca[n], cb[n])
         self.n = sum(v[0].size for v in self.need.values()) + sum(v[0].size + v[1].size for v in self.give.values())
+        # the largest message between any two ranks (same number on every rank: the table is global)
+        pair = dst_rank.astype(np.int64) * lay.world + src_rank.astype(np.int64)
+        self.max_msg = int(np.bincount(pair).max()) if pair.size else 0
         self._dev = None
 
     def _on(self, dev):
@@ -365,18 +734,9 @@ class RemoteCopies:
             return
         give, need = self._on(u.device)
         fu, fv = u.reshape(-1), v.reshape(-1)
-        ops, keep = [], []
-        for q in sorted(give):
-            iu, iv = give[q]
-            buf = torch.cat([fu[iu], fv[iv]])
-            keep.append(buf)
-            ops.append(dist.P2POp(dist.isend, buf, q, comm.group))
-        rbufs = {}
-        for q in sorted(need):
-            rbufs[q] = torch.empty(need[q][4].numel(), dtype=u.dtype, device=u.device)
-            ops.append(dist.P2POp(dist.irecv, rbufs[q], q, comm.group))
-        for r in dist.batch_isend_irecv(ops):
-            r.wait()
+        sbufs = {q: torch.cat([fu[iu], fv[iv]]) for q, (iu, iv) in give.items()}
+        rbufs = {q: torch.empty(need[q][4].numel(), dtype=u.dtype, device=u.device) for q in need}
+        comm.exchange_flat(sbufs, rbufs, self.max_msg)
         for q, buf in rbufs.items():
             du, dv, pu, pv, ca, cb = need[q]
             vals = ca * buf + cb
@@ -432,7 +792,7 @@ class SlabFluidSolver:
     All field arguments and results are extended slabs (lay.nl, Nx) with valid halos."""
 
     def __init__(self, lay, bc, eig, comm=None, spacing=None):
-        self.lay, self.comm = lay, comm or Comm()
+        self.lay, self.comm = lay, comm or default_comm()
         self.table, self.remote = local_bc_table(bc, lay)
         # wall-type layouts: the BC on every stored row, for stages whose halo rows are computed locally
         self.table_ext = None if lay.periodic else local_bc_table(bc, lay, extended=True)[0]
@@ -492,8 +852,6 @@ class SlabFluidSolver:
         sxx, sxy, syy, J = (torch.empty_like(u) for _ in range(4))
         _lib.check(lib.rmt_solid_stress(ptr(X1), ptr(X2), ptr(phi), ptr(sxx), ptr(sxy), ptr(syy), ptr(J), nl, Nx,
                                         dx, dy, mu_s, kappa, 0.0, 0.0, 0, st), "rmt_solid_stress")
-        sa_u, sa_v = u.clone(), v.clone()
-        self._bc_and_halo(sa_u, sa_v)
         sb_u, sb_v = torch.empty_like(u), torch.empty_like(u)
         acc_u, acc_v = torch.empty_like(u), torch.empty_like(u)
         un, vn = torch.empty_like(u), torch.empty_like(u)
@@ -504,6 +862,11 @@ class SlabFluidSolver:
         # Wall-type layouts therefore exchange the halo ONCE, after the last stage; the periodic layout
         # keeps the per-stage exchange (its wrap rows travel with the remote BC copies).
         lazy_halo = self.table_ext is not None and lay.H >= 10
+        sa_u, sa_v = u.clone(), v.clone()
+        if lazy_halo:
+            self.table_ext.apply_(sa_u, sa_v)       # the input halos are valid (contract): BC on every stored row
+        else:
+            self._bc_and_halo(sa_u, sa_v)
 
         def stage(k, iu, iv, ou, ov):
             _lib.check(lib.rmt_momentum_stage(ptr(iu), ptr(iv), ptr(p), ptr(sxx), ptr(sxy), ptr(syy), ptr(phi),
@@ -555,19 +918,21 @@ class SlabFluidSolver:
         _lib.check(lib.rmt_projection_rhs(ptr(a_star), ptr(b_star), ptr(p_prev), ptr(rd), rscalar,
                                           ptr(rsum_local), ptr(rhs), nl, Nx, dx, dy, dt, 0, st),
                    "rmt_projection_rhs")
-        sol_o, total = self.poisson.solve(lay.owned(rhs).contiguous())
         sol = torch.zeros_like(a_star)
-        lay.owned(sol).copy_(sol_o)
-        comm.halo_exchange(lay, (sol,))
+        total = self.poisson.solve(lay.owned(rhs), out=lay.owned(sol), reduce=False)
+        comm.halo_exchange(lay, (sol,), width=1, reduce=((total, "sum"),))    # the correction reads one row
         ssum_local = total * (float(nl * Nx) / float(ncell))
         a, b, p = torch.empty_like(a_star), torch.empty_like(a_star), torch.empty_like(a_star)
         _lib.check(lib.rmt_projection_correct(ptr(sol), ptr(ssum_local), ptr(a_star), ptr(b_star), ptr(rd),
                                               rscalar, ptr(p_prev), ptr(a), ptr(b), ptr(p), nl, Nx, dx, dy, dt,
                                               0, st), "rmt_projection_correct")
         self._apply_bc(a, b)
-        psum = comm.allreduce(self.ops.sum(lay.owned(p))) * (float(nl * Nx) / float(ncell))
+        # the halo rows of p travel BEFORE the mean is subtracted and lose the same mean afterwards (the same
+        # subtraction on the same values as on their owner): the sum(p) all-reduce shares the exchange's barrier
+        psum = self.ops.sum(lay.owned(p))
+        comm.halo_exchange(lay, (a, b, p), reduce=((psum, "sum"),))
+        psum = psum * (float(nl * Nx) / float(ncell))
         _lib.check(lib.rmt_subtract_mean(ptr(p), ptr(psum), p.numel(), st), "rmt_subtract_mean")
-        comm.halo_exchange(lay, (a, b, p))
         return a, b, p
 
     # -- functions.py:1277-1290 (bc_type='periodic') ---------------------------------------
@@ -655,30 +1020,7 @@ class SlabFSISolver(SlabFluidSolver):
 
     # rows [r0 - top, r1 + bot) of a field, from the neighbours' owned rows
     def _gather_big(self, fields):
-        lay, comm = self.lay, self.comm
-        n_own = lay.r1 - lay.r0
-        big = [torch.empty((self.top + n_own + self.bot, lay.Nx), dtype=F64, device=f.device) for f in fields]
-        for B, f in zip(big, fields):
-            B[self.top:self.top + n_own].copy_(lay.owned(f))
-        if comm.world > 1:
-            ops = []
-            # every rank uses the same `overlap`, so the neighbour's top overlap is min(overlap, its r0)
-            for B, f in zip(big, fields):
-                own = lay.owned(f)
-                if lay.rank + 1 < lay.world:
-                    want = min(self._overlap_of(lay.rank + 1), n_own)
-                    ops.append(dist.P2POp(dist.isend, own[n_own - want:], comm.rank + 1, comm.group))
-                    if self.bot:
-                        ops.append(dist.P2POp(dist.irecv, B[self.top + n_own:], comm.rank + 1, comm.group))
-                if lay.rank > 0:
-                    if self.top:
-                        ops.append(dist.P2POp(dist.irecv, B[:self.top], comm.rank - 1, comm.group))
-                    wantb = self._bot_of(lay.rank - 1)
-                    if wantb:
-                        ops.append(dist.P2POp(dist.isend, own[:wantb], comm.rank - 1, comm.group))
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
-        return big
+        return self.comm.gather_overlap(self.lay, fields, self.top, self.bot, self._overlap_of, self._bot_of)
 
     def _overlap_of(self, rank):
         return min(self._overlap, self.lay.rows[rank][0])
@@ -811,6 +1153,8 @@ def _timed(step, steps, warmup, comm):
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=F64, device="cuda")
     comm.allreduce(ms, "max")
+    if isinstance(comm, PeerComm):
+        comm.check()
     return float(ms.item()) / steps
 
 

@@ -27,9 +27,25 @@ ap.add_argument("--overlap", type=int, default=256)
 ap.add_argument("--steps", type=int, default=10)
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-torch.cuda.set_device(local)
+SAME_GPU = os.environ.get("RMT_SAME_GPU") == "1"      # all ranks on cuda:0, gloo for the set-up (PeerComm carries the data)
+torch.cuda.set_device(0 if SAME_GPU else local)
 if world > 1:
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if SAME_GPU:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+
+def allmax(t):
+    """MAX over the ranks of a small CUDA tensor (through the host when the group is gloo)."""
+    if world > 1:
+        if SAME_GPU:
+            h = t.cpu()
+            dist.all_reduce(h, op=dist.ReduceOp.MAX)
+            return h.to(t.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t
 
 from pyrmt_b200 import functions as F
 from pyrmt_b200.driver import LidBC, disc_lattice
@@ -81,8 +97,7 @@ if args.check:
         for ref, got in ((a, sa), (b, sb), (p, sp)):
             worst = max(worst, float(((got - ref[lay.e0:lay.e1]).abs().max() / ref.abs().max()).item()))
     t = torch.tensor([worst], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = allmax(t)
     out["check"] = {"N": N, "rel_linf_vs_single_gpu": float(t.item())}
     del a, b, p, X1, X2, phi, solver
     torch.cuda.empty_cache()
@@ -116,8 +131,7 @@ if args.fsi:
             err = float(((got - ref[lay.e0:lay.e1]).abs().max() / ref.abs().max()).item())   # owned rows + halos
             worst[nm] = max(worst.get(nm, 0.0), err)
     t = torch.tensor([worst[k] for k in ("a", "b", "p", "X1", "X2")], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = allmax(t)
     out["fsi_check"] = {"N": N, "steps": 4, "scheme": args.scheme, "rel_linf_vs_single_gpu": dict(zip(("a", "b", "p", "X1", "X2"), t.tolist()))}
     del state, sstate, solver, X1, X2, Xd, Yd, phi0
     torch.cuda.empty_cache()
@@ -164,8 +178,7 @@ if args.fsi_time:
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = allmax(ms)
     ms = float(ms.item()) / args.steps
     out["fsi_time"] = {"N": N, "discs": int(cx.size), "ms_per_step": ms, "Mcell_steps_per_s": N * N / ms / 1e3,
                        "finite": bool(torch.isfinite(sstate[0]).all().item())}
@@ -204,9 +217,14 @@ if args.pfsi:
         for nm, ref, got in zip(("a", "b", "p", "X1", "X2"), state, sstate):
             err = float(((got - ref[lay.e0:lay.e1]).abs().max() / ref.abs().max()).item())   # owned rows + halos
             worst[nm] = max(worst.get(nm, 0.0), err)
+            if os.environ.get("RMT_CHECK_DEBUG") and nm in ("X1", "X2") and err > 0:
+                d = (got - ref[lay.e0:lay.e1]).abs()
+                k = int(d.argmax()); jj, ii = k // N, k % N
+                print("[rank %d] step %d %s differs at stored row %d (global %d, owned [%d,%d)) col %d: %r vs %r; "
+                      "#cells %d" % (rank, n, nm, jj, jj + lay.e0, lay.r0, lay.r1, ii, float(got[jj, ii]),
+                                     float(ref[jj + lay.e0, ii]), int((d > 0).sum())), flush=True)
     t = torch.tensor([worst[k] for k in ("a", "b", "p", "X1", "X2")], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = allmax(t)
     out["periodic_fsi_check"] = {"N": N, "steps": 4, "scheme": args.scheme,
                                  "rel_linf_vs_single_gpu": dict(zip(("a", "b", "p", "X1", "X2"), t.tolist()))}
     del state, sstate, solver, X1, X2, Xd, Yd, phi0, eig, X, Y
@@ -250,11 +268,16 @@ if args.time:
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = allmax(ms)
     ms = float(ms.item()) / args.steps
     out["time"] = {"N": N, "ms_per_fluid_step": ms, "Mcell_steps_per_s": N * N / ms / 1e3,
                    "finite": bool(torch.isfinite(sa).all().item())}
+from pyrmt_b200.slab import PeerComm, default_comm
+comm = default_comm()
+out["comm"] = type(comm).__name__
+if isinstance(comm, PeerComm):
+    comm.check()                     # no barrier ever timed out
+    out["peer_barriers"] = comm.epoch
 if rank == 0:
     print(json.dumps(out))
 if world > 1:
