@@ -344,12 +344,14 @@ int rmt_peer_put2d(const rmt_put2d *desc, int n, void *stream);
  * dst[q] is a device pointer valid in this process (own memory or a mapped peer arena). */
 int rmt_transpose_scatter(const double *in, int R, int C, long ldi, int nparts, const int *start,
                           double *const *dst, const long *dst_ld, void *stream);
-/* Barrier over the ranks of the node on `stream`: flags[q] = rank q's array of >= world uint64 counters as
- * mapped in this process.  Rank r release-stores `epoch` into flags[q][r] of every peer (system scope, after a
- * system fence: everything this stream did before is visible to the peer first), then waits until
- * flags[r][q] >= epoch for every q.  `epoch` must grow by one per barrier, identically on all ranks.
- * A peer that never arrives sets *err (device int) after timeout_s seconds instead of hanging the GPU. */
-int rmt_peer_barrier(void *const *flags, int rank, int world, unsigned long long epoch, double timeout_s,
+/* Barrier on `stream` between this rank and the peers q with epochs[q] != 0 (host array of `world` entries):
+ * flags[q] = rank q's array of >= world uint64 counters as mapped in this process.  Rank r release-stores
+ * epochs[q] into flags[q][r] (system scope, after a system fence: everything this stream did before is visible
+ * to the peer first), then waits until flags[r][q] >= epochs[q].  The two sides of a pair must name each other
+ * in the same barriers and count them identically (epochs[q] grows by one per barrier that involves q).
+ * A peer that never arrives sets *err (device int) after timeout_s seconds instead of hanging the GPU; once
+ * *err is set every later barrier falls through at once. */
+int rmt_peer_barrier(void *const *flags, int rank, int world, const unsigned long long *epochs, double timeout_s,
                      int *err, void *stream);
 /* out[k] = reduction over q = 0..world-1, in that order, of slots[q*stride + k]; op 0 sum, 1 max, 2 min
  * (the local half of the peer all-reduce: bitwise identical on every rank). */

@@ -85,7 +85,7 @@ _SIG = {
     "rmt_peer_release": [vp],
     "rmt_peer_put2d": [vp, i32, vp],
     "rmt_transpose_scatter": [vp, i32, i32, i64, i32, vp, vp, vp, vp],
-    "rmt_peer_barrier": [vp, i32, i32, C.c_ulonglong, dbl, vp, vp],
+    "rmt_peer_barrier": [vp, i32, i32, vp, dbl, vp, vp],
     "rmt_peer_reduce": [vp, i32, i64, i32, i32, vp, vp],
 }
 _RESTYPE = {"rmt_launch_count": C.c_ulonglong, "rmt_extrapolate_workspace_bytes": i64, "rmt_projection_partials": i64, "rmt_poisson_plan_destroy": None}

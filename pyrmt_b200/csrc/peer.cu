@@ -82,6 +82,7 @@ k_transpose_scatter(const double *__restrict__ in, int R, int C, long ldi, const
 
 struct PeerFlags {
     unsigned long long *p[kMaxPeers];   // flag array of every rank (>= world entries), as mapped HERE
+    unsigned long long epoch[kMaxPeers];   // per peer: the value to publish / to wait for; 0 = peer not involved
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *a, unsigned long long v)
@@ -98,17 +99,19 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 // Thread q: tell rank q that this rank has reached `epoch` (everything this stream did before is visible
 // first: kernel boundary + system fence), then wait for rank q's own arrival.  A watchdog ends the wait
 // with *err = 1 instead of hanging the device when a peer never arrives.
-__global__ void k_peer_barrier(const PeerFlags F, int rank, int world, unsigned long long epoch,
-                               long long limit_cycles, int *err)
+__global__ void k_peer_barrier(const PeerFlags F, int rank, int world, long long limit_cycles, int *err)
 {
     const int q = threadIdx.x;
-    if (q >= world || q == rank) return;
+    if (q >= world || q == rank || F.epoch[q] == 0) return;
+    const unsigned long long epoch = F.epoch[q];
     __threadfence_system();
     st_release_sys(F.p[q] + rank, epoch);
     const unsigned long long *mine = F.p[rank] + q;
     const long long t0 = clock64();
     while (ld_acquire_sys(mine) < epoch) {
-        if (clock64() - t0 > limit_cycles) {
+        // after one time-out every later barrier falls through at once: the run ends quickly and wrong
+        // (PeerComm.check() reports it) instead of spinning for the limit again and again
+        if (*(volatile int *)err || clock64() - t0 > limit_cycles) {
             *err = 1;
             break;
         }
@@ -218,18 +221,22 @@ int rmt_transpose_scatter(const double *in, int R, int C, long ldi, int nparts, 
     return RMT_OK;
 }
 
-int rmt_peer_barrier(void *const *flags, int rank, int world, unsigned long long epoch, double timeout_s,
+int rmt_peer_barrier(void *const *flags, int rank, int world, const unsigned long long *epochs, double timeout_s,
                      int *err, void *stream)
 {
-    if (!flags || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !err) return RMT_EINVAL;
+    if (!flags || !epochs || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !err) return RMT_EINVAL;
     if (world == 1) return RMT_OK;
     PeerFlags F;
+    bool any = false;
     for (int q = 0; q < world; ++q) {
         if (!flags[q]) return RMT_EINVAL;
         F.p[q] = (unsigned long long *)flags[q];
+        F.epoch[q] = q == rank ? 0 : epochs[q];
+        any = any || F.epoch[q] != 0;
     }
+    if (!any) return RMT_OK;
     const long long limit = (long long)((timeout_s > 0 ? timeout_s : 5.0) * 1.9e9);
-    k_peer_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(F, rank, world, epoch, limit, err);
+    k_peer_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(F, rank, world, limit, err);
     RMT_LAUNCH_CHECK();
     return RMT_OK;
 }

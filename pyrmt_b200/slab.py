@@ -218,6 +218,12 @@ class _DevMem:
 class _Region:
     def __init__(self, nbytes, local, peers, meta=None):
         self.nbytes, self.local, self.peers, self.meta = nbytes, local, peers, meta
+        self.uses = 0
+
+    def flip(self):
+        """Which of the region's two copies this use takes (they alternate)."""
+        self.uses += 1
+        return (self.uses - 1) & 1
 
 
 class PeerComm(Comm):
@@ -228,16 +234,18 @@ class PeerComm(Comm):
     exchange; the all-to-all of the distributed transforms is fused with the local transpose
     (`scatter` = rmt_transpose_scatter) and the column lines are transformed in place in the arena.
 
-    Ordering: all ranks issue the same sequence of exchanges.  `self.epoch` counts barriers; a staging
-    region holds two copies and exchange e uses copy e & 1, so a copy written before barrier e is read after
-    it and written again before barrier e + 2 at the earliest -- by then its reader has signalled barrier
-    e + 1, which in stream order comes after its reads.  torch.distributed is used for set-up only (the IPC
-    handles travel by all_gather_object), so any backend does -- the 2-process single-GPU test runs on gloo."""
+    Ordering: a barrier involves exactly the ranks that exchange data (neighbours for halos, everybody for
+    the transposes and reductions); each pair of ranks counts the barriers it shares, and both sides of a pair
+    issue the same sequence of exchanges (SPMD).  A staging region holds two copies used alternately: a copy
+    written for use i is read after that use's barrier and written again for use i + 2 at the earliest -- by
+    then the writer has passed the barrier of use i + 1, which its reader signalled after (in stream order)
+    its reads of use i.  torch.distributed is used for set-up only (the IPC handles travel by
+    all_gather_object), so any backend does -- the multi-process single-GPU test runs on gloo."""
 
     SLOT = 64                                   # doubles per rank and all-reduce
     NRED = 4                                    # all-reduces that can share one barrier
 
-    def __init__(self, group=None, timeout_s=120.0):
+    def __init__(self, group=None, timeout_s=None):
         super().__init__(group)
         if not (self.on and self.world > 1):
             raise RuntimeError("PeerComm needs an initialised process group with more than one rank")
@@ -246,8 +254,10 @@ class PeerComm(Comm):
         import ctypes as C
         self.C = C
         self.lib = ctx().lib
-        self.timeout_s = float(timeout_s)
+        import os
+        self.timeout_s = float(timeout_s if timeout_s is not None else os.environ.get("RMT_PEER_TIMEOUT", 60.0))
         self.regions, self.epoch = {}, 0
+        self.pair = [0] * self.world                 # barriers shared with each peer
         self.dev = torch.device("cuda", torch.cuda.current_device())
         self.err = torch.zeros(1, dtype=torch.int32, device=self.dev)
         # control arena: barrier counters (256 B) + two copies of the all-reduce slots
@@ -325,9 +335,17 @@ class PeerComm(Comm):
             arr = (self._Put * len(chunk))(*[self._Put(*b) for b in chunk])
             _lib.check(self.lib.rmt_peer_put2d(arr, len(chunk), stream()), "rmt_peer_put2d")
 
-    def barrier(self):
+    def barrier(self, peers=None):
+        """On-stream barrier with `peers` (default: every other rank)."""
+        peers = [q for q in (range(self.world) if peers is None else set(peers)) if q != self.rank]
+        if not peers:
+            return
         self.epoch += 1
-        _lib.check(self.lib.rmt_peer_barrier(self._flags, self.rank, self.world, self.epoch, self.timeout_s,
+        ep = (self.C.c_ulonglong * self.world)()
+        for q in peers:
+            self.pair[q] += 1
+            ep[q] = self.pair[q]
+        _lib.check(self.lib.rmt_peer_barrier(self._flags, self.rank, self.world, ep, self.timeout_s,
                                              self.err.data_ptr(), stream()), "rmt_peer_barrier")
 
     def scatter(self, A, starts, dst, dst_ld):
@@ -345,7 +363,7 @@ class PeerComm(Comm):
         H = lay.H if width is None else width
         Nx, nf, me = lay.Nx, len(fields), self.rank
         reg = self.region(("halo", nf, H, Nx), 2 * nf * 2 * H * Nx * 8)
-        par = (self.epoch + 1) & 1
+        par = reg.flip()
         slot = lambda base, k, side: base + (((par * nf + k) * 2 + side) * H * Nx) * 8
         up, down = me + 1 < self.world, me > 0
         puts, gets = [], []
@@ -357,12 +375,13 @@ class PeerComm(Comm):
             if down:
                 puts.append((f[lay.o0:lay.o0 + H].data_ptr(), slot(reg.peers[me - 1], k, 1), H, Nx, ld, Nx))
                 gets.append((slot(reg.local, k, 0), f[lay.o0 - H:lay.o0].data_ptr(), H, Nx, Nx, ld))
-        red = [self._reduce_puts(t, k, par) for k, (t, _) in enumerate(reduce)]
+        rpar = self.ctrl.flip() if reduce else 0
+        red = [self._reduce_puts(t, k, rpar) for k, (t, _) in enumerate(reduce)]
         self.put(puts + [b for blocks in red for b in blocks])
-        self.barrier()
+        self.barrier(None if reduce else ([me - 1] if down else []) + ([me + 1] if up else []))
         self.put(gets)
         for k, (t, op) in enumerate(reduce):
-            self._reduce_finish(t, op, k, par)
+            self._reduce_finish(t, op, k, rpar)
 
     def ring_exchange(self, items):
         me, P = self.rank, self.world
@@ -373,7 +392,7 @@ class PeerComm(Comm):
         if max(t.numel() for t in blocks) > slot_n:
             raise RuntimeError("PeerComm.ring_exchange: blocks of at most 4 rows")
         reg = self.region(("ring", len(items), cols), 2 * len(items) * 2 * slot_n * 8)
-        par = (self.epoch + 1) & 1
+        par = reg.flip()
         slot = lambda base, k, side: base + (((par * len(items) + k) * 2 + side) * slot_n) * 8
         blk = lambda t: (t.shape[0], t.shape[1], t.stride(0)) if t.dim() == 2 else (1, t.numel(), t.numel())
         puts, gets = [], []
@@ -391,19 +410,21 @@ class PeerComm(Comm):
                 r, c, ld = blk(from_next)
                 gets.append((slot(reg.local, k, 1), from_next.data_ptr(), r, c, c, ld))
         self.put(puts)
-        self.barrier()
+        self.barrier([nxt, prv])
         self.put(gets)
 
     def exchange_flat(self, send, recv, slot_n):
         """slot_n: an upper bound of every message of this exchange pattern, the same on all ranks."""
         if max([t.numel() for t in list(send.values()) + list(recv.values())] or [0]) > slot_n:
             raise RuntimeError("PeerComm.exchange_flat: a message exceeds the agreed %d doubles" % slot_n)
-        reg = self.region(("flat", slot_n), 2 * self.world * slot_n * 8)
-        par = (self.epoch + 1) & 1
+        reg = self.region(("flat", slot_n), 2 * self.world * slot_n * 8)     # collective on first use
+        if not send and not recv:
+            return
+        par = reg.flip()
         slot = lambda base, src: base + ((par * self.world + src) * slot_n) * 8
         self.put([(t.data_ptr(), slot(reg.peers[q], self.rank), 1, t.numel(), t.numel(), t.numel())
                   for q, t in sorted(send.items())])
-        self.barrier()
+        self.barrier(list(send) + list(recv))
         self.put([(slot(reg.local, q), t.data_ptr(), 1, t.numel(), t.numel(), t.numel())
                   for q, t in sorted(recv.items())])
 
@@ -425,7 +446,7 @@ class PeerComm(Comm):
                    "rmt_peer_reduce")
 
     def allreduce(self, t, op="sum"):
-        par = (self.epoch + 1) & 1
+        par = self.ctrl.flip()
         self.put(self._reduce_puts(t, 0, par))
         self.barrier()
         self._reduce_finish(t, op, 0, par)
@@ -459,7 +480,7 @@ class PeerComm(Comm):
                 puts.append((own.data_ptr(), field_at(reg.peers[q], q, k) + (top_of(q) + n_q) * Nx * 8,
                              wantb, Nx, ld, Nx))
         self.put(puts)
-        self.barrier()
+        self.barrier([q for q in (me - 1, me + 1) if 0 <= q < self.world])
         return [self.view(reg, k * rows_of(me) * Nx * 8, (rows_of(me), Nx)) for k in range(nf)]
 
 
@@ -730,8 +751,8 @@ class RemoteCopies:
         return self._dev
 
     def apply_(self, u, v, comm):
-        if self.n == 0:
-            return
+        if self.max_msg == 0:          # no remote entry anywhere (ranks without entries of their own still
+            return                     # call the exchange: its first use sets up a region collectively)
         give, need = self._on(u.device)
         fu, fv = u.reshape(-1), v.reshape(-1)
         sbufs = {q: torch.cat([fu[iu], fv[iv]]) for q, (iu, iv) in give.items()}

@@ -91,21 +91,23 @@ def test_put2d_batch_and_reduce(lib):
     assert lib.rmt_peer_reduce(None, 5, 64, 7, 0, out.data_ptr(), None) == -1
 
 
-def test_two_ranks_on_one_gpu_match_single_gpu():
-    """Two processes on cuda:0 over CUDA-IPC peer memory: fluid step (halo + DCT solve), full FSI step
-    (overlap gather, extrapolation, lazy-halo RK4), periodic FSI step (ring exchange, remote BC copies,
-    Hartley solve) against the single-GPU operators."""
-    env = dict(os.environ, RMT_SAME_GPU="1", MASTER_ADDR="127.0.0.1")
+@pytest.mark.parametrize("world,N,overlap", [(2, 257, 128), (4, 513, 128)])
+def test_ranks_on_one_gpu_match_single_gpu(world, N, overlap):
+    """`world` processes on cuda:0 over CUDA-IPC peer memory: fluid step (halo + DCT solve), full FSI step
+    (overlap gather, extrapolation, lazy-halo RK4), periodic FSI step (ring exchange, remote BC copies between
+    the first and the last rank only, Hartley solve) against the single-GPU operators.  With 4 ranks the
+    middle ranks have two neighbours and take no part in the wrap-row exchange (pairwise barriers)."""
+    env = dict(os.environ, RMT_SAME_GPU="1", MASTER_ADDR="127.0.0.1", RMT_PEER_TIMEOUT="60")
     env.pop("RMT_SLAB_COMM", None)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-           "--master-addr", "127.0.0.1", "--master-port", "29541",
-           os.path.join(ROOT, "scripts", "slab_check.py"), "--check", "257", "--fsi", "257", "--pfsi", "257",
-           "--overlap", "128"]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29540 + world),
+           os.path.join(ROOT, "scripts", "slab_check.py"), "--check", str(N), "--fsi", str(N), "--pfsi", str(N),
+           "--overlap", str(overlap)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     out = json.loads(line)
-    assert out["world"] == 2 and out["comm"] == "PeerComm"
+    assert out["world"] == world and out["comm"] == "PeerComm"
     assert out["check"]["rel_linf_vs_single_gpu"] <= 1e-12
     for key in ("fsi_check", "periodic_fsi_check"):
         e = out[key]["rel_linf_vs_single_gpu"]
