@@ -27,7 +27,8 @@ operator API (pyrmt_b200.driver.fsi_step).
 --impl reference times that CPU oracle alone (the reference itself is pure
 Python + Numba and cannot travel to the GPU box).
 N > 1: the SAME 4097^2 problem is slab-decomposed over the N GPUs (pyrmt_b200/slab.py: y-slabs,
-NCCL halo exchange, all-to-all transposes in the DCT solve, overlap-swept extrapolation) --
+halo exchange and the transpose + all-to-all of the DCT solve as kernels storing into the peers' memory
+over NVLink (pyrmt_b200/slab.py PeerComm; RMT_SLAB_COMM=nccl: NCCL calls), overlap-swept extrapolation) --
 strong scaling; the results equal the single-GPU step (xi bit for bit).  Beside it: the fluid
 half of the step on one 8193^2 grid (`slab_fluid_step`, Neumann/DCT) and BASELINE configs[4]
 (`config5_periodic`: periodic Taylor-Green FSI at 8193^2 and the periodic fluid step at 16385^2,
@@ -100,7 +101,8 @@ def workload_config(N, scheme, world):
                         % (N, N, N - 1, scheme),
             "grid": [N, N], "discs": 64, "scheme": scheme,
             "cache": "working set ~%.1f GB per step >> 126 MB L2 (no flush needed)" % (25 * cells * 8 / 1e9),
-            "parallelism": ("one grid in %d y-slabs: NCCL halo exchange, all-to-all transposes in the DCT solve, "
+            "parallelism": ("one grid in %d y-slabs: halo rows and the fused transpose + all-to-all of the DCT solve stored "
+                            "straight into the peers' memory over NVLink (CUDA IPC arenas, on-stream barriers), "
                             "overlap-swept extrapolation (strong scaling)" % world) if world > 1 else "single GPU"}
 
 
@@ -247,7 +249,7 @@ def cpu_rate(n_nodes, steps, warmup, scheme, want_reference=True):
 
 
 def slab_fluid_rate(N, steps, rank, world):
-    """Momentum predictor + DCT projection on y-slabs over all ranks (NCCL halo exchange +
+    """Momentum predictor + DCT projection on y-slabs over all ranks (peer-memory halo exchange +
     all-to-all transposes, pyrmt_b200/slab.py): ms per step, max over ranks."""
     import numpy as np
     import torch
@@ -280,7 +282,7 @@ def slab_fluid_rate(N, steps, rank, world):
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / steps
-    return {"what": "momentum_step_rk4 + Neumann/DCT projection, y-slabs, NCCL halo exchange + all-to-all "
+    return {"what": "momentum_step_rk4 + Neumann/DCT projection, y-slabs, peer-memory halo exchange + fused transpose / all-to-all "
                     "transposes (strong scaling: one %dx%d grid over %d GPUs)" % (N, N, world),
             "grid": [N, N], "ms_per_step": ms, "value": N * N / ms / 1e3, "unit": "Mcell-steps/s",
             "finite": bool(torch.isfinite(a).all().item())}
@@ -405,7 +407,7 @@ def main():
         def step(st):
             return fsi_step(st, prm)[0]
     else:
-        # ONE grid over all ranks: y-slabs, NCCL halo exchange, all-to-all transposes in the DCT solve,
+        # ONE grid over all ranks: y-slabs, peer-memory halo exchange, fused transpose + all-to-all in the DCT solve,
         # overlap-swept extrapolation (pyrmt_b200/slab.py); strong scaling of the N = 1 workload
         from pyrmt_b200 import functions as Fn
         from pyrmt_b200.slab import SlabFSISolver, SlabLayout
@@ -415,7 +417,7 @@ def main():
         sprm = dict(prm, X=None, Y=None)
 
         def step(st):
-            return solver.fsi_step(st, sprm, solver.compute_timestep(st[0], st[1], prm), check_guard=False)
+            return solver.fsi_step(st, sprm, None, check_guard=False)      # dt = compute_timestep of the whole grid
         solver.fsi_step(state, sprm, 1e-7, check_guard=True)      # validates the overlap once (raises if too small)
     for _ in range(args.warmup):
         state = step(state)
@@ -429,11 +431,11 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    # Per-entry-point CUDA events (two per call) are recorded inside the timed region when N = 1 (GPU-bound:
-    # they cost nothing there and the roofline is then measured live over the timed steps).  With N > 1 the
-    # step is short enough to be host-bound, so the timed region runs clean and the breakdown comes from
-    # a few extra profiled steps right after it.
-    profiler.reset(timing=(world == 1))
+    # The timed region runs clean: per-entry-point CUDA events (two per call, ~100 per step) cost 0.15 ms per
+    # step at N = 1 (measured: 6.32 ms with them, 6.17 without) and more when the step is host-bound (N > 1).
+    # The kernel breakdown and the roofline come from extra profiled steps right after the timed region,
+    # same state, same stream.
+    profiler.reset(timing=False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     from pyrmt_b200 import _lib as _rmt_lib
     barrier()
@@ -445,13 +447,11 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = int(_rmt_lib.load().rmt_launch_count() - launches0)   # counted inside librmt_b200.so
-    prof_steps = args.steps
-    if world > 1:
-        prof_steps = min(5, args.steps)
-        profiler.reset(timing=True)
-        for _ in range(prof_steps):
-            state = step(state)
-        torch.cuda.synchronize()
+    prof_steps = min(5 if world > 1 else 10, args.steps)
+    profiler.reset(timing=True)
+    for _ in range(prof_steps):
+        state = step(state)
+    torch.cuda.synchronize()
     per_kernel = profiler.summary()
     profiler.reset(timing=False)
     clocks = sampler.stop() if sampler else None
@@ -481,6 +481,7 @@ def main():
         roofline["traffic"] = NCU_TRAFFIC_BYTES_4097.get(kname)
         if roofline["traffic"]:
             roofline["frac_by_traffic"] = roofline["traffic"] / (kavg_ms * 1e-3) / 1e9 / peak
+    roofline["measured_over"] = "%d profiled steps right after the timed region (the timed region itself runs without per-call events)" % prof_steps
     roofline["note"] = ("dominant entry point by summed CUDA-event time; rmt_extrapolate* is bound by the serial "
                         "dependency chain of the reference's raster sweep (latency), not by HBM -- see DESIGN.md 5; "
                         "`kernels_roofline` lists every entry point")
@@ -592,6 +593,13 @@ def main():
     elif world > 1 and not args.no_slab:
         parity = slab_parity_vs_1gpu(1025, args.scheme, rank, world)
 
+    comm_kind = None
+    if world > 1:
+        from pyrmt_b200.slab import PeerComm, default_comm
+        c = default_comm()
+        comm_kind = type(c).__name__
+        if isinstance(c, PeerComm):
+            c.check()                                  # raises if any on-stream barrier ever timed out
     if rank == 0:
         line = {"metric": "Mcell-steps/s full FSI step", "value": value, "unit": "Mcell-steps/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -602,7 +610,7 @@ def main():
                 "step_roofline": {"alg_bytes_per_cell_step": ALG_BYTES_PER_CELL_STEP.get(args.scheme, 512.0),
                                   "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak},
                 "cpu_baseline": cpu, "parity": parity, "kernels": breakdown, "kernels_roofline": kernels_roofline[:8],
-                "finite": finite, "slab_fluid_step": slab, "config5_periodic": cfg5}
+                "finite": finite, "slab_comm": comm_kind, "slab_fluid_step": slab, "config5_periodic": cfg5}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

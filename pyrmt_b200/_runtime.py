@@ -227,6 +227,18 @@ class _Ctx:
                    "rmt_max_speed")
         return out
 
+    def max_speed_async(self, a, b):
+        """max_speed with the two numbers on their way to pinned host memory: returns (host tensor, event);
+        the caller queues whatever does not need them, then `event.synchronize()`."""
+        out = self.max_speed(a, b)
+        ring = self.__dict__.setdefault("_pinned2", [torch.empty(2, dtype=F64, pin_memory=True) for _ in range(8)])
+        host = ring.pop(0)                       # a small ring of pinned landing buffers, reused
+        ring.append(host)
+        host.copy_(out, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return host, ev
+
 
 _ctxs = {}
 

@@ -19,12 +19,15 @@ def fsi_step(state, prm, dt=None):
     """Advance (a, b, p, X1, X2) by one step.  Returns (state, dt, extras)."""
     a, b, p, X1, X2 = state
     dx, dy = prm["dx"], prm["dy"]
-    if dt is None:
-        dt = F.compute_timestep(a, b, dx, dy, prm["CFL"], prm["dt_cap"], prm["mu_s"], prm["rho_s"],
-                                prm.get("gamma", 0.0), prm["rho_f"], mu_f=prm["mu_f"], eta_s=prm["eta_s"],
-                                kappa=prm["kappa"])
+    # compute_timestep needs a host value: its reduction is queued first, the level set (which does not need
+    # dt) behind it, and only then the host waits -- the GPU works through the round trip
+    pending = F.compute_timestep_begin(a, b) if dt is None else None
     phi = F.rebuild_phi_from_reference_map(X1, X2, prm["phi_init"])
     phi = F.reinitialize_level_set(phi, dx, dy, "none")
+    if pending is not None:
+        dt = F.compute_timestep_end(pending, dx, dy, prm["CFL"], prm["dt_cap"], prm["mu_s"], prm["rho_s"],
+                                    prm.get("gamma", 0.0), prm["rho_f"], mu_f=prm["mu_f"], eta_s=prm["eta_s"],
+                                    kappa=prm["kappa"])
     sch, wc = prm["scheme"], prm.get("w_cut", 0.0)
     if prm.get("fuse_pair", True):      # xi1, xi2 and the "* solid_mask" in one pass (bitwise identical)
         X1, X2 = F.advect_reference_map_pair(X1, X2, a, b, prm["X"], prm["Y"], dt, dx, dy, phi, sch, wc,
@@ -81,12 +84,13 @@ def fsi_step_host(host_state, prm, dt=None):
         t.record_stream(main)
     dx, dy = prm["dx"], prm["dy"]
     main.wait_event(ev_ab)
-    if dt is None:
-        dt = F.compute_timestep(a, b, dx, dy, prm["CFL"], prm["dt_cap"], prm["mu_s"], prm["rho_s"],
-                                prm.get("gamma", 0.0), prm["rho_f"], mu_f=prm["mu_f"], eta_s=prm["eta_s"],
-                                kappa=prm["kappa"])
+    pending = F.compute_timestep_begin(a, b) if dt is None else None
     main.wait_event(ev_x)
     phi = F.rebuild_phi_from_reference_map(X1, X2, prm["phi_init"])
+    if pending is not None:
+        dt = F.compute_timestep_end(pending, dx, dy, prm["CFL"], prm["dt_cap"], prm["mu_s"], prm["rho_s"],
+                                    prm.get("gamma", 0.0), prm["rho_f"], mu_f=prm["mu_f"], eta_s=prm["eta_s"],
+                                    kappa=prm["kappa"])
     X1, X2 = F.advect_reference_map_pair(X1, X2, a, b, prm["X"], prm["Y"], dt, dx, dy, phi, prm["scheme"],
                                          prm.get("w_cut", 0.0), mask_solid=True)
     X1, X2 = F.extrapolate_reference_map(X1, X2, phi, dx, dy, prm["layers"])

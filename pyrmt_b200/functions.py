@@ -78,6 +78,25 @@ def compute_timestep(a, b, dx, dy, CFL, dt_min_cap, mu_s, rho_s, gamma, rho_f, m
     return timestep_from_speed(speed, dx, dy, CFL, dt_min_cap, mu_s, rho_s, gamma, rho_f, mu_f, eta_s, kappa)
 
 
+def compute_timestep_begin(a, b):
+    """First half of `compute_timestep` for device tensors: the reduction is queued and its result travels to
+    pinned host memory asynchronously.  Kernels that do not need dt (the level set of the current map) can be
+    queued before `compute_timestep_end` waits for it, so the GPU is not idle during the host round trip."""
+    host, ev = ctx().max_speed_async(to_dev(a), to_dev(b))
+    return (a, b, host, ev)
+
+
+def compute_timestep_end(handle, dx, dy, CFL, dt_min_cap, mu_s, rho_s, gamma, rho_f, mu_f=0.0, eta_s=0.0, kappa=0.0):
+    a, b, host, ev = handle
+    ev.synchronize()
+    speed, bad = float(host[0]), float(host[1])
+    if isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor):
+        finite_cache.put(a, b, bad == 0.0)
+    if bad:
+        speed = float("nan")
+    return timestep_from_speed(speed, dx, dy, CFL, dt_min_cap, mu_s, rho_s, gamma, rho_f, mu_f, eta_s, kappa)
+
+
 def timestep_from_speed(speed, dx, dy, CFL, dt_min_cap, mu_s, rho_s, gamma, rho_f, mu_f=0.0, eta_s=0.0, kappa=0.0):
     """The host formula of compute_timestep (functions.py:177-192) for a given max sqrt(a^2 + b^2)
     (a slab-decomposed run reduces the speed over the ranks first)."""
