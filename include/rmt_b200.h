@@ -125,7 +125,8 @@ int rmt_euler_rhs(const double *q, const double *a, const double *b, const doubl
                   int Ny, int Nx, double dx, double dy, double w_cut, int scheme, void *stream);
 
 /* ------------------------------------------------------------ extrapolation */
-/* pyRMT/functions.py:48-163 extrapolate_reference_map + utils.py:134-167. */
+/* pyRMT/functions.py:48-163 extrapolate_reference_map + utils.py:134-167.  X1e, X2e receive the copies of
+ * :69-70 with the band filled in; X1e == X1 and X2e == X2 (in place, no copy pass) is allowed. */
 long rmt_extrapolate_workspace_bytes(int Ny, int Nx);
 int rmt_extrapolate(const double *X1, const double *X2, const double *phi, double *X1e, double *X2e,
                     int Ny, int Nx, double dx, double dy, int max_layers, void *workspace,

@@ -68,6 +68,27 @@ _LAUNCHES = {"rmt_max_speed": 2, "rmt_field_stats": 2, "rmt_advect_euler_rk3": 5
              "rmt_poisson_plan_create": 0, "rmt_poisson_plan_destroy": 0, "rmt_poisson_plan_is_fast": 0, "rmt_poisson_plan_invalidate": 0}
 
 
+def check_separable_periodic_symbol(eig, null):
+    """The fast periodic solve (csrc/fft.cu: separable Hartley pair, no mean removal before the transform)
+    is the reference's fft2 -> /eig -> ifft2 (functions.py:1216-1233) only for a symbol that is even in each
+    wavenumber separately and whose (0, 0) mode is in the null mask -- what
+    _precompute_poisson_eigenvalues_periodic builds.  The reference accepts any (eig, null) pair, so a table
+    that breaks either assumption is refused here instead of being solved differently (once per table)."""
+    e = torch.as_tensor(eig)
+    n = torch.as_tensor(null).to(torch.bool)
+    fx = lambda t: torch.roll(torch.flip(t, dims=(1,)), 1, dims=1)       # k -> (m - k) mod m along x
+    fy = lambda t: torch.roll(torch.flip(t, dims=(0,)), 1, dims=0)
+    ok = bool(n[0, 0]) and all(bool(torch.equal(n, f(n))) for f in (fx, fy))
+    if ok:
+        m = ~n
+        tol = 1e-12 * float(e[m].abs().max()) if bool(m.any()) else 0.0
+        ok = all(float(((e - f(e)).abs() * m).max()) <= tol for f in (fx, fy))
+    if not ok:
+        raise ValueError("the fast periodic Poisson solve needs a symbol that is even in each wavenumber with the "
+                         "(0, 0) mode in the null mask (as _precompute_poisson_eigenvalues_periodic builds it); "
+                         "this (eig, null_mask) table is not")
+
+
 class Profiler:
     """Optional per-entry-point CUDA-event timing and launch counting (bench.py)."""
 
@@ -175,6 +196,8 @@ class _Ctx:
                     d = torch.from_numpy(np.ascontiguousarray(t, dtype=npdt)).to(self.dev)
                 devs.append(d)
             _lib.check(self.lib.rmt_poisson_plan_invalidate(plan), "rmt_poisson_plan_invalidate")
+            if kind == 1 and self.lib.rmt_poisson_plan_is_fast(plan) == 1:
+                check_separable_periodic_symbol(devs[0], devs[1])
             ent = (ident, tuple(devs), tuple(tables))
             self.plan_tables[key] = ent
         return plan, ent[1]

@@ -14,6 +14,8 @@ callable->device round trip per application (slow path).
 """
 from __future__ import annotations
 
+import collections
+
 import numpy as np
 import torch
 
@@ -130,19 +132,56 @@ def classify(bc, Ny, Nx):
     return table
 
 
-_cache = {}
+_cache = collections.OrderedDict()      # LRU, bounded: key -> (keep-alive objects, table)
+_CACHE_MAX = 64
+
+
+def _callable_key(bc):
+    """What identifies a BC callable for the table cache.
+
+    The reference calls ``bc(u, v)`` on every stage; here the callable is probed ONCE per grid and replayed as
+    a gather table, so it must be a PURE function of (u, v): the same rim copies and constants on every call.
+    Two things follow.  (1) A plain function or lambda is keyed by its code object and the VALUES of its
+    closure cells and defaults, not by ``id``: a lambda re-created inside the time loop hits the cache
+    instead of being re-probed every step, and a closure whose captured lid speed has changed gets a new
+    table.  (2) State the key cannot see (globals, attributes mutated in place, time read from a clock) needs
+    the opt-out ``bc.rmt_dynamic = True``, which sends every application down the host round-trip path.
+    Returns (key, keep_alive) or (None, None) for the dynamic opt-out."""
+    if getattr(bc, "rmt_dynamic", False):
+        return None, None
+    if hasattr(bc, "__self__"):                      # bound method: the object it is bound to is the identity
+        return ("self", id(bc.__self__), getattr(bc.__func__, "__code__", None)), (bc.__self__,)
+    code = getattr(bc, "__code__", None)
+    if code is not None and not hasattr(bc, "rmt_table"):
+        try:
+            vals = tuple(c.cell_contents for c in (bc.__closure__ or ())) + tuple(bc.__defaults__ or ())
+            import types
+            const = (int, float, bool, str, type(None), types.ModuleType, types.FunctionType,
+                     types.BuiltinFunctionType, type)        # values, or objects that stand for themselves
+            if all(isinstance(v, const) for v in vals):
+                return ("code", code, tuple(v if isinstance(v, (int, float, bool, str, type(None))) else id(v)
+                                            for v in vals)), (code, vals)
+        except ValueError:                           # an empty closure cell
+            pass
+    return ("id", id(bc)), (bc,)
 
 
 def table_for(bc, Ny, Nx):
-    key = (id(bc), Ny, Nx)
+    """The gather table of ``bc`` on an (Ny, Nx) grid, or None (slow host path).  See `_callable_key` for
+    the purity requirement and the ``rmt_dynamic`` opt-out."""
+    ck, keep = _callable_key(bc)
+    if ck is None:
+        return None
+    key = (ck, Ny, Nx)
     hit = _cache.get(key)
-    if hit is not None and hit[0] is bc:
+    if hit is not None:
+        _cache.move_to_end(key)
         return hit[1]
     t = getattr(bc, "rmt_table", None)
     table = t(Ny, Nx) if callable(t) else classify(bc, Ny, Nx)
-    if len(_cache) > 256:
-        _cache.clear()
-    _cache[key] = (bc, table)
+    _cache[key] = (keep, table)
+    while len(_cache) > _CACHE_MAX:
+        _cache.popitem(last=False)
     return table
 
 

@@ -93,13 +93,15 @@ __device__ __forceinline__ void st_release(int *p, int v)
 constexpr unsigned char ST_UNKNOWN = 0, ST_KNOWN = 1, ST_TARGET = 2, ST_FRESH = 3;
 
 // seed: copies of X1/X2, known = (phi < 0)          functions.py:69-74
-__global__ void k_ext_seed(const double *__restrict__ X1, const double *__restrict__ X2,
-                           const double *__restrict__ phi, double *__restrict__ X1e,
-                           double *__restrict__ X2e, unsigned char *__restrict__ st, long n)
+__global__ void k_ext_seed(const double *X1, const double *X2, const double *__restrict__ phi, double *X1e,
+                           double *X2e, unsigned char *__restrict__ st, long n)
 {
+    const bool copy = (X1e != X1) || (X2e != X2);      // in place (X1e == X1, X2e == X2): only the state bytes
     for (long k = blockIdx.x * (long)blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x) {
-        X1e[k] = X1[k];
-        X2e[k] = X2[k];
+        if (copy) {
+            X1e[k] = X1[k];
+            X2e[k] = X2[k];
+        }
         st[k] = (phi[k] < 0.0) ? ST_KNOWN : ST_UNKNOWN;
     }
 }
@@ -283,6 +285,11 @@ __device__ __forceinline__ void st_relaxed_gpu(int *p, int v)
     asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// The cross-CTA progress counters are POLLED with relaxed loads (an acquire load per poll would invalidate
+// L1 every time); the acquire that orders the dependent reads of the other CTA's results behind the poll
+// that saw the counter is one fence after the spin loop (PTX memory model: relaxed load + fence.acq_rel
+// synchronises with the writer's fence + relaxed store).
+#define ACQUIRE_GPU() asm volatile("fence.acq_rel.gpu;" ::: "memory")
 __device__ __forceinline__ int ld_relaxed_gpu(const int *p)
 {
     int v;
@@ -587,7 +594,7 @@ k_ext_sweep(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                         }
                     } else {
                         const int *g = prog + jr * nxt + xq;
-                        while (ld_relaxed_gpu(g) <= need) __nanosleep(100);
+                        { while (ld_relaxed_gpu(g) <= need) __nanosleep(100); ACQUIRE_GPU(); }
                     }
                 }
             }
@@ -857,7 +864,10 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                         }
                     }
                     if (need)
+                    {
                         while (ld_relaxed_gpu(progP + jr * nxt + xq) != INT_MAX) __nanosleep(200);
+                        ACQUIRE_GPU();
+                    }
                 }
             }
             __syncwarp();
@@ -966,7 +976,7 @@ k_ext_fused(double *__restrict__ X1e, double *__restrict__ X2e, unsigned char *_
                         if (jr != j) while (sp[jr - row0] <= need) __nanosleep(20);
                     } else {
                         const int *g = progL + jr * nxt + xq;
-                        while (ld_relaxed_gpu(g) <= need) __nanosleep(100);
+                        { while (ld_relaxed_gpu(g) <= need) __nanosleep(100); ACQUIRE_GPU(); }
                     }
                 }
             }

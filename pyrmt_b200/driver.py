@@ -35,7 +35,7 @@ def fsi_step(state, prm, dt=None):
     else:                               # the reference's loop, operator by operator
         X1 = F.mask_solid(F.advect_reference_map(X1, a, b, prm["X"], prm["Y"], dt, dx, dy, phi, sch, wc), phi)
         X2 = F.mask_solid(F.advect_reference_map(X2, a, b, prm["X"], prm["Y"], dt, dx, dy, phi, sch, wc), phi)
-    X1, X2 = F.extrapolate_reference_map(X1, X2, phi, dx, dy, prm["layers"])
+    X1, X2 = F.extrapolate_reference_map(X1, X2, phi, dx, dy, prm["layers"], inplace=bool(prm.get("fuse_pair", True)))
     # level set of the extrapolated map + the stress the predictor needs, in one pass (two operators upstream)
     phi, stress = F.rebuild_phi_and_stress(X1, X2, prm["phi_init"], dx, dy, prm["mu_s"], prm["kappa"], prm["w_t"])
     a_s, b_s, sxx, sxy, syy, J = F.momentum_step_rk4_with_stress(
@@ -93,7 +93,7 @@ def fsi_step_host(host_state, prm, dt=None):
                                     kappa=prm["kappa"])
     X1, X2 = F.advect_reference_map_pair(X1, X2, a, b, prm["X"], prm["Y"], dt, dx, dy, phi, prm["scheme"],
                                          prm.get("w_cut", 0.0), mask_solid=True)
-    X1, X2 = F.extrapolate_reference_map(X1, X2, phi, dx, dy, prm["layers"])
+    X1, X2 = F.extrapolate_reference_map(X1, X2, phi, dx, dy, prm["layers"], inplace=True)   # fresh pair tensors
     ev_xi = main.record_event()
     out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in host_state]
     with torch.cuda.stream(s_out):

@@ -269,15 +269,20 @@ def advect_reference_map(q, a, b, X, Y, dt, dx, dy, phi, scheme='semilagrangian'
 # --------------------------------------------------------------------------
 # narrow-band extrapolation
 # --------------------------------------------------------------------------
-def extrapolate_reference_map(X1, X2, phi, dx, dy, max_layers, row_offset=0):
+def extrapolate_reference_map(X1, X2, phi, dx, dy, max_layers, row_offset=0, inplace=False):
     """pyRMT/functions.py:48-163 -- serial-order-faithful least-squares extrapolation.
     ``row_offset`` (not upstream; default 0): the arrays are rows [row_offset, ...) of a taller
-    grid -- the fit then uses the global y coordinates, which the slab decomposition needs."""
+    grid -- the fit then uses the global y coordinates, which the slab decomposition needs.
+    ``inplace`` (not upstream; device tensors only): X1, X2 are temporaries of the caller and are
+    extrapolated in place instead of into the copies of functions.py:69-70 (saves one pass over both)."""
     as_np = is_np(X1)
     x1, x2, ph = to_dev(X1), to_dev(X2), to_dev(phi)
     Ny, Nx = shape2(x1)
     c = ctx()
-    o1, o2 = torch.empty_like(x1), torch.empty_like(x2)
+    if inplace and not as_np and x1 is X1 and x2 is X2 and x1.data_ptr() != x2.data_ptr():
+        o1, o2 = x1, x2
+    else:
+        o1, o2 = torch.empty_like(x1), torch.empty_like(x2)
     ws = c.extrap_workspace(Ny, Nx)
     profiler.launches += 5 * int(max_layers)
     _chk(c.lib.rmt_extrapolate_rows(ptr(x1), ptr(x2), ptr(ph), ptr(o1), ptr(o2), Ny, Nx, int(row_offset),

@@ -638,6 +638,9 @@ class DistPoissonFFT:
         c0, c1 = lay.c0, lay.c1
         if eig is not None:
             e, null = eig
+            from ._runtime import check_separable_periodic_symbol
+            check_separable_periodic_symbol(torch.from_numpy(np.asarray(e, dtype=np.float64)),
+                                            torch.from_numpy(np.asarray(null, dtype=bool)))
             e, null = np.asarray(e, dtype=np.float64)[:, c0:c1], np.asarray(null, dtype=bool)[:, c0:c1]
             if e.shape[0] != my or np.asarray(eig[0]).shape != (my, mx):
                 raise ValueError("periodic eigenvalues do not match the reduced grid %s" % ((my, mx),))
@@ -1121,7 +1124,8 @@ class SlabFSISolver(SlabFluidSolver):
             if not ok:
                 raise RuntimeError("slab extrapolation: a body reaches above the %d-row overlap of some rank "
                                    "(this is rank %d); increase `overlap`" % (self.top, lay.rank))
-        E1, E2 = F.extrapolate_reference_map(B1, B2, Bphi, dx, dy, self.layers, row_offset=lay.r0 - self.top)
+        E1, E2 = F.extrapolate_reference_map(B1, B2, Bphi, dx, dy, self.layers, row_offset=lay.r0 - self.top,
+                                             inplace=True)             # B1, B2 are this step's work fields
         self._dbg("extrapolated", E1, E2)
         n_own = lay.r1 - lay.r0
         X1n, X2n = torch.empty_like(a), torch.empty_like(a)

@@ -221,6 +221,26 @@ def test_extrapolation_linear_exact(P):
     assert np.max(np.abs(X2e[band] - Y[band])) < 1e-8
 
 
+def test_extrapolation_in_place_equals_copy(P):
+    """inplace=True (the step drivers' temporaries) writes the same bits as the copying form of
+    functions.py:69-70 and leaves ndarray / aliased inputs to the copying form."""
+    import torch
+    N = 257
+    X, Y, dx, dy = P.create_grid(N, N, 1.0, 1.0)
+    phi = np.minimum(np.sqrt((X - 0.3) ** 2 + (Y - 0.35) ** 2) - 0.17, np.sqrt((X - 0.7) ** 2 + (Y - 0.7) ** 2) - 0.2)
+    m = (phi <= 0).astype(float)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    x1, x2, ph = up(np.sin(X) * m), up((Y + 0.1 * X * X) * m), up(phi)
+    r1, r2 = P.extrapolate_reference_map(x1, x2, ph, dx, dy, 3)
+    assert r1.data_ptr() != x1.data_ptr() and torch.equal(x1, up(np.sin(X) * m))      # inputs untouched
+    y1, y2 = x1.clone(), x2.clone()
+    q1, q2 = P.extrapolate_reference_map(y1, y2, ph, dx, dy, 3, inplace=True)
+    assert q1 is y1 and q2 is y2
+    assert torch.equal(q1, r1) and torch.equal(q2, r2)
+    a1, a2 = P.extrapolate_reference_map(np.sin(X) * m, (Y + 0.1 * X * X) * m, phi, dx, dy, 3, inplace=True)
+    assert same(a1, r1.cpu().numpy()) and same(a2, r2.cpu().numpy())                  # ndarrays: copying form
+
+
 # ----------------------------------------------------------------- advection
 @pytest.mark.parametrize("scheme", ["semilagrangian", "semilagrangian_cubic", "central2", "weno5",
                                     "conservative"])
@@ -634,6 +654,32 @@ def test_periodic_fast_solve_vs_oracle(P, O, Ny, Nx):
     from pyrmt_b200._runtime import ctx
     assert ctx().lib.rmt_poisson_plan_is_fast(ctx().plan(Ny, Nx, 1)) == 1
     assert rel_linf(P._solve_poisson_fft(rhs, eig), O._solve_poisson_fft(rhs, eig)) < 1e-11
+
+
+def test_periodic_fast_solve_refuses_a_non_separable_symbol(P, O):
+    """the Hartley fast path equals fft2 -> /eig -> ifft2 only for a symbol even in each wavenumber
+    with the (0, 0) mode masked.  The reference accepts ANY (eig, null) pair: on a power-of-two grid such a
+    table must be refused (never solved differently); the dense path of the other sizes solves it like the
+    reference does."""
+    rng = np.random.default_rng(11)
+    for N, fast in ((129, 1), (101, 0)):
+        X, Y, dx, dy = O.create_grid(N, N, 1.0, 1.0)
+        eig, null = O._precompute_poisson_eigenvalues_periodic(N, N, dx, dy)
+        odd = eig.copy()
+        odd[3, 5] *= 1.5                                   # breaks eig[j, k] == eig[j, m - k]
+        rhs = rng.standard_normal((N, N))
+        from pyrmt_b200._runtime import ctx
+        assert ctx().lib.rmt_poisson_plan_is_fast(ctx().plan(N, N, 1)) == fast
+        if fast:
+            with pytest.raises(ValueError):
+                P._solve_poisson_fft(rhs, (odd, null))
+            unmasked = null.copy()
+            unmasked[0, 0] = False
+            with pytest.raises(ValueError):
+                P._solve_poisson_fft(rhs, (eig, unmasked))
+        else:
+            assert rel_linf(P._solve_poisson_fft(rhs, (odd, null)), O._solve_poisson_fft(rhs, (odd, null))) < 1e-11
+        assert rel_linf(P._solve_poisson_fft(rhs, (eig, null)), O._solve_poisson_fft(rhs, (eig, null))) < 1e-11
 
 
 def test_dht_lines_building_block(P):

@@ -58,7 +58,7 @@ def test_signatures_match_reference_names():
     expect = {
         F.create_grid: "(Nx, Ny, Lx, Ly)",
         F.apply_phi_BCs: "(phi)",
-        F.extrapolate_reference_map: "(X1, X2, phi, dx, dy, max_layers, row_offset=0)",
+        F.extrapolate_reference_map: "(X1, X2, phi, dx, dy, max_layers, row_offset=0, inplace=False)",
         F.compute_timestep: "(a, b, dx, dy, CFL, dt_min_cap, mu_s, rho_s, gamma, rho_f, mu_f=0.0, eta_s=0.0, kappa=0.0)",
         F.advect_semilagrangian_rk4: "(q, a, b, X, Y, dt, dx, dy)",
         F.advect_semilagrangian_cubic_rk4: "(q, a, b, X, Y, dt, dx, dy)",
@@ -198,3 +198,34 @@ def test_disc_bins_are_a_superset():
         b = by[k] * gb + bx[k]
         assert best[k] in cand[start[b]:start[b + 1]]
     assert start[-1] < 12 * gb * gb          # the lists stay short
+
+
+def test_bc_table_cache_keys_closures_by_value(monkeypatch):
+    """a lambda re-created every step must not be re-probed every step, a closure whose captured
+    value changed must get a new table, and `rmt_dynamic = True` opts out of the table altogether."""
+    from pyrmt_b200 import bc as B
+    calls = {"n": 0}
+    real = B.classify
+
+    def counting(f, Ny, Nx):
+        calls["n"] += 1
+        return real(f, Ny, Nx)
+    monkeypatch.setattr(B, "classify", counting)
+    B._cache.clear()
+
+    def make(speed):
+        return lambda u, v: B.no_slip_lid_bc(u, v, speed)
+    t1 = B.table_for(make(1.0), 17, 19)
+    for _ in range(5):                              # "per-step lambdas": same code, same captured value
+        assert B.table_for(make(1.0), 17, 19) is t1
+    assert calls["n"] == 1
+    t2 = B.table_for(make(2.0), 17, 19)             # a ramped lid speed: new value, new table
+    assert calls["n"] == 2 and t2 is not t1
+    u = np.zeros((17, 19)); v = np.zeros((17, 19))
+    assert t2.apply_host(u, v)[0][-1, 5] == 2.0 and t1.apply_host(u, v)[0][-1, 5] == 1.0
+    dyn = make(3.0)
+    dyn.rmt_dynamic = True
+    assert B.table_for(dyn, 17, 19) is None and calls["n"] == 2
+    for k in range(B._CACHE_MAX + 10):              # bounded
+        B.table_for(make(10.0 + k), 9, 9)
+    assert len(B._cache) <= B._CACHE_MAX
