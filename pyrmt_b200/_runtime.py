@@ -254,8 +254,10 @@ class _Ctx:
         """max_speed with the two numbers on their way to pinned host memory: returns (host tensor, event);
         the caller queues whatever does not need them, then `event.synchronize()`."""
         out = self.max_speed(a, b)
-        ring = self.__dict__.setdefault("_pinned2", [torch.empty(2, dtype=F64, pin_memory=True) for _ in range(8)])
-        host = ring.pop(0)                       # a small ring of pinned landing buffers, reused
+        ring = self.__dict__.get("_pinned2")
+        if ring is None:                         # a small ring of pinned landing buffers, made once
+            ring = self.__dict__["_pinned2"] = [torch.empty(2, dtype=F64, pin_memory=True) for _ in range(8)]
+        host = ring.pop(0)
         ring.append(host)
         host.copy_(out, non_blocking=True)
         ev = torch.cuda.Event()

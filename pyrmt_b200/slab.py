@@ -864,7 +864,9 @@ class SlabFluidSolver:
         """The reduction, its all-reduce and the copy to pinned host memory, all queued; the caller queues
         what does not need dt (the level set) before `compute_timestep_end` waits for the two numbers."""
         out = self.max_speed(a, b)
-        ring = self.__dict__.setdefault("_pinned2", [torch.empty(2, dtype=F64, pin_memory=True) for _ in range(8)])
+        ring = self.__dict__.get("_pinned2")
+        if ring is None:                         # pinned landing buffers, made once
+            ring = self.__dict__["_pinned2"] = [torch.empty(2, dtype=F64, pin_memory=True) for _ in range(8)]
         host = ring.pop(0)
         ring.append(host)
         host.copy_(out, non_blocking=True)
