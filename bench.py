@@ -541,9 +541,27 @@ def main():
     # ---- the sharded sides of the path: the Neumann fluid half at 8193^2 (N > 1) and BASELINE configs[4]
     #      (periodic Taylor-Green: FSI at 8193^2, fluid half at 16385^2) -- at EVERY N including 1, so that
     #      the driver's scaling run carries its own 1 -> 8 curve for them
-    slab = cfg5 = None
+    slab = cfg5 = also_L32 = None
     del state
     torch.cuda.empty_cache()
+    if world == 1 and not args.no_slab:
+        # "run L = 1 as the headline and also L = 32 (dx = 1/128)" -- the same grid, discs and
+        # kernels on the larger box, where the reference's absolute |det| > 1e-10 gate (functions.py:155) is wide open
+        st32, prm32 = make_case(N, L=32.0, k_side=8, R_frac=0.04, scheme=args.scheme, bc_kind="lid")
+        for _ in range(3):
+            st32 = fsi_step(st32, prm32)[0]
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        g0.record()
+        for _ in range(5):
+            st32 = fsi_step(st32, prm32)[0]
+        g1.record()
+        torch.cuda.synchronize()
+        also_L32 = {"what": "the same step on the L = 32 box (dx = 1/128), 5 steps after 3", "grid": [N, N], "L": 32.0,
+                    "ms_per_step": g0.elapsed_time(g1) / 5, "value": cells * 5 / (g0.elapsed_time(g1) * 1e-3) / 1e6,
+                    "unit": "Mcell-steps/s", "finite": bool(torch.isfinite(st32[0]).all().item())}
+        del st32, prm32
+        torch.cuda.empty_cache()
     if not args.no_slab:
         if world > 1:
             slab = slab_fluid_rate(args.slab_size, 10, rank, world)
@@ -610,7 +628,8 @@ def main():
                 "step_roofline": {"alg_bytes_per_cell_step": ALG_BYTES_PER_CELL_STEP.get(args.scheme, 512.0),
                                   "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak},
                 "cpu_baseline": cpu, "parity": parity, "kernels": breakdown, "kernels_roofline": kernels_roofline[:8],
-                "finite": finite, "slab_comm": comm_kind, "slab_fluid_step": slab, "config5_periodic": cfg5}
+                "finite": finite, "also_L32": also_L32, "slab_comm": comm_kind, "slab_fluid_step": slab,
+                "config5_periodic": cfg5}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
