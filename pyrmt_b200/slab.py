@@ -226,6 +226,10 @@ class _Region:
         return (self.uses - 1) & 1
 
 
+class PeerUnavailable(RuntimeError):
+    """The peer-memory transport cannot be set up on this node (raised on EVERY rank together)."""
+
+
 class PeerComm(Comm):
     """The same exchange patterns as `Comm`, but over NVLink PEER MEMORY instead of NCCL calls: every rank
     owns arenas (csrc/peer.cu: cudaMalloc + CUDA IPC) that all other ranks of the node map, and an exchange
@@ -284,22 +288,39 @@ class PeerComm(Comm):
         dist.all_gather_object(sizes, (int(nbytes), meta), group=self.group)
         total = (max(x[0] for x in sizes) + 255) // 256 * 256
         meta = max(x[1] for x in sizes) if meta is not None else None
-        base = C.c_void_p()
-        _lib.check(self.lib.rmt_peer_alloc(total, C.byref(base)), "rmt_peer_alloc")
-        handle = (C.c_ubyte * 64)()
-        _lib.check(self.lib.rmt_peer_export(base, handle), "rmt_peer_export")
+        # every step's verdict is shared before anybody acts on it: a rank-local raise would leave the others
+        # waiting in the next collective
+        base, handle, why = C.c_void_p(), (C.c_ubyte * 64)(), None
+        try:
+            import os
+            if os.environ.get("RMT_PEER_DISABLE_IPC") == "1":       # test hook: exercise the fallback
+                raise RuntimeError("CUDA IPC disabled by RMT_PEER_DISABLE_IPC")
+            _lib.check(self.lib.rmt_peer_alloc(total, C.byref(base)), "rmt_peer_alloc(%d bytes)" % total)
+            _lib.check(self.lib.rmt_peer_export(base, handle), "rmt_peer_export")
+        except Exception as e:
+            why = repr(e)
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle), group=self.group)
+        dist.all_gather_object(handles, (why, bytes(handle)), group=self.group)
+        if any(h[0] for h in handles):
+            raise PeerUnavailable("arena %r: %s" % (key, [h[0] for h in handles if h[0]][0]))
         peers = []
         for q in range(self.world):
             if q == self.rank:
                 peers.append(base.value)
                 continue
-            h = (C.c_ubyte * 64).from_buffer_copy(handles[q])
+            h = (C.c_ubyte * 64).from_buffer_copy(handles[q][1])
             mapped = C.c_void_p()
-            _lib.check(self.lib.rmt_peer_import(h, C.byref(mapped)), "rmt_peer_import (CUDA IPC between the ranks)")
+            try:
+                _lib.check(self.lib.rmt_peer_import(h, C.byref(mapped)), "rmt_peer_import (CUDA IPC between ranks %d and %d)"
+                           % (self.rank, q))
+            except Exception as e:
+                why = repr(e)
+                break
             peers.append(mapped.value)
-        dist.barrier(group=self.group)                 # nobody stores into an arena that is not mapped yet
+        verdicts = [None] * self.world               # doubles as the barrier: nobody stores into an unmapped arena
+        dist.all_gather_object(verdicts, why, group=self.group)
+        if any(verdicts):
+            raise PeerUnavailable("arena %r: %s" % (key, [v for v in verdicts if v][0]))
         r = self.regions[key] = _Region(total, base.value, peers, meta)
         return r
 
@@ -493,7 +514,14 @@ def default_comm(group=None):
             and os.environ.get("RMT_SLAB_COMM", "peer").lower() != "nccl":
         key = (id(group), torch.cuda.current_device())
         if key not in _peer_comms:                     # one set of arenas per process group and device
-            _peer_comms[key] = PeerComm(group)
+            try:
+                _peer_comms[key] = PeerComm(group)
+            except PeerUnavailable as e:               # e.g. CUDA IPC forbidden between the ranks' containers
+                import sys
+                if dist.get_rank(group) == 0:
+                    print("pyrmt_b200.slab: peer-memory exchanges unavailable (%s); using torch.distributed "
+                          "collectives" % e, file=sys.stderr)
+                _peer_comms[key] = Comm(group)
         return _peer_comms[key]
     return Comm(group)
 
