@@ -510,13 +510,7 @@ def main():
         def host_step(hs):
             if world == 1:                    # the package's host-state entry point (copies overlapped with the step)
                 return fsi_step_host(hs, prm)
-            st = tuple(t.to("cuda", non_blocking=True) for t in hs)
-            new = step(st)
-            out = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in new)
-            for h, d in zip(out, new):
-                h.copy_(d, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return out
+            return solver.fsi_step_host(hs, sprm)   # the slab counterpart: same overlap of the PCIe traffic, per rank
         hstate = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in state)
         hstate = host_step(hstate)            # warm-up
         barrier()
@@ -538,7 +532,8 @@ def main():
                "call": ("pyrmt_b200.driver.fsi_step_host: the five state fields pinned host -> device -> fsi step -> "
                         "pinned host every step, uploads ordered by first use and xi downloads overlapped with "
                         "the predictor/projection on copy streams") if world == 1 else
-                       "the five state fields (per rank: its slab) pinned host -> device -> slab fsi step -> pinned host"}
+                       "pyrmt_b200.slab.SlabFSISolver.fsi_step_host: the five state fields (per rank: its slab) pinned host -> "
+                       "device -> slab fsi step -> pinned host every step, copies overlapped like the single-GPU call"}
 
     # ---- N > 1: the part of the step that IS slab-decomposed (momentum + projection) ----
     # ---- the sharded sides of the path: the Neumann fluid half at 8193^2 (N > 1) and BASELINE configs[4]

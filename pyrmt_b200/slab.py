@@ -1115,15 +1115,19 @@ class SlabFSISolver(SlabFluidSolver):
             print("[rank %d] %s max|.|: %s" % (self.lay.rank, tag, ["%.3e" % float(f.abs().max().item()) for f in fields]),
                   flush=True)
 
-    def fsi_step(self, state, prm, dt=None, check_guard=True):
+    def fsi_step(self, state, prm, dt=None, check_guard=True, hooks=None):
         """dt=None: compute_timestep of the whole grid (prm carries CFL, dt_cap, ...), its host round trip
-        hidden behind the level-set kernel."""
+        hidden behind the level-set kernel.  hooks (fsi_step_host): 'need_xi' / 'need_p' are called before the
+        first use of the map / the pressure, 'xi_done'(X1, X2) as soon as the new map is final."""
         from . import functions as F
         lay, comm = self.lay, self.comm
+        hooks = hooks or {}
         a, b, p, X1, X2 = state
         self._dbg("state", a, b, p, X1, X2)
         dx, dy = prm["dx"], prm["dy"]
         pending = self.compute_timestep_begin(a, b) if dt is None else None
+        if "need_xi" in hooks:
+            hooks["need_xi"]()
         phi = F.rebuild_phi_from_reference_map(X1, X2, self.phi_init)
         if pending is not None:
             dt = self.compute_timestep_end(pending, prm)
@@ -1162,9 +1166,13 @@ class SlabFSISolver(SlabFluidSolver):
         lay.owned(X1n).copy_(E1[self.top:self.top + n_own])
         lay.owned(X2n).copy_(E2[self.top:self.top + n_own])
         comm.halo_exchange(lay, (X1n, X2n))
+        if "xi_done" in hooks:
+            hooks["xi_done"](X1n, X2n)
         # rows of the halo that lie outside every neighbour's ownership do not exist; domain-edge slabs
         # have no halo there.  (Halo rows are now the neighbours' exact values.)
         phi = F.rebuild_phi_from_reference_map(X1n, X2n, self.phi_init)
+        if "need_p" in hooks:
+            hooks["need_p"]()
         a_s, b_s, *_ = self.momentum_step(a, b, p, X1n, X2n, phi, prm["mu_s"], prm["kappa"], prm["eta_s"], dx, dy,
                                           dt, prm["rho_s"], prm["rho_f"], prm["mu_f"], prm["w_t"])
         self._dbg("predictor", a_s, b_s)
@@ -1177,6 +1185,54 @@ class SlabFSISolver(SlabFluidSolver):
             a, b, p = self.projection(a_s, b_s, p, rho_local, dx, dy, dt)
         self._dbg("projected", a, b, p)
         return (a, b, p, X1n, X2n)
+
+    def fsi_step_host(self, host_state, prm, dt=None, check_guard=False):
+        """One step with this rank's slab of the state in pinned HOST tensors (what bench.py times as `e2e` with
+        more than one GPU) -- the slab counterpart of driver.fsi_step_host: the five fields go up on a copy
+        stream in the order the step consumes them (a, b for dt; xi1, xi2 for the advection; p only before the
+        predictor) and xi1, xi2 start their way back as soon as their halos are exchanged, while the predictor
+        and the projection still run."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if not hasattr(self, "_copy_streams"):
+            self._copy_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, s_out = self._copy_streams
+        main = torch.cuda.current_stream(dev)
+        ha, hb, hp, h1, h2 = host_state
+        s_in.wait_stream(main)
+        with torch.cuda.stream(s_in):
+            a, b = ha.to(dev, non_blocking=True), hb.to(dev, non_blocking=True)
+            ev_ab = s_in.record_event()
+            X1, X2 = h1.to(dev, non_blocking=True), h2.to(dev, non_blocking=True)
+            ev_x = s_in.record_event()
+            p = hp.to(dev, non_blocking=True)
+            ev_p = s_in.record_event()
+        for t in (a, b, p, X1, X2):
+            t.record_stream(main)
+        out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in host_state]
+
+        def xi_done(X1n, X2n):
+            ev = main.record_event()
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev)
+                out[3].copy_(X1n, non_blocking=True)
+                out[4].copy_(X2n, non_blocking=True)
+            X1n.record_stream(s_out)
+            X2n.record_stream(s_out)
+
+        main.wait_event(ev_ab)
+        new = self.fsi_step((a, b, p, X1, X2), prm, dt, check_guard=check_guard,
+                            hooks={"need_xi": lambda: main.wait_event(ev_x), "xi_done": xi_done,
+                                   "need_p": lambda: main.wait_event(ev_p)})
+        ev_done = main.record_event()
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_done)
+            for h, d in zip(out[:3], new[:3]):
+                h.copy_(d, non_blocking=True)
+        for t in new[:3]:
+            t.record_stream(s_out)
+        s_out.synchronize()
+        main.wait_stream(s_out)
+        return tuple(out)
 
 
 def slab_initial_state(solver, L, sdf, velocity=None):
@@ -1279,7 +1335,8 @@ def time_periodic_fsi(N, world, rank, steps=5, warmup=3, L=None, overlap=512, sc
             "value": N * N / ms / 1e3, "unit": "Mcell-steps/s",
             "finite": bool(fin),
             "max_abs_xi": float(xi_max.item()),
-            "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}
+            "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30,
+            "peer_arena_GB": sum(r.nbytes for r in getattr(solver.comm, "regions", {}).values()) / 2 ** 30}
 
 
 def time_periodic_fluid(N, world, rank, steps=5, warmup=3, L=1.0):
@@ -1312,4 +1369,5 @@ def time_periodic_fluid(N, world, rank, steps=5, warmup=3, L=1.0):
                     "%dx%d grid" % (world, type(solver.comm).__name__, N, N),
             "grid": [N, N], "ms_per_step": ms, "value": N * N / ms / 1e3, "unit": "Mcell-steps/s",
             "finite": bool(torch.isfinite(a).all().item()), "max_abs_u": float(a.abs().max().item()),
-            "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}
+            "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30,
+            "peer_arena_GB": sum(r.nbytes for r in getattr(solver.comm, "regions", {}).values()) / 2 ** 30}
