@@ -574,6 +574,13 @@ def main():
         torch.cuda.empty_cache()
         cfg5["fluid_step"] = time_periodic_fluid(args.cfg5_fluid_size, world, rank, steps=5, warmup=3)
         torch.cuda.empty_cache()
+        if world > 1:        # P GPUs against one at the full size of config 5 (untimed; every rank holds the whole grid too)
+            from pyrmt_b200.slab import periodic_fluid_parity
+            try:
+                cfg5["fluid_step_parity_vs_1gpu"] = periodic_fluid_parity(args.cfg5_fluid_size, world, rank, steps=2)
+            except (ValueError, RuntimeError, NotImplementedError) as e:
+                cfg5["fluid_step_parity_vs_1gpu"] = {"error": repr(e)[:300], "ok": False}
+            torch.cuda.empty_cache()
         cfg5["note"] = ("full FSI at 16385^2 is not runnable with the reference's own algorithm (absolute-coordinate "
                         "normal equations lose all significance at index ~16384: pinned by "
                         "tests/test_gpu_parity.py::test_extrapolation_large_row_offset_matches_oracle, DESIGN.md 6): "

@@ -741,7 +741,7 @@ def pressure_projection_amg(a_star, b_star, dx, dy, dt, rho, velocity_bc, A=None
     ssum = torch.empty(4, dtype=F64, device=ad.device)
     if periodic:
         eig_h, null_h = eigenvalues
-        if tuple(np.shape(eig_h)) != (Ny - 1, Nx - 1):
+        if tuple(eig_h.shape if isinstance(eig_h, torch.Tensor) else np.shape(eig_h)) != (Ny - 1, Nx - 1):
             raise ValueError("periodic eigenvalues do not match the reduced grid")
         plan, (eig, null) = c.plan_with_tables(Ny, Nx, 1, (eig_h, null_h), (F64, torch.uint8))
         _chk(lib.rmt_poisson_solve_fft(plan, ptr(rhs), ptr(eig), ptr(null), ptr(sol), ptr(ssum),

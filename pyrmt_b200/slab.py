@@ -1371,3 +1371,54 @@ def time_periodic_fluid(N, world, rank, steps=5, warmup=3, L=1.0):
             "finite": bool(torch.isfinite(a).all().item()), "max_abs_u": float(a.abs().max().item()),
             "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30,
             "peer_arena_GB": sum(r.nbytes for r in getattr(solver.comm, "regions", {}).values()) / 2 ** 30}
+
+
+def periodic_fluid_parity(N, world, rank, steps=2, L=1.0):
+    """P GPUs against ONE: the fluid half of config 5 (momentum RK4 + periodic Hartley/FFT projection of a
+    Taylor-Green flow) at full size.  Every rank also runs the single-GPU operators on the whole N x N grid
+    (47 GB at 16385^2: it fits) and compares its own rows after every step; the verdict is all-reduced.
+    The full-grid fields and the (eig, null) tables of functions.py:1177-1202 are built on the device (the 1-D
+    factors with NumPy, as the reference does; their outer sum is the same fp64 addition)."""
+    from . import functions as F
+    from .bc import apply_bc_
+    from .driver import PeriodicBC
+    bc = PeriodicBC()
+    lay = SlabLayout(N, N, world, rank, halo=4, periodic=True)
+    dx = L / (N - 1)
+    solver = SlabFluidSolver(lay, bc, None, spacing=(dx, dx))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    up = lambda arr: torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(dev)
+    x = np.linspace(0.0, L, N)
+    k, U0 = 2.0 * np.pi / L, 0.05
+    a = torch.outer(up(np.cos(k * x)), up(U0 * k * np.sin(k * x)))         # a[j, i] = U0 k sin(k x_i) cos(k y_j)
+    b = torch.outer(up(np.sin(k * x)), up(-U0 * k * np.cos(k * x)))
+    a, b = apply_bc_(bc, a, b)
+    p = torch.zeros_like(a)
+    sa, sb, sp = (lay.take(t).clone() for t in (a, b, p))
+    mx = my = N - 1
+    lam = -(np.sin(2.0 * np.pi * np.arange(mx) / mx) / dx) ** 2
+    eig = up(lam)[None, :] + up(lam)[:, None]
+    null = eig.abs() < 1e-12
+    eig = torch.where(null, torch.ones_like(eig), eig)
+    null = null.to(torch.uint8)
+    ones, sones = torch.ones_like(a), torch.ones_like(sa)
+    mu_f = 1e-3
+    dt = min(0.2 * dx / 0.32, 0.2 * dx * dx / (4 * mu_f))
+    prm = dict(dx=dx, dy=dx, mu_s=0.0, kappa=0.0, eta_s=0.0, rho_s=1.0, rho_f=1.0, mu_f=mu_f, w_t=2 * dx)
+    worst = torch.zeros(3, dtype=F64, device=dev)
+    for _ in range(steps):
+        a_s, b_s, *_ = F.momentum_step_rk4(a, b, p, a, b, bc, 0.0, 0.0, 0.0, dx, dx, dt, 1.0, 1.0, ones, mu_f, 2 * dx)
+        a, b, p, _, _ = F.pressure_projection_amg(a_s, b_s, dx, dx, dt, 1.0, bc, p_prev=p, eigenvalues=(eig, null),
+                                                  bc_type="periodic")
+        del a_s, b_s
+        sa, sb, sp = solver.fluid_step(sa, sb, sp, sa, sb, sones, prm, dt)
+        for q, (ref, got) in enumerate(((a, sa), (b, sb), (p, sp))):
+            err = (ref[lay.r0:lay.r1] - lay.owned(got)).abs().max() / ref.abs().max().clamp_min(1e-300)
+            worst[q] = torch.maximum(worst[q], err)
+    solver.comm.allreduce(worst, "max")
+    rel = dict(zip(("u", "v", "p"), (float(v) for v in worst.tolist())))
+    return {"what": "periodic fluid step on %d GPUs against the single-GPU operators on the same %dx%d grid, %d "
+                    "steps, own rows of every rank" % (world, N, N, steps),
+            "grid": [N, N], "rel_linf": rel, "max_rel_linf": max(rel.values()), "tolerance": 1e-10,
+            "ok": bool(max(rel.values()) <= 1e-10)}
+
