@@ -1826,8 +1826,13 @@ __global__ void k_ext_decide(const int *__restrict__ cnt0, const int *__restrict
     }
 }
 
-// layer-0 target counts per (row, x-tile), without touching the state bytes
-__global__ void k_ext_count0(const unsigned char *__restrict__ st, int *__restrict__ cnt0,
+// layer-0 target counts per (row, x-tile), without touching the state bytes.
+// SEED: the state bytes do not exist yet -- "known" is phi < 0 (functions.py:72), read for the three rows as
+// coalesced doubles and turned into neighbour masks with ballots; the task also WRITES the state bytes of its
+// own row segment, so the seed pass is not needed (in-place extrapolation: nothing to copy either).
+template <bool SEED>
+__global__ void k_ext_count0(const unsigned char *__restrict__ st, const double *__restrict__ phi,
+                             unsigned char *__restrict__ st_out, int *__restrict__ cnt0,
                              int *__restrict__ rows_macro /* [macro-row][x-tile], zeroed */, int macro,
                              int *__restrict__ rows_band /* [row band][x-tile], zeroed */, int band,
                              int *__restrict__ cmin0, int *__restrict__ cmax0 /* first / last target column */,
@@ -1842,9 +1847,9 @@ __global__ void k_ext_count0(const unsigned char *__restrict__ st, int *__restri
     // in flight the better
     for (int task = warp; task < Ny * nxt; task += nwarp) {
         const int j = task / nxt;
-        const unsigned char *r1 = st + (size_t)j * Nx;
         const bool inner = (j >= 1 && j < Ny - 1);
-        const unsigned char *r0 = inner ? r1 - Nx : r1, *r2 = inner ? r1 + Nx : r1;
+        const size_t o1 = (size_t)j * Nx, o0 = inner ? o1 - Nx : o1, o2 = inner ? o1 + Nx : o1;
+        const unsigned char *r1 = st + o1, *r0 = st + o0, *r2 = st + o2;
         {
             const int xt = task - j * nxt;
             int cnt = 0, cmin = INT_MAX, cmax = -1, chunks = 0;
@@ -1853,6 +1858,45 @@ __global__ void k_ext_count0(const unsigned char *__restrict__ st, int *__restri
             // of L2 round trips otherwise (96 us at 4097^2 when the eight neighbours waited for the cell itself)
             for (int base0 = xt * XT; base0 < cend; base0 += 128) {
                 unsigned me[4], nb[4];
+                unsigned tm[4];                      // SEED: target mask of each chunk
+                if (SEED) {
+                    double p0[4], p1[4], p2[4], q0[4], q1[4], q2[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int base = base0 + 32 * u, i = base + lane;
+                        p0[u] = p1[u] = p2[u] = q0[u] = q1[u] = q2[u] = 1.0;     // "not known"
+                        if (i < Nx && base < cend) {
+                            p0[u] = __ldg(phi + o0 + i);
+                            p1[u] = __ldg(phi + o1 + i);
+                            p2[u] = __ldg(phi + o2 + i);
+                        }
+                        // the columns just outside the chunk: lane 0 fetches base - 1, lane 31 base + 32
+                        const int e = (lane == 0) ? base - 1 : ((lane == 31) ? base + 32 : -1);
+                        if (e >= 0 && e < Nx && base < cend) {
+                            q0[u] = __ldg(phi + o0 + e);
+                            q1[u] = __ldg(phi + o1 + e);
+                            q2[u] = __ldg(phi + o2 + e);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int base = base0 + 32 * u, i = base + lane;
+                        const unsigned k0 = __ballot_sync(0xffffffffu, p0[u] < 0.0);
+                        const unsigned k1 = __ballot_sync(0xffffffffu, p1[u] < 0.0);
+                        const unsigned k2 = __ballot_sync(0xffffffffu, p2[u] < 0.0);
+                        const unsigned e0 = __ballot_sync(0xffffffffu, q0[u] < 0.0);   // bit 0: left column, bit 31: right
+                        const unsigned e1 = __ballot_sync(0xffffffffu, q1[u] < 0.0);
+                        const unsigned e2 = __ballot_sync(0xffffffffu, q2[u] < 0.0);
+                        if (i < cend) st_out[o1 + i] = ((k1 >> lane) & 1u) ? ST_KNOWN : ST_UNKNOWN;
+                        // known neighbours: left / right shifts of the three rows (edge columns spliced in) + above, below
+                        const unsigned l0 = (k0 << 1) | (e0 & 1u), rr0 = (k0 >> 1) | (e0 & 0x80000000u);
+                        const unsigned l1 = (k1 << 1) | (e1 & 1u), rr1 = (k1 >> 1) | (e1 & 0x80000000u);
+                        const unsigned l2 = (k2 << 1) | (e2 & 1u), rr2 = (k2 >> 1) | (e2 & 0x80000000u);
+                        const unsigned nbm = l0 | k0 | rr0 | l1 | rr1 | l2 | k2 | rr2;
+                        const bool valid = inner && i >= 1 && i < Nx - 1 && i < cend;
+                        tm[u] = ~k1 & nbm & __ballot_sync(0xffffffffu, valid);
+                    }
+                } else {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int i = base0 + 32 * u + lane;
@@ -1863,11 +1907,12 @@ __global__ void k_ext_count0(const unsigned char *__restrict__ st, int *__restri
                         nb[u] = r0[i - 1] | r0[i] | r0[i + 1] | r1[i - 1] | r1[i + 1] | r2[i - 1] | r2[i] | r2[i + 1];
                     }
                 }
+                }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int base = base0 + 32 * u;
                     const bool tgt = !(me[u] & 1) && (nb[u] & 1);
-                    const unsigned m = __ballot_sync(0xffffffffu, tgt);
+                    const unsigned m = SEED ? tm[u] : __ballot_sync(0xffffffffu, tgt);
                     cnt += __popc(m);
                     if (m) {
                         cmin = min(cmin, base + __ffs(m) - 1);
@@ -2072,8 +2117,15 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
     volatile double rr = 4.0 * sqrt(ssum);
     double r2 = rr * rr;
 
-    k_ext_seed<<<flat_blocks((long)ncell), 256, 0, s>>>(X1, X2, phi, X1e, X2e, st, (long)ncell);
-    RMT_LAUNCH_CHECK();
+    // The seed pass (copies + state bytes) is skipped when there is nothing to copy (in place) AND the layer-0
+    // count below runs: that kernel then derives "known" from phi itself and writes the state bytes.
+    const bool in_place = (X1e == X1) && (X2e == X2);
+    bool seeded = false;
+    if (!in_place) {
+        k_ext_seed<<<flat_blocks((long)ncell), 256, 0, s>>>(X1, X2, phi, X1e, X2e, st, (long)ncell);
+        RMT_LAUNCH_CHECK();
+        seeded = true;
+    }
     RMT_CUDA(cudaMemsetAsync(tile_counter, 0, 6 * sizeof(int), s));      // tile counter, mode[0..3] = per-layer
 
     // ---- all layers in one launch when that is faster; which variant is decided on the device ----
@@ -2127,10 +2179,16 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
                 RMT_CUDA(cudaMemsetAsync(progF, 0, (size_t)(prog_ints + nbusy + ntile_total + BODY_KMAX) * sizeof(int), s));
                 int rwb = rmt_cdiv((long)Ny * nxtf * 32, 256);
                 if (rwb > 148 * 8) rwb = 148 * 8;
-                k_ext_count0<<<rwb, 256, 0, s>>>(st, cnt0, busy, macro, busy + nmac, band, cnt0 + nsegf,
-                                                 cnt0 + 2 * nsegf, cnt0 + 3 * nsegf, tilecnt, bviol, Lyr + 5, Ny, Nx,
-                                                 nxtf, XTf);
+                if (seeded)
+                    k_ext_count0<false><<<rwb, 256, 0, s>>>(st, phi, st, cnt0, busy, macro, busy + nmac, band, cnt0 + nsegf,
+                                                            cnt0 + 2 * nsegf, cnt0 + 3 * nsegf, tilecnt, bviol, Lyr + 5,
+                                                            Ny, Nx, nxtf, XTf);
+                else
+                    k_ext_count0<true><<<rwb, 256, 0, s>>>(st, phi, st, cnt0, busy, macro, busy + nmac, band, cnt0 + nsegf,
+                                                           cnt0 + 2 * nsegf, cnt0 + 3 * nsegf, tilecnt, bviol, Lyr + 5,
+                                                           Ny, Nx, nxtf, XTf);
                 RMT_LAUNCH_CHECK();
+                seeded = true;
                 k_ext_decide<<<1, 64, 0, s>>>(cnt0, busy, nmrb, macro, busy + nmac, nbnd / nxtf, band, nxtf, Ny,
                                               Lyr, D.resident16 * 9 / 10, D.resident8 * 9 / 10, force.variant,
                                               force.rows, force.pre_warps, tilecnt, bviol, body_ok, fused_ok, mode);
@@ -2177,6 +2235,10 @@ int rmt_extrapolate_rows(const double *X1, const double *X2, const double *phi, 
         }
     }
 
+    if (!seeded) {        // in place and no all-layers candidate: the per-layer kernels need the state bytes
+        k_ext_seed<<<flat_blocks((long)ncell), 256, 0, s>>>(X1, X2, phi, X1e, X2e, st, (long)ncell);
+        RMT_LAUNCH_CHECK();
+    }
     const size_t sweep_smem = sizeof(SweepSmem);
     int row_warps_blocks = rmt_cdiv((long)Ny * 32, 256);
     if (row_warps_blocks > 148 * 8) row_warps_blocks = 148 * 8;
