@@ -62,7 +62,7 @@ ALG_BYTES_PER_CELL_LAUNCH = {
     "rmt_projection_correct_centered": 8.0 * 7.0,   # sol, a*, b*, p in; a, b, p out
     "rmt_disc_sdf_stress": 8.0 * 7.0,     # xi1, xi2 in; phi, sxx, sxy, syy, J out
     "rmt_extrapolate": 8.0 * 5.0,        # a dependency-chain (latency) kernel, not a bandwidth one
-    "rmt_extrapolate_rows": 8.0 * 5.0,
+    "rmt_extrapolate_rows": 8.0 * 1.0,   # in place (the step drivers): phi in, state bytes + band cells out
     "rmt_advect_euler_rk3_pair": 8.0 * 7.0,    # operator boundary: xi1, xi2, a, b, phi in, xi1', xi2' out (the three
                                                # SSP-RK3 stages move more: see `traffic`)
     "rmt_dct_lines": 8.0 * 2.0,
@@ -78,19 +78,19 @@ ALG_BYTES_PER_CELL_LAUNCH = {
 
 
 # DRAM bytes per call (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full` capture of
-# this workload at 4097^2 on one B200 (profiles/r01e_/r01h_/r01j_ncu_full_summary.txt); per-call = sum over the
+# this workload at 4097^2 on one B200 (profiles/r0*_ncu_full_summary.txt, one per round); per-call = sum over the
 # kernels the entry point launches.  Only reported for N = 1 at the default size.
-NCU_TRAFFIC_BYTES_4097 = {                 # profiles/r02_ncu_full_summary.txt (one steady step, round 2)
-    "rmt_extrapolate_rows": 0.70e9,        # k_ext_body 0.036 GB (it works out of L1/L2 and shared memory) + the seed
-                                           # kernel's 5 fields (0.65 GB) + the layer-0 count (0.02 GB)
-    "rmt_momentum_stage": 1.595e9,         # mean of the four stages (1.46 / 1.73 / 1.73 / 1.47 GB)
-    "rmt_advect_euler_rk3_pair": 1.83e9,   # classify 0.14 + three stage kernels 0.38 + 0.50 + 0.81 GB
-    "rmt_poisson_solve_dct": 1.235e9,      # 2 x lines<0> (0.22 + 0.21) + lines<1> (0.36) + 2 x transpose (0.22)
-    "rmt_projection_correct_centered": 0.904e9,
-    "rmt_projection_rhs": 0.519e9,
-    "rmt_disc_sdf_stress": 1.02e9,
-    "rmt_disc_sdf": 0.376e9,
-    "rmt_max_speed": 0.272e9,
+NCU_TRAFFIC_BYTES_4097 = {                 # profiles/r02h_ncu_full_summary.txt (one steady step, end of round 2)
+    "rmt_extrapolate_rows": 0.185e9,       # in place: layer-0 count + state bytes 0.148 GB (phi once, 1 B/cell out),
+                                           # k_ext_body 0.036 GB (it works out of L1/L2 and shared memory)
+    "rmt_momentum_stage": 1.594e9,         # mean of the four stages (1.45 / 1.72 / 1.72 / 1.47 GB)
+    "rmt_advect_euler_rk3_pair": 1.84e9,   # classify 0.14 + three stage kernels 0.38 + 0.50 + 0.81 GB
+    "rmt_poisson_solve_dct": 1.238e9,      # 2 x lines<0> (0.22 + 0.21) + lines<1> (0.36) + 2 x transpose (0.22)
+    "rmt_projection_correct_centered": 0.903e9,
+    "rmt_projection_rhs": 0.520e9,
+    "rmt_disc_sdf_stress": 0.887e9,
+    "rmt_disc_sdf": 0.377e9,
+    "rmt_max_speed": 0.275e9,
 }
 
 
