@@ -239,6 +239,20 @@ __device__ __forceinline__ double unpack_dct(const double *re, const double *im,
     return 0.5 * ((ar + br) + w.x * (ai + bi) - w.y * (ar - br));
 }
 
+// The pair (X_k, X_{M-k}), 0 < k <= M/2, from ONE set of shared-memory reads: both coefficients are built from
+// Z_k and Z_{M-k}, and (cos, sin)(pi (M-k) / M) = (-cos, sin)(pi k / M).
+__device__ __forceinline__ void unpack_dct_pair(const double *re, const double *im, int k, int M, int lg,
+                                                const double2 *__restrict__ tw2, double &xk, double &xmk)
+{
+    const int pa = padi(rev_pos(k, lg)), pb = padi(rev_pos(M - k, lg));
+    const double ar = re[pa], ai = im[pa], br = re[pb], bi = im[pb];
+    const double2 w = __ldg(tw2 + k);
+    const double sr = ar + br, si = ai + bi, dr = ar - br;
+    const double t = w.x * si - w.y * dr;
+    xk = 0.5 * (sr + t);
+    xmk = 0.5 * (sr - t);
+}
+
 __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src)
 {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -291,8 +305,13 @@ k_dct_lines(const double *in, double *out, const double *__restrict__ eig, int n
         if (MODE == 1) {
             // spectrum x scale/eig -> staging buffer (natural order) -> packed again -> second FFT
             const double *er = eig + (size_t)r * N;
-            for (int k = g.tid; k <= M; k += g.nthr)
-                stage[k] = unpack_dct(re, im, k, M, lg, tw2) * (scale / __ldg(er + k));
+            for (int k = g.tid; k <= (M >> 1); k += g.nthr) {       // coefficients k and M - k together
+                double xk, xmk;
+                if (k == 0) { xk = re[0] + im[0]; xmk = re[0] - im[0]; }
+                else unpack_dct_pair(re, im, k, M, lg, tw2, xk, xmk);
+                stage[k] = xk * (scale / __ldg(er + k));
+                if (k != M - k) stage[M - k] = xmk * (scale / __ldg(er + M - k));
+            }
             g.sync();
             pack_even(stage, re, im, M, g);
             g.sync();
@@ -302,10 +321,18 @@ k_dct_lines(const double *in, double *out, const double *__restrict__ eig, int n
         }
         double *o = out + (size_t)r * N;
         const double sc = (MODE == 1) ? 1.0 : scale;
-        for (int k = g.tid; k <= M; k += g.nthr) {
-            double v = unpack_dct(re, im, k, M, lg, tw2) * sc;
-            o[k] = v;
-            s += v;
+        for (int k = g.tid; k <= (M >> 1); k += g.nthr) {           // coefficients k and M - k together
+            double xk, xmk;
+            if (k == 0) { xk = re[0] + im[0]; xmk = re[0] - im[0]; }
+            else unpack_dct_pair(re, im, k, M, lg, tw2, xk, xmk);
+            xk *= sc;
+            o[k] = xk;
+            s += xk;
+            if (k != M - k) {
+                xmk *= sc;
+                o[M - k] = xmk;
+                s += xmk;
+            }
         }
     }
     if (partial) {
