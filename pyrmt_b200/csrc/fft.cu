@@ -143,19 +143,32 @@ __device__ __forceinline__ void stage_radix4(double *re, double *im, int L, int 
     g.sync();
 }
 
-// two fused radix-4 DIF levels (sub-lengths n and n/4) on 16 register-resident points
+// two fused radix-4 DIF levels (sub-lengths n and n/4) on 16 register-resident points.
+// xline != nullptr (first pass of a DCT line, n == L): the inputs are taken straight from the real line
+// x[0..L] in shared memory -- point p of the packed even extension is (e[2p], e[2p+1]), e[m] = x[m] for
+// m <= L and x[2L - m] beyond -- so no separate packing pass (and its barrier) is needed.
 __device__ __forceinline__ void stage_radix16(double *re, double *im, int L, int n,
-                                              const double2 *__restrict__ tw, const Grp &g)
+                                              const double2 *__restrict__ tw, const Grp &g,
+                                              const double *xline = nullptr)
 {
     const int st = n >> 4;                       // spacing of the 16 points
     const int ts1 = L / n;                       // twiddle stride: w_n^k = tw[k * ts1]
     for (int b = g.tid; b < (L >> 4); b += g.nthr) {
         const int k0 = b & (st - 1), base = ((b - k0) << 4) + k0;
         cplx a[16];
+        if (xline) {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                int i0 = 2 * (base + m * st), i1 = i0 + 1;
+                if (i1 > L) { i0 = 2 * L - i0; i1 = 2 * L - i1; }
+                a[m] = {xline[i0], xline[i1]};
+            }
+        } else {
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
             const int p = padi(base + m * st);
             a[m] = {re[p], im[p]};
+        }
         }
         // ONE table lookup per pass: b1 = w_n^k0.  Everything else follows by powers:
         // w_n^(q (k0 + r n/16)) = b1^q * w_16^(q r)  and  w_(n/4)^(q' k0) = (b1^4)^q'.
@@ -200,6 +213,26 @@ __device__ void fft_dif(double *re, double *im, int L, const double2 *__restrict
 {
     int n = L;
     for (; n >= 16; n >>= 4) stage_radix16(re, im, L, n, tw, g);
+    for (; n >= 4; n >>= 2) stage_radix4(re, im, L, n, tw, g);
+    if (n == 2) stage_radix2(re, im, L, g);
+}
+
+// DCT lines of compile-time length: first pass straight from the real line (see stage_radix16), ...
+template <int L>
+__device__ __forceinline__ void fft_first_from_line(const double *xline, double *re, double *im,
+                                                    const double2 *__restrict__ tw, const Grp &g)
+{
+    static_assert(L >= 16, "radix-16 first pass");
+    stage_radix16(re, im, L, L, tw, g, xline);
+}
+// ... then the remaining passes
+template <int L>
+__device__ __forceinline__ void fft_rest_ct(double *re, double *im, const double2 *__restrict__ tw, const Grp &g)
+{
+    int n = L >> 4;
+#pragma unroll
+    for (; n >= 16; n >>= 4) stage_radix16(re, im, L, n, tw, g);
+#pragma unroll
     for (; n >= 4; n >>= 2) stage_radix4(re, im, L, n, tw, g);
     if (n == 2) stage_radix2(re, im, L, g);
 }
@@ -296,12 +329,19 @@ k_dct_lines(const double *in, double *out, const double *__restrict__ eig, int n
     for (; r < nrows; r += ngroups) {
         cp_async_wait_all();
         g.sync();                                   // staged line complete; previous unpack done
-        pack_even(stage, re, im, M, g);
-        g.sync();
         const int rn = r + ngroups;                 // prefetch the next line behind the (last) FFT
-        if (MODE == 0 && rn < nrows)
-            for (int k = g.tid; k < N; k += g.nthr) cp_async8(stage + k, in + (size_t)rn * N + k);
-        if (LGT) fft_dif_ct<(LGT ? (1 << LGT) : 2)>(re, im, tw, g); else fft_dif(re, im, M, tw, g);
+        if (LGT) {                                  // first pass reads the line itself: no packing pass
+            fft_first_from_line<(LGT ? (1 << LGT) : 16)>(stage, re, im, tw, g);
+            if (MODE == 0 && rn < nrows)            // (the staging buffer is free once that pass is through)
+                for (int k = g.tid; k < N; k += g.nthr) cp_async8(stage + k, in + (size_t)rn * N + k);
+            fft_rest_ct<(LGT ? (1 << LGT) : 16)>(re, im, tw, g);
+        } else {
+            pack_even(stage, re, im, M, g);
+            g.sync();
+            if (MODE == 0 && rn < nrows)
+                for (int k = g.tid; k < N; k += g.nthr) cp_async8(stage + k, in + (size_t)rn * N + k);
+            fft_dif(re, im, M, tw, g);
+        }
         if (MODE == 1) {
             // spectrum x scale/eig -> staging buffer (natural order) -> packed again -> second FFT
             const double *er = eig + (size_t)r * N;
@@ -313,11 +353,18 @@ k_dct_lines(const double *in, double *out, const double *__restrict__ eig, int n
                 if (k != M - k) stage[M - k] = xmk * (scale / __ldg(er + M - k));
             }
             g.sync();
-            pack_even(stage, re, im, M, g);
-            g.sync();
-            if (rn < nrows)
-                for (int k = g.tid; k < N; k += g.nthr) cp_async8(stage + k, in + (size_t)rn * N + k);
-            if (LGT) fft_dif_ct<(LGT ? (1 << LGT) : 2)>(re, im, tw, g); else fft_dif(re, im, M, tw, g);
+            if (LGT) {
+                fft_first_from_line<(LGT ? (1 << LGT) : 16)>(stage, re, im, tw, g);
+                if (rn < nrows)
+                    for (int k = g.tid; k < N; k += g.nthr) cp_async8(stage + k, in + (size_t)rn * N + k);
+                fft_rest_ct<(LGT ? (1 << LGT) : 16)>(re, im, tw, g);
+            } else {
+                pack_even(stage, re, im, M, g);
+                g.sync();
+                if (rn < nrows)
+                    for (int k = g.tid; k < N; k += g.nthr) cp_async8(stage + k, in + (size_t)rn * N + k);
+                fft_dif(re, im, M, tw, g);
+            }
         }
         double *o = out + (size_t)r * N;
         const double sc = (MODE == 1) ? 1.0 : scale;
