@@ -134,6 +134,21 @@ def _worker(rank, world, port, Ny, Nx, out):
         sol, total = solver.solve(torch.from_numpy(np.ascontiguousarray(rhs[lay.r0:lay.r1])))
         sol = sol.numpy() - float(total) / (Ny * Nx)
         err = float(np.max(np.abs(sol - ref[lay.r0:lay.r1])) / np.max(np.abs(ref)))
+        # round 2: the solution written straight into a caller's slab with the partial sum all-reduced on the
+        # barrier of the next halo exchange (one row wide), and the overlap gather of the extrapolation
+        ext = torch.full((lay.nl, Nx), -5.0, dtype=torch.float64)
+        part = solver.solve(torch.from_numpy(np.ascontiguousarray(rhs[lay.r0:lay.r1])), out=lay.owned(ext),
+                            reduce=False)
+        comm.halo_exchange(lay, (ext,), width=1, reduce=((part, "sum"),))
+        lo, hi = (lay.o0 - 1 if rank > 0 else lay.o0), (lay.o1 + 1 if rank + 1 < world else lay.o1)
+        got = ext[lo:hi].numpy() - float(part) / (Ny * Nx)
+        err = max(err, float(np.max(np.abs(got - ref[lay.e0 + lo:lay.e0 + hi])) / np.max(np.abs(ref))))
+        err = max(err, abs(float(part) - float(total)) / max(abs(float(total)), 1e-300))
+        glob = torch.from_numpy(rng.standard_normal((Ny, Nx)))
+        top_of = lambda q: min(5, lay.rows[q][0])
+        bot_of = lambda q: min(3, Ny - lay.rows[q][1])
+        (big,) = comm.gather_overlap(lay, (lay.take(glob).clone(),), top_of(rank), bot_of(rank), top_of, bot_of)
+        ok_halo = ok_halo and bool(torch.equal(big, glob[lay.r0 - top_of(rank):lay.r1 + bot_of(rank)]))
         mx = comm.allreduce(torch.tensor([float(rank + 3)]), "max")
         # collective verdicts: one rank's failure must become every rank's verdict
         agree = comm.all_agree([True, rank != world - 1, rank != 0])
