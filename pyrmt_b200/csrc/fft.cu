@@ -170,6 +170,29 @@ __device__ __forceinline__ void stage_radix16(double *re, double *im, int L, int
             a[m] = {re[p], im[p]};
         }
         }
+        if (st == 1) {
+            // the n = 16 pass (the last one of a 4096-point transform): k0 = 0, so every w_n^k0 is exactly 1 --
+            // only the constant w_16^(q r) remain in the first level and the second level has no twiddles
+            // (multiplying by (1, 0) returns the operand bit for bit, so this is the same arithmetic with the
+            // no-ops left out; n is a compile-time constant on the specialised paths and the branch folds)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                bfly4(a[r], a[r + 4], a[r + 8], a[r + 12]);
+                if (r) {
+#pragma unroll
+                    for (int q = 1; q < 4; ++q) a[r + 4 * q] = cmul(a[r + 4 * q], kW16[(q * r) & 15]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) bfly4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int p = padi(base + m * st);
+                re[p] = a[m].x;
+                im[p] = a[m].y;
+            }
+            continue;
+        }
         // ONE table lookup per pass: b1 = w_n^k0.  Everything else follows by powers:
         // w_n^(q (k0 + r n/16)) = b1^q * w_16^(q r)  and  w_(n/4)^(q' k0) = (b1^4)^q'.
         const double2 b1 = __ldg(tw + k0 * ts1);
