@@ -11,13 +11,16 @@
 //   * rmt_transpose_scatter                 the local transpose AND the all-to-all of the distributed
 //                                           DCT / Hartley solve in one kernel: every 32x32 tile is turned
 //                                           in shared memory and written to the rank that owns its columns
-//   * rmt_peer_barrier                      one release-store per peer + acquire polls (system scope)
-//   * rmt_peer_allreduce                    every rank stores its vector into every peer's slot; after the
-//                                           barrier each rank adds the slots in rank order (same bits on all)
+//   * rmt_peer_barrier                      one release-store per involved peer + acquire polls (system scope)
+//   * rmt_peer_reduce                       the local half of the all-reduce: every rank has stored its vector
+//                                           into slot [rank] of every rank (rmt_peer_put2d); after the barrier
+//                                           each rank reduces the slots in rank order (same bits on all ranks)
 //
-// Ordering contract: all ranks issue the same sequence of exchanges (SPMD); a region of the arena that is
-// written before barrier k is read after it and not written again before barrier k + 2 (the Python side
-// alternates two copies of every staging region, pyrmt_b200/slab.py PeerComm).
+// Ordering contract (pyrmt_b200/slab.py PeerComm): a barrier names the peers that trade data in this exchange;
+// each PAIR of ranks counts the barriers it shares, and both sides of a pair issue the same sequence (SPMD).
+// A staging region holds two copies used alternately: a copy written for use i is read after that use's
+// barrier and written again for use i + 2 at the earliest -- by then the writer has passed the barrier of use
+// i + 1, which its reader signalled after (in stream order) its reads of use i.
 #include <string.h>
 
 #include "common.cuh"
